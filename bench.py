@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: Annex-B NAL split + EPB strip (BASELINE.json config 2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size-mb M]
+
+A step = one pass of the hot path (fused scan + strip kernel) over one 4 GiB synthetic
+Annex-B buffer per GPU (weak scaling: rank r holds byte-range shard r of a 4N GiB
+stream; no data-path collective — per-shard results are merged on the host).
+
+value  : input GB/s with the buffer resident in HBM (CUDA events around K steps).
+e2e    : same metric through h264gpu_split_strip_host — pinned HOST input, H2D, kernel,
+         D2H of NAL tables + RBSP inside the timed region.
+roofline: algorithmic bytes (N_in + N_rbsp + 24 B per NAL) / step time vs measured HBM peak.
+cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref/libh264_ref.so:
+         h264_find_nalu loop + h264_bs_read_bits(8) loop) on the box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "annexb_split_strip_throughput"
+UNIT = "GB/s"
+SEED = 0x264
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_workload(L, size_bytes, seed, out=None, nthreads=None):
+    """Config-2 stream: NAL sizes log-uniform 64 B..256 KiB, P(00)=3/16, escaped, mixed
+    3/4-byte start codes, 0-2 trailing zero bytes on a quarter of the NALs."""
+    target = int(size_bytes * 0.992)  # escaping + start codes add ~0.7 %
+    offs = L.synth_offsets(seed, target)
+    rbsp = L.synth_payloads(seed, offs, nthreads=nthreads)
+    stream, nal_off = L.synth_annexb(seed, rbsp, offs, out=out, nthreads=nthreads)
+    return stream, rbsp, offs
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev_index):
+        self.dev, self.rows, self.proc = dev_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8 and f[0] == str(self.dev):
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in self.rows)]
+        top = sorted(sm)[len(sm) // 2:] if sm else []  # upper half = samples under load
+        return {"sm_mhz": statistics.median(top) if top else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def ref_lib():
+    so = os.path.join(ROOT, "oracle", "_ref", "libh264_ref.so")
+    kind = "reference"
+    if not os.path.exists(so):
+        return None, None
+    lib = C.CDLL(so)
+    lib.ref_mt_split_strip.restype = C.c_double
+    lib.ref_mt_split_strip.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    return lib, kind
+
+
+def cpu_reference_run(stream, sample_bytes, cores, reps=1):
+    """Reference scan + strip of stream[:sample_bytes] on `cores` threads; best of reps."""
+    lib, kind = ref_lib()
+    if lib is None:
+        return None
+    sample = stream[:sample_bytes]
+    scratch = np.empty(len(sample) + 64, np.uint8)
+    nn, rb = C.c_uint64(0), C.c_uint64(0)
+    best = None
+    for _ in range(reps):
+        dt = lib.ref_mt_split_strip(sample.ctypes.data_as(C.c_void_p), len(sample), cores, 1,
+                                    scratch.ctypes.data_as(C.c_void_p), C.byref(nn), C.byref(rb))
+        best = dt if best is None else min(best, dt)
+    return {"value": len(sample) / best / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "first %.0f MiB of the same stream, reference h264_find_nalu loop + "
+                      "h264_bs_read_bits(8) strip loop, %d threads over byte ranges, best of %d"
+                      % (len(sample) / 2**20, cores, reps),
+            "seconds": best, "nals": nn.value}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    import libh264_b200 as L
+    cores = min(os.cpu_count() or 1, 256)
+    size = args.size_mb << 20
+    # bounded sample: ~0.12 GB/s per core, aim at ~3 s per step
+    sample = min(size, max(64 << 20, int(0.12e9 * cores * 3)))
+    stream, _, _ = make_workload(L, sample, SEED)
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(stream, len(stream), cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libh264_ref.so missing"}))
+            return
+        if i >= args.warmup:
+            times.append(r["seconds"])
+    ms = 1e3 * sum(times) / len(times)
+    val = len(stream) / (ms / 1e3) / 1e9
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "annexb_scan_strip", "sample_mib": len(stream) >> 20,
+                   "full_size_mib_per_gpu": args.size_mb, "nal_bytes": "loguniform[64,262144]",
+                   "p_zero": 0.1875},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "each step = reference scan+strip of a %d MiB prefix-shaped stream "
+                                   "(same generator/seed as the GPU arm) on %d threads" % (len(stream) >> 20, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--size-mb", type=int, default=4096, help="input MiB per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import libh264_b200 as L
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    g = L.Gpu(local_rank)
+    size = args.size_mb << 20
+    nthreads = max(1, min(os.cpu_count() or 1, 64) // max(1, min(world, 8)))
+
+    # ---- workload: rank r's shard, generated straight into pinned host memory ----
+    t0 = time.time()
+    pin_in = g.pinned(size + 4096)
+    stream, rbsp_ref, offs = make_workload(L, size, SEED + rank, out=pin_in.array, nthreads=nthreads)
+    n_in = len(stream)
+    n_nal_expected = len(offs) - 1
+    n_rbsp_expected = len(rbsp_ref)
+    del rbsp_ref
+    gen_s = time.time() - t0
+
+    cap = n_nal_expected + 1024
+    d_in = g.alloc(n_in + 16)
+    d_rbsp = g.alloc(n_in + 16)
+    d_tab = g.alloc(cap * 8 * 3)
+    d_res = g.alloc(C.sizeof(L.ScanResult))
+    L._check(g.lib.h264gpu_memcpy_h2d(g.h, C.c_void_p(d_in.ptr), pin_in.array.ctypes.data_as(C.c_void_p),
+                                     n_in, None), "h2d")
+    g.sync()
+
+    edge = None
+    if world > 1:  # shard r of a 4N GiB stream: neighbours' bytes are setup, not data path
+        import torch
+        mine = torch.tensor([int(stream[0]), int(stream[1]), int(stream[-2]), int(stream[-1])],
+                            dtype=torch.int32, device="cuda")
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        edge = L.ShardEdge()
+        if rank > 0:
+            edge.has_left, edge.left[0], edge.left[1] = 1, int(allh[rank - 1][2]), int(allh[rank - 1][3])
+            edge.assume_in = 1
+        if rank < world - 1:
+            edge.has_right, edge.right[0], edge.right[1] = 1, int(allh[rank + 1][0]), int(allh[rank + 1][1])
+
+    def step():
+        g.split_strip_dev(d_in.ptr, n_in, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8, d_tab.ptr + cap * 16,
+                          cap, d_res.ptr, base=rank * n_in, edge=edge)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident leg -------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    g.sync()
+    barrier()
+    launches0 = g.launch_count()
+    tm = g.timer()
+    g.timer_start(tm)
+    for _ in range(args.steps):
+        step()
+    g.timer_stop(tm)
+    ms_total = g.timer_ms(tm)
+    g.sync()
+    barrier()
+    launches = g.launch_count() - launches0
+    ms_step = max_over_ranks(ms_total / args.steps)
+
+    res = L.ScanResult.from_buffer_copy(d_res.download().tobytes())
+    ok = (res.n_nal == n_nal_expected and res.rbsp_bytes == n_rbsp_expected)
+    if not ok:
+        print("bench: result mismatch: n_nal %d (want %d) rbsp %d (want %d)" %
+              (res.n_nal, n_nal_expected, res.rbsp_bytes, n_rbsp_expected), file=sys.stderr)
+        sys.exit(1)
+
+    total_in = sum_over_ranks(float(n_in))
+    value = total_in / (ms_step / 1e3) / 1e9
+    alg_bytes = n_in + res.rbsp_bytes + 24 * res.n_nal
+    achieved = alg_bytes / (ms_total / args.steps / 1e3) / 1e9
+    peak, peak_src = measured_peak()
+
+    # ---- end-to-end leg: pinned host in -> tables + RBSP in pinned host out ----
+    pin_rbsp = g.pinned(n_in + 4096)
+    tabs = g.pinned(cap * 8 * 3)
+    tv = tabs.view(np.uint64)
+    out = dict(start=tv[:cap], end=tv[cap:2 * cap], rbsp_off=tv[2 * cap:3 * cap], rbsp=pin_rbsp.array)
+    h = g.split_strip_host(stream, cap=cap, out=out)  # warm-up (allocates the chunk pipeline)
+    if h["n_nal"] != n_nal_expected or h["rbsp_bytes"] != n_rbsp_expected:
+        print("bench: e2e result mismatch", file=sys.stderr)
+        sys.exit(1)
+    barrier()
+    e2e_t = []
+    for _ in range(args.e2e_steps):
+        t1 = time.perf_counter()
+        h = g.split_strip_host(stream, cap=cap, out=out)
+        e2e_t.append(time.perf_counter() - t1)
+    barrier()
+    e2e_s = max_over_ranks(sum(e2e_t) / len(e2e_t))
+    e2e_val = total_in / e2e_s / 1e9
+    clocks = sampler.stop()
+
+    # ---- CPU baseline (rank 0, N=1): the unmodified reference on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = min(os.cpu_count() or 1, 256)
+        sample = min(n_in, max(64 << 20, int(0.12e9 * cores * 4)))
+        cpu = cpu_reference_run(stream, sample, cores, reps=3)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "annexb_scan_strip (BASELINE config 2)",
+                       "bytes_per_gpu": n_in, "nals_per_gpu": int(res.n_nal),
+                       "rbsp_bytes_per_gpu": int(res.rbsp_bytes),
+                       "nal_bytes": "loguniform[64,262144]", "p_zero": 0.1875,
+                       "start_codes": "3/4-byte mixed, 0-2 trailing zeros on 1/4 of NALs",
+                       "l2": "input %.1f GiB >> 126 MB L2, no flush needed" % (n_in / 2**30),
+                       "parallelism": "byte-range shards, 1 per GPU, host merge, no collective",
+                       "kernel": "annexb::scan_kernel<%s,strip>" % os.environ.get("H264GPU_SCAN_ITEMS", "4"),
+                       "gen_seconds": round(gen_s, 2)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "note": "duration = CUDA-event step time (kernel + two tiny memsets) on the launch stream"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n_in),
+                    "d2h_bytes_per_step": int(res.rbsp_bytes + 24 * res.n_nal),
+                    "ms_per_step": e2e_s * 1e3, "api": "h264gpu_split_strip_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+            "extra": {"macroblocks_per_s": None},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    g.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+/*
+ * h264gpu.h — C-ABI of the B200 (sm_100a) data-parallel stages of the H.264
+ * bitstream front end.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * Every entry point returns 0 or a negative errno, like libh264 itself
+ * (reference convention: include/h264/h264_reader.h, src/h264_reader.c:66-143).
+ *
+ * What each stage replaces in the reference (Parrot-Developers/libh264):
+ *
+ *   h264gpu_split_strip_*   Annex-B start-code scan + NAL table + (optionally)
+ *                           emulation-prevention-byte removal.
+ *                           Replaces the NAL loop of h264_reader_parse
+ *                           (src/h264_reader.c:133-140) over h264_find_nalu
+ *                           (src/h264_bitstream.c:159-184; start/end code search
+ *                           :87-154) and the per-byte EPB test of h264_bs_fetch
+ *                           (include/h264/h264_bitstream.h:168-190).
+ *   h264gpu_frame_*         Writer side: EPB insertion + start-code framing of
+ *                           RBSP payloads.  Replaces h264_bs_flush
+ *                           (src/h264_bitstream.c:54-81) driven by
+ *                           h264_bs_write_bits (:211-239); the 4-byte start code
+ *                           is the one h264_avcc_to_byte_stream writes
+ *                           (src/h264.c:251-272).
+ *   h264gpu_cavlc_*         Slice-parallel CAVLC macroblock syntax parse.
+ *                           Replaces _h264_read_slice_data_internal
+ *                           (src/h264_syntax_slice_data.h:701-787) and callees
+ *                           (see include/h264gpu_slice.h).
+ *
+ * Device pointers ("d_*") must come from the same device the context was made
+ * on and be 16-byte aligned.  All *_dev calls are asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = the legacy default stream).
+ */
+#ifndef H264GPU_H
+#define H264GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H264GPU_API __attribute__((visibility("default")))
+
+#define H264GPU_NONE UINT64_MAX
+
+typedef struct h264gpu_ctx h264gpu_ctx;
+
+/* Neighbour bytes of a byte-range shard (multi-GPU byte-range partitioning,
+ * SURVEY.md §8e).  A shard that is the whole buffer passes NULL. */
+struct h264gpu_shard_edge {
+	uint8_t left[2];   /* the 2 bytes before the shard (left[1] is adjacent) */
+	uint8_t right[2];  /* the 2 bytes after the shard  (right[0] is adjacent) */
+	uint8_t has_left;  /* 0: shard starts the stream */
+	uint8_t has_right; /* 0: shard ends the stream (end-of-buffer rule applies) */
+	uint8_t assume_in; /* 1: bytes before the shard's first boundary event are
+			      assumed to lie inside a NAL (resolved at merge time) */
+	uint8_t pad;
+};
+
+/* Result of one scan(+strip) launch; lives in device or host memory. */
+struct h264gpu_scan_result {
+	uint64_t n_nal;           /* NALs whose start code begins in this shard */
+	uint64_t rbsp_bytes;      /* bytes written to d_rbsp */
+	uint64_t first_event_pos; /* absolute offset of the shard's first boundary
+				     event, H264GPU_NONE when it has none */
+	uint64_t head_bytes;      /* RBSP bytes emitted before that first event
+				     (only non-zero with assume_in) */
+	uint32_t first_event_is_sc; /* that event is a start code */
+	uint32_t any_event;
+	uint32_t end_open;        /* the last boundary event is a start code: the
+				     last NAL runs to the shard end / next shard */
+	uint32_t reserved;
+};
+
+H264GPU_API int h264gpu_device_count(void);
+H264GPU_API int h264gpu_create(int device, h264gpu_ctx **out);
+H264GPU_API int h264gpu_destroy(h264gpu_ctx *ctx);
+H264GPU_API int h264gpu_device(const h264gpu_ctx *ctx);
+H264GPU_API const char *h264gpu_version(void);
+/* Number of kernels this library launched on ctx since creation. */
+H264GPU_API uint64_t h264gpu_launch_count(const h264gpu_ctx *ctx);
+
+/* Plain device/pinned memory helpers so a C host needs no CUDA headers. */
+H264GPU_API int h264gpu_malloc(h264gpu_ctx *ctx, size_t bytes, void **d_ptr);
+H264GPU_API int h264gpu_free(h264gpu_ctx *ctx, void *d_ptr);
+H264GPU_API int h264gpu_host_alloc(h264gpu_ctx *ctx, size_t bytes, void **h_ptr);
+H264GPU_API int h264gpu_host_free(h264gpu_ctx *ctx, void *h_ptr);
+H264GPU_API int h264gpu_memcpy_h2d(h264gpu_ctx *ctx, void *d_dst, const void *h_src,
+				   size_t bytes, void *stream);
+H264GPU_API int h264gpu_memcpy_d2h(h264gpu_ctx *ctx, void *h_dst, const void *d_src,
+				   size_t bytes, void *stream);
+H264GPU_API int h264gpu_sync(h264gpu_ctx *ctx, void *stream);
+
+/*
+ * Annex-B scan (+ EPB strip when d_rbsp != NULL) of d_in[0,len).
+ *   base       absolute offset of d_in[0] in the whole stream; every offset
+ *              written to the tables is base-relative + base
+ *   d_nal_*    tables of nal_cap entries: start (first byte after the start
+ *              code), end (exclusive), rbsp (offset of the NAL's RBSP in d_rbsp;
+ *              may be NULL when d_rbsp is NULL)
+ *   d_result   struct h264gpu_scan_result in device memory
+ * NAL k's end is written by whoever sees the boundary event that closes it; the
+ * last NAL's end is len+base when the shard ends the stream and is left
+ * untouched (end_open=1) when it does not.
+ */
+H264GPU_API int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in,
+					uint64_t len, uint64_t base,
+					const struct h264gpu_shard_edge *edge,
+					uint8_t *d_rbsp, uint64_t *d_nal_start,
+					uint64_t *d_nal_end, uint64_t *d_nal_rbsp,
+					uint64_t nal_cap,
+					struct h264gpu_scan_result *d_result,
+					void *stream);
+
+/*
+ * Host-side merge of per-shard results (byte-range shards of one stream, in
+ * stream order: chunks of the host pipeline, or one shard per GPU).  No device
+ * work and no collective: each shard contributes its small result struct and
+ * its NAL table.
+ *
+ *   h264gpu_merge_shard   call once per shard AFTER appending that shard's
+ *                         table entries (shard_nals_copied of them) to the
+ *                         merged tables at index m->n_nal.  Closes the NAL left
+ *                         open by earlier shards, rebases the appended RBSP
+ *                         offsets, and tells the caller which slice
+ *                         [rbsp_skip, rbsp_skip+rbsp_take) of the shard's RBSP
+ *                         output belongs to the merged RBSP (appended at the
+ *                         previous m->rbsp_bytes).
+ *   h264gpu_merge_finish  closes the last NAL at stream_len and yields the
+ *                         *off value of h264_reader_parse (src/h264_reader.c:139).
+ */
+struct h264gpu_merge {
+	uint64_t n_nal;
+	uint64_t rbsp_bytes;
+	uint32_t open;   /* a NAL is still open at the end of the shards seen so far */
+	uint32_t shards;
+};
+
+H264GPU_API void h264gpu_merge_init(struct h264gpu_merge *m);
+H264GPU_API int h264gpu_merge_shard(struct h264gpu_merge *m,
+				    const struct h264gpu_scan_result *r,
+				    uint64_t *tab_start, uint64_t *tab_end,
+				    uint64_t *tab_rbsp, uint64_t tab_cap,
+				    uint64_t shard_nals_copied, uint64_t *rbsp_skip,
+				    uint64_t *rbsp_take);
+H264GPU_API int h264gpu_merge_finish(struct h264gpu_merge *m, uint64_t stream_len,
+				     uint64_t *tab_end, uint64_t tab_cap,
+				     uint64_t *final_off);
+
+/*
+ * Host-buffer form (the call a libh264 user's buffer goes through): copies
+ * h_in to the device in chunks overlapped with the kernel, and copies the
+ * tables (and RBSP when h_rbsp != NULL) back.  Synchronous.
+ *   *n_nal      in: capacity of the h_nal_* arrays; out: NALs found
+ *   *final_off  what h264_reader_parse would leave in *off
+ * Returns -ENOBUFS when the tables were too small (n_nal still set).
+ */
+H264GPU_API int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in,
+					 uint64_t len, uint8_t *h_rbsp,
+					 uint64_t *h_nal_start, uint64_t *h_nal_end,
+					 uint64_t *h_nal_rbsp, uint64_t *n_nal,
+					 uint64_t *rbsp_bytes, uint64_t *final_off);
+
+/*
+ * Writer side: escape n payloads d_rbsp[d_off[k], d_off[k+1]) and put a start
+ * code of sc_len (3 or 4; 0 = none) bytes in front of each.
+ *   d_out       capacity out_cap bytes (worst case 3/2 * payload + n*sc_len)
+ *   d_out_off   n+1 entries: offset of NAL k's start code; entry n = total
+ *   d_total     one uint64: total bytes the output needs (also when > out_cap,
+ *               in which case nothing beyond out_cap is written)
+ */
+H264GPU_API int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp,
+				  const uint64_t *d_off, uint64_t n, int sc_len,
+				  uint8_t *d_out, uint64_t out_cap,
+				  uint64_t *d_out_off, uint64_t *d_total,
+				  void *stream);
+
+H264GPU_API int h264gpu_frame_host(h264gpu_ctx *ctx, const uint8_t *h_rbsp,
+				   const uint64_t *h_off, uint64_t n, int sc_len,
+				   uint8_t *h_out, uint64_t out_cap,
+				   uint64_t *h_out_off, uint64_t *total);
+
+/* Event timing on a stream, for callers without CUDA headers (bench harness). */
+H264GPU_API int h264gpu_timer_create(h264gpu_ctx *ctx, void **timer);
+H264GPU_API int h264gpu_timer_destroy(h264gpu_ctx *ctx, void *timer);
+H264GPU_API int h264gpu_timer_start(h264gpu_ctx *ctx, void *timer, void *stream);
+H264GPU_API int h264gpu_timer_stop(h264gpu_ctx *ctx, void *timer, void *stream);
+/* Synchronises on the stop event; elapsed milliseconds. */
+H264GPU_API int h264gpu_timer_elapsed_ms(h264gpu_ctx *ctx, void *timer, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* H264GPU_H */

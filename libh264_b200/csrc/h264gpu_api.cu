@@ -1,0 +1,662 @@
+/*
+ * h264gpu_api.cu — C-ABI entry points (include/h264gpu.h): context, memory and
+ * timing helpers, the scan(+strip) launcher, the shard merge and the host-buffer
+ * pipeline.  Host code here only moves bytes and launches kernels; there is no
+ * CPU implementation of any stage (a missing GPU is an error, never a fallback).
+ */
+#include "h264gpu_internal.h"
+
+#include "annexb_scan.cuh"
+
+extern "C" {
+
+const char *h264gpu_version(void)
+{
+	return "libh264gpu 0.1 (sm_100a)";
+}
+
+int h264gpu_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess)
+		return -ENODEV;
+	return n;
+}
+
+int h264gpu_create(int device, h264gpu_ctx **out)
+{
+	if (out == NULL)
+		return -EINVAL;
+	*out = NULL;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+		return -ENODEV;
+	if (device < 0 || device >= n)
+		return -EINVAL;
+	CU_TRY(cudaSetDevice(device));
+	h264gpu_ctx *ctx = (h264gpu_ctx *)calloc(1, sizeof(*ctx));
+	if (ctx == NULL)
+		return -ENOMEM;
+	ctx->device = device;
+	ctx->scan_items = 4;
+	const char *e = getenv("H264GPU_SCAN_ITEMS");
+	if (e != NULL) {
+		int v = atoi(e);
+		if (v == 1 || v == 2 || v == 4)
+			ctx->scan_items = v;
+	}
+	size_t chunk_mb = 128;
+	e = getenv("H264GPU_CHUNK_MB");
+	if (e != NULL && atoi(e) > 0)
+		chunk_mb = (size_t)atoi(e);
+	ctx->chunk_bytes = chunk_mb << 20;
+	*out = ctx;
+	return 0;
+}
+
+static void free_pipeline(h264gpu_ctx *ctx)
+{
+	for (int b = 0; b < 2; b++) {
+		cudaFree(ctx->d_chunk_in[b]);
+		cudaFree(ctx->d_chunk_out[b]);
+		cudaFree(ctx->d_tab[b]);
+		cudaFree(ctx->d_res[b]);
+		ctx->d_chunk_in[b] = ctx->d_chunk_out[b] = NULL;
+		ctx->d_tab[b] = NULL;
+		ctx->d_res[b] = NULL;
+		if (ctx->ev_k[b]) {
+			cudaEventDestroy(ctx->ev_in[b]);
+			cudaEventDestroy(ctx->ev_k[b]);
+			cudaEventDestroy(ctx->ev_out[b]);
+			ctx->ev_k[b] = NULL;
+		}
+	}
+	if (ctx->h_res)
+		cudaFreeHost(ctx->h_res);
+	ctx->h_res = NULL;
+	if (ctx->s_in) {
+		cudaStreamDestroy(ctx->s_in);
+		cudaStreamDestroy(ctx->s_out);
+		cudaStreamDestroy(ctx->s_tab);
+		ctx->s_in = ctx->s_out = ctx->s_tab = NULL;
+	}
+}
+
+int h264gpu_destroy(h264gpu_ctx *ctx)
+{
+	if (ctx == NULL)
+		return 0;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	free_pipeline(ctx);
+	cudaFree(ctx->ws);
+	free(ctx);
+	return 0;
+}
+
+int h264gpu_device(const h264gpu_ctx *ctx)
+{
+	return ctx ? ctx->device : -EINVAL;
+}
+
+uint64_t h264gpu_launch_count(const h264gpu_ctx *ctx)
+{
+	return ctx ? ctx->launches : 0;
+}
+
+int h264gpu_malloc(h264gpu_ctx *ctx, size_t bytes, void **d_ptr)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0 || d_ptr == NULL)
+		return r < 0 ? r : -EINVAL;
+	CU_TRY(cudaMalloc(d_ptr, bytes ? bytes : 16));
+	return 0;
+}
+
+int h264gpu_free(h264gpu_ctx *ctx, void *d_ptr)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaFree(d_ptr));
+	return 0;
+}
+
+int h264gpu_host_alloc(h264gpu_ctx *ctx, size_t bytes, void **h_ptr)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0 || h_ptr == NULL)
+		return r < 0 ? r : -EINVAL;
+	CU_TRY(cudaMallocHost(h_ptr, bytes ? bytes : 16));
+	return 0;
+}
+
+int h264gpu_host_free(h264gpu_ctx *ctx, void *h_ptr)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaFreeHost(h_ptr));
+	return 0;
+}
+
+int h264gpu_memcpy_h2d(h264gpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes,
+		       void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+	return 0;
+}
+
+int h264gpu_memcpy_d2h(h264gpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes,
+		       void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	return 0;
+}
+
+int h264gpu_sync(h264gpu_ctx *ctx, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+
+/* ---- timers ------------------------------------------------------------ */
+
+struct gpu_timer {
+	cudaEvent_t a, b;
+};
+
+int h264gpu_timer_create(h264gpu_ctx *ctx, void **timer)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0 || timer == NULL)
+		return r < 0 ? r : -EINVAL;
+	gpu_timer *t = (gpu_timer *)calloc(1, sizeof(*t));
+	if (t == NULL)
+		return -ENOMEM;
+	CU_TRY(cudaEventCreate(&t->a));
+	CU_TRY(cudaEventCreate(&t->b));
+	*timer = t;
+	return 0;
+}
+
+int h264gpu_timer_destroy(h264gpu_ctx *ctx, void *timer)
+{
+	gpu_timer *t = (gpu_timer *)timer;
+	if (t == NULL || h264gpu_use(ctx) < 0)
+		return -EINVAL;
+	cudaEventDestroy(t->a);
+	cudaEventDestroy(t->b);
+	free(t);
+	return 0;
+}
+
+int h264gpu_timer_start(h264gpu_ctx *ctx, void *timer, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0 || timer == NULL)
+		return r < 0 ? r : -EINVAL;
+	CU_TRY(cudaEventRecord(((gpu_timer *)timer)->a, (cudaStream_t)stream));
+	return 0;
+}
+
+int h264gpu_timer_stop(h264gpu_ctx *ctx, void *timer, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0 || timer == NULL)
+		return r < 0 ? r : -EINVAL;
+	CU_TRY(cudaEventRecord(((gpu_timer *)timer)->b, (cudaStream_t)stream));
+	return 0;
+}
+
+int h264gpu_timer_elapsed_ms(h264gpu_ctx *ctx, void *timer, float *ms)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0 || timer == NULL || ms == NULL)
+		return r < 0 ? r : -EINVAL;
+	gpu_timer *t = (gpu_timer *)timer;
+	CU_TRY(cudaEventSynchronize(t->b));
+	CU_TRY(cudaEventElapsedTime(ms, t->a, t->b));
+	return 0;
+}
+
+} /* extern "C" */
+
+/* ---- workspace ---------------------------------------------------------- */
+
+int h264gpu_ws_reserve(h264gpu_ctx *ctx, size_t bytes)
+{
+	if (bytes <= ctx->ws_bytes)
+		return 0;
+	/* growing is rare: drain the device, then replace the buffer */
+	CU_TRY(cudaDeviceSynchronize());
+	if (ctx->ws)
+		CU_TRY(cudaFree(ctx->ws));
+	ctx->ws = NULL;
+	ctx->ws_bytes = 0;
+	size_t want = (bytes + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+	CU_TRY(cudaMalloc(&ctx->ws, want));
+	ctx->ws_bytes = want;
+	return 0;
+}
+
+/* ---- scan (+strip) ------------------------------------------------------- */
+
+template <int ITEMS>
+static cudaError_t launch_scan(const annexb::ScanArgs &a, bool strip, cudaStream_t st)
+{
+	if (strip)
+		annexb::scan_kernel<ITEMS, true><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
+	else
+		annexb::scan_kernel<ITEMS, false><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
+	return cudaGetLastError();
+}
+
+extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len,
+				       uint64_t base, const struct h264gpu_shard_edge *edge,
+				       uint8_t *d_rbsp, uint64_t *d_nal_start, uint64_t *d_nal_end,
+				       uint64_t *d_nal_rbsp, uint64_t nal_cap,
+				       struct h264gpu_scan_result *d_result, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (d_in == NULL || d_result == NULL || (nal_cap && (!d_nal_start || !d_nal_end)))
+		return -EINVAL;
+	if (((uintptr_t)d_in & 15) || ((uintptr_t)d_rbsp & 15))
+		return -EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (len == 0) {
+		CU_TRY(cudaMemsetAsync(d_result, 0, sizeof(*d_result), st));
+		return 0;
+	}
+	const int items = ctx->scan_items;
+	const uint64_t tile = (uint64_t)annexb::kBlock * items * 16;
+	const uint64_t ntiles = (len + tile - 1) / tile;
+	if (ntiles > 0x7fffffffull)
+		return -E2BIG;
+	const size_t need = 256 + (size_t)ntiles * 32;
+	r = h264gpu_ws_reserve(ctx, need);
+	if (r < 0)
+		return r;
+	/* one memset arms the ticket and invalidates every tile descriptor */
+	CU_TRY(cudaMemsetAsync(ctx->ws, 0xff, need, st));
+	CU_TRY(cudaMemsetAsync(d_result, 0xff, sizeof(*d_result), st));
+
+	annexb::ScanArgs a;
+	memset(&a, 0, sizeof(a));
+	a.in = d_in;
+	a.len = len;
+	a.base = base;
+	a.rbsp = d_rbsp;
+	a.nal_start = d_nal_start;
+	a.nal_end = d_nal_end;
+	a.nal_rbsp = d_nal_rbsp;
+	a.nal_cap = nal_cap;
+	a.ticket = (uint32_t *)ctx->ws;
+	a.desc = (uint64_t *)((uint8_t *)ctx->ws + 256);
+	a.result = d_result;
+	a.num_tiles = (uint32_t)ntiles;
+	a.halo_left = 0xffffffffu;
+	a.right[0] = a.right[1] = 0xff;
+	if (edge != NULL) {
+		if (edge->has_left)
+			a.halo_left = 0xffffu | (uint32_t)edge->left[0] << 16 |
+				      (uint32_t)edge->left[1] << 24;
+		a.has_right = edge->has_right ? 1 : 0;
+		a.right[0] = edge->right[0];
+		a.right[1] = edge->right[1];
+		a.init_in = edge->assume_in ? 1 : 0;
+	}
+	cudaError_t ce;
+	const bool strip = d_rbsp != NULL;
+	if (items == 1)
+		ce = launch_scan<1>(a, strip, st);
+	else if (items == 2)
+		ce = launch_scan<2>(a, strip, st);
+	else
+		ce = launch_scan<4>(a, strip, st);
+	CU_TRY(ce);
+	ctx->launches++;
+	return 0;
+}
+
+/* ---- shard merge (host) --------------------------------------------------- */
+
+extern "C" void h264gpu_merge_init(struct h264gpu_merge *m)
+{
+	memset(m, 0, sizeof(*m));
+}
+
+extern "C" int h264gpu_merge_shard(struct h264gpu_merge *m, const struct h264gpu_scan_result *r,
+				   uint64_t *tab_start, uint64_t *tab_end, uint64_t *tab_rbsp,
+				   uint64_t tab_cap, uint64_t shard_nals_copied,
+				   uint64_t *rbsp_skip, uint64_t *rbsp_take)
+{
+	if (m == NULL || r == NULL)
+		return -EINVAL;
+	/* Was the byte before this shard inside a NAL?  The shard assumed "yes"
+	 * for every shard but the first; undo that if it was wrong. */
+	const int assumed_in = m->shards > 0;
+	const int actual_in = m->shards > 0 && m->open;
+	uint64_t skip = (assumed_in && !actual_in) ? r->head_bytes : 0;
+	uint64_t take = r->rbsp_bytes - skip;
+	/* the open NAL of earlier shards ends at this shard's first event */
+	if (m->open && r->any_event && m->n_nal >= 1 && m->n_nal - 1 < tab_cap)
+		tab_end[m->n_nal - 1] = r->first_event_pos;
+	/* rebase the RBSP offsets of the entries just appended at [n_nal, n_nal+copied) */
+	if (tab_rbsp != NULL) {
+		for (uint64_t k = 0; k < shard_nals_copied; k++)
+			tab_rbsp[m->n_nal + k] = tab_rbsp[m->n_nal + k] - skip + m->rbsp_bytes;
+	}
+	(void)tab_start;
+	m->n_nal += r->n_nal;
+	m->rbsp_bytes += take;
+	if (r->any_event)
+		m->open = r->end_open ? 1 : 0;
+	m->shards++;
+	if (rbsp_skip)
+		*rbsp_skip = skip;
+	if (rbsp_take)
+		*rbsp_take = take;
+	return 0;
+}
+
+extern "C" int h264gpu_merge_finish(struct h264gpu_merge *m, uint64_t stream_len,
+				    uint64_t *tab_end, uint64_t tab_cap, uint64_t *final_off)
+{
+	if (m == NULL)
+		return -EINVAL;
+	uint64_t off = 0;
+	if (m->n_nal >= 1) {
+		if (m->open) {
+			if (m->n_nal - 1 < tab_cap)
+				tab_end[m->n_nal - 1] = stream_len;
+			off = stream_len;
+		} else if (m->n_nal - 1 < tab_cap) {
+			off = tab_end[m->n_nal - 1];
+		}
+	}
+	if (final_off)
+		*final_off = off;
+	return 0;
+}
+
+/* ---- host-buffer pipeline -------------------------------------------------- */
+
+static int pipeline_init(h264gpu_ctx *ctx)
+{
+	if (ctx->s_in != NULL)
+		return 0;
+	CU_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+	CU_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+	CU_TRY(cudaStreamCreateWithFlags(&ctx->s_tab, cudaStreamNonBlocking));
+	if (ctx->tab_cap == 0)
+		ctx->tab_cap = ctx->chunk_bytes / 64 > 4096 ? ctx->chunk_bytes / 64 : 4096;
+	for (int b = 0; b < 2; b++) {
+		CU_TRY(cudaMalloc(&ctx->d_chunk_in[b], ctx->chunk_bytes + 16));
+		CU_TRY(cudaMalloc(&ctx->d_chunk_out[b], ctx->chunk_bytes + 16));
+		CU_TRY(cudaMalloc(&ctx->d_tab[b], ctx->tab_cap * 3 * sizeof(uint64_t)));
+		CU_TRY(cudaMalloc(&ctx->d_res[b], sizeof(struct h264gpu_scan_result)));
+		CU_TRY(cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming));
+		CU_TRY(cudaEventCreateWithFlags(&ctx->ev_k[b], cudaEventDisableTiming));
+		CU_TRY(cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming));
+	}
+	CU_TRY(cudaMallocHost(&ctx->h_res, 2 * sizeof(struct h264gpu_scan_result)));
+	return 0;
+}
+
+extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, uint64_t len,
+					uint8_t *h_rbsp, uint64_t *h_nal_start,
+					uint64_t *h_nal_end, uint64_t *h_nal_rbsp, uint64_t *n_nal,
+					uint64_t *rbsp_bytes, uint64_t *final_off)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (h_in == NULL || n_nal == NULL || (*n_nal && (!h_nal_start || !h_nal_end)))
+		return -EINVAL;
+	const uint64_t cap = *n_nal;
+	*n_nal = 0;
+	if (rbsp_bytes)
+		*rbsp_bytes = 0;
+	if (final_off)
+		*final_off = 0;
+	if (len == 0)
+		return 0;
+	r = pipeline_init(ctx);
+	if (r < 0)
+		return r;
+
+	const uint64_t chunk = ctx->chunk_bytes;
+	const uint64_t nchunks = (len + chunk - 1) / chunk;
+	struct h264gpu_merge mg;
+	h264gpu_merge_init(&mg);
+	int overflow = 0;
+	bool used[2] = {false, false};
+
+	/* software pipeline: upload+kernel of chunk c overlaps download of chunk c-1 */
+	for (uint64_t c = 0; c <= nchunks; c++) {
+		if (c < nchunks) {
+			const int b = (int)(c & 1);
+			const uint64_t lo = c * chunk;
+			const uint64_t n = len - lo < chunk ? len - lo : chunk;
+			struct h264gpu_shard_edge e;
+			memset(&e, 0, sizeof(e));
+			if (lo >= 2) {
+				e.has_left = 1;
+				e.left[0] = h_in[lo - 2];
+				e.left[1] = h_in[lo - 1];
+			}
+			if (lo + n < len) {
+				e.has_right = 1;
+				e.right[0] = h_in[lo + n];
+				e.right[1] = lo + n + 1 < len ? h_in[lo + n + 1] : 0xff;
+			}
+			e.assume_in = c > 0;
+			if (used[b]) /* chunk c-2's downloads must have left buffer b */
+				CU_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[b], 0));
+			CU_TRY(cudaMemcpyAsync(ctx->d_chunk_in[b], h_in + lo, n, cudaMemcpyHostToDevice,
+					       ctx->s_in));
+			r = h264gpu_split_strip_dev(ctx, ctx->d_chunk_in[b], n, lo, &e,
+						    h_rbsp ? ctx->d_chunk_out[b] : NULL, ctx->d_tab[b],
+						    ctx->d_tab[b] + ctx->tab_cap,
+						    ctx->d_tab[b] + 2 * ctx->tab_cap, ctx->tab_cap,
+						    ctx->d_res[b], ctx->s_in);
+			if (r < 0)
+				return r;
+			CU_TRY(cudaMemcpyAsync(&ctx->h_res[b], ctx->d_res[b], sizeof(ctx->h_res[b]),
+					       cudaMemcpyDeviceToHost, ctx->s_in));
+			CU_TRY(cudaEventRecord(ctx->ev_k[b], ctx->s_in));
+			used[b] = true;
+		}
+		if (c >= 1) {
+			const int b = (int)((c - 1) & 1);
+			CU_TRY(cudaEventSynchronize(ctx->ev_k[b]));
+			const struct h264gpu_scan_result res = ctx->h_res[b];
+			if (res.n_nal > ctx->tab_cap) {
+				/* per-chunk table too small: extremely NAL-dense input */
+				fprintf(stderr, "h264gpu: chunk holds %llu NALs > table %zu; set "
+						"H264GPU_CHUNK_MB lower\n",
+					(unsigned long long)res.n_nal, ctx->tab_cap);
+				return -E2BIG;
+			}
+			uint64_t room = mg.n_nal < cap ? cap - mg.n_nal : 0;
+			uint64_t ncopy = res.n_nal < room ? res.n_nal : room;
+			if (ncopy < res.n_nal)
+				overflow = 1;
+			if (ncopy) {
+				CU_TRY(cudaMemcpyAsync(h_nal_start + mg.n_nal, ctx->d_tab[b],
+						       ncopy * 8, cudaMemcpyDeviceToHost, ctx->s_tab));
+				CU_TRY(cudaMemcpyAsync(h_nal_end + mg.n_nal, ctx->d_tab[b] + ctx->tab_cap,
+						       ncopy * 8, cudaMemcpyDeviceToHost, ctx->s_tab));
+				if (h_nal_rbsp)
+					CU_TRY(cudaMemcpyAsync(h_nal_rbsp + mg.n_nal,
+							       ctx->d_tab[b] + 2 * ctx->tab_cap, ncopy * 8,
+							       cudaMemcpyDeviceToHost, ctx->s_tab));
+			}
+			CU_TRY(cudaStreamSynchronize(ctx->s_tab)); /* tables of this chunk are home */
+			const uint64_t dst = mg.rbsp_bytes;
+			uint64_t skip = 0, take = 0;
+			h264gpu_merge_shard(&mg, &res, h_nal_start, h_nal_end,
+					    h_rbsp ? h_nal_rbsp : NULL, cap, ncopy, &skip, &take);
+			if (h_rbsp && take)
+				CU_TRY(cudaMemcpyAsync(h_rbsp + dst, ctx->d_chunk_out[b] + skip, take,
+						       cudaMemcpyDeviceToHost, ctx->s_out));
+			CU_TRY(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+		}
+	}
+	CU_TRY(cudaStreamSynchronize(ctx->s_out));
+	uint64_t off = 0;
+	h264gpu_merge_finish(&mg, len, h_nal_end, cap, &off);
+	*n_nal = mg.n_nal;
+	if (rbsp_bytes)
+		*rbsp_bytes = mg.rbsp_bytes;
+	if (final_off)
+		*final_off = off;
+	return overflow ? -ENOBUFS : 0;
+}
+
+/* ---- writer side: EPB insert + framing --------------------------------------- */
+
+#include "annexb_frame.cuh"
+
+template <int ITEMS>
+static cudaError_t launch_frame(const frame::FrameArgs &a, cudaStream_t st)
+{
+	const uint32_t pthreads = 128;
+	const uint32_t pblocks = (a.num_tiles + 1 + pthreads - 1) / pthreads;
+	frame::frame_prepass<ITEMS><<<pblocks, pthreads, 0, st>>>(a);
+	frame::frame_kernel<ITEMS><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
+	return cudaGetLastError();
+}
+
+extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const uint64_t *d_off,
+				 uint64_t n, int sc_len, uint8_t *d_out, uint64_t out_cap,
+				 uint64_t *d_out_off, uint64_t *d_total, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (d_off == NULL || d_out == NULL || d_out_off == NULL || d_total == NULL)
+		return -EINVAL;
+	if (sc_len != 0 && sc_len != 3 && sc_len != 4)
+		return -EINVAL;
+	if (((uintptr_t)d_rbsp & 15) || ((uintptr_t)d_out & 15))
+		return -EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	/* total payload length = off[n]: needed on the host to size the grid */
+	uint64_t len = 0;
+	CU_TRY(cudaMemcpyAsync(&len, d_off + n, sizeof(len), cudaMemcpyDeviceToHost, st));
+	CU_TRY(cudaStreamSynchronize(st));
+	if (len && d_rbsp == NULL)
+		return -EINVAL;
+	const int items = ctx->scan_items;
+	const uint64_t tile = (uint64_t)annexb::kBlock * items * 16;
+	uint64_t ntiles = (len + tile - 1) / tile;
+	if (ntiles == 0)
+		ntiles = 1;
+	if (ntiles > 0x7fffffffull)
+		return -E2BIG;
+	/* workspace: [256 control][desc: ntiles u64][first: ntiles+1 u64][tail: ntiles u32] */
+	const size_t desc_bytes = 256 + (size_t)ntiles * 8;
+	const size_t first_off = (desc_bytes + 15) & ~(size_t)15;
+	const size_t tail_off = first_off + ((size_t)ntiles + 1) * 8;
+	const size_t need = tail_off + (size_t)ntiles * 4;
+	r = h264gpu_ws_reserve(ctx, need);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaMemsetAsync(ctx->ws, 0xff, desc_bytes, st));
+
+	frame::FrameArgs a;
+	memset(&a, 0, sizeof(a));
+	a.rbsp = d_rbsp;
+	a.len = len;
+	a.off = d_off;
+	a.n = n;
+	a.sc_len = (uint32_t)sc_len;
+	a.out = d_out;
+	a.out_cap = out_cap;
+	a.out_off = d_out_off;
+	a.total = d_total;
+	a.ticket = (uint32_t *)ctx->ws;
+	a.desc = (uint64_t *)((uint8_t *)ctx->ws + 256);
+	a.first = (uint64_t *)((uint8_t *)ctx->ws + first_off);
+	a.tail = (uint32_t *)((uint8_t *)ctx->ws + tail_off);
+	a.num_tiles = (uint32_t)ntiles;
+	cudaError_t ce;
+	if (items == 1)
+		ce = launch_frame<1>(a, st);
+	else if (items == 2)
+		ce = launch_frame<2>(a, st);
+	else
+		ce = launch_frame<4>(a, st);
+	CU_TRY(ce);
+	ctx->launches += 2;
+	return 0;
+}
+
+extern "C" int h264gpu_frame_host(h264gpu_ctx *ctx, const uint8_t *h_rbsp, const uint64_t *h_off,
+				  uint64_t n, int sc_len, uint8_t *h_out, uint64_t out_cap,
+				  uint64_t *h_out_off, uint64_t *total)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (h_off == NULL || h_out == NULL || total == NULL)
+		return -EINVAL;
+	const uint64_t len = h_off[n];
+	if (len && h_rbsp == NULL)
+		return -EINVAL;
+	uint8_t *d_rbsp = NULL, *d_out = NULL;
+	uint64_t *d_off = NULL, *d_out_off = NULL, *d_total = NULL;
+	const uint64_t dcap = out_cap;
+	int rc = 0;
+	cudaStream_t st = 0;
+#define FR_TRY(expr)                                                                       \
+	do {                                                                               \
+		if ((expr) != cudaSuccess) {                                               \
+			rc = -EIO;                                                         \
+			goto out;                                                          \
+		}                                                                          \
+	} while (0)
+	FR_TRY(cudaMalloc(&d_rbsp, len + 16));
+	FR_TRY(cudaMalloc(&d_out, dcap + 16));
+	FR_TRY(cudaMalloc(&d_off, (n + 1) * 8));
+	FR_TRY(cudaMalloc(&d_out_off, (n + 2) * 8));
+	d_total = d_out_off + n + 1;
+	if (len)
+		FR_TRY(cudaMemcpyAsync(d_rbsp, h_rbsp, len, cudaMemcpyHostToDevice, st));
+	FR_TRY(cudaMemcpyAsync(d_off, h_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	rc = h264gpu_frame_dev(ctx, d_rbsp, d_off, n, sc_len, d_out, dcap, d_out_off, d_total, st);
+	if (rc < 0)
+		goto out;
+	FR_TRY(cudaMemcpyAsync(total, d_total, 8, cudaMemcpyDeviceToHost, st));
+	FR_TRY(cudaStreamSynchronize(st));
+	if (h_out_off)
+		FR_TRY(cudaMemcpyAsync(h_out_off, d_out_off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+	{
+		const uint64_t ncopy = *total < out_cap ? *total : out_cap;
+		if (ncopy)
+			FR_TRY(cudaMemcpyAsync(h_out, d_out, ncopy, cudaMemcpyDeviceToHost, st));
+	}
+	FR_TRY(cudaStreamSynchronize(st));
+	if (*total > out_cap)
+		rc = -ENOBUFS;
+out:
+#undef FR_TRY
+	cudaFree(d_rbsp);
+	cudaFree(d_out);
+	cudaFree(d_off);
+	cudaFree(d_out_off);
+	return rc;
+}

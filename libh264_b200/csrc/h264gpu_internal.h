@@ -1,0 +1,55 @@
+/*
+ * h264gpu_internal.h — context object shared by the C-ABI translation units.
+ */
+#ifndef H264GPU_INTERNAL_H
+#define H264GPU_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "h264gpu.h"
+
+struct h264gpu_ctx {
+	int device;
+	uint64_t launches;
+	/* scan/frame workspace: [256 B control][tile descriptors / tile tables] */
+	void *ws;
+	size_t ws_bytes;
+	/* host-buffer pipeline */
+	cudaStream_t s_in, s_out, s_tab;
+	uint8_t *d_chunk_in[2];
+	uint8_t *d_chunk_out[2];
+	uint64_t *d_tab[2]; /* start | end | rbsp, tab_cap entries each */
+	struct h264gpu_scan_result *d_res[2];
+	struct h264gpu_scan_result *h_res; /* pinned, 2 entries */
+	size_t chunk_bytes;
+	size_t tab_cap;
+	cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+	int scan_items; /* 16-byte vectors per thread (1, 2 or 4) */
+};
+
+#define CU_TRY(expr)                                                                       \
+	do {                                                                               \
+		cudaError_t _e = (expr);                                                   \
+		if (_e != cudaSuccess) {                                                   \
+			fprintf(stderr, "h264gpu: %s failed: %s (%s:%d)\n", #expr,         \
+				cudaGetErrorString(_e), __FILE__, __LINE__);               \
+			return _e == cudaErrorMemoryAllocation ? -ENOMEM : -EIO;           \
+		}                                                                          \
+	} while (0)
+
+static inline int h264gpu_use(const h264gpu_ctx *ctx)
+{
+	if (ctx == NULL)
+		return -EINVAL;
+	CU_TRY(cudaSetDevice(ctx->device));
+	return 0;
+}
+
+int h264gpu_ws_reserve(h264gpu_ctx *ctx, size_t bytes);
+
+#endif /* H264GPU_INTERNAL_H */

@@ -1,0 +1,110 @@
+/*
+ * emu_kernels.cpp — runs the CUDA kernels' source on the CPU SIMT emulator
+ * (tests/emu/cuda_emu.h) so their logic is checked against the oracle without a
+ * GPU.  TEST INFRASTRUCTURE ONLY; built by tests/emu/build.py with g++ -DH264_EMU.
+ */
+#include "annexb_scan.cuh"
+#include "annexb_frame.cuh"
+
+#include <vector>
+
+extern "C" void emu_set_prefix_every(uint32_t n) { annexb::emu_prefix_every = n; }
+
+extern "C" int emu_split_strip(const uint8_t *in, uint64_t len, uint64_t base,
+			       const struct h264gpu_shard_edge *edge, uint8_t *rbsp,
+			       uint64_t *nal_start, uint64_t *nal_end, uint64_t *nal_rbsp,
+			       uint64_t nal_cap, struct h264gpu_scan_result *result, int items)
+{
+	using namespace annexb;
+	if (len == 0)
+		return -1;
+	const uint64_t tile = (uint64_t)kBlock * items * 16;
+	const uint32_t ntiles = (uint32_t)((len + tile - 1) / tile);
+	std::vector<uint64_t> desc((size_t)ntiles * 4, ~0ull);
+	uint32_t ticket = 0xffffffffu;
+	memset(result, 0xff, sizeof(*result));
+	/* 16-byte aligned private copy, exactly len bytes (catches over-reads under ASan) */
+	uint8_t *buf = (uint8_t *)aligned_alloc(16, (len + 15) & ~15ull);
+	memcpy(buf, in, len);
+	ScanArgs a;
+	memset(&a, 0, sizeof(a));
+	a.in = buf;
+	a.len = len;
+	a.base = base;
+	a.rbsp = rbsp;
+	a.nal_start = nal_start;
+	a.nal_end = nal_end;
+	a.nal_rbsp = nal_rbsp;
+	a.nal_cap = nal_cap;
+	a.desc = desc.data();
+	a.ticket = &ticket;
+	a.result = result;
+	a.num_tiles = ntiles;
+	a.halo_left = 0xffffffffu;
+	a.right[0] = a.right[1] = 0xff;
+	if (edge) {
+		if (edge->has_left)
+			a.halo_left = 0xffffu | (uint32_t)edge->left[0] << 16 | (uint32_t)edge->left[1] << 24;
+		a.has_right = edge->has_right;
+		a.right[0] = edge->right[0];
+		a.right[1] = edge->right[1];
+		a.init_in = edge->assume_in;
+	}
+	dim3 grid(ntiles), block(kBlock);
+	if (rbsp) {
+		if (items == 1) EMU_LAUNCH((scan_kernel<1, true>), grid, block, a);
+		else if (items == 2) EMU_LAUNCH((scan_kernel<2, true>), grid, block, a);
+		else EMU_LAUNCH((scan_kernel<4, true>), grid, block, a);
+	} else {
+		if (items == 1) EMU_LAUNCH((scan_kernel<1, false>), grid, block, a);
+		else if (items == 2) EMU_LAUNCH((scan_kernel<2, false>), grid, block, a);
+		else EMU_LAUNCH((scan_kernel<4, false>), grid, block, a);
+	}
+	free(buf);
+	return 0;
+}
+
+extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off, uint64_t n,
+			 int sc_len, uint8_t *out, uint64_t out_cap, uint64_t *out_off,
+			 uint64_t *total, int items)
+{
+	using namespace frame;
+	const uint64_t tile = (uint64_t)kBlock * items * 16;
+	uint32_t ntiles = (uint32_t)((len + tile - 1) / tile);
+	if (ntiles == 0)
+		ntiles = 1;
+	std::vector<uint64_t> desc(ntiles, ~0ull), first(ntiles + 1, 0);
+	std::vector<uint32_t> tail(ntiles, 0);
+	uint32_t ticket = 0xffffffffu;
+	uint8_t *buf = (uint8_t *)aligned_alloc(16, ((len + 15) & ~15ull) + 16);
+	memcpy(buf, rbsp, len);
+	FrameArgs a;
+	memset(&a, 0, sizeof(a));
+	a.rbsp = buf;
+	a.len = len;
+	a.off = off;
+	a.n = n;
+	a.sc_len = (uint32_t)sc_len;
+	a.out = out;
+	a.out_cap = out_cap;
+	a.out_off = out_off;
+	a.total = total;
+	a.desc = desc.data();
+	a.ticket = &ticket;
+	a.first = first.data();
+	a.tail = tail.data();
+	a.num_tiles = ntiles;
+	dim3 pgrid((ntiles + 1 + 127) / 128), pblock(128), grid(ntiles), block(kBlock);
+	if (items == 1) {
+		EMU_LAUNCH((frame_prepass<1>), pgrid, pblock, a);
+		EMU_LAUNCH((frame_kernel<1>), grid, block, a);
+	} else if (items == 2) {
+		EMU_LAUNCH((frame_prepass<2>), pgrid, pblock, a);
+		EMU_LAUNCH((frame_kernel<2>), grid, block, a);
+	} else {
+		EMU_LAUNCH((frame_prepass<4>), pgrid, pblock, a);
+		EMU_LAUNCH((frame_kernel<4>), grid, block, a);
+	}
+	free(buf);
+	return 0;
+}

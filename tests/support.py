@@ -1,0 +1,260 @@
+"""Shared test plumbing: ctypes bindings for the oracle (CPU restatement), the
+compiled reference (when present), the SIMT-emulated kernels, and the product's
+C-ABI library; plus seeded synthetic Annex-B generators.
+
+Only tests/ (and bench.py's cpu_baseline leg / smoke()) may touch oracle/.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libh264_ref.so")
+PORT_SO = os.path.join(ORACLE_DIR, "_ref", "liboracle.so")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_SO = os.path.join(EMU_DIR, "libemu_kernels.so")
+
+u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+NONE64 = 0xFFFFFFFFFFFFFFFF
+
+
+class ShardEdge(C.Structure):
+    _fields_ = [("left", C.c_uint8 * 2), ("right", C.c_uint8 * 2), ("has_left", C.c_uint8),
+                ("has_right", C.c_uint8), ("assume_in", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class ScanResult(C.Structure):
+    _fields_ = [("n_nal", C.c_uint64), ("rbsp_bytes", C.c_uint64),
+                ("first_event_pos", C.c_uint64), ("head_bytes", C.c_uint64),
+                ("first_event_is_sc", C.c_uint32), ("any_event", C.c_uint32),
+                ("end_open", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources if os.path.exists(s))
+
+
+def build_oracle():
+    """make port (always) and ref (when /root/reference is here)."""
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+
+
+def build_emu():
+    srcs = [os.path.join(EMU_DIR, "emu_kernels.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")]
+    csrc = os.path.join(ROOT, "libh264_b200", "csrc")
+    srcs += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    srcs.append(os.path.join(ROOT, "include", "h264gpu.h"))
+    if _newer(EMU_SO, srcs):
+        return
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DH264_EMU", "-fPIC", "-shared",
+                           "-I" + EMU_DIR, "-I" + csrc, "-I" + os.path.join(ROOT, "include"),
+                           "-o", EMU_SO, srcs[0]])
+
+
+_cache = {}
+
+
+def oracle():
+    if "port" not in _cache:
+        if not os.path.exists(PORT_SO) or os.path.isdir("/root/reference/src"):
+            build_oracle()
+        lib = C.CDLL(PORT_SO)
+        lib.oracle_scan.restype = C.c_size_t
+        lib.oracle_scan.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    u64p, C.POINTER(C.c_int)]
+        lib.oracle_strip.restype = C.c_size_t
+        lib.oracle_strip.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.oracle_insert.restype = C.c_size_t
+        lib.oracle_insert.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.oracle_insert_count.restype = C.c_size_t
+        lib.oracle_insert_count.argtypes = [C.c_void_p, C.c_size_t]
+        lib.oracle_split_strip.restype = C.c_size_t
+        lib.oracle_split_strip.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_size_t, C.c_void_p, u64p, u64p]
+        lib.oracle_frame.restype = C.c_size_t
+        lib.oracle_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                     C.c_void_p]
+        _cache["port"] = lib
+    return _cache["port"]
+
+
+def have_ref():
+    if not os.path.exists(REF_SO) and os.path.isdir("/root/reference/src"):
+        build_oracle()
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    if "ref" not in _cache:
+        assert have_ref()
+        lib = C.CDLL(REF_SO)
+        lib.ref_scan.restype = C.c_size_t
+        lib.ref_scan.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, u64p]
+        lib.ref_strip.restype = C.c_size_t
+        lib.ref_strip.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, u64p]
+        lib.ref_insert.restype = C.c_size_t
+        lib.ref_insert.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        lib.ref_mt_split_strip.restype = C.c_double
+        lib.ref_mt_split_strip.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                           u64p, u64p]
+        lib.ref_mt_insert.restype = C.c_double
+        lib.ref_mt_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, u64p]
+        _cache["ref"] = lib
+    return _cache["ref"]
+
+
+def emu():
+    if "emu" not in _cache:
+        build_emu()
+        lib = C.CDLL(EMU_SO)
+        lib.emu_split_strip.restype = C.c_int
+        lib.emu_split_strip.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                        C.c_void_p, C.c_int]
+        _cache["emu"] = lib
+    return _cache["emu"]
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ----------------------------------------------------------------------------
+# oracle / reference wrappers returning numpy
+
+def oracle_scan(buf):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    cap = len(buf) // 3 + 2
+    s = np.zeros(cap, np.uint64)
+    e = np.zeros(cap, np.uint64)
+    off = C.c_uint64(0)
+    op = C.c_int(0)
+    n = oracle().oracle_scan(ptr(buf), len(buf), ptr(s), ptr(e), cap, C.byref(off), C.byref(op))
+    return s[:n].copy(), e[:n].copy(), off.value, op.value
+
+
+def ref_scan(buf):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    cap = len(buf) // 3 + 2
+    s = np.zeros(cap, np.uint64)
+    e = np.zeros(cap, np.uint64)
+    off = C.c_uint64(0)
+    n = ref().ref_scan(ptr(buf), len(buf), ptr(s), ptr(e), cap, C.byref(off))
+    return s[:n].copy(), e[:n].copy(), off.value
+
+
+def oracle_strip(nal):
+    nal = np.ascontiguousarray(nal, dtype=np.uint8)
+    out = np.zeros(len(nal) + 1, np.uint8)
+    n = oracle().oracle_strip(ptr(nal), len(nal), ptr(out))
+    return out[:n].copy()
+
+
+def ref_strip(nal):
+    nal = np.ascontiguousarray(nal, dtype=np.uint8)
+    out = np.zeros(len(nal) + 1, np.uint8)
+    off = C.c_uint64(0)
+    n = ref().ref_strip(ptr(nal), len(nal), ptr(out), C.byref(off))
+    return out[:n].copy(), off.value
+
+
+def oracle_insert(rbsp):
+    rbsp = np.ascontiguousarray(rbsp, dtype=np.uint8)
+    out = np.zeros(len(rbsp) * 3 // 2 + 2, np.uint8)
+    n = oracle().oracle_insert(ptr(rbsp), len(rbsp), ptr(out))
+    return out[:n].copy()
+
+
+def ref_insert(rbsp):
+    rbsp = np.ascontiguousarray(rbsp, dtype=np.uint8)
+    out = np.zeros(len(rbsp) * 3 // 2 + 2, np.uint8)
+    n = ref().ref_insert(ptr(rbsp), len(rbsp), ptr(out), len(out))
+    return out[:n].copy()
+
+
+def oracle_split_strip(buf):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    cap = len(buf) // 3 + 2
+    s = np.zeros(cap, np.uint64)
+    e = np.zeros(cap, np.uint64)
+    r = np.zeros(cap + 1, np.uint64)
+    out = np.zeros(len(buf) + 1, np.uint8)
+    tot = C.c_uint64(0)
+    off = C.c_uint64(0)
+    n = oracle().oracle_split_strip(ptr(buf), len(buf), ptr(s), ptr(e), ptr(r), cap, ptr(out),
+                                    C.byref(tot), C.byref(off))
+    return dict(start=s[:n].copy(), end=e[:n].copy(), rbsp_off=r[:n + 1].copy(),
+                rbsp=out[:tot.value].copy(), final_off=off.value)
+
+
+def oracle_frame(rbsp, offs, sc_len=4):
+    rbsp = np.ascontiguousarray(rbsp, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    n = len(offs) - 1
+    out = np.zeros(len(rbsp) * 3 // 2 + 4 * n + 16, np.uint8)
+    oo = np.zeros(n + 1, np.uint64)
+    tot = oracle().oracle_frame(ptr(rbsp), ptr(offs), n, sc_len, ptr(out), ptr(oo))
+    return out[:tot].copy(), oo
+
+
+def emu_split_strip(buf, strip=True, items=4, edge=None, base=0):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    cap = len(buf) // 3 + 2
+    s = np.full(cap, NONE64, np.uint64)
+    e = np.full(cap, NONE64, np.uint64)
+    r = np.full(cap, NONE64, np.uint64)
+    out = np.full(len(buf) + 16, 0xAA, np.uint8) if strip else None
+    res = ScanResult()
+    rc = emu().emu_split_strip(ptr(buf), len(buf), base, C.byref(edge) if edge else None, ptr(out),
+                               ptr(s), ptr(e), ptr(r), cap, C.byref(res), items)
+    assert rc == 0
+    n = res.n_nal
+    return dict(start=s[:n].copy(), end=e[:n].copy(), rbsp_off=r[:n].copy(),
+                rbsp=out[:res.rbsp_bytes].copy() if strip else None,
+                guard=out[res.rbsp_bytes:].copy() if strip else None, res=res)
+
+
+# ----------------------------------------------------------------------------
+# synthetic streams (SURVEY.md §8d config 2 shape, small)
+
+def gen_payloads(rng, n, lo=1, hi=4096, p_zero=3 / 16):
+    """n random RBSP payloads: first byte a legal NAL header, rest iid with P(00)=p_zero."""
+    sizes = np.exp(rng.uniform(np.log(lo), np.log(hi), n)).astype(np.int64)
+    sizes = np.maximum(sizes, 1)
+    offs = np.zeros(n + 1, np.uint64)
+    offs[1:] = np.cumsum(sizes)
+    tot = int(offs[-1])
+    data = rng.integers(1, 256, tot, dtype=np.uint8)
+    data[rng.random(tot) < p_zero] = 0
+    # NAL header: forbidden_zero_bit 0, nal_ref_idc random, type 1..23
+    hdr = (rng.integers(0, 4, n) << 5 | rng.integers(1, 24, n)).astype(np.uint8)
+    data[offs[:-1].astype(np.int64)] = hdr
+    return data, offs
+
+
+def gen_annexb(rng, n, lo=1, hi=4096, p_zero=3 / 16, mixed_sc=True, trailing=True, lead=b""):
+    """Valid Annex-B stream: payloads escaped by the oracle writer, 3/4-byte codes,
+    optional 0-2 trailing zero bytes after a NAL."""
+    data, offs = gen_payloads(rng, n, lo, hi, p_zero)
+    parts = [np.frombuffer(lead, np.uint8)] if lead else []
+    for k in range(n):
+        p = data[int(offs[k]):int(offs[k + 1])]
+        esc = oracle_insert(p)
+        sc = 3 if (mixed_sc and rng.random() < 0.5) else 4
+        parts.append(np.array([0] * (sc - 1) + [1], np.uint8))
+        parts.append(esc)
+        if trailing:
+            tz = int(rng.integers(0, 3)) if rng.random() < 0.3 else 0
+            if tz:
+                parts.append(np.zeros(tz, np.uint8))
+    return np.concatenate(parts) if parts else np.zeros(0, np.uint8)

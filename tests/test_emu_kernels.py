@@ -1,0 +1,224 @@
+"""Kernel LOGIC on the CPU SIMT emulator (tests/emu/) against the oracle: the very
+source the GPU runs (libh264_b200/csrc/*.cuh) compiled with -DH264_EMU.  Covers
+tile/warp/lane seams, the look-back fold, shard edges + host merge."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import known_answers as KA
+import libh264_b200 as L
+import support as S
+
+ALPHA = np.array([0, 0, 0, 1, 2, 3, 0xFF, 0x65, 0x77], np.uint8)
+
+
+def check_scan(b, items=4, tag=""):
+    o = S.oracle_split_strip(b)
+    em = S.emu_split_strip(b, items=items)
+    assert em["res"].n_nal == len(o["start"]), tag
+    assert np.array_equal(em["start"], o["start"]), tag
+    assert np.array_equal(em["end"], o["end"]), tag
+    assert np.array_equal(em["rbsp_off"], o["rbsp_off"][:-1]), tag
+    assert np.array_equal(em["rbsp"], o["rbsp"]), tag
+    assert (em["guard"] == 0xAA).all(), tag  # nothing written past the RBSP end
+    em2 = S.emu_split_strip(b, strip=False, items=items)
+    assert np.array_equal(em2["start"], o["start"]) and np.array_equal(em2["end"], o["end"]), tag
+
+
+@pytest.mark.parametrize("case", KA.SCAN)
+def test_emu_scan_known_answers(case):
+    hexs, exp, _ = case
+    b = KA.hx(hexs)
+    em = S.emu_split_strip(b)
+    assert list(zip(em["start"].tolist(), em["end"].tolist())) == exp
+    check_scan(b, 1)
+
+
+def test_emu_scan_random_streams():
+    rng = np.random.default_rng(1)
+    for it in range(4):
+        b = S.gen_annexb(rng, 40, 1, 6000)
+        for items in (1, 2, 4):
+            check_scan(b, items, ("valid", it, items))
+    for it in range(12):
+        b = rng.choice(ALPHA, int(rng.integers(1, 30000)))
+        check_scan(b, int(rng.choice([1, 2, 4])), ("adv", it))
+
+
+def test_emu_scan_events_on_every_seam():
+    # a start code / EPB / zero run planted at every offset around lane (16 B),
+    # warp item (512 B), warp region and tile (4096 B at ITEMS=1) boundaries
+    rng = np.random.default_rng(3)
+    base = rng.integers(4, 256, 3 * 4096 + 40, dtype=np.uint8)
+    pats = [[0, 0, 1], [0, 0, 0, 1], [0, 0, 3, 0, 0, 3], [0, 0, 0], [0, 0, 0, 0, 0, 1, 0x65, 0, 0, 3]]
+    for seam in (16, 512, 4096, 8192):
+        for d in range(-6, 3):
+            b = base.copy()
+            b[0:4] = [0, 0, 1, 0x65]
+            for i, p in enumerate(pats):
+                pos = seam + d + (i * 1024 if seam < 4096 else 0)
+                b[pos:pos + len(p)] = p
+            check_scan(b, 1, ("seam", seam, d))
+
+
+def test_emu_scan_lookback_fold():
+    lib = S.emu()
+    rng = np.random.default_rng(4)
+    try:
+        for every in (3, 40):
+            lib.emu_set_prefix_every(every)
+            check_scan(S.gen_annexb(rng, 300, 1, 3000), 1, ("fold", every))
+            check_scan(rng.choice(ALPHA, 200000), 1, ("foldadv", every))
+    finally:
+        lib.emu_set_prefix_every(1)
+
+
+def _merge_shards(b, cuts, strip=True, items=1):
+    """Run byte-range shards through the emulated kernel + the product's host merge."""
+    lib = L.load_gpu_lib()
+    n = len(b)
+    cap = n // 3 + 2
+    st = np.zeros(cap, np.uint64)
+    en = np.zeros(cap, np.uint64)
+    ro = np.zeros(cap, np.uint64)
+    rbsp = []
+    m = L.Merge()
+    lib.h264gpu_merge_init(C.byref(m))
+    bounds = [0] + list(cuts) + [n]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        e = S.ShardEdge()
+        if lo >= 2:
+            e.has_left, e.left[0], e.left[1] = 1, int(b[lo - 2]), int(b[lo - 1])
+        if hi < n:
+            e.has_right = 1
+            e.right[0] = int(b[hi])
+            e.right[1] = int(b[hi + 1]) if hi + 1 < n else 0xFF
+        e.assume_in = 1 if lo > 0 else 0
+        r = S.emu_split_strip(b[lo:hi], strip=strip, items=items, edge=e, base=lo)
+        k = int(r["res"].n_nal)
+        st[m.n_nal:m.n_nal + k] = r["start"]
+        en[m.n_nal:m.n_nal + k] = r["end"]
+        if strip:
+            ro[m.n_nal:m.n_nal + k] = r["rbsp_off"]
+        res = L.ScanResult.from_buffer_copy(bytes(r["res"]))
+        skip, take = C.c_uint64(0), C.c_uint64(0)
+        lib.h264gpu_merge_shard(C.byref(m), C.byref(res), S.ptr(st), S.ptr(en),
+                                S.ptr(ro) if strip else None, cap, k, C.byref(skip), C.byref(take))
+        if strip:
+            rbsp.append(r["rbsp"][skip.value:skip.value + take.value])
+    off = C.c_uint64(0)
+    lib.h264gpu_merge_finish(C.byref(m), n, S.ptr(en), cap, C.byref(off))
+    k = int(m.n_nal)
+    return dict(start=st[:k], end=en[:k], rbsp_off=ro[:k],
+                rbsp=np.concatenate(rbsp) if rbsp else np.zeros(0, np.uint8), final_off=off.value)
+
+
+def test_emu_sharded_scan_merges_to_whole():
+    rng = np.random.default_rng(5)
+    for it in range(10):
+        b = S.gen_annexb(rng, 30, 1, 3000) if it % 2 else rng.choice(ALPHA, int(rng.integers(200, 20000)))
+        n = len(b)
+        ncut = int(rng.integers(1, 5))
+        cuts = sorted(set(int(c) // 16 * 16 for c in rng.integers(16, max(n, 17), ncut)) - {0})
+        cuts = [c for c in cuts if c < n]
+        o = S.oracle_split_strip(b)
+        g = _merge_shards(b, cuts)
+        assert np.array_equal(g["start"], o["start"]), (it, cuts)
+        assert np.array_equal(g["end"], o["end"]), (it, cuts)
+        assert np.array_equal(g["rbsp"], o["rbsp"]), (it, cuts)
+        assert np.array_equal(g["rbsp_off"], o["rbsp_off"][:-1]), (it, cuts)
+        assert g["final_off"] == o["final_off"], (it, cuts)
+
+
+def test_emu_shard_cut_inside_start_code_and_gap():
+    # cuts landing inside a start code, inside trailing zeros, and in inter-NAL garbage
+    b = np.array([0x41] * 13 + [0, 0, 0, 1, 0x65, 9, 9, 0, 0, 0, 7, 7, 7, 7, 7, 0, 0, 1, 0x41] + [5] * 29, np.uint8)
+    o = S.oracle_split_strip(b)
+    for cut in (16, 32, 48):
+        g = _merge_shards(b, [cut])
+        assert np.array_equal(g["start"], o["start"]) and np.array_equal(g["end"], o["end"])
+        assert np.array_equal(g["rbsp"], o["rbsp"]) and g["final_off"] == o["final_off"]
+
+
+# ---- K3: EPB insert + framing ----------------------------------------------
+
+def emu_frame(rbsp, offs, sc_len, items):
+    lib = S.emu()
+    lib.emu_frame.restype = C.c_int
+    lib.emu_frame.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p,
+                              C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+    rbsp = np.ascontiguousarray(rbsp, np.uint8)
+    offs = np.ascontiguousarray(offs, np.uint64)
+    n = len(offs) - 1
+    cap = len(rbsp) * 3 // 2 + 4 * n + 64
+    out = np.full(cap, 0xAA, np.uint8)
+    oo = np.full(n + 1, S.NONE64, np.uint64)
+    tot = C.c_uint64(0)
+    lib.emu_frame(S.ptr(rbsp), len(rbsp), S.ptr(offs), n, sc_len, S.ptr(out), cap, S.ptr(oo),
+                  C.byref(tot), items)
+    return out, oo, tot.value
+
+
+def expected_frame(rbsp, offs, sc_len):
+    if sc_len:
+        return S.oracle_frame(rbsp, offs, sc_len)
+    parts = [S.oracle_insert(rbsp[int(offs[k]):int(offs[k + 1])]) for k in range(len(offs) - 1)]
+    exp = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+    eoo = np.zeros(len(offs), np.uint64)
+    eoo[1:] = np.cumsum([len(p) for p in parts])
+    return exp, eoo
+
+
+def check_frame(rbsp, offs, sc_len, items, tag=""):
+    exp, eoo = expected_frame(rbsp, offs, sc_len)
+    out, oo, tot = emu_frame(rbsp, offs, sc_len, items)
+    assert tot == len(exp), tag
+    assert np.array_equal(out[:tot], exp), tag
+    assert (out[tot:] == 0xAA).all(), tag
+    assert np.array_equal(oo, eoo), tag
+
+
+def test_emu_frame_known_answer():
+    p = KA.hx(KA.INSERT_IN)
+    out, oo, tot = emu_frame(p, np.array([0, len(p)], np.uint64), 0, 1)
+    assert bytes(out[:tot]) == bytes(KA.hx(KA.INSERT_OUT))
+
+
+def test_emu_frame_random_and_adversarial():
+    lib = S.emu()
+    rng = np.random.default_rng(5)
+    try:
+        for every in (1, 3, 50):
+            lib.emu_set_prefix_every(every)
+            for it in range(4):
+                data, offs = S.gen_payloads(rng, int(rng.integers(1, 60)), 1, 5000)
+                check_frame(data, offs, 4 if it % 2 else 3, int(rng.choice([1, 2, 4])), ("rand", every, it))
+            for it in range(8):
+                tot = int(rng.integers(0, 40000))
+                data = rng.choice(np.array([0, 0, 0, 0, 1, 2, 3, 4, 0xFF], np.uint8), tot)
+                n = int(rng.integers(0, 30))
+                cuts = np.sort(rng.integers(0, tot + 1, n)) if n else np.zeros(0, np.int64)
+                offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+                check_frame(data, offs, int(rng.choice([0, 3, 4])), int(rng.choice([1, 2, 4])), ("adv", every, it))
+            for it in range(3):  # zero runs spanning whole tiles, unstaged (50 % growth) tiles
+                tot = int(rng.integers(9000, 30000))
+                data = np.zeros(tot, np.uint8)
+                for p in rng.integers(0, tot, 3):
+                    data[p] = rng.choice([1, 3, 7])
+                check_frame(data, np.array([0, tot // 3, tot // 3, tot], np.uint64), 4, 1, ("zeros", every, it))
+    finally:
+        lib.emu_set_prefix_every(1)
+    check_frame(np.zeros(0, np.uint8), np.array([0, 0, 0], np.uint64), 4, 1, "empty payloads only")
+    check_frame(np.zeros(0, np.uint8), np.array([0], np.uint64), 4, 1, "no payloads")
+
+
+def test_emu_frame_then_scan_round_trip():
+    rng = np.random.default_rng(8)
+    data, offs = S.gen_payloads(rng, 50, 2, 3000)
+    data[offs[1:].astype(np.int64) - 1] = 0x80  # RBSP never ends in 00
+    out, oo, tot = emu_frame(data, offs, 4, 2)
+    back = S.emu_split_strip(out[:tot], items=2)
+    assert np.array_equal(back["rbsp"], data)
+    assert np.array_equal(back["rbsp_off"], offs[:-1])
+    assert np.array_equal(back["start"], oo[:-1] + 4)

@@ -1,0 +1,232 @@
+"""GPU parity (B200): the CUDA stages called through the C-ABI (libh264gpu.so)
+against the oracle on the same seeded inputs; bit-exact (byte / index work)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import known_answers as KA
+import libh264_b200 as L
+import support as S
+
+pytestmark = pytest.mark.gpu
+ALPHA = np.array([0, 0, 0, 1, 2, 3, 0xFF, 0x65, 0x77], np.uint8)
+
+
+def dev_split_strip(gpu, b, strip=True, edge=None, base=0):
+    """h264gpu_split_strip_dev on device-resident data."""
+    n = len(b)
+    cap = n // 3 + 2
+    d_in = gpu.alloc(n + 16)
+    d_in.upload(b)
+    d_rbsp = gpu.alloc(n + 16) if strip else None
+    d_tab = gpu.alloc(cap * 8 * 3)
+    d_res = gpu.alloc(C.sizeof(L.ScanResult))
+    if strip:
+        d_rbsp.upload(np.full(n + 16, 0xAA, np.uint8))
+    gpu.split_strip_dev(d_in.ptr, n, d_rbsp.ptr if strip else None, d_tab.ptr, d_tab.ptr + cap * 8,
+                        d_tab.ptr + cap * 16, cap, d_res.ptr, base=base, edge=edge)
+    gpu.sync()
+    res = L.ScanResult.from_buffer_copy(d_res.download().tobytes())
+    k = int(res.n_nal)
+    tab = d_tab.download(dtype=np.uint64)
+    out = dict(start=tab[:k].copy(), end=tab[cap:cap + k].copy(), rbsp_off=tab[2 * cap:2 * cap + k].copy(),
+               res=res)
+    if strip:
+        full = d_rbsp.download()
+        out["rbsp"] = full[:res.rbsp_bytes].copy()
+        out["guard"] = full[res.rbsp_bytes:].copy()
+    for d in (d_in, d_rbsp, d_tab, d_res):
+        if d is not None:
+            d.free()
+    return out
+
+
+def check(gpu, b, tag=""):
+    o = S.oracle_split_strip(b)
+    g = dev_split_strip(gpu, b)
+    assert g["res"].n_nal == len(o["start"]), tag
+    assert np.array_equal(g["start"], o["start"]), tag
+    assert np.array_equal(g["end"], o["end"]), tag
+    assert np.array_equal(g["rbsp_off"], o["rbsp_off"][:-1]), tag
+    assert np.array_equal(g["rbsp"], o["rbsp"]), tag
+    assert (g["guard"] == 0xAA).all(), tag
+    g2 = dev_split_strip(gpu, b, strip=False)
+    assert np.array_equal(g2["start"], o["start"]) and np.array_equal(g2["end"], o["end"]), tag
+
+
+@pytest.mark.parametrize("case", KA.SCAN)
+def test_scan_known_answers(gpu, case):
+    hexs, exp, off = case
+    b = KA.hx(hexs)
+    g = dev_split_strip(gpu, b)
+    assert list(zip(g["start"].tolist(), g["end"].tolist())) == exp
+    h = gpu.split_strip_host(b)
+    assert list(zip(h["start"].tolist(), h["end"].tolist())) == exp and h["final_off"] == off
+
+
+def test_strip_known_answer(gpu):
+    b = np.concatenate([np.array([0, 0, 1], np.uint8), KA.hx(KA.STRIP_IN)])
+    g = dev_split_strip(gpu, b)
+    assert bytes(g["rbsp"]) == bytes(KA.hx(KA.STRIP_OUT))
+
+
+def test_random_streams_and_adversarial(gpu):
+    rng = np.random.default_rng(21)
+    for it in range(6):
+        check(gpu, S.gen_annexb(rng, 200, 1, 9000), ("valid", it))
+    for it in range(12):
+        check(gpu, rng.choice(ALPHA, int(rng.integers(1, 300000))), ("adv", it))
+
+
+def test_events_on_every_seam(gpu):
+    rng = np.random.default_rng(3)
+    base = rng.integers(4, 256, 3 * 16384 + 40, dtype=np.uint8)
+    pats = [[0, 0, 1], [0, 0, 0, 1], [0, 0, 3, 0, 0, 3], [0, 0, 0], [0, 0, 0, 0, 0, 1, 0x65, 0, 0, 3]]
+    for seam in (16, 512, 2048, 16384, 32768):
+        for d in range(-6, 3):
+            b = base.copy()
+            b[0:4] = [0, 0, 1, 0x65]
+            for i, p in enumerate(pats):
+                pos = seam + d + (i * 3000 if seam < 16384 else 0)
+                b[pos:pos + len(p)] = p
+            check(gpu, b, ("seam", seam, d))
+
+
+def test_ragged_lengths(gpu):
+    rng = np.random.default_rng(4)
+    big = S.gen_annexb(rng, 60, 1, 4000)
+    for n in (1, 2, 3, 4, 15, 16, 17, 511, 512, 513, 16383, 16384, 16385, len(big) - 1, len(big)):
+        check(gpu, big[:n], ("ragged", n))
+
+
+def test_sharded_device_scan_merges_to_whole(gpu):
+    lib = L.load_gpu_lib()
+    rng = np.random.default_rng(5)
+    for it in range(6):
+        b = S.gen_annexb(rng, 120, 1, 8000) if it % 2 else rng.choice(ALPHA, int(rng.integers(40000, 200000)))
+        n = len(b)
+        cuts = sorted(set(int(c) // 16 * 16 for c in rng.integers(16, n, 3)))
+        o = S.oracle_split_strip(b)
+        cap = n // 3 + 2
+        st, en, ro = (np.zeros(cap, np.uint64) for _ in range(3))
+        m = L.Merge()
+        lib.h264gpu_merge_init(C.byref(m))
+        parts = []
+        bounds = [0] + cuts + [n]
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            e = L.ShardEdge()
+            if lo >= 2:
+                e.has_left, e.left[0], e.left[1] = 1, int(b[lo - 2]), int(b[lo - 1])
+            if hi < n:
+                e.has_right, e.right[0] = 1, int(b[hi])
+                e.right[1] = int(b[hi + 1]) if hi + 1 < n else 0xFF
+            e.assume_in = 1 if lo > 0 else 0
+            r = dev_split_strip(gpu, b[lo:hi], edge=e, base=lo)
+            k = int(r["res"].n_nal)
+            st[m.n_nal:m.n_nal + k], en[m.n_nal:m.n_nal + k], ro[m.n_nal:m.n_nal + k] = \
+                r["start"], r["end"], r["rbsp_off"]
+            skip, take = C.c_uint64(0), C.c_uint64(0)
+            lib.h264gpu_merge_shard(C.byref(m), C.byref(r["res"]), S.ptr(st), S.ptr(en), S.ptr(ro), cap, k,
+                                    C.byref(skip), C.byref(take))
+            parts.append(r["rbsp"][skip.value:skip.value + take.value])
+        off = C.c_uint64(0)
+        lib.h264gpu_merge_finish(C.byref(m), n, S.ptr(en), cap, C.byref(off))
+        k = int(m.n_nal)
+        assert np.array_equal(st[:k], o["start"]) and np.array_equal(en[:k], o["end"]), (it, cuts)
+        assert np.array_equal(np.concatenate(parts), o["rbsp"]), (it, cuts)
+        assert np.array_equal(ro[:k], o["rbsp_off"][:-1]) and off.value == o["final_off"], (it, cuts)
+
+
+def test_host_pipeline_small_chunks():
+    """h264gpu_split_strip_host with 1 MiB chunks: many seams through the merge."""
+    os.environ["H264GPU_CHUNK_MB"] = "1"
+    try:
+        g = L.Gpu(0)
+    finally:
+        del os.environ["H264GPU_CHUNK_MB"]
+    try:
+        seed = 77
+        offs = L.synth_offsets(seed, 9_000_000, lo=64, hi=256 * 1024)
+        rbsp = L.synth_payloads(seed, offs)
+        stream, _ = L.synth_annexb(seed, rbsp, offs)
+        o = S.oracle_split_strip(stream)
+        h = g.split_strip_host(stream)
+        assert np.array_equal(h["start"], o["start"]) and np.array_equal(h["end"], o["end"])
+        assert np.array_equal(h["rbsp"], o["rbsp"]) and np.array_equal(h["rbsp"], rbsp)
+        assert np.array_equal(h["rbsp_off"], o["rbsp_off"][:-1]) and h["final_off"] == o["final_off"]
+        h2 = g.split_strip_host(stream, want_rbsp=False)
+        assert np.array_equal(h2["start"], o["start"]) and np.array_equal(h2["end"], o["end"])
+        # adversarial content through the same seams
+        rng = np.random.default_rng(6)
+        b = rng.choice(ALPHA, 5_000_001)
+        o = S.oracle_split_strip(b)
+        h = g.split_strip_host(b)
+        assert np.array_equal(h["start"], o["start"]) and np.array_equal(h["end"], o["end"])
+        assert np.array_equal(h["rbsp"], o["rbsp"]) and h["final_off"] == o["final_off"]
+    finally:
+        g.close()
+
+
+def test_full_size_properties(gpu):
+    """256 MiB (BASELINE config-2 shape): too big for byte-wise oracle diffing in the
+    test budget, so check size-independent properties: round trip and table sanity."""
+    seed = 0x264
+    offs = L.synth_offsets(seed, 256 << 20)
+    rbsp = L.synth_payloads(seed, offs)
+    stream, nal_off = L.synth_annexb(seed, rbsp, offs)
+    h = gpu.split_strip_host(stream)
+    assert h["n_nal"] == len(offs) - 1
+    assert np.array_equal(h["rbsp_off"], offs[:-1])          # checksum of offsets
+    assert np.array_equal(h["rbsp"], rbsp)                    # strip(escape(x)) == x
+    assert (h["end"] >= h["start"]).all() and (h["start"][1:] >= h["end"][:-1] + 3).all()
+    assert h["final_off"] == len(stream)
+
+
+# ---- writer side ------------------------------------------------------------
+
+def test_frame_known_answer(gpu):
+    p = KA.hx(KA.INSERT_IN)
+    out, oo = gpu.frame_host(p, np.array([0, len(p)], np.uint64), sc_len=0)
+    assert bytes(out) == bytes(KA.hx(KA.INSERT_OUT))
+
+
+def test_frame_random_and_adversarial(gpu):
+    rng = np.random.default_rng(5)
+    for it in range(8):
+        data, offs = S.gen_payloads(rng, int(rng.integers(1, 300)), 1, 20000)
+        sc = 4 if it % 2 else 3
+        exp, eoo = S.oracle_frame(data, offs, sc)
+        out, oo = gpu.frame_host(data, offs, sc_len=sc)
+        assert np.array_equal(out, exp) and np.array_equal(oo, eoo), ("rand", it)
+    for it in range(10):
+        tot = int(rng.integers(0, 400000))
+        data = rng.choice(np.array([0, 0, 0, 0, 1, 2, 3, 4, 0xFF], np.uint8), tot)
+        n = int(rng.integers(0, 60))
+        cuts = np.sort(rng.integers(0, tot + 1, n)) if n else np.zeros(0, np.int64)
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        exp, eoo = S.oracle_frame(data, offs, 4)
+        out, oo = gpu.frame_host(data, offs, sc_len=4)
+        assert np.array_equal(out, exp) and np.array_equal(oo, eoo), ("adv", it)
+    data = np.zeros(100000, np.uint8)
+    data[[5, 40000, 99999]] = [1, 3, 7]
+    offs = np.array([0, 30000, 30000, 100000], np.uint64)
+    exp, eoo = S.oracle_frame(data, offs, 4)
+    out, oo = gpu.frame_host(data, offs, sc_len=4)
+    assert np.array_equal(out, exp) and np.array_equal(oo, eoo)
+    out, oo = gpu.frame_host(np.zeros(0, np.uint8), np.array([0, 0, 0], np.uint64), sc_len=4)
+    assert bytes(out) == bytes([0, 0, 0, 1, 0, 0, 0, 1])
+
+
+def test_writer_round_trip_full_size(gpu):
+    """Config 5 shape at 64 MiB: frame on the GPU, then the reference-side reader
+    semantics (GPU scan+strip, itself oracle-checked above) give back the payloads."""
+    seed = 5
+    offs = L.synth_offsets(seed, 64 << 20)
+    rbsp = L.synth_payloads(seed, offs)
+    out, oo = gpu.frame_host(rbsp, offs, sc_len=4)
+    exp, eoo = L.synth_annexb(seed, rbsp, offs, mixed_sc=False, trailing=False)
+    assert np.array_equal(out, exp) and np.array_equal(oo, eoo)   # byte-identical to the CPU writer
+    back = gpu.split_strip_host(out)
+    assert np.array_equal(back["rbsp"], rbsp) and np.array_equal(back["rbsp_off"], offs[:-1])
