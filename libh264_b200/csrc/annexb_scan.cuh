@@ -171,7 +171,7 @@ __device__ __forceinline__ uint64_t pack_agg(uint32_t head, uint32_t body, uint3
 }
 
 template <int ITEMS, bool STRIP>
-__global__ void __launch_bounds__(kBlock) scan_kernel(const ScanArgs a)
+__global__ void __launch_bounds__(kBlock, 4) scan_kernel(const ScanArgs a)
 {
 	constexpr int WARP_BYTES = ITEMS * 512;
 	constexpr int TILE = kBlock * ITEMS * 16;
@@ -378,24 +378,42 @@ __global__ void __launch_bounds__(kBlock) scan_kernel(const ScanArgs a)
 						break;
 				}
 				const int fp = pm ? __ffs((int)pm) - 1 : 32;
-				for (int k = 0; k < fp; k++) {
-					uint64_t gw = __shfl_sync(FULL_MASK, agg, k);
-					if (j0 - k < 0)
-						break; /* only when no prefix exists: cannot happen */
-					Agg g = unpack_agg(gw);
-					/* acc = combine(g, acc), g on the left */
-					if (!g.ev) {
-						ah = g.head + ah;
-						ab = g.body + ab;
-					} else {
-						ab = g.body + (g.st ? ah : 0) + ab;
-						ah = g.head;
+				/* Ordered tree reduction of the window's aggregates: lane k
+				 * holds tile j0-k, so a higher lane is the LEFT operand. */
+				uint32_t eh = 0, eb = 0, em = 0; /* em: nsc | ev<<30 | st<<31 */
+				if ((int)lane < fp && need) {
+					Agg g = unpack_agg(agg);
+					eh = g.head;
+					eb = g.body;
+					em = g.nsc | (g.ev ? 1u << 30 : 0u) | (g.st ? 1u << 31 : 0u);
+				}
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					uint32_t oh = __shfl_down_sync(FULL_MASK, eh, d);
+					uint32_t ob = __shfl_down_sync(FULL_MASK, eb, d);
+					uint32_t om = __shfl_down_sync(FULL_MASK, em, d);
+					if (lane + d < 32) {
+						const bool oev = (om >> 30) & 1, ost = om >> 31;
+						const bool mev = (em >> 30) & 1;
+						eb = ob + eb + ((oev && ost) ? eh : 0u);
+						eh = oev ? oh : oh + eh;
+						em = ((om & 0x3fffffffu) + (em & 0x3fffffffu)) |
+						     ((oev || mev) ? 1u << 30 : 0u) |
+						     (mev ? (em & 0x80000000u) : (om & 0x80000000u));
 					}
-					an += g.nsc;
-					if (!aev) {
-						ast = g.st;
-					}
-					aev = aev || g.ev;
+				}
+				{
+					/* acc = combine(window, acc): the window is LEFT of acc */
+					const uint32_t wh = __shfl_sync(FULL_MASK, eh, 0);
+					const uint32_t wb = __shfl_sync(FULL_MASK, eb, 0);
+					const uint32_t wm = __shfl_sync(FULL_MASK, em, 0);
+					const bool wev = (wm >> 30) & 1, wst = wm >> 31;
+					ab = wb + ab + ((wev && wst) ? ah : 0);
+					ah = wev ? wh : wh + ah;
+					an += wm & 0x3fffffffu;
+					if (!aev)
+						ast = wst;
+					aev = aev || wev;
 				}
 				if (fp < 32) {
 					uint64_t p2 = kInvalid;
@@ -632,13 +650,13 @@ __global__ void __launch_bounds__(kBlock) scan_kernel(const ScanArgs a)
 		const uint32_t nvec = (total + 15) >> 4;
 		uint8_t *gbase = a.rbsp + (kept_in - shift);
 		for (uint32_t x = tid; x < nvec; x += kBlock) {
-			uint4 raw = *(const uint4 *)(s_out + 16 * x);
+			/* word m of vector x lives at 4x + (m ^ r); r is constant per thread */
 			const uint32_t r = (x >> 3) & 3;
 			uint4 val;
-			val.x = r == 0 ? raw.x : r == 1 ? raw.y : r == 2 ? raw.z : raw.w;
-			val.y = r == 0 ? raw.y : r == 1 ? raw.x : r == 2 ? raw.w : raw.z;
-			val.z = r == 0 ? raw.z : r == 1 ? raw.w : r == 2 ? raw.x : raw.y;
-			val.w = r == 0 ? raw.w : r == 1 ? raw.z : r == 2 ? raw.y : raw.x;
+			val.x = so32[4 * x + r];
+			val.y = so32[4 * x + (1 ^ r)];
+			val.z = so32[4 * x + (2 ^ r)];
+			val.w = so32[4 * x + (3 ^ r)];
 			const uint32_t lo = x * 16;
 			if (lo >= shift && lo + 16 <= total) {
 				stg_stream16(gbase + lo, val);
