@@ -1,0 +1,152 @@
+/*
+ * h264gpu_slice.h — C-ABI of the slice-parallel macroblock syntax parse (K4 CAVLC,
+ * K5 CABAC).  One independent slice per GPU thread; the host supplies, per slice,
+ * the parameter block the reference keeps in struct h264_ctx while it walks
+ * slice_data (src/h264_priv.h:67-140), and gets back one record per macroblock —
+ * what the reference delivers through h264_ctx_cbs.slice_data_mb
+ * (include/h264/h264_ctx.h:78-82) plus a checksum of the macroblock's syntax
+ * elements (the reference keeps those in the private ctx->mb,
+ * src/h264_macroblock.h:105-167).
+ *
+ * Replaces (Parrot-Developers/libh264):
+ *   _h264_read_slice_data_internal   src/h264_syntax_slice_data.h:701-787
+ *   _h264_read_macroblock_layer      src/h264_syntax_slice_data.h:604-696
+ *   mb_pred / sub_mb_pred            src/h264_syntax_slice_data.h:422-601
+ *   residual / residual_luma / residual_block   src/h264_syntax_slice_data.h:103-419
+ *   h264_read_mb_type / _sub_mb_type / _coded_block_pattern / _coeff_token /
+ *   _total_zeros / _run_before, h264_new_macroblock   src/h264_slice_data.c:839-1416
+ *   neighbour derivation             src/h264_macroblock.c:306-433
+ *   bit reader + EPB skip            include/h264/h264_bitstream.h:168-304
+ *   h264_bs_more_rbsp_data           src/h264_bitstream.c:325-355
+ */
+#ifndef H264GPU_SLICE_H
+#define H264GPU_SLICE_H
+
+#include "h264gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes of a slice parse (negative errno like the reference, or:) */
+#define H264GPU_SLICE_OK 0
+#define H264GPU_SLICE_SKIPPED 1 /* CABAC slice without the CABAC flag: the reference
+				    parses no slice data either (F2) */
+
+/* Per-slice parameter block (56 bytes). */
+struct h264gpu_slice_params {
+	uint64_t nal_off;      /* offset of the NAL's header byte in the device stream */
+	uint32_t nal_len;      /* NAL length in bytes (escaped, header included) */
+	uint32_t data_bit_off; /* raw bit offset of slice_data() inside the NAL
+				  (ctx->slice.hdr_len, src/h264_syntax.h:1383) */
+	uint32_t first_mb_in_slice;
+	uint32_t mb_out_off;   /* first record index of this slice in the record array */
+	uint32_t mb_out_cap;   /* records this slice may write */
+	uint32_t row_state_off; /* scratch offset (units of PicWidthInMbs entries) */
+	uint16_t pic_width_in_mbs;
+	uint16_t pic_height_in_mbs; /* PicHeightInMbs of the slice's picture */
+	uint8_t slice_type;         /* 0 P, 1 B, 2 I, 3 SP, 4 SI (slice_type % 5) */
+	uint8_t chroma_array_type;
+	uint8_t bit_depth_luma;
+	uint8_t bit_depth_chroma;
+	uint8_t transform_8x8_mode_flag;
+	uint8_t direct_8x8_inference_flag;
+	uint8_t num_ref_idx_l0_active_minus1;
+	uint8_t num_ref_idx_l1_active_minus1;
+	uint8_t field_pic_flag;
+	uint8_t mbaff_frame_flag;
+	uint8_t entropy_coding_mode_flag;
+	uint8_t num_slice_groups_minus1;
+	uint8_t cabac_init_idc;
+	int8_t slice_qp;            /* SliceQPY (CABAC context init) */
+	uint8_t reserved[2];
+};
+
+/* One record per macroblock, in slice_data_mb callback order. */
+struct h264gpu_mb_record {
+	uint32_t mb_addr;
+	uint32_t mb_type; /* enum h264_mb_type value */
+	uint64_t hash;    /* h264gpu_mb_hash of the macroblock's syntax elements */
+};
+
+struct h264gpu_slice_result {
+	int32_t status;    /* 0, H264GPU_SLICE_SKIPPED, or negative errno */
+	uint32_t mb_count; /* what slice_data_end reports */
+	uint64_t end_bit;  /* raw bit position in the NAL after the last macroblock */
+};
+
+/*
+ * Syntax-element checksum.  Every element that the reference stores in ctx->mb
+ * contributes value * weight(field, index); zero-valued elements contribute
+ * nothing, so a parser only touches what it decodes.  Order independent.
+ */
+enum h264gpu_mb_field {
+	H264GPU_F_RAW_MB_TYPE = 1,
+	H264GPU_F_TRANSFORM_8X8 = 2,
+	H264GPU_F_MB_QP_DELTA = 3,
+	H264GPU_F_CBP = 4,
+	H264GPU_F_CBP_LUMA = 5,
+	H264GPU_F_CBP_CHROMA = 6,
+	H264GPU_F_INTRA_CHROMA_PRED_MODE = 7,
+	H264GPU_F_INTRA4X4_PRED_MODE = 8,  /* [16] */
+	H264GPU_F_INTRA8X8_PRED_MODE = 9,  /* [4] */
+	H264GPU_F_REF_IDX_L0 = 10,         /* [4] */
+	H264GPU_F_REF_IDX_L1 = 11,
+	H264GPU_F_MVD_L0 = 12,             /* [(part*4+sub)*2+comp] */
+	H264GPU_F_MVD_L1 = 13,
+	H264GPU_F_RAW_SUB_MB_TYPE = 14,    /* [4] */
+	H264GPU_F_MB_FIELD_DECODING_FLAG = 15,
+	H264GPU_F_I16_DC = 16,             /* + 3*comp : [16]            comp 0 Y,1 Cb,2 Cr */
+	H264GPU_F_I16_AC = 17,             /* + 3*comp : [blk*16+i]      */
+	H264GPU_F_LEVEL4X4 = 18,           /* + 3*comp : [blk*16+i]      */
+	H264GPU_F_CHROMA_DC = 25,          /* [iCbCr*16+i] */
+	H264GPU_F_CHROMA_AC = 26,          /* [(iCbCr*16+blk)*16+i] */
+	H264GPU_F_PCM_LUMA = 27,           /* [256] */
+	H264GPU_F_PCM_CHROMA = 28,         /* [iCbCr*256+i] */
+	H264GPU_F_I16_PRED_MODE = 29,
+};
+
+static inline uint64_t h264gpu_mb_hash_weight(uint32_t field, uint32_t index)
+{
+	uint64_t key = ((uint64_t)field << 16) | index;
+	return ((key + 1) * 0x9E3779B97F4A7C15ull) | 1ull;
+}
+
+static inline uint64_t h264gpu_mb_hash_term(uint32_t field, uint32_t index, int64_t value)
+{
+	return (uint64_t)value * h264gpu_mb_hash_weight(field, index);
+}
+
+/*
+ * Parse n_slices CAVLC slices of the device-resident stream d_stream (escaped
+ * Annex-B bytes; the bit reader skips emulation prevention bytes itself, exactly
+ * like the reference's, keeping the two raw bytes of left context).
+ *   d_params   n_slices parameter blocks
+ *   d_records  record array (capacity = sum of mb_out_cap)
+ *   d_results  n_slices results
+ * Unsupported stream features (MBAFF, more than one slice group) give
+ * status -ENOSYS for that slice; there is no CPU fallback.
+ */
+H264GPU_API int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
+					uint64_t stream_len,
+					const struct h264gpu_slice_params *d_params,
+					uint32_t n_slices,
+					struct h264gpu_mb_record *d_records,
+					struct h264gpu_slice_result *d_results,
+					void *stream);
+
+/* Host-buffer form: uploads the stream and parameter blocks, runs the kernel,
+ * downloads records and results.  Synchronous. */
+H264GPU_API int h264gpu_cavlc_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stream,
+					 uint64_t stream_len,
+					 const struct h264gpu_slice_params *h_params,
+					 uint32_t n_slices,
+					 struct h264gpu_mb_record *h_records,
+					 uint64_t n_records,
+					 struct h264gpu_slice_result *h_results);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* H264GPU_SLICE_H */

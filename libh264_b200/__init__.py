@@ -40,6 +40,38 @@ class Merge(C.Structure):
                 ("shards", C.c_uint32)]
 
 
+class SliceParams(C.Structure):
+    """struct h264gpu_slice_params (include/h264gpu_slice.h)."""
+    _fields_ = [("nal_off", C.c_uint64), ("nal_len", C.c_uint32), ("data_bit_off", C.c_uint32),
+                ("first_mb_in_slice", C.c_uint32), ("mb_out_off", C.c_uint32),
+                ("mb_out_cap", C.c_uint32), ("row_state_off", C.c_uint32),
+                ("pic_width_in_mbs", C.c_uint16), ("pic_height_in_mbs", C.c_uint16),
+                ("slice_type", C.c_uint8), ("chroma_array_type", C.c_uint8),
+                ("bit_depth_luma", C.c_uint8), ("bit_depth_chroma", C.c_uint8),
+                ("transform_8x8_mode_flag", C.c_uint8), ("direct_8x8_inference_flag", C.c_uint8),
+                ("num_ref_idx_l0_active_minus1", C.c_uint8), ("num_ref_idx_l1_active_minus1", C.c_uint8),
+                ("field_pic_flag", C.c_uint8), ("mbaff_frame_flag", C.c_uint8),
+                ("entropy_coding_mode_flag", C.c_uint8), ("num_slice_groups_minus1", C.c_uint8),
+                ("cabac_init_idc", C.c_uint8), ("slice_qp", C.c_int8), ("reserved", C.c_uint8 * 2)]
+
+
+MB_RECORD = np.dtype([("mb_addr", "<u4"), ("mb_type", "<u4"), ("hash", "<u8")])
+SLICE_RESULT = np.dtype([("status", "<i4"), ("mb_count", "<u4"), ("end_bit", "<u8")])
+SLICE_PARAMS = np.dtype([("nal_off", "<u8"), ("nal_len", "<u4"), ("data_bit_off", "<u4"),
+                         ("first_mb_in_slice", "<u4"), ("mb_out_off", "<u4"), ("mb_out_cap", "<u4"),
+                         ("row_state_off", "<u4"), ("pic_width_in_mbs", "<u2"),
+                         ("pic_height_in_mbs", "<u2"), ("slice_type", "u1"), ("chroma_array_type", "u1"),
+                         ("bit_depth_luma", "u1"), ("bit_depth_chroma", "u1"),
+                         ("transform_8x8_mode_flag", "u1"), ("direct_8x8_inference_flag", "u1"),
+                         ("num_ref_idx_l0_active_minus1", "u1"), ("num_ref_idx_l1_active_minus1", "u1"),
+                         ("field_pic_flag", "u1"), ("mbaff_frame_flag", "u1"),
+                         ("entropy_coding_mode_flag", "u1"), ("num_slice_groups_minus1", "u1"),
+                         ("cabac_init_idc", "u1"), ("slice_qp", "i1"), ("reserved", "u1", (2,)),
+                         ("pad", "u1", (4,))])
+assert SLICE_PARAMS.itemsize == C.sizeof(SliceParams) == 56
+
+SLICE_SYMBOLS = ["h264gpu_cavlc_parse_dev", "h264gpu_cavlc_parse_host"]
+
 # every symbol include/h264gpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = [
     "h264gpu_device_count", "h264gpu_create", "h264gpu_destroy", "h264gpu_device",
@@ -88,14 +120,15 @@ def load_gpu_lib():
         lib.h264gpu_timer_start.argtypes = [vp, vp, vp]
         lib.h264gpu_timer_stop.argtypes = [vp, vp, vp]
         lib.h264gpu_timer_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
+        lib.h264gpu_cavlc_parse_dev.argtypes = [vp, vp, u64, vp, C.c_uint32, vp, vp, vp]
+        lib.h264gpu_cavlc_parse_host.argtypes = [vp, vp, u64, vp, C.c_uint32, vp, u64, vp]
         _libs["gpu"] = lib
     return _libs["gpu"]
 
 
 def load_synth_lib():
     if "synth" not in _libs:
-        if not os.path.exists(_build.SYNTH_SO):
-            _build.build_synth()
+        _build.build_synth()
         lib = C.CDLL(_build.SYNTH_SO)
         vp, u64, i = C.c_void_p, C.c_uint64, C.c_int
         lib.synth_sizes.restype = u64
@@ -104,6 +137,8 @@ def load_synth_lib():
         lib.synth_fill.argtypes = [u64, vp, u64, vp, i]
         lib.synth_frame.restype = u64
         lib.synth_frame.argtypes = [u64, vp, vp, u64, i, i, vp, u64, vp, i]
+        lib.synth_video.restype = u64
+        lib.synth_video.argtypes = [vp, vp, u64, u64p, u64p, vp, u64]
         _libs["synth"] = lib
     return _libs["synth"]
 
@@ -248,6 +283,23 @@ class Gpu:
         _check(rc, "h264gpu_frame_host")
         return out[:tot.value], out_off
 
+    def cavlc_parse_host(self, stream, params, n_records):
+        """params: uint8 array of packed struct h264gpu_slice_params.  Returns (records, results)."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        params = np.ascontiguousarray(params, dtype=np.uint8)
+        n = len(params) // C.sizeof(SliceParams)
+        recs = np.zeros(max(int(n_records), 1), dtype=MB_RECORD)
+        res = np.zeros(max(n, 1), dtype=SLICE_RESULT)
+        _check(self.lib.h264gpu_cavlc_parse_host(self.h, _ptr(stream), len(stream), _ptr(params), n,
+                                                 _ptr(recs), int(n_records), _ptr(res)),
+               "h264gpu_cavlc_parse_host")
+        return recs[:int(n_records)], res[:n]
+
+    def cavlc_parse_dev(self, d_stream, stream_len, d_params, n_slices, d_records, d_results, stream=None):
+        _check(self.lib.h264gpu_cavlc_parse_dev(self.h, C.c_void_p(d_stream), stream_len,
+                                                C.c_void_p(d_params), n_slices, C.c_void_p(d_records),
+                                                C.c_void_p(d_results), stream), "h264gpu_cavlc_parse_dev")
+
     # ---- timers ----------------------------------------------------------
     def timer(self):
         t = C.c_void_p()
@@ -301,3 +353,39 @@ def synth_annexb(seed, rbsp, offs, mixed_sc=True, trailing=True, out=None, nthre
     if tot > len(out):
         raise ValueError("synth_annexb: output buffer too small (%d > %d)" % (tot, len(out)))
     return out[:tot], oo
+
+
+class VideoCfg(C.Structure):
+    """struct synth_video_cfg (libh264_b200/csrc/synth_video.c)."""
+    _fields_ = [("width_mbs", C.c_uint32), ("height_mbs", C.c_uint32), ("frames", C.c_uint32),
+                ("slices_per_frame", C.c_uint32), ("profile_idc", C.c_uint32),
+                ("chroma_format_idc", C.c_uint32), ("transform_8x8", C.c_uint32),
+                ("idr_period", C.c_uint32), ("b_frames", C.c_uint32), ("num_ref_frames", C.c_uint32),
+                ("entropy_cabac", C.c_uint32), ("pct_skip", C.c_uint32),
+                ("pct_intra_in_inter", C.c_uint32), ("pct_pcm", C.c_uint32),
+                ("coef_density", C.c_uint32), ("seed", C.c_uint64)]
+
+
+def synth_video(width_mbs, height_mbs, frames, slices_per_frame=1, profile_idc=66, chroma_format_idc=1,
+                transform_8x8=0, idr_period=30, b_frames=0, num_ref_frames=1, pct_skip=30,
+                pct_intra_in_inter=10, pct_pcm=5, coef_density=60, seed=0x264, out=None,
+                want_params=False):
+    """Synthetic CAVLC elementary stream (Annex-B).  Returns (stream, total_mbs, total_slices)
+    and, with want_params, the packed h264gpu_slice_params block of every slice."""
+    lib = load_synth_lib()
+    cfg = VideoCfg(width_mbs, height_mbs, frames, slices_per_frame, profile_idc, chroma_format_idc,
+                   transform_8x8, idr_period, b_frames, num_ref_frames, 0, pct_skip,
+                   pct_intra_in_inter, pct_pcm, coef_density, seed)
+    mbs, sl = C.c_uint64(0), C.c_uint64(0)
+    if out is None:
+        need = lib.synth_video(C.byref(cfg), None, 0, C.byref(mbs), C.byref(sl), None, 0)
+        out = np.empty(need, np.uint8)
+    nsl = frames * max(1, slices_per_frame)
+    params = np.zeros(nsl, SLICE_PARAMS) if want_params else None
+    n = lib.synth_video(C.byref(cfg), _ptr(out), len(out), C.byref(mbs), C.byref(sl),
+                        _ptr(params.view(np.uint8)) if want_params else None, nsl)
+    if n > len(out):
+        raise ValueError("synth_video: buffer too small")
+    if want_params:
+        return out[:n], mbs.value, sl.value, params[:sl.value].view(np.uint8).copy()
+    return out[:n], mbs.value, sl.value

@@ -55,10 +55,11 @@ def build_gpu(force=False, verbose=False):
 
 
 def build_synth(force=False):
-    src = os.path.join(CSRC, "synth.c")
-    if force or _stale(SYNTH_SO, [src]):
+    srcs = [os.path.join(CSRC, "synth.c"), os.path.join(CSRC, "synth_video.c")]
+    deps = srcs + [os.path.join(CSRC, "cavlc_luts.h")]
+    if force or _stale(SYNTH_SO, deps):
         subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", "-pthread", "-Wall",
-                               "-o", SYNTH_SO, src, "-lm"])
+                               "-I" + CSRC, "-o", SYNTH_SO] + srcs + ["-lm"])
     return SYNTH_SO
 
 

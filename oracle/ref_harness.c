@@ -210,3 +210,378 @@ double ref_mt_insert(const uint8_t *rbsp, const uint64_t *off, size_t n, int nth
 	}
 	return t1 - t0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Full-reader trace: every callback of h264_reader_parse, in order, plus the
+ * slice parameter block and per-macroblock syntax checksum the GPU path must
+ * reproduce.  The reference does all the parsing; this only records.        */
+
+#include "h264gpu_slice.h"
+
+enum {
+	TR_NALU_BEGIN = 1, /* u32 type, u32 ref_idc, u64 off, u64 len */
+	TR_NALU_END = 2,   /* same */
+	TR_AU_END = 3,
+	TR_SPS = 4,        /* struct h264_sps bytes */
+	TR_PPS = 5,        /* struct h264_pps bytes */
+	TR_SLICE = 6,      /* struct h264_slice_header bytes */
+	TR_SLICE_DATA_BEGIN = 7,
+	TR_SLICE_DATA_END = 8, /* u32 mb_count */
+	TR_AUD = 9,        /* u32 primary_pic_type */
+	TR_SEI = 10,       /* u32 type, raw payload bytes */
+	TR_SLICE_PARAMS = 11, /* struct h264gpu_slice_params (off/out fields filled) */
+};
+
+struct ref_tracer {
+	const uint8_t *base;
+	uint8_t *log;
+	size_t log_cap, log_len;
+	struct h264gpu_mb_record *mbs;
+	size_t mb_cap, mb_n;
+	int overflow;
+	uint64_t cur_nal_off;
+	uint64_t cur_nal_len;
+	size_t nal_mb0; /* records written before the current NAL */
+};
+
+static void tr_put(struct ref_tracer *t, uint32_t tag, const void *p, uint32_t n)
+{
+	if (t->log_len + 8 + n > t->log_cap) {
+		t->overflow = 1;
+		return;
+	}
+	memcpy(t->log + t->log_len, &tag, 4);
+	memcpy(t->log + t->log_len + 4, &n, 4);
+	if (n)
+		memcpy(t->log + t->log_len + 8, p, n);
+	t->log_len += 8 + ((n + 7) & ~7u);
+}
+
+static uint64_t mb_hash(const struct h264_macroblock *mb)
+{
+	uint64_t h = 0;
+#define T(f, i, v) h += h264gpu_mb_hash_term((f), (uint32_t)(i), (int64_t)(v))
+	T(H264GPU_F_RAW_MB_TYPE, 0, mb->raw_mb_type);
+	T(H264GPU_F_TRANSFORM_8X8, 0, mb->transform_size_8x8_flag);
+	T(H264GPU_F_MB_QP_DELTA, 0, mb->mb_qp_delta);
+	T(H264GPU_F_CBP, 0, mb->coded_block_pattern);
+	T(H264GPU_F_CBP_LUMA, 0, mb->CodedBlockPatternLuma);
+	T(H264GPU_F_CBP_CHROMA, 0, mb->CodedBlockPatternChroma);
+	T(H264GPU_F_INTRA_CHROMA_PRED_MODE, 0, mb->intra_chroma_pred_mode);
+	T(H264GPU_F_I16_PRED_MODE, 0, mb->Intra16x16PredMode);
+	T(H264GPU_F_MB_FIELD_DECODING_FLAG, 0, mb->mb_field_decoding_flag);
+	for (int i = 0; i < 16; i++)
+		T(H264GPU_F_INTRA4X4_PRED_MODE, i, mb->intra4x4_pred_mode[i]);
+	for (int i = 0; i < 4; i++) {
+		T(H264GPU_F_INTRA8X8_PRED_MODE, i, mb->intra8x8_pred_mode[i]);
+		T(H264GPU_F_REF_IDX_L0, i, mb->ref_idx_l0[i]);
+		T(H264GPU_F_REF_IDX_L1, i, mb->ref_idx_l1[i]);
+		T(H264GPU_F_RAW_SUB_MB_TYPE, i, mb->raw_sub_mb_type[i]);
+	}
+	for (int p = 0; p < 4; p++)
+		for (int s = 0; s < 4; s++)
+			for (int c = 0; c < 2; c++) {
+				T(H264GPU_F_MVD_L0, (p * 4 + s) * 2 + c, mb->mvd_l0[p][s][c]);
+				T(H264GPU_F_MVD_L1, (p * 4 + s) * 2 + c, mb->mvd_l1[p][s][c]);
+			}
+	const int16_t(*dc[3])[16] = {&mb->Intra16x16DCLevel, &mb->CbIntra16x16DCLevel,
+				     &mb->CrIntra16x16DCLevel};
+	const int16_t(*ac[3])[16][15] = {&mb->Intra16x16ACLevel, &mb->CbIntra16x16ACLevel,
+					 &mb->CrIntra16x16ACLevel};
+	const int16_t(*l4[3])[16][16] = {&mb->LumaLevel4x4, &mb->CbLevel4x4, &mb->CrLevel4x4};
+	for (int comp = 0; comp < 3; comp++) {
+		for (int i = 0; i < 16; i++)
+			T(H264GPU_F_I16_DC + 3 * comp, i, (*dc[comp])[i]);
+		for (int b = 0; b < 16; b++) {
+			for (int i = 0; i < 15; i++)
+				T(H264GPU_F_I16_AC + 3 * comp, b * 16 + i, (*ac[comp])[b][i]);
+			for (int i = 0; i < 16; i++)
+				T(H264GPU_F_LEVEL4X4 + 3 * comp, b * 16 + i, (*l4[comp])[b][i]);
+		}
+	}
+	for (int c = 0; c < 2; c++) {
+		for (int i = 0; i < 16; i++)
+			T(H264GPU_F_CHROMA_DC, c * 16 + i, mb->ChromaDCLevel[c][i]);
+		for (int b = 0; b < 16; b++)
+			for (int i = 0; i < 15; i++)
+				T(H264GPU_F_CHROMA_AC, (c * 16 + b) * 16 + i, mb->ChromaACLevel[c][b][i]);
+		for (int i = 0; i < 256; i++)
+			T(H264GPU_F_PCM_CHROMA, c * 256 + i, mb->pcm_sample_chroma[c][i]);
+	}
+	for (int i = 0; i < 256; i++)
+		T(H264GPU_F_PCM_LUMA, i, mb->pcm_sample_luma[i]);
+#undef T
+	return h;
+}
+
+static void tr_nalu(struct ref_tracer *t, uint32_t tag, enum h264_nalu_type type,
+		    const uint8_t *buf, size_t len, const struct h264_nalu_header *nh)
+{
+	uint64_t rec[3] = {(uint64_t)type | (uint64_t)nh->nal_ref_idc << 32,
+			   (uint64_t)(buf - t->base), (uint64_t)len};
+	tr_put(t, tag, rec, sizeof(rec));
+}
+
+static void cb_nalu_begin(struct h264_ctx *ctx, enum h264_nalu_type type, const uint8_t *buf,
+			  size_t len, const struct h264_nalu_header *nh, void *ud)
+{
+	struct ref_tracer *t = ud;
+	t->cur_nal_off = (uint64_t)(buf - t->base);
+	t->cur_nal_len = len;
+	t->nal_mb0 = t->mb_n;
+	tr_nalu(t, TR_NALU_BEGIN, type, buf, len, nh);
+}
+
+static void cb_nalu_end(struct h264_ctx *ctx, enum h264_nalu_type type, const uint8_t *buf,
+			size_t len, const struct h264_nalu_header *nh, void *ud)
+{
+	tr_nalu(ud, TR_NALU_END, type, buf, len, nh);
+}
+
+static void cb_au_end(struct h264_ctx *ctx, void *ud)
+{
+	tr_put(ud, TR_AU_END, NULL, 0);
+}
+
+static void cb_sps(struct h264_ctx *ctx, const uint8_t *buf, size_t len,
+		   const struct h264_sps *sps, void *ud)
+{
+	tr_put(ud, TR_SPS, sps, sizeof(*sps));
+}
+
+static void cb_pps(struct h264_ctx *ctx, const uint8_t *buf, size_t len,
+		   const struct h264_pps *pps, void *ud)
+{
+	tr_put(ud, TR_PPS, pps, sizeof(*pps));
+}
+
+static void cb_aud(struct h264_ctx *ctx, const uint8_t *buf, size_t len,
+		   const struct h264_aud *aud, void *ud)
+{
+	tr_put(ud, TR_AUD, aud, sizeof(*aud));
+}
+
+static void cb_sei(struct h264_ctx *ctx, enum h264_sei_type type, const uint8_t *buf,
+		   size_t len, void *ud)
+{
+	struct ref_tracer *t = ud;
+	uint32_t ty = type;
+	if (t->log_len + 16 + len > t->log_cap) {
+		t->overflow = 1;
+		return;
+	}
+	uint8_t *tmp = malloc(len + 4);
+	memcpy(tmp, &ty, 4);
+	memcpy(tmp + 4, buf, len);
+	tr_put(t, TR_SEI, tmp, (uint32_t)len + 4);
+	free(tmp);
+}
+
+/* the parameter block a slice-parallel parser needs, read off the reference ctx */
+static void fill_params(struct ref_tracer *t, struct h264_ctx *ctx,
+			struct h264gpu_slice_params *p)
+{
+	const struct h264_slice_header *sh = &ctx->slice.hdr;
+	memset(p, 0, sizeof(*p));
+	p->nal_off = t->cur_nal_off;
+	p->nal_len = (uint32_t)t->cur_nal_len;
+	p->data_bit_off = (uint32_t)ctx->slice.hdr_len;
+	p->first_mb_in_slice = sh->first_mb_in_slice;
+	p->mb_out_off = (uint32_t)t->nal_mb0;
+	p->mb_out_cap = (uint32_t)(t->mb_n - t->nal_mb0);
+	p->pic_width_in_mbs = (uint16_t)ctx->sps_derived.PicWidthInMbs;
+	p->pic_height_in_mbs = (uint16_t)ctx->derived.PicHeightInMbs;
+	p->slice_type = (uint8_t)ctx->slice.type;
+	p->chroma_array_type = (uint8_t)ctx->sps_derived.ChromaArrayType;
+	p->bit_depth_luma = (uint8_t)ctx->sps_derived.BitDepthLuma;
+	p->bit_depth_chroma = (uint8_t)ctx->sps_derived.BitDepthChroma;
+	p->transform_8x8_mode_flag = (uint8_t)ctx->pps->transform_8x8_mode_flag;
+	p->direct_8x8_inference_flag = (uint8_t)ctx->sps->direct_8x8_inference_flag;
+	p->num_ref_idx_l0_active_minus1 = (uint8_t)sh->num_ref_idx_l0_active_minus1;
+	p->num_ref_idx_l1_active_minus1 = (uint8_t)sh->num_ref_idx_l1_active_minus1;
+	p->field_pic_flag = (uint8_t)sh->field_pic_flag;
+	p->mbaff_frame_flag = (uint8_t)ctx->derived.MbaffFrameFlag;
+	p->entropy_coding_mode_flag = (uint8_t)ctx->pps->entropy_coding_mode_flag;
+	p->num_slice_groups_minus1 = (uint8_t)ctx->pps->num_slice_groups_minus1;
+	p->cabac_init_idc = (uint8_t)sh->cabac_init_idc;
+	p->slice_qp = (int8_t)ctx->derived.SliceQPLuma;
+}
+
+static void cb_slice(struct h264_ctx *ctx, const uint8_t *buf, size_t len,
+		     const struct h264_slice_header *sh, void *ud)
+{
+	struct ref_tracer *t = ud;
+	struct h264gpu_slice_params p;
+	tr_put(t, TR_SLICE, sh, sizeof(*sh));
+	/* emitted after the slice's macroblocks: mb_out_off/mb_out_cap delimit its records */
+	fill_params(t, ctx, &p);
+	tr_put(t, TR_SLICE_PARAMS, &p, sizeof(p));
+}
+
+static void cb_sd_begin(struct h264_ctx *ctx, const struct h264_slice_header *sh, void *ud)
+{
+	tr_put(ud, TR_SLICE_DATA_BEGIN, NULL, 0);
+}
+
+static void cb_sd_end(struct h264_ctx *ctx, const struct h264_slice_header *sh,
+		      uint32_t mb_count, void *ud)
+{
+	tr_put(ud, TR_SLICE_DATA_END, &mb_count, 4);
+}
+
+static void cb_sd_mb(struct h264_ctx *ctx, const struct h264_slice_header *sh,
+		     uint32_t mb_addr, enum h264_mb_type mb_type, void *ud)
+{
+	struct ref_tracer *t = ud;
+	if (t->mb_n < t->mb_cap) {
+		t->mbs[t->mb_n].mb_addr = mb_addr;
+		t->mbs[t->mb_n].mb_type = mb_type;
+		t->mbs[t->mb_n].hash = t->mbs ? mb_hash(ctx->mb) : 0;
+	}
+	t->mb_n++;
+}
+
+/*
+ * h264_reader_parse(flags) over buf with recording callbacks.
+ * Returns 0, or 1 when a buffer was too small (counts are still exact).
+ * hash_mbs = 0 skips the (slow) per-MB checksum: used by the CPU baseline timing.
+ */
+int ref_trace_parse(const uint8_t *buf, size_t len, uint32_t flags, uint8_t *log,
+		    size_t log_cap, size_t *log_len, struct h264gpu_mb_record *mbs,
+		    size_t mb_cap, size_t *mb_n, size_t *final_off)
+{
+	struct h264_ctx_cbs cbs;
+	struct h264_reader *reader = NULL;
+	struct ref_tracer t;
+	size_t off = 0;
+	memset(&cbs, 0, sizeof(cbs));
+	memset(&t, 0, sizeof(t));
+	t.base = buf;
+	t.log = log;
+	t.log_cap = log_cap;
+	t.mbs = mbs;
+	t.mb_cap = mb_cap;
+	cbs.nalu_begin = cb_nalu_begin;
+	cbs.nalu_end = cb_nalu_end;
+	cbs.au_end = cb_au_end;
+	cbs.sps = cb_sps;
+	cbs.pps = cb_pps;
+	cbs.aud = cb_aud;
+	cbs.sei = cb_sei;
+	cbs.slice = cb_slice;
+	cbs.slice_data_begin = cb_sd_begin;
+	cbs.slice_data_end = cb_sd_end;
+	cbs.slice_data_mb = cb_sd_mb;
+	if (h264_reader_new(&cbs, &t, &reader) < 0)
+		return -1;
+	h264_reader_parse(reader, flags, buf, len, &off);
+	h264_reader_destroy(reader);
+	if (log_len)
+		*log_len = t.log_len;
+	if (mb_n)
+		*mb_n = t.mb_n;
+	if (final_off)
+		*final_off = off;
+	return t.overflow || t.mb_n > mb_cap;
+}
+
+/* ---- CPU baseline for the macroblock parse: counting callbacks only ---------- */
+
+struct count_ud {
+	uint64_t mbs, slices, nals;
+};
+static void cnt_mb(struct h264_ctx *ctx, const struct h264_slice_header *sh, uint32_t a,
+		   enum h264_mb_type ty, void *ud)
+{
+	((struct count_ud *)ud)->mbs++;
+}
+static void cnt_slice(struct h264_ctx *ctx, const uint8_t *buf, size_t len,
+		      const struct h264_slice_header *sh, void *ud)
+{
+	((struct count_ud *)ud)->slices++;
+}
+
+struct parse_job {
+	const uint8_t *buf;
+	size_t len;
+	uint32_t flags;
+	struct count_ud c;
+};
+
+static void *parse_worker(void *arg)
+{
+	struct parse_job *j = arg;
+	struct h264_ctx_cbs cbs;
+	struct h264_reader *reader = NULL;
+	size_t off = 0;
+	memset(&cbs, 0, sizeof(cbs));
+	cbs.slice_data_mb = cnt_mb;
+	cbs.slice = cnt_slice;
+	if (h264_reader_new(&cbs, &j->c, &reader) < 0)
+		return NULL;
+	h264_reader_parse(reader, j->flags, j->buf, j->len, &off);
+	h264_reader_destroy(reader);
+	return NULL;
+}
+
+/*
+ * h264_reader_parse(flags) of nstreams independent streams (stream i =
+ * bufs[i], lens[i]) on up to nthreads threads, one reader per stream, streams
+ * dealt round-robin.  Returns seconds; *mbs = slice_data_mb callbacks seen.
+ */
+struct parse_thread {
+	struct parse_job *jobs;
+	size_t n, first, stride;
+};
+static void *parse_thread_main(void *arg)
+{
+	struct parse_thread *p = arg;
+	for (size_t i = p->first; i < p->n; i += p->stride)
+		parse_worker(&p->jobs[i]);
+	return NULL;
+}
+
+double ref_mt_parse(const uint8_t *const *bufs, const size_t *lens, size_t nstreams,
+		    uint32_t flags, int nthreads, uint64_t *mbs, uint64_t *slices)
+{
+	pthread_t th[256];
+	struct parse_thread pt[256];
+	struct parse_job *jobs = calloc(nstreams, sizeof(*jobs));
+	double t0, t1;
+	if (nthreads < 1)
+		nthreads = 1;
+	if (nthreads > 256)
+		nthreads = 256;
+	if ((size_t)nthreads > nstreams)
+		nthreads = (int)nstreams;
+	for (size_t i = 0; i < nstreams; i++) {
+		jobs[i].buf = bufs[i];
+		jobs[i].len = lens[i];
+		jobs[i].flags = flags;
+	}
+	for (int i = 0; i < nthreads; i++) {
+		pt[i].jobs = jobs;
+		pt[i].n = nstreams;
+		pt[i].first = (size_t)i;
+		pt[i].stride = (size_t)nthreads;
+	}
+	t0 = now_s();
+	for (int i = 1; i < nthreads; i++)
+		pthread_create(&th[i], NULL, parse_thread_main, &pt[i]);
+	parse_thread_main(&pt[0]);
+	for (int i = 1; i < nthreads; i++)
+		pthread_join(th[i], NULL);
+	t1 = now_s();
+	if (mbs) {
+		*mbs = 0;
+		for (size_t i = 0; i < nstreams; i++)
+			*mbs += jobs[i].c.mbs;
+	}
+	if (slices) {
+		*slices = 0;
+		for (size_t i = 0; i < nstreams; i++)
+			*slices += jobs[i].c.slices;
+	}
+	free(jobs);
+	return t1 - t0;
+}

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Generate tests/golden/cavlc_*.npz from the COMPILED REFERENCE (dev container only).
+
+For a few tiny synthetic CAVLC streams this records what the unmodified reference
+(oracle/_ref/libh264_ref.so, h264_reader_parse with H264_READER_FLAGS_SLICE_DATA)
+delivers: per-macroblock (mb_addr, mb_type), the checksum of ctx->mb
+(include/h264gpu_slice.h), slice_data_end counts, and the slice parameter blocks
+its ctx held.  The streams themselves are regenerated from their configs by the
+deterministic generator (libh264_b200/csrc/synth_video.c); a CRC pins them.
+"""
+import os
+import sys
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+import libh264_b200 as L  # noqa: E402
+import support as S  # noqa: E402
+
+CASES = {
+    "baseline": dict(width_mbs=8, height_mbs=6, frames=6, idr_period=3),
+    "main_b_multislice": dict(width_mbs=11, height_mbs=9, frames=8, slices_per_frame=3, b_frames=1,
+                              num_ref_frames=3, profile_idc=77),
+    "high_t8": dict(width_mbs=10, height_mbs=7, frames=6, slices_per_frame=2, profile_idc=100,
+                    transform_8x8=1, b_frames=1, num_ref_frames=2),
+    "high_422": dict(width_mbs=6, height_mbs=5, frames=4, profile_idc=100, chroma_format_idc=2),
+    "high_444": dict(width_mbs=6, height_mbs=5, frames=4, profile_idc=100, chroma_format_idc=3,
+                     transform_8x8=1),
+    "high_mono": dict(width_mbs=6, height_mbs=5, frames=4, profile_idc=100, chroma_format_idc=0),
+}
+
+
+def main():
+    for name, kw in CASES.items():
+        stream, nmb, nsl = L.synth_video(**kw)
+        ev, mbs, off = S.ref_trace(stream)
+        params = S.slice_params_from_trace(ev)
+        counts = np.array([int(p.view(np.uint32)[0]) for t, p in ev if t == S.TR_SLICE_DATA_END], np.uint32)
+        order = np.array([t for t, _ in ev], np.uint8)
+        np.savez_compressed(os.path.join(HERE, "cavlc_%s.npz" % name), crc=np.uint32(zlib.crc32(stream.tobytes())),
+                            mbs=mbs, params=params, mb_counts=counts, callback_order=order,
+                            final_off=np.uint64(off))
+        print(name, len(stream), "bytes", nmb, "mbs", nsl, "slices")
+
+
+if __name__ == "__main__":
+    main()

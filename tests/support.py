@@ -225,6 +225,60 @@ def emu_split_strip(buf, strip=True, items=4, edge=None, base=0):
 
 
 # ----------------------------------------------------------------------------
+# full-reader trace through the compiled reference (oracle/ref_harness.c)
+
+TR_NALU_BEGIN, TR_NALU_END, TR_AU_END, TR_SPS, TR_PPS, TR_SLICE = 1, 2, 3, 4, 5, 6
+TR_SLICE_DATA_BEGIN, TR_SLICE_DATA_END, TR_AUD, TR_SEI, TR_SLICE_PARAMS = 7, 8, 9, 10, 11
+MB_RECORD = np.dtype([("mb_addr", "<u4"), ("mb_type", "<u4"), ("hash", "<u8")])
+SLICE_RESULT = np.dtype([("status", "<i4"), ("mb_count", "<u4"), ("end_bit", "<u8")])
+PARAMS_SIZE = 56
+
+
+def ref_trace(stream, flags=1, mb_cap=None, log_cap=None):
+    """h264_reader_parse(flags) of the UNMODIFIED reference with recording callbacks.
+    Returns (events [(tag, payload bytes)], mb records, final off)."""
+    lib = ref()
+    lib.ref_trace_parse.restype = C.c_int
+    lib.ref_trace_parse.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t,
+                                    C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t,
+                                    C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    mb_cap = mb_cap or max(1024, len(stream))
+    log_cap = log_cap or (len(stream) * 4 + (32 << 20))
+    log = np.zeros(log_cap, np.uint8)
+    mbs = np.zeros(mb_cap, MB_RECORD)
+    ll, mn, off = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    rc = lib.ref_trace_parse(ptr(stream), len(stream), flags, ptr(log), len(log), C.byref(ll),
+                             ptr(mbs), mb_cap, C.byref(mn), C.byref(off))
+    assert rc == 0, "ref_trace_parse: buffers too small"
+    log = log[:ll.value]
+    ev, i = [], 0
+    while i < len(log):
+        tag = int(log[i:i + 4].view(np.uint32)[0])
+        n = int(log[i + 4:i + 8].view(np.uint32)[0])
+        ev.append((tag, log[i + 8:i + 8 + n]))
+        i += 8 + ((n + 7) & ~7)
+    return ev, mbs[:mn.value].copy(), off.value
+
+
+def slice_params_from_trace(ev):
+    """The packed h264gpu_slice_params blocks the reference's ctx held for every slice."""
+    parts = [bytes(p[:PARAMS_SIZE]) for t, p in ev if t == TR_SLICE_PARAMS]
+    return np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+
+
+def emu_cavlc_parse(stream, params, n_records):
+    lib = emu()
+    lib.emu_cavlc_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    n = len(params) // PARAMS_SIZE
+    recs = np.zeros(max(n_records, 1), MB_RECORD)
+    res = np.zeros(max(n, 1), SLICE_RESULT)
+    lib.emu_cavlc_parse(ptr(stream), len(stream), ptr(params), n, ptr(recs), ptr(res))
+    return recs[:n_records], res[:n]
+
+
+# ----------------------------------------------------------------------------
 # synthetic streams (SURVEY.md §8d config 2 shape, small)
 
 def gen_payloads(rng, n, lo=1, hi=4096, p_zero=3 / 16):

@@ -26,6 +26,10 @@ def test_gpu_library_exports_header_symbols():
         assert hasattr(lib, n), "missing export " + n
     assert sorted(L.GPU_SYMBOLS) == names
     assert b"sm_100a" in lib.h264gpu_version()
+    slice_names = declared("h264gpu_slice.h", "H264GPU_API")
+    assert sorted(L.SLICE_SYMBOLS) == slice_names
+    for n in slice_names:
+        assert hasattr(lib, n), "missing export " + n
 
 
 def test_no_device_is_an_error_not_a_fallback():

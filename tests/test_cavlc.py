@@ -1,0 +1,112 @@
+"""K4 CAVLC slice parse: generator validity, kernel logic on CPU (emu build of the
+kernel source) against the compiled reference and the committed golden fixtures."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import libh264_b200 as L
+import support as S
+from golden.make_golden import CASES
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not S.have_ref(), reason="oracle/_ref/libh264_ref.so not built")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLD, "cavlc_%s.npz" % name))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_emu_parse_matches_golden(name):
+    g = load_golden(name)
+    stream, nmb, nsl = L.synth_video(**CASES[name])
+    assert zlib.crc32(stream.tobytes()) == int(g["crc"]), "generator output changed"
+    recs, res = S.emu_cavlc_parse(stream, g["params"], len(g["mbs"]))
+    assert (res["status"] == 0).all()
+    assert np.array_equal(res["mb_count"], g["mb_counts"])
+    assert np.array_equal(recs["mb_addr"], g["mbs"]["mb_addr"])
+    assert np.array_equal(recs["mb_type"], g["mbs"]["mb_type"])
+    assert np.array_equal(recs["hash"], g["mbs"]["hash"])
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_is_what_the_reference_says(name):
+    g = load_golden(name)
+    stream, nmb, nsl = L.synth_video(**CASES[name])
+    ev, mbs, off = S.ref_trace(stream)
+    assert len(mbs) == nmb and np.array_equal(mbs, g["mbs"])
+    assert np.array_equal(S.slice_params_from_trace(ev), g["params"])
+    assert off == int(g["final_off"]) == len(stream)
+
+
+@needs_ref
+def test_generator_streams_are_valid_for_the_reference():
+    # every macroblock consumed, every slice ends at its stop bit, across seeds / mixes
+    for seed in range(6):
+        kw = dict(width_mbs=9, height_mbs=5, frames=5, slices_per_frame=1 + seed % 3, b_frames=seed & 1,
+                  num_ref_frames=1 + seed % 4, profile_idc=[66, 77, 100][seed % 3],
+                  transform_8x8=int(seed % 3 == 2), pct_skip=10 * seed, coef_density=20 + 15 * seed,
+                  pct_pcm=10 * (seed % 2), seed=seed)
+        stream, nmb, nsl = L.synth_video(**kw)
+        ev, mbs, off = S.ref_trace(stream)
+        tags = [t for t, _ in ev]
+        assert len(mbs) == nmb and tags.count(S.TR_SLICE) == nsl and tags.count(S.TR_NALU_END) == nsl + 2
+        assert sum(int(p.view(np.uint32)[0]) for t, p in ev if t == S.TR_SLICE_DATA_END) == nmb
+        recs, res = S.emu_cavlc_parse(stream, S.slice_params_from_trace(ev), nmb)
+        assert (res["status"] == 0).all() and np.array_equal(recs, mbs), seed
+
+
+@needs_ref
+def test_emu_parse_1080p_frame():
+    stream, nmb, nsl = L.synth_video(width_mbs=120, height_mbs=68, frames=2, idr_period=2, slices_per_frame=4)
+    ev, mbs, off = S.ref_trace(stream)
+    recs, res = S.emu_cavlc_parse(stream, S.slice_params_from_trace(ev), nmb)
+    assert (res["status"] == 0).all() and np.array_equal(recs, mbs)
+
+
+def test_cabac_slice_is_skipped_like_the_reference():
+    g = load_golden("baseline")
+    stream, _, _ = L.synth_video(**CASES["baseline"])
+    p = g["params"].copy().view(L.SLICE_PARAMS)
+    p["entropy_coding_mode_flag"] = 1
+    recs, res = S.emu_cavlc_parse(stream, p.view(np.uint8), len(g["mbs"]))
+    assert (res["status"] == 1).all() and (res["mb_count"] == 0).all()
+
+
+def test_truncated_slice_reports_eio_not_garbage():
+    g = load_golden("baseline")
+    stream, _, _ = L.synth_video(**CASES["baseline"])
+    p = g["params"].copy().view(L.SLICE_PARAMS)
+    p["nal_len"] = p["nal_len"] // 2
+    recs, res = S.emu_cavlc_parse(stream, p.view(np.uint8), len(g["mbs"]))
+    assert ((res["status"] == -5) | (res["status"] == 0)).all() and (res["status"] == -5).any()
+    assert (res["mb_count"] <= g["mb_counts"]).all()
+
+
+# ---- GPU ---------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_parse_matches_golden(gpu, name):
+    g = load_golden(name)
+    stream, nmb, nsl = L.synth_video(**CASES[name])
+    recs, res = gpu.cavlc_parse_host(stream, g["params"], len(g["mbs"]))
+    assert (res["status"] == 0).all() and np.array_equal(res["mb_count"], g["mb_counts"])
+    assert np.array_equal(recs, g["mbs"])
+
+
+@pytest.mark.gpu
+def test_gpu_parse_many_slices_vs_reference(gpu):
+    if not S.have_ref():
+        pytest.skip("oracle/_ref/libh264_ref.so not available")
+    # 1080p, 16 slices per frame, P/B/I mix: 640 independent slices
+    stream, nmb, nsl = L.synth_video(width_mbs=120, height_mbs=68, frames=40, slices_per_frame=16,
+                                     profile_idc=100, transform_8x8=1, b_frames=1, num_ref_frames=2,
+                                     idr_period=10, seed=9)
+    ev, mbs, off = S.ref_trace(stream)
+    recs, res = gpu.cavlc_parse_host(stream, S.slice_params_from_trace(ev), nmb)
+    assert (res["status"] == 0).all() and int(res["mb_count"].sum()) == nmb
+    assert np.array_equal(recs, mbs)
