@@ -1,0 +1,24 @@
+/*
+ * h264/h264_dump.h — JSON dump API of the reference (include/h264/h264_dump.h:31-73).
+ * The reference implements it with json-c, which this build does not have and
+ * which is off the parse/serialise hot path (out of scope): the
+ * types and flags are declared for source compatibility, the functions are not
+ * provided.
+ */
+#ifndef H264B200_DUMP_H
+#define H264B200_DUMP_H
+
+struct json_object;
+struct h264_dump;
+
+#define H264_DUMP_FLAGS_SLICE_DATA 0x01
+
+enum h264_dump_type {
+	H264_DUMP_TYPE_JSON,
+};
+
+struct h264_dump_cfg {
+	enum h264_dump_type type;
+};
+
+#endif /* H264B200_DUMP_H */

@@ -76,21 +76,34 @@ struct BitReader {
 __device__ __forceinline__ void br_refill(BitReader &b)
 {
 	while (b.nbits <= 56 && b.pos < b.len) {
-		uint32_t c = b.p[b.pos];
-		uint32_t skipped = 0;
-		if (b.zeros >= 2 && c == 3) {
-			if (b.pos + 1 >= b.len)
-				break; /* the reference fails the fetch here */
-			b.pos++;
-			c = b.p[b.pos];
-			skipped = 1;
-			b.zeros = 0;
+		/* up to 5 raw bytes in flight at once (independent loads), then the EPB
+		 * state machine runs on registers */
+		const uint32_t avail = b.len - b.pos;
+		uint64_t pk = 0;
+#pragma unroll
+		for (int j = 0; j < 5; j++)
+			pk |= (uint64_t)((uint32_t)j < avail ? b.p[b.pos + j] : 0u) << (8 * j);
+		uint32_t k = 0;
+		while (b.nbits <= 56 && k < 4 && k < avail) {
+			uint32_t c = (uint32_t)(pk >> (8 * k)) & 0xffu;
+			uint32_t skipped = 0;
+			if (b.zeros >= 2 && c == 3) {
+				if (k + 1 >= avail) {
+					b.pos += k;
+					return; /* the reference fails the fetch here */
+				}
+				k++;
+				c = (uint32_t)(pk >> (8 * k)) & 0xffu;
+				skipped = 1;
+				b.zeros = 0;
+			}
+			b.zeros = c == 0 ? b.zeros + 1 : 0;
+			k++;
+			b.cache |= (uint64_t)c << (56 - b.nbits);
+			b.nbits += 8;
+			b.epbq = (b.epbq << 1) | skipped;
 		}
-		b.zeros = c == 0 ? b.zeros + 1 : 0;
-		b.pos++;
-		b.cache |= (uint64_t)c << (56 - b.nbits);
-		b.nbits += 8;
-		b.epbq = (b.epbq << 1) | skipped;
+		b.pos += k;
 	}
 }
 
@@ -807,11 +820,24 @@ struct CavlcArgs {
 	uint8_t *ring; /* n_slices x ring_stride bytes */
 	uint64_t ring_stride;
 	uint32_t ring_w; /* widest picture (in MBs) a ring slot row can hold */
+	uint32_t lanes_log2; /* log2 of the slices carried by one warp (0..5) */
 };
 
-__global__ void __launch_bounds__(64) cavlc_parse_kernel(const CavlcArgs a)
+/*
+ * Slices diverge completely (every lane is at a different point of a different
+ * macroblock), so a warp runs its lanes one after the other.  Few slices are
+ * therefore spread over MANY warps (down to one slice per warp) to fill the SMs'
+ * issue slots, and only packed into the lanes of a warp once there are more slices
+ * than resident warps.
+ */
+__global__ void __launch_bounds__(128) cavlc_parse_kernel(const CavlcArgs a)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t step = 32u >> a.lanes_log2; /* active lanes are multiples of this */
+	if (lane & (step - 1))
+		return;
+	const uint32_t i = (gwarp << a.lanes_log2) + lane / step;
 	if (i >= a.n_slices)
 		return;
 	const h264gpu_slice_params sp = a.params[i];

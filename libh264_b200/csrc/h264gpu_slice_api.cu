@@ -38,8 +38,22 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	a.ring = (uint8_t *)ctx->ws;
 	a.ring_stride = ring_stride;
 	a.ring_w = ring_w;
-	const uint32_t threads = 64;
-	const uint32_t blocks = (n_slices + threads - 1) / threads;
+	/* slices per warp: 1 until there are more slices than ~48 warps per SM can hold */
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	const uint64_t warp_slots = (uint64_t)sms * 48;
+	uint32_t lanes_log2 = 0;
+	const char *env = getenv("H264GPU_CAVLC_LANES_LOG2");
+	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
+		lanes_log2 = (uint32_t)atoi(env);
+	} else {
+		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > warp_slots)
+			lanes_log2++;
+	}
+	a.lanes_log2 = lanes_log2;
+	const uint32_t threads = 128; /* 4 warps per block */
+	const uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
+	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
 	cavlc::cavlc_parse_kernel<<<blocks, threads, 0, st>>>(a);
 	CU_TRY(cudaGetLastError());
 	ctx->launches++;
