@@ -128,6 +128,17 @@ MB_CFG = dict(width_mbs=120, height_mbs=68, slices_per_frame=16, profile_idc=100
               b_frames=1, num_ref_frames=2, idr_period=30, pct_skip=30, coef_density=60, seed=SEED)
 
 
+def SCAN_KERNEL_NAME():
+    it = int(os.environ.get("H264GPU_SCAN_ITEMS", "108"))
+    if it >= 400:
+        return "annexb3::scan4_kernel<256,8,strip> (classify + emit work items)"
+    if it >= 200:
+        thr, cpt, nt = {208: (256, 8, 2), 228: (512, 4, 2), 204: (256, 4, 2), 244: (256, 4, 4)}[it]
+        return "annexb3::scan3_kernel<%d,%d,%d,strip>" % (thr, cpt, nt)
+    return ("annexb2::scan2_kernel<%d,strip>" % (it % 10)) if it >= 100 else \
+        ("annexb::scan_kernel<%d,strip>" % it)
+
+
 def mb_parse_leg(g, L, frames, steps, warmup, rank, with_cpu):
     """Slice-parallel CAVLC macroblock parse (1080p High, 16 slices/frame): macroblocks/s
     device-resident, end-to-end from host buffers, and the reference reader on the host cores."""
@@ -390,7 +401,7 @@ def main():
                        "start_codes": "3/4-byte mixed, 0-2 trailing zeros on 1/4 of NALs",
                        "l2": "input %.1f GiB >> 126 MB L2, no flush needed" % (n_in / 2**30),
                        "parallelism": "byte-range shards, 1 per GPU, host merge, no collective",
-                       "kernel": "annexb::scan_kernel<%s,strip>" % os.environ.get("H264GPU_SCAN_ITEMS", "4"),
+                       "kernel": SCAN_KERNEL_NAME(),
                        "gen_seconds": round(gen_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

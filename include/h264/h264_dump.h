@@ -21,4 +21,13 @@ struct h264_dump_cfg {
 	enum h264_dump_type type;
 };
 
+/* JSON dump of the NAL unit held in a context (reference: include/h264/h264_dump.h:49-73).
+ * It needs json-c; this library reports -ENOSYS (out of scope). */
+H264_API int h264_dump_new(const struct h264_dump_cfg *cfg, struct h264_dump **ret_obj);
+H264_API int h264_dump_destroy(struct h264_dump *dump);
+H264_API int h264_dump_clear(struct h264_dump *dump);
+H264_API int h264_dump_get_json_object(struct h264_dump *dump, struct json_object **jobj);
+H264_API int h264_dump_get_json_str(struct h264_dump *dump, const char **str);
+H264_API int h264_dump_nalu(struct h264_dump *dump, struct h264_ctx *ctx, uint32_t flags);
+
 #endif /* H264B200_DUMP_H */

@@ -72,7 +72,7 @@ def build_host(force=False):
     if force or _stale(H264_SO, deps + [GPU_SO]):
         subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-D_GNU_SOURCE", "-DH264_API_EXPORTS",
                                "-fPIC", "-fvisibility=hidden", "-shared", "-Wall",
-                               "-I" + INC, "-I" + HOST, "-o", H264_SO] + srcs +
+                               "-I" + INC, "-I" + HOST, "-I" + CSRC, "-o", H264_SO] + srcs +
                               ["-L" + HERE, "-lh264gpu", "-Wl,-rpath,$ORIGIN"])
     return H264_SO
 

@@ -17,6 +17,17 @@ static inline uint32_t ldg_u32(const void *p) { return *(const uint32_t *)p; }
 static inline uint64_t ld_relaxed_u64(const uint64_t *p) { return *(const volatile uint64_t *)p; }
 static inline void st_relaxed_u64(uint64_t *p, uint64_t v) { *(volatile uint64_t *)p = v; }
 static inline void stg_stream16(void *p, uint4 v) { *(uint4 *)p = v; }
+static inline void bulk_load_start(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+	(void)bar;
+	memcpy(sdst, gsrc, bytes);
+}
+static inline void bulk_load_wait(uint64_t *bar) { (void)bar; }
+static inline void spin_pause(unsigned ns) { (void)ns; }
+static inline uint4 ldcg16(const void *p) { return *(const uint4 *)p; }
+static inline uint32_t ldcg_u32(const void *p) { return *(const volatile uint32_t *)p; }
+static inline uint32_t ld_relaxed_u32(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+static inline void st_relaxed_u32(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
 #else
 #include <cuda_runtime.h>
 #define H264_HD __host__ __device__
@@ -52,6 +63,72 @@ __device__ __forceinline__ void stg_stream16(void *p, uint4 v)
 {
 	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p),
 		     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+		     : "memory");
+}
+/* loads that bypass the (non-coherent) L1: data another CTA wrote */
+__device__ __forceinline__ uint4 ldcg16(const void *p)
+{
+	uint4 r;
+	asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+		     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+		     : "l"(p)
+		     : "memory");
+	return r;
+}
+__device__ __forceinline__ uint32_t ldcg_u32(const void *p)
+{
+	uint32_t r;
+	asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+	return r;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+/* back off inside a polling loop so the spinning warp leaves the issue slots alone */
+__device__ __forceinline__ void spin_pause(unsigned ns)
+{
+	asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+}
+/*
+ * Bulk asynchronous copy global -> shared (TMA, 1-D form) completing on an
+ * mbarrier: one thread arms the barrier with the byte count and issues the copy;
+ * every consumer waits on phase 0.  dst/src 16-byte aligned, bytes % 16 == 0.
+ */
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void bulk_load_start(void *sdst, const void *gsrc, uint32_t bytes,
+						uint64_t *bar)
+{
+	const uint32_t b = smem_u32(bar), d = smem_u32(sdst);
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes)
+		     : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+		     "[%0], [%1], %2, [%3];" ::"r"(d),
+		     "l"(gsrc), "r"(bytes), "r"(b)
+		     : "memory");
+}
+__device__ __forceinline__ void bulk_load_wait(uint64_t *bar)
+{
+	const uint32_t b = smem_u32(bar);
+	asm volatile("{\n"
+		     ".reg .pred p;\n"
+		     "BULK_WAIT:\n"
+		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+		     "@p bra BULK_DONE;\n"
+		     "bra BULK_WAIT;\n"
+		     "BULK_DONE:\n"
+		     "}" ::"r"(b)
 		     : "memory");
 }
 #endif

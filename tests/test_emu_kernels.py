@@ -70,6 +70,9 @@ def test_emu_scan_lookback_fold():
             lib.emu_set_prefix_every(every)
             check_scan(S.gen_annexb(rng, 300, 1, 3000), 1, ("fold", every))
             check_scan(rng.choice(ALPHA, 200000), 1, ("foldadv", every))
+        # more than one 128-tile look-back window without any published prefix
+        lib.emu_set_prefix_every(300)
+        check_scan(S.gen_annexb(rng, 500, 1, 5000), 1, ("fold", 300))
     finally:
         lib.emu_set_prefix_every(1)
 
@@ -222,3 +225,33 @@ def test_emu_frame_then_scan_round_trip():
     assert np.array_equal(back["rbsp"], data)
     assert np.array_equal(back["rbsp_off"], offs[:-1])
     assert np.array_equal(back["start"], oo[:-1] + 4)
+
+
+# ---- gen-2 scan kernel: dense / degenerate inputs (list overflow, unlisted paths) -------
+
+def test_emu_scan2_dense_and_degenerate_inputs():
+    rng = np.random.default_rng(7)
+    cases = []
+    b = np.tile(np.array([0, 0, 3], np.uint8), 30000)
+    b[:4] = [0, 0, 1, 0x65]
+    cases.append(("dense epb", b, (1, 4)))          # every chunk deletes: lists overflow
+    cases.append(("dense sc", np.tile(np.array([0, 0, 1], np.uint8), 30000), (1, 4)))
+    cases.append(("dense sc2", np.tile(np.array([0, 0, 1, 0x41, 0, 0, 0, 9], np.uint8), 12000), (1, 4)))
+    cases.append(("zeros", np.zeros(100000, np.uint8), (1, 4)))
+    b = np.zeros(100000, np.uint8)
+    b[5000:5004] = [0, 0, 1, 0x65]
+    b[5004:9000] = rng.integers(1, 256, 3996)
+    b[70000:70003] = [0, 0, 1]
+    b[70003:70100] = 7
+    cases.append(("islands", b, (1, 2, 4)))
+    b = rng.integers(4, 256, 150000).astype(np.uint8)  # long inter-NAL garbage over tiles
+    b[:4] = [0, 0, 1, 0x65]
+    b[1000:1003] = 0
+    b[120000:120004] = [0, 0, 0, 1]
+    cases.append(("garbage", b, (1, 2, 4)))
+    cases.append(("no start code", rng.integers(1, 256, 70000).astype(np.uint8), (4,)))
+    for it in range(2):
+        cases.append(("big%d" % it, S.gen_annexb(rng, 60, 1, 20000), (2, 4)))
+    for tag, b, items in cases:
+        for it in items:
+            check_scan(b, it, (tag, it))
