@@ -906,3 +906,18 @@ long hh_gen(const char *libpath, uint64_t seed, int rounds, int conceal, uint8_t
 	dlclose(a.h);
 	return r < 0 ? r : (long)o.len;
 }
+
+/* ---- ABI: struct sizes as this repo's headers lay them out ---------- */
+int hh_sizes(uint32_t *out, int cap)
+{
+	const uint32_t v[] = {sizeof(struct h264_bitstream), sizeof(struct h264_nalu_header), sizeof(struct h264_sps),
+			      sizeof(struct h264_pps),       sizeof(struct h264_vui),         sizeof(struct h264_hrd),
+			      sizeof(struct h264_scaling_matrix), sizeof(struct h264_slice_header), sizeof(struct h264_rplm),
+			      sizeof(struct h264_pwt),       sizeof(struct h264_drpm),        sizeof(struct h264_aud),
+			      sizeof(struct h264_sei),       sizeof(struct h264_sps_derived), sizeof(struct h264_info),
+			      sizeof(struct h264_ctx_cbs)};
+	int n = (int)(sizeof(v) / sizeof(v[0]));
+	for (int i = 0; i < n && i < cap; i++)
+		out[i] = v[i];
+	return n;
+}

@@ -121,3 +121,67 @@ def test_synthetic_video_headers():
                                  transform_8x8=1, b_frames=1, num_ref_frames=2, idr_period=4, pct_skip=20,
                                  coef_density=40, seed=3)
     assert_same_trace(trace(lib, OURS, stream), trace(lib, REF, stream), "synth video")
+
+
+def test_abi_struct_sizes_and_exports():
+    """x86-64 sizes measured on the reference and the 64 exported functions
+    (Appendix C)."""
+    lib = harness()
+    out = (C.c_uint32 * 32)()
+    n = lib.hh_sizes(out, 32)
+    assert list(out[:n]) == [48, 12, 4184, 3276, 952, 412, 2064, 3968, 520, 2056, 1292, 4, 544, 88, 92, 144]
+    names = """h264_reader_new h264_reader_destroy h264_reader_get_ctx h264_reader_stop h264_reader_parse
+    h264_reader_parse_nalu h264_parse_nalu_header h264_parse_sps h264_parse_pps h264_find_nalu h264_bs_write_bits
+    h264_bs_read_bits_ue h264_bs_write_bits_ue h264_bs_read_bits_ff_coded h264_bs_write_bits_ff_coded
+    h264_bs_more_rbsp_data h264_bs_next_bits h264_bs_read_rbsp_trailing_bits h264_bs_write_rbsp_trailing_bits
+    h264_bs_read_raw_bytes h264_bs_write_raw_bytes h264_bs_acquire_buf h264_ctx_new h264_ctx_destroy h264_ctx_clear
+    h264_ctx_clear_nalu h264_ctx_set_nalu_header h264_ctx_is_nalu_unknown h264_ctx_set_aud h264_ctx_set_sps
+    h264_ctx_set_pps h264_ctx_set_filler h264_ctx_get_sps h264_ctx_get_pps h264_ctx_add_sei h264_ctx_get_sei_count
+    h264_ctx_sei_pic_timing_to_ts h264_ctx_sei_pic_timing_to_us h264_ctx_set_slice_header h264_ctx_get_info
+    h264_write_nalu h264_write_grey_i_slice h264_write_skipped_p_slice h264_rewrite_slice_header
+    h264_get_sps_derived h264_get_info h264_sar_to_aspect_ratio_idc h264_byte_stream_to_avcc
+    h264_avcc_to_byte_stream h264_nalu_type_str h264_slice_type_str h264_mb_type_str h264_mb_type_is_intra
+    h264_mb_type_is_inter h264_profile_str h264_color_format_str h264_aspect_ratio_str_alloc h264_sei_type_str
+    h264_dump_new h264_dump_destroy h264_dump_clear h264_dump_get_json_object h264_dump_get_json_str
+    h264_dump_nalu""".split()
+    assert len(names) == 64
+    ours = C.CDLL(OURS)
+    for nm in names:
+        assert hasattr(ours, nm), nm
+
+
+def test_small_utilities_match_reference():
+    """find_nalu, Exp-Golomb, AVCC conversion, enum strings, info: same answers from both libraries."""
+    ours, ref = C.CDLL(OURS), C.CDLL(REF)
+    rng = np.random.default_rng(12)
+    alpha = np.array([0, 0, 0, 1, 2, 3, 0xFF, 0x65], np.uint8)
+    for lib_ in (ours, ref):
+        lib_.h264_find_nalu.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    for it in range(300):
+        b = rng.choice(alpha, int(rng.integers(1, 60)))
+        got = []
+        for lib_ in (ours, ref):
+            s, e = C.c_size_t(7777), C.c_size_t(7777)
+            rc = lib_.h264_find_nalu(b.ctypes.data, len(b), C.byref(s), C.byref(e))
+            got.append((rc, s.value if rc in (0, -11) else None, e.value if rc in (0, -11) else None))
+        assert got[0] == got[1], (bytes(b).hex(), got)
+    for fn, rng_ in (("h264_nalu_type_str", range(-1, 40)), ("h264_slice_type_str", range(-2, 8)),
+                     ("h264_mb_type_str", range(-1, 20)), ("h264_profile_str", range(0, 256)),
+                     ("h264_color_format_str", range(-1, 6)), ("h264_sei_type_str", range(-1, 60))):
+        for lib_ in (ours, ref):
+            getattr(lib_, fn).restype = C.c_char_p
+        for v in rng_:
+            assert getattr(ours, fn)(v) == getattr(ref, fn)(v), (fn, v)
+    for v in range(0, 24):
+        assert ours.h264_mb_type_is_intra(v) == ref.h264_mb_type_is_intra(v)
+        assert ours.h264_mb_type_is_inter(v) == ref.h264_mb_type_is_inter(v)
+    for w, h in ((1, 1), (12, 11), (4, 3), (5, 7), (160, 99), (2, 1)):
+        assert ours.h264_sar_to_aspect_ratio_idc(w, h) == ref.h264_sar_to_aspect_ratio_idc(w, h)
+    # Annex-B <-> AVCC in place
+    hl = harness()
+    base = gen(hl, REF, 5, rounds=3)
+    a, b = base.copy(), base.copy()
+    assert ours.h264_byte_stream_to_avcc(a.ctypes.data, len(a)) == ref.h264_byte_stream_to_avcc(b.ctypes.data, len(b))
+    assert np.array_equal(a, b) and not np.array_equal(a, base)
+    assert ours.h264_avcc_to_byte_stream(a.ctypes.data, len(a)) == ref.h264_avcc_to_byte_stream(b.ctypes.data, len(b))
+    assert np.array_equal(a, b) and np.array_equal(a, base)
