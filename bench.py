@@ -130,11 +130,6 @@ MB_CFG = dict(width_mbs=120, height_mbs=68, slices_per_frame=16, profile_idc=100
 
 def SCAN_KERNEL_NAME():
     it = int(os.environ.get("H264GPU_SCAN_ITEMS", "108"))
-    if it >= 400:
-        return "annexb3::scan4_kernel<256,8,strip> (classify + emit work items)"
-    if it >= 200:
-        thr, cpt, nt = {208: (256, 8, 2), 228: (512, 4, 2), 204: (256, 4, 2), 244: (256, 4, 4)}[it]
-        return "annexb3::scan3_kernel<%d,%d,%d,strip>" % (thr, cpt, nt)
     return ("annexb2::scan2_kernel<%d,strip>" % (it % 10)) if it >= 100 else \
         ("annexb::scan_kernel<%d,strip>" % it)
 

@@ -8,7 +8,6 @@
 
 #include "annexb_scan.cuh"
 #include "annexb_scan2.cuh"
-#include "annexb_scan3.cuh"
 
 extern "C" {
 
@@ -46,8 +45,7 @@ int h264gpu_create(int device, h264gpu_ctx **out)
 	const char *e = getenv("H264GPU_SCAN_ITEMS");
 	if (e != NULL) {
 		int v = atoi(e);
-		if (v == 1 || v == 2 || v == 4 || v == 104 || v == 108 || v == 114 || v == 118 || v == 208 || v == 408 || v == 418 ||
-		    v == 228 || v == 204 || v == 244)
+		if (v == 1 || v == 2 || v == 4 || v == 104 || v == 108 || v == 114 || v == 118)
 			ctx->scan_items = v;
 	}
 	size_t chunk_mb = 128;
@@ -284,62 +282,9 @@ static cudaError_t launch_scan2(const annexb::ScanArgs &a, bool strip, cudaStrea
 	return cudaGetLastError();
 }
 
-template <int THREADS, int CPT, int NT, int MINB>
-static cudaError_t launch_scan3(const annexb::ScanArgs &a, bool strip, cudaStream_t st)
-{
-	const size_t smem = annexb3::scan3_smem_bytes<THREADS, CPT, NT>();
-	static bool prepared = false;
-	if (!prepared) {
-		cudaFuncSetAttribute(annexb3::scan3_kernel<THREADS, CPT, NT, true, MINB>,
-				     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		cudaFuncSetAttribute(annexb3::scan3_kernel<THREADS, CPT, NT, false, MINB>,
-				     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		cudaFuncSetAttribute(annexb3::scan3_kernel<THREADS, CPT, NT, true, MINB>,
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-		cudaFuncSetAttribute(annexb3::scan3_kernel<THREADS, CPT, NT, false, MINB>,
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-		prepared = true;
-	}
-	const uint32_t grid = (a.num_tiles + NT - 1) / NT;
-	if (strip)
-		annexb3::scan3_kernel<THREADS, CPT, NT, true, MINB><<<grid, THREADS, smem, st>>>(a);
-	else
-		annexb3::scan3_kernel<THREADS, CPT, NT, false, MINB><<<grid, THREADS, smem, st>>>(a);
-	return cudaGetLastError();
-}
-
-template <int THREADS, int CPT, int MINB>
-static cudaError_t launch_scan4(const annexb::ScanArgs &a, const annexb3::Scan4Ws &w, bool strip,
-				cudaStream_t st)
-{
-	static bool prepared = false;
-	if (!prepared) {
-		cudaFuncSetAttribute(annexb3::scan4_kernel<THREADS, CPT, true, MINB>,
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-		cudaFuncSetAttribute(annexb3::scan4_kernel<THREADS, CPT, false, MINB>,
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-		prepared = true;
-	}
-	const uint32_t grid = 2 * a.num_tiles; /* one classify + one emit work item per tile */
-	if (strip)
-		annexb3::scan4_kernel<THREADS, CPT, true, MINB><<<grid, THREADS, 0, st>>>(a, w);
-	else
-		annexb3::scan4_kernel<THREADS, CPT, false, MINB><<<grid, THREADS, 0, st>>>(a, w);
-	return cudaGetLastError();
-}
-
 /* scan kernel configurations selectable by H264GPU_SCAN_ITEMS (A/B testing) */
 static uint64_t scan_tile_bytes(int items)
 {
-	switch (items) {
-	case 408: return 32768; /* gen 4: 256 thr x 8 chunks, split classify/emit items */
-	case 418: return 32768; /* same, 5 CTAs/SM */
-	case 208: return 32768; /* gen 3: 256 thr x 8 chunks, 2 tiles/CTA */
-	case 228: return 32768; /* gen 3: 512 thr x 4 chunks, 2 tiles/CTA */
-	case 204: return 16384; /* gen 3: 256 thr x 4 chunks, 2 tiles/CTA */
-	case 244: return 16384; /* gen 3: 256 thr x 4 chunks, 4 tiles/CTA */
-	default: break;
-	}
 	if (items >= 100)
 		return (uint64_t)annexb2::kT * (items % 10) * 16;
 	return (uint64_t)annexb::kBlock * items * 16;
@@ -368,24 +313,9 @@ extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, ui
 	const uint64_t ntiles = (len + tile - 1) / tile;
 	if (ntiles > 0x3fffffffull)
 		return -E2BIG;
-	/* workspace: [256 control][32 B descriptor per tile][gen 4: ring_done][gen 4: table ring] */
-	const bool gen4 = items >= 400;
-	uint32_t slots = annexb3::kRing, lag = annexb3::kLag;
-	if (gen4) {
-		const char *es = getenv("H264GPU_SCAN_RING"), *el = getenv("H264GPU_SCAN_LAG");
-		if (el != NULL && atoi(el) > 0)
-			lag = (uint32_t)atoi(el);
-		if (es != NULL)
-			slots = atoi(es) > 0 ? (uint32_t)atoi(es) : (uint32_t)ntiles;
-		if (slots > ntiles)
-			slots = (uint32_t)ntiles;
-		if (slots < ntiles && slots < lag + 2048)
-			slots = lag + 2048 < ntiles ? lag + 2048 : (uint32_t)ntiles;
-	}
-	const size_t desc_end = 256 + (size_t)ntiles * 32;
-	const size_t need = gen4 ? desc_end + (size_t)slots * 4 : desc_end;
-	const size_t ring_off = (need + 255) & ~(size_t)255;
-	r = h264gpu_ws_reserve(ctx, gen4 ? ring_off + (size_t)slots * annexb3::scan4_slot_bytes<256, 8>() : need);
+	/* workspace: [256 control][32 B descriptor per tile] */
+	const size_t need = 256 + (size_t)ntiles * 32;
+	r = h264gpu_ws_reserve(ctx, need);
 	if (r < 0)
 		return r;
 	/* one memset arms the ticket and invalidates every tile descriptor */
@@ -419,24 +349,7 @@ extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, ui
 	}
 	cudaError_t ce;
 	const bool strip = d_rbsp != NULL;
-	annexb3::Scan4Ws w4;
-	w4.ring_done = (uint32_t *)((uint8_t *)ctx->ws + desc_end);
-	w4.ring = (uint8_t *)ctx->ws + ring_off;
-	w4.slots = slots;
-	w4.lag = lag;
-	if (items == 408)
-		ce = launch_scan4<256, 8, 4>(a, w4, strip, st);
-	else if (items == 418)
-		ce = launch_scan4<256, 8, 5>(a, w4, strip, st);
-	else if (items == 208)
-		ce = launch_scan3<256, 8, 2, 2>(a, strip, st);
-	else if (items == 228)
-		ce = launch_scan3<512, 4, 2, 2>(a, strip, st);
-	else if (items == 204)
-		ce = launch_scan3<256, 4, 2, 5>(a, strip, st);
-	else if (items == 244)
-		ce = launch_scan3<256, 4, 4, 2>(a, strip, st);
-	else if (items == 108)
+	if (items == 108)
 		ce = launch_scan2<8, 4>(a, strip, st);
 	else if (items == 118)
 		ce = launch_scan2<8, 5>(a, strip, st);

@@ -5,7 +5,6 @@
  */
 #include "annexb_scan.cuh"
 #include "annexb_scan2.cuh"
-#include "annexb_scan3.cuh"
 #include "annexb_frame.cuh"
 
 #include <vector>
@@ -20,19 +19,10 @@ extern "C" int emu_split_strip(const uint8_t *in, uint64_t len, uint64_t base,
 	using namespace annexb;
 	if (len == 0)
 		return -1;
-	/* items 1xx selects the second-generation kernel with CPT = items - 100;
-	 * items 2xx the pipelined third generation (2 tiles per CTA), CPT = items - 200;
-	 * items 3xx the same with 64 threads x CPT = items - 300 and 3 tiles per CTA */
-	const bool gen4 = items >= 400;
-	if (gen4)
-		items -= 200; /* 4xx: same tile shapes as 2xx */
-	const bool gen3 = items >= 200 && !gen4;
-	const bool gen2 = items >= 100 && !gen3;
+	/* items 1xx selects the second-generation kernel with CPT = items - 100 */
+	const bool gen2 = items >= 100;
 	const int cpt = items % 100;
-	const int thr3 = items >= 300 ? 64 : 256;
-	const int nt3 = items >= 300 ? 3 : 2;
-	const uint64_t tile = (gen3 || gen4) ? (uint64_t)thr3 * cpt * 16
-				   : gen2 ? (uint64_t)annexb2::kT * cpt * 16 : (uint64_t)kBlock * items * 16;
+	const uint64_t tile = gen2 ? (uint64_t)annexb2::kT * cpt * 16 : (uint64_t)kBlock * items * 16;
 	const uint32_t ntiles = (uint32_t)((len + tile - 1) / tile);
 	std::vector<uint64_t> desc((size_t)ntiles * 4, ~0ull);
 	uint32_t ticket = 0xffffffffu;
@@ -65,35 +55,7 @@ extern "C" int emu_split_strip(const uint8_t *in, uint64_t len, uint64_t base,
 		a.init_in = edge->assume_in;
 	}
 	dim3 grid(ntiles), block(kBlock);
-	if (gen4) {
-		dim3 g4(2 * ntiles), b4(256);
-		std::vector<uint32_t> ring_done(annexb3::kRing, 0xffffffffu);
-		annexb3::Scan4Ws w;
-		w.ring_done = ring_done.data();
-		std::vector<uint8_t> ring(annexb3::kRing *
-					  (cpt == 1 ? annexb3::scan4_slot_bytes<256, 1>() : annexb3::scan4_slot_bytes<256, 8>()));
-		w.ring = ring.data();
-		w.slots = annexb3::kRing;
-		w.lag = annexb3::kLag;
-		if (rbsp) {
-			if (cpt == 1) EMU_LAUNCH((annexb3::scan4_kernel<256, 1, true, 1>), g4, b4, a, w);
-			else EMU_LAUNCH((annexb3::scan4_kernel<256, 8, true, 1>), g4, b4, a, w);
-		} else {
-			if (cpt == 1) EMU_LAUNCH((annexb3::scan4_kernel<256, 1, false, 1>), g4, b4, a, w);
-			else EMU_LAUNCH((annexb3::scan4_kernel<256, 8, false, 1>), g4, b4, a, w);
-		}
-	} else if (gen3) {
-		dim3 g3((ntiles + nt3 - 1) / nt3), b3(thr3);
-		if (rbsp) {
-			if (items == 201) EMU_LAUNCH((annexb3::scan3_kernel<256, 1, 2, true, 1>), g3, b3, a);
-			else if (items == 208) EMU_LAUNCH((annexb3::scan3_kernel<256, 8, 2, true, 1>), g3, b3, a);
-			else EMU_LAUNCH((annexb3::scan3_kernel<64, 2, 3, true, 1>), g3, b3, a);
-		} else {
-			if (items == 201) EMU_LAUNCH((annexb3::scan3_kernel<256, 1, 2, false, 1>), g3, b3, a);
-			else if (items == 208) EMU_LAUNCH((annexb3::scan3_kernel<256, 8, 2, false, 1>), g3, b3, a);
-			else EMU_LAUNCH((annexb3::scan3_kernel<64, 2, 3, false, 1>), g3, b3, a);
-		}
-	} else if (gen2) {
+	if (gen2) {
 		dim3 b2(annexb2::kT);
 		if (rbsp) {
 			if (cpt == 1) EMU_LAUNCH((annexb2::scan2_kernel<1, true>), grid, b2, a);

@@ -207,7 +207,7 @@ def oracle_frame(rbsp, offs, sc_len=4):
     return out[:tot].copy(), oo
 
 
-SCAN_GEN = 4  # which scan kernel generation the emulator tests exercise
+SCAN_GEN = 2  # which scan kernel generation the emulator tests exercise
 
 
 def emu_split_strip(buf, strip=True, items=4, edge=None, base=0, gen=None):
@@ -215,10 +215,6 @@ def emu_split_strip(buf, strip=True, items=4, edge=None, base=0, gen=None):
     g = gen or SCAN_GEN
     if g == 2 and items < 100:
         items = 100 + (8 if items == 4 else items)
-    elif g == 3 and items < 100:
-        items = {1: 201, 2: 302, 4: 208}[items]
-    elif g == 4 and items < 100:
-        items = {1: 401, 2: 401, 4: 408}[items]
     buf = np.ascontiguousarray(buf, dtype=np.uint8)
     cap = len(buf) // 3 + 2
     s = np.full(cap, NONE64, np.uint64)
