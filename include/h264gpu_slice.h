@@ -145,6 +145,31 @@ H264GPU_API int h264gpu_cavlc_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stre
 					 uint64_t n_records,
 					 struct h264gpu_slice_result *h_results);
 
+/*
+ * K5: the same for CABAC slices (entropy_coding_mode_flag = 1).  The reference has no
+ * counterpart: its reader returns before CABAC slice data (src/h264_syntax_slice_data.h:
+ * 715-717), so slice_data_begin / slice_data_mb / slice_data_end never fire for such slices.
+ * Records use the same mb_type values and checksum fields as the CAVLC parse; end_bit is the
+ * raw bit position after the last bit the arithmetic decoder consumed (the stop bit).
+ * CAVLC slices get H264GPU_SLICE_SKIPPED; MBAFF, several slice groups, 4:4:4 and SI slices
+ * -ENOSYS.
+ */
+H264GPU_API int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
+					uint64_t stream_len,
+					const struct h264gpu_slice_params *d_params,
+					uint32_t n_slices,
+					struct h264gpu_mb_record *d_records,
+					struct h264gpu_slice_result *d_results,
+					void *stream);
+
+H264GPU_API int h264gpu_cabac_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stream,
+					 uint64_t stream_len,
+					 const struct h264gpu_slice_params *h_params,
+					 uint32_t n_slices,
+					 struct h264gpu_mb_record *h_records,
+					 uint64_t n_records,
+					 struct h264gpu_slice_result *h_results);
+
 #ifdef __cplusplus
 }
 #endif

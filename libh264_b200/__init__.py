@@ -70,7 +70,8 @@ SLICE_PARAMS = np.dtype([("nal_off", "<u8"), ("nal_len", "<u4"), ("data_bit_off"
                          ("pad", "u1", (4,))])
 assert SLICE_PARAMS.itemsize == C.sizeof(SliceParams) == 56
 
-SLICE_SYMBOLS = ["h264gpu_cavlc_parse_dev", "h264gpu_cavlc_parse_host"]
+SLICE_SYMBOLS = ["h264gpu_cavlc_parse_dev", "h264gpu_cavlc_parse_host",
+                 "h264gpu_cabac_parse_dev", "h264gpu_cabac_parse_host"]
 
 # every symbol include/h264gpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = [
@@ -122,6 +123,8 @@ def load_gpu_lib():
         lib.h264gpu_timer_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
         lib.h264gpu_cavlc_parse_dev.argtypes = [vp, vp, u64, vp, C.c_uint32, vp, vp, vp]
         lib.h264gpu_cavlc_parse_host.argtypes = [vp, vp, u64, vp, C.c_uint32, vp, u64, vp]
+        lib.h264gpu_cabac_parse_dev.argtypes = [vp, vp, u64, vp, C.c_uint32, vp, vp, vp]
+        lib.h264gpu_cabac_parse_host.argtypes = [vp, vp, u64, vp, C.c_uint32, vp, u64, vp]
         _libs["gpu"] = lib
     return _libs["gpu"]
 
@@ -283,16 +286,24 @@ class Gpu:
         _check(rc, "h264gpu_frame_host")
         return out[:tot.value], out_off
 
-    def cavlc_parse_host(self, stream, params, n_records):
+    def cabac_parse_host(self, stream, params, n_records):
+        """K5: like cavlc_parse_host for CABAC slices."""
+        return self.cavlc_parse_host(stream, params, n_records, fn="h264gpu_cabac_parse_host")
+
+    def cabac_parse_dev(self, d_stream, stream_len, d_params, n_slices, d_records, d_results, stream=None):
+        _check(self.lib.h264gpu_cabac_parse_dev(self.h, C.c_void_p(d_stream), stream_len,
+                                                C.c_void_p(d_params), n_slices, C.c_void_p(d_records),
+                                                C.c_void_p(d_results), stream), "h264gpu_cabac_parse_dev")
+
+    def cavlc_parse_host(self, stream, params, n_records, fn="h264gpu_cavlc_parse_host"):
         """params: uint8 array of packed struct h264gpu_slice_params.  Returns (records, results)."""
         stream = np.ascontiguousarray(stream, dtype=np.uint8)
         params = np.ascontiguousarray(params, dtype=np.uint8)
         n = len(params) // C.sizeof(SliceParams)
         recs = np.zeros(max(int(n_records), 1), dtype=MB_RECORD)
         res = np.zeros(max(n, 1), dtype=SLICE_RESULT)
-        _check(self.lib.h264gpu_cavlc_parse_host(self.h, _ptr(stream), len(stream), _ptr(params), n,
-                                                 _ptr(recs), int(n_records), _ptr(res)),
-               "h264gpu_cavlc_parse_host")
+        _check(getattr(self.lib, fn)(self.h, _ptr(stream), len(stream), _ptr(params), n,
+                                      _ptr(recs), int(n_records), _ptr(res)), fn)
         return recs[:int(n_records)], res[:n]
 
     def cavlc_parse_dev(self, d_stream, stream_len, d_params, n_slices, d_records, d_results, stream=None):
@@ -355,6 +366,13 @@ def synth_annexb(seed, rbsp, offs, mixed_sc=True, trailing=True, out=None, nthre
     return out[:tot], oo
 
 
+def mb_hash_term(field, index, value):
+    """h264gpu_mb_hash_term (include/h264gpu_slice.h) as a Python int modulo 2**64."""
+    key = (field << 16) | index
+    w = (((key + 1) * 0x9E3779B97F4A7C15) | 1) & (2**64 - 1)
+    return (value * w) & (2**64 - 1)
+
+
 class VideoCfg(C.Structure):
     """struct synth_video_cfg (libh264_b200/csrc/synth_video.c)."""
     _fields_ = [("width_mbs", C.c_uint32), ("height_mbs", C.c_uint32), ("frames", C.c_uint32),
@@ -363,19 +381,21 @@ class VideoCfg(C.Structure):
                 ("idr_period", C.c_uint32), ("b_frames", C.c_uint32), ("num_ref_frames", C.c_uint32),
                 ("entropy_cabac", C.c_uint32), ("pct_skip", C.c_uint32),
                 ("pct_intra_in_inter", C.c_uint32), ("pct_pcm", C.c_uint32),
-                ("coef_density", C.c_uint32), ("seed", C.c_uint64)]
+                ("coef_density", C.c_uint32), ("seed", C.c_uint64),
+                ("cabac_twin", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 def synth_video(width_mbs, height_mbs, frames, slices_per_frame=1, profile_idc=66, chroma_format_idc=1,
                 transform_8x8=0, idr_period=30, b_frames=0, num_ref_frames=1, pct_skip=30,
                 pct_intra_in_inter=10, pct_pcm=5, coef_density=60, seed=0x264, out=None,
-                want_params=False):
-    """Synthetic CAVLC elementary stream (Annex-B).  Returns (stream, total_mbs, total_slices)
-    and, with want_params, the packed h264gpu_slice_params block of every slice."""
+                want_params=False, entropy_cabac=0, cabac_twin=0):
+    """Synthetic elementary stream (Annex-B), CAVLC or (entropy_cabac=1) CABAC slice data.
+    Returns (stream, total_mbs, total_slices) and, with want_params, the packed
+    h264gpu_slice_params block of every slice."""
     lib = load_synth_lib()
     cfg = VideoCfg(width_mbs, height_mbs, frames, slices_per_frame, profile_idc, chroma_format_idc,
-                   transform_8x8, idr_period, b_frames, num_ref_frames, 0, pct_skip,
-                   pct_intra_in_inter, pct_pcm, coef_density, seed)
+                   transform_8x8, idr_period, b_frames, num_ref_frames, entropy_cabac, pct_skip,
+                   pct_intra_in_inter, pct_pcm, coef_density, seed, cabac_twin, 0)
     mbs, sl = C.c_uint64(0), C.c_uint64(0)
     if out is None:
         need = lib.synth_video(C.byref(cfg), None, 0, C.byref(mbs), C.byref(sl), None, 0)

@@ -55,11 +55,27 @@ def build_gpu(force=False, verbose=False):
 
 
 def build_synth(force=False):
-    srcs = [os.path.join(CSRC, "synth.c"), os.path.join(CSRC, "synth_video.c")]
-    deps = srcs + [os.path.join(CSRC, "cavlc_luts.h")]
+    """Workload generators: synth.c / synth_video.c (C) + synth_cabac.cpp (C++, shares the
+    CABAC syntax walker header with the GPU kernel)."""
+    csrcs = [os.path.join(CSRC, "synth.c"), os.path.join(CSRC, "synth_video.c")]
+    cxx = os.path.join(CSRC, "synth_cabac.cpp")
+    deps = csrcs + [cxx] + [os.path.join(CSRC, h) for h in
+                            ("cavlc_luts.h", "cabac_syntax.h", "cabac_engine.h", "cabac_tables.h",
+                             "mb_syntax.h")] + [os.path.join(INC, "h264gpu_slice.h")]
     if force or _stale(SYNTH_SO, deps):
-        subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", "-pthread", "-Wall",
-                               "-I" + CSRC, "-o", SYNTH_SO] + srcs + ["-lm"])
+        objdir = os.path.join(HERE, "_obj")
+        os.makedirs(objdir, exist_ok=True)
+        objs = []
+        for src in csrcs:
+            o = os.path.join(objdir, os.path.basename(src) + ".o")
+            subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-pthread", "-Wall",
+                                   "-I" + CSRC, "-c", "-o", o, src])
+            objs.append(o)
+        o = os.path.join(objdir, "synth_cabac.o")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function",
+                               "-I" + CSRC, "-I" + INC, "-c", "-o", o, cxx])
+        objs.append(o)
+        subprocess.check_call(["g++", "-shared", "-pthread", "-o", SYNTH_SO] + objs + ["-lm"])
     return SYNTH_SO
 
 

@@ -1,0 +1,145 @@
+/*
+ * cabac_parse.cuh — K5: slice-parallel CABAC macroblock syntax parse.  One independent slice
+ * per thread; a slice's 460 context states live in SHARED memory (one byte each, interleaved
+ * over the block's slices so lanes hit different banks), the range / transition tables too.
+ *
+ * The reference cannot decode CABAC slice data (src/h264_syntax_slice_data.h:715-717 returns
+ * before slice_data_begin).  What this kernel delivers per macroblock is what
+ * the reference delivers for a CAVLC slice (h264_ctx_cbs.slice_data_mb: mb_addr, mb_type,
+ * include/h264/h264_ctx.h:78-82) plus the same syntax-element checksum as K4, so a CABAC
+ * slice and a CAVLC slice carrying the same syntax elements give identical records — that is
+ * how tests pin this path to the reference's own parse (tests/test_cabac.py).
+ * Syntax walk: cabac_syntax.h (Rec. ITU-T H.264 7.3.4, 7.3.5, 9.3); engine: cabac_engine.h.
+ */
+#ifndef CABAC_PARSE_CUH
+#define CABAC_PARSE_CUH
+
+#include <stdint.h>
+
+#include "h264gpu_slice.h"
+
+#define CABAC_HD __device__
+#define CABAC_CONST __device__ const
+#include "cabac_engine.h"
+#include "cabac_syntax.h"
+#define CABAC_TAB __device__ const
+#include "cabac_tables.h"
+
+#ifndef EIO
+#define EIO 5
+#endif
+#ifndef ENOSYS
+#define ENOSYS 38
+#endif
+#ifndef ENOBUFS
+#define ENOBUFS 105
+#endif
+
+namespace cabac {
+
+struct CabacArgs {
+	const uint8_t *stream;
+	const h264gpu_slice_params *params;
+	uint32_t n_slices;
+	h264gpu_mb_record *records;
+	h264gpu_slice_result *results;
+	Nb *ring;             /* n_slices x ring_stride neighbour records */
+	uint64_t ring_stride; /* in Nb units */
+	uint32_t ring_w;      /* widest picture (in MBs) a ring row can hold */
+	uint32_t lanes_log2;  /* log2 of the slices carried by one warp (0..5) */
+};
+
+constexpr uint32_t kTabBytes = 256 + 64 + 64;
+
+__device__ __forceinline__ void parse_slice(const uint8_t *stream, const h264gpu_slice_params &sp, Nb *ring,
+					     h264gpu_mb_record *rec, h264gpu_slice_result &res, uint8_t *ctx_states,
+					     uint32_t ctx_stride, const uint8_t *tabs)
+{
+	res.status = 0;
+	res.mb_count = 0;
+	res.end_bit = 0;
+	if (!sp.entropy_coding_mode_flag) {
+		res.status = H264GPU_SLICE_SKIPPED;
+		return;
+	}
+	if (sp.mbaff_frame_flag || sp.num_slice_groups_minus1 != 0 || sp.pic_width_in_mbs == 0 ||
+	    sp.chroma_array_type == 3 || sp.slice_type == ST_SI || sp.slice_type > ST_SI) {
+		res.status = -ENOSYS;
+		return;
+	}
+	Walk<Dec> w;
+	w.begin_slice(&sp, ring);
+	w.c.st = ctx_states;
+	w.c.stride = ctx_stride;
+	w.c.t.range_lps = tabs;
+	w.c.t.trans_lps = tabs + 256;
+	w.c.t.trans_mps = tabs + 320;
+	init_contexts(ctx_states, ctx_stride, cabac_init_mn[sp.slice_type == ST_I ? 0 : 1 + (sp.cabac_init_idc % 3)],
+		      sp.slice_qp);
+	w.c.start(stream + sp.nal_off, sp.nal_len, sp.data_bit_off);
+	const uint32_t pic_size = (uint32_t)sp.pic_width_in_mbs * sp.pic_height_in_mbs;
+	uint32_t cur = sp.first_mb_in_slice, count = 0;
+	int status = w.c.failed() ? -EIO : 0;
+	while (!status) {
+		if (count >= sp.mb_out_cap || cur >= pic_size) {
+			status = -ENOBUFS;
+			break;
+		}
+		Mb m;
+		bool skipped = false, end = false;
+		if (!w.mb_step(cur, skipped, m, end)) {
+			status = -EIO;
+			break;
+		}
+		rec[count].mb_addr = cur;
+		rec[count].mb_type = m.mb_type;
+		rec[count].hash = w.hash;
+		count++;
+		cur++;
+		if (end)
+			break;
+	}
+	res.status = status;
+	res.mb_count = count;
+	res.end_bit = w.c.raw_bitpos();
+}
+
+/*
+ * Like K4, slices diverge completely, so few slices are spread one per warp and only packed
+ * into the lanes of a warp once there are more slices than resident warps.  Dynamic shared
+ * memory: [384 B tables][460 x (slices per block) context bytes].
+ */
+__global__ void __launch_bounds__(128) cabac_parse_kernel(const CabacArgs a)
+{
+	extern __shared__ uint8_t smem[];
+	for (uint32_t i = threadIdx.x; i < kTabBytes; i += blockDim.x)
+		smem[i] = i < 256 ? cabac_range_lps[i >> 2][i & 3]
+				  : i < 320 ? cabac_trans_lps[i - 256] : cabac_trans_mps[i - 320];
+	__syncthreads();
+	const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t step = 32u >> a.lanes_log2; /* active lanes are multiples of this */
+	if (lane & (step - 1))
+		return;
+	const uint32_t i = (gwarp << a.lanes_log2) + lane / step;
+	if (i >= a.n_slices)
+		return;
+	const uint32_t per_block = (blockDim.x >> 5) << a.lanes_log2;
+	const uint32_t slot = ((threadIdx.x >> 5) << a.lanes_log2) + lane / step;
+	const h264gpu_slice_params sp = a.params[i];
+	h264gpu_slice_result res;
+	if (sp.pic_width_in_mbs > a.ring_w) {
+		res.status = -7; /* -E2BIG */
+		res.mb_count = 0;
+		res.end_bit = 0;
+		a.results[i] = res;
+		return;
+	}
+	parse_slice(a.stream, sp, a.ring + (uint64_t)i * a.ring_stride, a.records + sp.mb_out_off, res,
+		    smem + kTabBytes + slot, per_block, smem);
+	a.results[i] = res;
+}
+
+} /* namespace cabac */
+
+#endif /* CABAC_PARSE_CUH */

@@ -5,6 +5,7 @@
 #include "h264gpu_internal.h"
 
 #include "cavlc_parse.cuh"
+#include "cabac_parse.cuh"
 
 extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
 				       uint64_t stream_len,
@@ -60,11 +61,13 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	return 0;
 }
 
-extern "C" int h264gpu_cavlc_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stream,
-					uint64_t stream_len,
-					const struct h264gpu_slice_params *h_params,
-					uint32_t n_slices, struct h264gpu_mb_record *h_records,
-					uint64_t n_records, struct h264gpu_slice_result *h_results)
+typedef int (*parse_dev_fn)(h264gpu_ctx *, const uint8_t *, uint64_t, const struct h264gpu_slice_params *,
+			    uint32_t, struct h264gpu_mb_record *, struct h264gpu_slice_result *, void *);
+
+static int parse_host(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_stream, uint64_t stream_len,
+		      const struct h264gpu_slice_params *h_params, uint32_t n_slices,
+		      struct h264gpu_mb_record *h_records, uint64_t n_records,
+		      struct h264gpu_slice_result *h_results)
 {
 	int r = h264gpu_use(ctx);
 	if (r < 0)
@@ -93,8 +96,7 @@ extern "C" int h264gpu_cavlc_parse_host(h264gpu_ctx *ctx, const uint8_t *h_strea
 	SL_TRY(cudaMemcpyAsync(d_stream, h_stream, stream_len, cudaMemcpyHostToDevice, st));
 	SL_TRY(cudaMemcpyAsync(d_params, h_params, (size_t)n_slices * sizeof(*d_params),
 			       cudaMemcpyHostToDevice, st));
-	rc = h264gpu_cavlc_parse_dev(ctx, d_stream, stream_len, d_params, n_slices, d_records,
-				     d_results, st);
+	rc = dev(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, st);
 	if (rc < 0)
 		goto out;
 	SL_TRY(cudaMemcpyAsync(h_records, d_records, n_records * sizeof(*d_records),
@@ -109,4 +111,86 @@ out:
 	cudaFree(d_records);
 	cudaFree(d_results);
 	return rc;
+}
+
+extern "C" int h264gpu_cavlc_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stream,
+					uint64_t stream_len,
+					const struct h264gpu_slice_params *h_params,
+					uint32_t n_slices, struct h264gpu_mb_record *h_records,
+					uint64_t n_records, struct h264gpu_slice_result *h_results)
+{
+	return parse_host(h264gpu_cavlc_parse_dev, ctx, h_stream, stream_len, h_params, n_slices, h_records,
+			  n_records, h_results);
+}
+
+extern "C" int h264gpu_cabac_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stream,
+					uint64_t stream_len,
+					const struct h264gpu_slice_params *h_params,
+					uint32_t n_slices, struct h264gpu_mb_record *h_records,
+					uint64_t n_records, struct h264gpu_slice_result *h_results)
+{
+	return parse_host(h264gpu_cabac_parse_dev, ctx, h_stream, stream_len, h_params, n_slices, h_records,
+			  n_records, h_results);
+}
+
+/* ---- K5: CABAC ------------------------------------------------------------------------ */
+
+extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
+				       uint64_t stream_len,
+				       const struct h264gpu_slice_params *d_params,
+				       uint32_t n_slices, struct h264gpu_mb_record *d_records,
+				       struct h264gpu_slice_result *d_results, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (n_slices == 0)
+		return 0;
+	if (d_stream == NULL || d_params == NULL || d_records == NULL || d_results == NULL)
+		return -EINVAL;
+	(void)stream_len;
+	cudaStream_t st = (cudaStream_t)stream;
+	/* neighbour ring per slice: (PicWidthInMbs + 1) records of 64 B, sized for pictures up
+	 * to 8192 luma samples wide (512 MBs); wider slices get -E2BIG. */
+	const uint32_t ring_w = 512;
+	const uint64_t ring_stride = (uint64_t)(ring_w + 1);
+	r = h264gpu_ws_reserve(ctx, (size_t)n_slices * ring_stride * sizeof(cabac::Nb));
+	if (r < 0)
+		return r;
+	cabac::CabacArgs a;
+	a.stream = d_stream;
+	a.params = d_params;
+	a.n_slices = n_slices;
+	a.records = d_records;
+	a.results = d_results;
+	a.ring = (cabac::Nb *)ctx->ws;
+	a.ring_stride = ring_stride;
+	a.ring_w = ring_w;
+	/* slices per warp: 1 until there are more slices than ~48 warps per SM can hold */
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	const uint64_t warp_slots = (uint64_t)sms * 48;
+	uint32_t lanes_log2 = 0;
+	const char *env = getenv("H264GPU_CABAC_LANES_LOG2");
+	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
+		lanes_log2 = (uint32_t)atoi(env);
+	} else {
+		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > warp_slots)
+			lanes_log2++;
+	}
+	a.lanes_log2 = lanes_log2;
+	const uint32_t threads = 128; /* 4 warps per block */
+	const uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
+	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
+	const size_t smem = cabac::kTabBytes + (size_t)cabac::kNumCtx * ((threads / 32) << lanes_log2);
+	static size_t smem_set = 0;
+	if (smem > smem_set) {
+		CU_TRY(cudaFuncSetAttribute(cabac::cabac_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					    (int)smem));
+		smem_set = smem;
+	}
+	cabac::cabac_parse_kernel<<<blocks, threads, smem, st>>>(a);
+	CU_TRY(cudaGetLastError());
+	ctx->launches++;
+	return 0;
 }

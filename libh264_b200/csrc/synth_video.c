@@ -31,13 +31,28 @@ struct synth_video_cfg {
 	uint32_t idr_period;        /* IDR every n frames */
 	uint32_t b_frames;          /* 1: odd non-IDR frames are B slices */
 	uint32_t num_ref_frames;    /* num_ref_idx_lX_default_active = this (1..4) */
-	uint32_t entropy_cabac;     /* must be 0 here (CAVLC generator) */
+	uint32_t entropy_cabac;     /* 1: slice data comes from synth_cabac.cpp (CABAC) */
 	uint32_t pct_skip;          /* % of P/B macroblocks skipped */
 	uint32_t pct_intra_in_inter;/* % of coded P/B macroblocks that are intra */
 	uint32_t pct_pcm;           /* % of intra macroblocks that are I_PCM (x0.1) */
 	uint32_t coef_density;      /* 0..100: how many residual blocks carry coefficients */
 	uint64_t seed;
+	uint32_t cabac_twin;        /* CAVLC only: restrict to syntax CABAC can carry too (no
+				       P_8x8ref0, 8x8-transform blocks with a set cbp bit are
+				       never empty), for the CAVLC <-> CABAC twin test */
+	uint32_t reserved;
 };
+
+/* CABAC slice data (synth_cabac.cpp): RBSP bytes of slice_data() incl. the stop bit */
+struct synth_cabac_slice_cfg {
+	uint32_t width_mbs, height_mbs, first_mb, count;
+	uint32_t slice_type, chroma_array_type, transform_8x8, direct_8x8_inference;
+	uint32_t num_ref_l0, num_ref_l1, cabac_init_idc;
+	int32_t slice_qp;
+	uint32_t pct_skip, pct_intra_in_inter, pct_pcm, coef_density;
+};
+uint64_t synth_cabac_slice(const struct synth_cabac_slice_cfg *cfg, uint64_t *rng_state, uint8_t *out,
+			   uint64_t cap);
 
 /* ---- random ---------------------------------------------------------------- */
 struct rng {
@@ -221,6 +236,9 @@ struct gen {
 	uint32_t cat;        /* ChromaArrayType */
 	uint32_t mbw_c, mbh_c;
 	int slice_type;      /* 0 P, 1 B, 2 I */
+	int cur_t8;          /* current macroblock uses the 8x8 transform */
+	uint8_t *cabac_buf;  /* scratch for one slice's CABAC RBSP */
+	uint64_t cabac_cap;
 	uint64_t n_mbs;
 	/* optional: the parameter block of every slice (include/h264gpu_slice.h layout) */
 	struct slice_params_out *params;
@@ -459,7 +477,10 @@ static void clamp_levels(int16_t *c, int n)
 static void put_block(struct gen *g, int comp, int blk, int n, int chroma_ac)
 {
 	int16_t c[16];
-	gen_coeffs(g, c, n);
+	int nz = gen_coeffs(g, c, n);
+	/* twin mode: CABAC has no coded_block_flag for an 8x8 block, so it must not be empty */
+	if (g->cfg.cabac_twin && g->cur_t8 && !chroma_ac && comp == 0 && (blk & 3) == 0 && nz == 0)
+		c[rnd_n(&g->r, (uint32_t)n)] = (rnd(&g->r) & 1) ? -1 : 1;
 	clamp_levels(c, n);
 	uint32_t nc = calc_nc(g, comp, blk, chroma_ac);
 	int tc = put_residual_block(g, c, n, table_for_nc(nc));
@@ -548,6 +569,7 @@ static void put_intra_mb(struct gen *g, uint32_t type_base)
 			t8 = (int)(rnd(&g->r) & 1);
 			bw_bits(w, (uint32_t)t8, 1);
 		}
+		g->cur_t8 = t8;
 		for (int i = 0; i < (t8 ? 4 : 16); i++) {
 			if (rnd(&g->r) & 1) {
 				bw_bits(w, 1, 1);
@@ -582,8 +604,10 @@ static void put_inter_tail(struct gen *g, int allow_t8)
 	struct bw *w = &g->w;
 	uint32_t cbp = rand_cbp(g);
 	put_cbp(g, 0, cbp);
-	if ((cbp & 15) && g->cfg.transform_8x8 && allow_t8)
-		bw_bits(w, rnd(&g->r) & 1, 1);
+	if ((cbp & 15) && g->cfg.transform_8x8 && allow_t8) {
+		g->cur_t8 = (int)(rnd(&g->r) & 1);
+		bw_bits(w, (uint32_t)g->cur_t8, 1);
+	}
 	if (cbp) {
 		bw_se(w, (int32_t)rnd_n(&g->r, 7) - 3);
 		put_residual(g, 0, cbp & 15, cbp >> 4);
@@ -612,7 +636,7 @@ static void put_p_mb(struct gen *g)
 			bw_se(w, rand_mvd(g));
 		put_inter_tail(g, 1);
 	} else {
-		int ref0 = rnd_n(&g->r, 5) == 0;
+		int ref0 = rnd_n(&g->r, 5) == 0 && !g->cfg.cabac_twin;
 		bw_ue(w, ref0 ? 4 : 3); /* P_8x8ref0 / P_8x8 */
 		uint32_t sub[4];
 		int no_small = 1;
@@ -753,6 +777,9 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 	} else if (type != 1) {
 		bw_bits(w, 0, 1); /* adaptive_ref_pic_marking_mode_flag (nal_ref_idc != 0) */
 	}
+	const uint32_t cabac_init_idc = (g->cfg.entropy_cabac && type != 2) ? rnd_n(&g->r, 3) : 0;
+	if (g->cfg.entropy_cabac && type != 2)
+		bw_ue(w, cabac_init_idc);
 	const int32_t qp_delta = (int32_t)rnd_n(&g->r, 9) - 4;
 	bw_se(w, qp_delta); /* slice_qp_delta */
 	bw_ue(w, 0);        /* disable_deblocking_filter_idc */
@@ -768,8 +795,44 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 	g->first_mb = first;
 	memset(g->mbs, 0, sizeof(struct mbstate) * W * H);
 	uint32_t pending_skip = 0;
+	if (g->cfg.entropy_cabac) {
+		struct synth_cabac_slice_cfg cc;
+		memset(&cc, 0, sizeof(cc));
+		cc.width_mbs = W;
+		cc.height_mbs = H;
+		cc.first_mb = first;
+		cc.count = count;
+		cc.slice_type = (uint32_t)type;
+		cc.chroma_array_type = g->cat;
+		cc.transform_8x8 = g->cfg.transform_8x8 ? 1 : 0;
+		cc.direct_8x8_inference = 1;
+		cc.num_ref_l0 = cc.num_ref_l1 = g->cfg.num_ref_frames;
+		cc.cabac_init_idc = cabac_init_idc;
+		cc.slice_qp = 26 + qp_delta;
+		cc.pct_skip = g->cfg.pct_skip;
+		cc.pct_intra_in_inter = g->cfg.pct_intra_in_inter;
+		cc.pct_pcm = g->cfg.pct_pcm;
+		cc.coef_density = g->cfg.coef_density;
+		while (w->nacc)
+			bw_bits(w, 1, 1); /* cabac_alignment_one_bit */
+		w->mark = NULL;
+		const uint64_t saved = g->r.s;
+		uint64_t need = synth_cabac_slice(&cc, &g->r.s, g->cabac_buf, g->cabac_cap);
+		if (need > g->cabac_cap) { /* grow and redo with the same random state */
+			free(g->cabac_buf);
+			g->cabac_cap = need + (need >> 2) + 4096;
+			g->cabac_buf = malloc(g->cabac_cap);
+			g->r.s = saved;
+			need = synth_cabac_slice(&cc, &g->r.s, g->cabac_buf, g->cabac_cap);
+		}
+		for (uint64_t i = 0; i < need && i < g->cabac_cap; i++)
+			bw_byte(w, g->cabac_buf[i]);
+		g->n_mbs += count;
+		count = 0; /* the CAVLC loop below does nothing */
+	}
 	for (uint32_t a = first; a < first + count; a++) {
 		g->cur_mb = a;
+		g->cur_t8 = 0;
 		g->mbs[a].avail = 1;
 		g->n_mbs++;
 		if (type != 2 && rnd_pct(&g->r, g->cfg.pct_skip)) {
@@ -791,7 +854,8 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 	}
 	if (type != 2 && pending_skip)
 		bw_ue(w, pending_skip);
-	bw_trailing(w);
+	if (!g->cfg.entropy_cabac)
+		bw_trailing(w); /* CABAC: the flush wrote the stop bit, the slice is byte aligned */
 	w->mark = NULL;
 	if (g->params && g->params_n < g->params_cap) {
 		struct slice_params_out *p = &g->params[g->params_n];
@@ -801,7 +865,7 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 		p->data_bit_off = data_bit_off;
 		p->first_mb_in_slice = first;
 		p->mb_out_off = (uint32_t)mb0;
-		p->mb_out_cap = count;
+		p->mb_out_cap = (uint32_t)(g->n_mbs - mb0);
 		p->pic_width_in_mbs = (uint16_t)W;
 		p->pic_height_in_mbs = (uint16_t)H;
 		p->slice_type = (uint8_t)type;
@@ -813,6 +877,7 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 		p->num_ref_idx_l0_active_minus1 = (uint8_t)(g->cfg.num_ref_frames - 1);
 		p->num_ref_idx_l1_active_minus1 = (uint8_t)(g->cfg.num_ref_frames - 1);
 		p->entropy_coding_mode_flag = (uint8_t)(g->cfg.entropy_cabac ? 1 : 0);
+		p->cabac_init_idc = (uint8_t)cabac_init_idc;
 		p->slice_qp = (int8_t)(26 + qp_delta);
 	}
 	g->params_n++;
@@ -920,6 +985,7 @@ uint64_t synth_video(const struct synth_video_cfg *cfg, uint8_t *out, uint64_t c
 		}
 	}
 	free(g.mbs);
+	free(g.cabac_buf);
 	if (total_mbs)
 		*total_mbs = g.n_mbs;
 	if (total_slices)

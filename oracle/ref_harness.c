@@ -217,6 +217,7 @@ double ref_mt_insert(const uint8_t *rbsp, const uint64_t *off, size_t n, int nth
  * reproduce.  The reference does all the parsing; this only records.        */
 
 #include "h264gpu_slice.h"
+#include "../libh264_b200/csrc/mb_syntax.h"
 
 enum {
 	TR_NALU_BEGIN = 1, /* u32 type, u32 ref_idc, u64 off, u64 len */
@@ -242,6 +243,7 @@ struct ref_tracer {
 	uint64_t cur_nal_off;
 	uint64_t cur_nal_len;
 	size_t nal_mb0; /* records written before the current NAL */
+	struct h264_mb_syntax *syn; /* optional: full syntax elements per macroblock */
 };
 
 static void tr_put(struct ref_tracer *t, uint32_t tag, const void *p, uint32_t n)
@@ -312,6 +314,54 @@ static uint64_t mb_hash(const struct h264_macroblock *mb)
 		T(H264GPU_F_PCM_LUMA, i, mb->pcm_sample_luma[i]);
 #undef T
 	return h;
+}
+
+/* copy the reference's ctx->mb (src/h264_macroblock.h:105-167) into the coder-neutral record */
+static void mb_syntax_from_ref(const struct h264_macroblock *mb, uint32_t mb_addr,
+			       enum h264_mb_type mb_type, struct h264_mb_syntax *o)
+{
+	memset(o, 0, sizeof(*o));
+	o->mb_addr = mb_addr;
+	o->mb_type = (uint32_t)mb_type;
+	o->raw_mb_type = mb->raw_mb_type;
+	o->mb_qp_delta = mb->mb_qp_delta;
+	o->transform_size_8x8_flag = (uint8_t)mb->transform_size_8x8_flag;
+	o->intra_chroma_pred_mode = mb->intra_chroma_pred_mode;
+	o->cbp_luma = mb->CodedBlockPatternLuma;
+	o->cbp_chroma = mb->CodedBlockPatternChroma;
+	for (int i = 0; i < 16; i++)
+		o->intra4x4_pred_mode[i] = mb->intra4x4_pred_mode[i];
+	for (int i = 0; i < 4; i++) {
+		o->raw_sub_mb_type[i] = mb->raw_sub_mb_type[i];
+		o->intra8x8_pred_mode[i] = mb->intra8x8_pred_mode[i];
+		o->ref_idx[0][i] = mb->ref_idx_l0[i];
+		o->ref_idx[1][i] = mb->ref_idx_l1[i];
+		for (int s = 0; s < 4; s++)
+			for (int c = 0; c < 2; c++) {
+				o->mvd[0][i * 4 + s][c] = mb->mvd_l0[i][s][c];
+				o->mvd[1][i * 4 + s][c] = mb->mvd_l1[i][s][c];
+			}
+	}
+	for (int i = 0; i < 16; i++)
+		o->dc16[i] = mb->Intra16x16DCLevel[i];
+	for (int b = 0; b < 16; b++) {
+		for (int i = 0; i < 15; i++)
+			o->ac16[b][i] = mb->Intra16x16ACLevel[b][i];
+		for (int i = 0; i < 16; i++)
+			o->l4[b][i] = mb->LumaLevel4x4[b][i];
+	}
+	for (int c = 0; c < 2; c++) {
+		for (int i = 0; i < 16; i++)
+			o->cdc[c][i] = mb->ChromaDCLevel[c][i];
+		for (int b = 0; b < 16; b++)
+			for (int i = 0; i < 15; i++)
+				o->cac[c][b][i] = mb->ChromaACLevel[c][b][i];
+	}
+	for (int i = 0; i < 256; i++)
+		o->pcm[i] = (uint8_t)mb->pcm_sample_luma[i];
+	for (int c = 0; c < 2; c++)
+		for (int i = 0; i < 256; i++)
+			o->pcm[256 + c * 256 + i] = (uint8_t)mb->pcm_sample_chroma[c][i];
 }
 
 static void tr_nalu(struct ref_tracer *t, uint32_t tag, enum h264_nalu_type type,
@@ -437,6 +487,8 @@ static void cb_sd_mb(struct h264_ctx *ctx, const struct h264_slice_header *sh,
 		t->mbs[t->mb_n].mb_addr = mb_addr;
 		t->mbs[t->mb_n].mb_type = mb_type;
 		t->mbs[t->mb_n].hash = t->mbs ? mb_hash(ctx->mb) : 0;
+		if (t->syn)
+			mb_syntax_from_ref(ctx->mb, mb_addr, mb_type, &t->syn[t->mb_n]);
 	}
 	t->mb_n++;
 }
@@ -446,6 +498,28 @@ static void cb_sd_mb(struct h264_ctx *ctx, const struct h264_slice_header *sh,
  * Returns 0, or 1 when a buffer was too small (counts are still exact).
  * hash_mbs = 0 skips the (slow) per-MB checksum: used by the CPU baseline timing.
  */
+static struct h264_mb_syntax *g_syn_out; /* set by ref_trace_parse_syntax for one call */
+
+int ref_trace_parse(const uint8_t *buf, size_t len, uint32_t flags, uint8_t *log,
+		    size_t log_cap, size_t *log_len, struct h264gpu_mb_record *mbs,
+		    size_t mb_cap, size_t *mb_n, size_t *final_off);
+
+/* same, and syn[mb_cap] receives every macroblock's syntax elements (single-threaded use) */
+int ref_trace_parse_syntax(const uint8_t *buf, size_t len, uint32_t flags, uint8_t *log,
+			   size_t log_cap, size_t *log_len, struct h264gpu_mb_record *mbs,
+			   size_t mb_cap, size_t *mb_n, size_t *final_off, struct h264_mb_syntax *syn)
+{
+	g_syn_out = syn;
+	int r = ref_trace_parse(buf, len, flags, log, log_cap, log_len, mbs, mb_cap, mb_n, final_off);
+	g_syn_out = NULL;
+	return r;
+}
+
+uint32_t ref_sizeof_mb_syntax(void)
+{
+	return (uint32_t)sizeof(struct h264_mb_syntax);
+}
+
 int ref_trace_parse(const uint8_t *buf, size_t len, uint32_t flags, uint8_t *log,
 		    size_t log_cap, size_t *log_len, struct h264gpu_mb_record *mbs,
 		    size_t mb_cap, size_t *mb_n, size_t *final_off)
@@ -461,6 +535,7 @@ int ref_trace_parse(const uint8_t *buf, size_t len, uint32_t flags, uint8_t *log
 	t.log_cap = log_cap;
 	t.mbs = mbs;
 	t.mb_cap = mb_cap;
+	t.syn = g_syn_out;
 	cbs.nalu_begin = cb_nalu_begin;
 	cbs.nalu_end = cb_nalu_end;
 	cbs.au_end = cb_au_end;
@@ -584,4 +659,39 @@ double ref_mt_parse(const uint8_t *const *bufs, const size_t *lens, size_t nstre
 	}
 	free(jobs);
 	return t1 - t0;
+}
+
+/* ---- the reference's CABAC encoder engine driven by a bin script ------------------------
+ * ops[i] = kind << 24 | ctxIdx << 8 | bin (kind 0 decision, 1 bypass, 2 terminate); contexts
+ * initialised by the reference's h264_bac_state_init from ITS tables for (table, slice_qp):
+ * table 0 = I slices, 1..3 = cabac_init_idc 0..2.  Returns bytes written (zero padded to a
+ * byte).  Pins the generator's encoder and, through it, the GPU decoder's arithmetic. */
+size_t ref_bac_ops(const uint32_t *ops, size_t n, uint32_t table, int32_t slice_qp, uint8_t *out,
+		   size_t cap)
+{
+	struct h264_bitstream bs;
+	struct h264_ctx *ctx = NULL;
+	static struct h264_cabac cab;
+	if (h264_ctx_new(&ctx) < 0)
+		return 0;
+	ctx->slice.type = table == 0 ? H264_SLICE_TYPE_I : H264_SLICE_TYPE_P;
+	ctx->slice.hdr.cabac_init_idc = table == 0 ? 0 : table - 1;
+	ctx->derived.SliceQPLuma = slice_qp;
+	memset(out, 0, cap);
+	h264_bs_init(&bs, out, cap, 0);
+	h264_cabac_init_states(&cab, ctx); /* the reference's own tables + h264_bac_state_init */
+	h264_bac_encode_init(&cab.enc, &bs, 1);
+	for (size_t i = 0; i < n; i++) {
+		uint32_t kind = ops[i] >> 24, c = (ops[i] >> 8) & 0x3ff, b = ops[i] & 1;
+		if (kind == 0)
+			h264_bac_encode_bin(&cab.enc, &cab.states[c], (int)b);
+		else if (kind == 1)
+			h264_bac_encode_bypass(&cab.enc, (int)b);
+		else
+			h264_bac_encode_terminate(&cab.enc, (int)b);
+	}
+	while (bs.cachebits % 8 != 0)
+		h264_bs_write_bits(&bs, 0, 1);
+	h264_ctx_destroy(ctx);
+	return bs.off;
 }

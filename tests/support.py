@@ -239,6 +239,9 @@ TR_SLICE_DATA_BEGIN, TR_SLICE_DATA_END, TR_AUD, TR_SEI, TR_SLICE_PARAMS = 7, 8, 
 MB_RECORD = np.dtype([("mb_addr", "<u4"), ("mb_type", "<u4"), ("hash", "<u8")])
 SLICE_RESULT = np.dtype([("status", "<i4"), ("mb_count", "<u4"), ("end_bit", "<u8")])
 PARAMS_SIZE = 56
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from libh264_b200 import SLICE_PARAMS  # noqa: E402
 
 
 def ref_trace(stream, flags=1, mb_cap=None, log_cap=None):
@@ -266,6 +269,36 @@ def ref_trace(stream, flags=1, mb_cap=None, log_cap=None):
         ev.append((tag, log[i + 8:i + 8 + n]))
         i += 8 + ((n + 7) & ~7)
     return ev, mbs[:mn.value].copy(), off.value
+
+
+def ref_trace_syntax(stream, flags=1):
+    """ref_trace plus the reference's full per-macroblock syntax elements (ctx->mb) as raw
+    struct h264_mb_syntax blobs (libh264_b200/csrc/mb_syntax.h).  Returns (ev, mbs, syn bytes
+    [n_mb, sizeof])."""
+    lib = ref()
+    lib.ref_trace_parse_syntax.restype = C.c_int
+    lib.ref_trace_parse_syntax.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t,
+                                           C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t,
+                                           C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p]
+    lib.ref_sizeof_mb_syntax.restype = C.c_uint32
+    sz = lib.ref_sizeof_mb_syntax()
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    mb_cap = max(1024, len(stream))
+    log = np.zeros(len(stream) * 4 + (32 << 20), np.uint8)
+    mbs = np.zeros(mb_cap, MB_RECORD)
+    syn = np.zeros((mb_cap, sz), np.uint8)
+    ll, mn, off = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    rc = lib.ref_trace_parse_syntax(ptr(stream), len(stream), flags, ptr(log), len(log), C.byref(ll),
+                                    ptr(mbs), mb_cap, C.byref(mn), C.byref(off), ptr(syn))
+    assert rc == 0
+    log = log[:ll.value]
+    ev, i = [], 0
+    while i < len(log):
+        tag = int(log[i:i + 4].view(np.uint32)[0])
+        n = int(log[i + 4:i + 8].view(np.uint32)[0])
+        ev.append((tag, log[i + 8:i + 8 + n]))
+        i += 8 + ((n + 7) & ~7)
+    return ev, mbs[:mn.value].copy(), syn[:mn.value].copy()
 
 
 def slice_params_from_trace(ev):
