@@ -128,7 +128,9 @@ MB_CFG = dict(width_mbs=120, height_mbs=68, slices_per_frame=16, profile_idc=100
               b_frames=1, num_ref_frames=2, idr_period=30, pct_skip=30, coef_density=60, seed=SEED)
 
 
-def SCAN_KERNEL_NAME():
+def SCAN_KERNEL_NAME(gen=2):
+    if gen == 5:
+        return "annexb5::scan5_kernel<8,strip> + scan5_finalize (RBSP in place per NAL)"
     it = int(os.environ.get("H264GPU_SCAN_ITEMS", "108"))
     return ("annexb2::scan2_kernel<%d,strip>" % (it % 10)) if it >= 100 else \
         ("annexb::scan_kernel<%d,strip>" % it)
@@ -234,6 +236,8 @@ def main():
     ap.add_argument("--size-mb", type=int, default=4096, help="input MiB per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scan-gen", type=int, default=5, choices=[2, 5],
+                    help="5: RBSP in place per NAL (h264gpu_split_strip_inplace_dev); 2: packed RBSP")
     ap.add_argument("--mb-frames", type=int, default=250, help="frames of the macroblock-parse workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -291,7 +295,7 @@ def main():
     cap = n_nal_expected + 1024
     d_in = g.alloc(n_in + 16)
     d_rbsp = g.alloc(n_in + 16)
-    d_tab = g.alloc(cap * 8 * 3)
+    d_tab = g.alloc(cap * 8 * 4)
     d_res = g.alloc(C.sizeof(L.ScanResult))
     L._check(g.lib.h264gpu_memcpy_h2d(g.h, C.c_void_p(d_in.ptr), pin_in.array.ctypes.data_as(C.c_void_p),
                                      n_in, None), "h2d")
@@ -312,8 +316,13 @@ def main():
             edge.has_right, edge.right[0], edge.right[1] = 1, int(allh[rank + 1][0]), int(allh[rank + 1][1])
 
     def step():
-        g.split_strip_dev(d_in.ptr, n_in, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8, d_tab.ptr + cap * 16,
-                          cap, d_res.ptr, base=rank * n_in, edge=edge)
+        if args.scan_gen == 5:
+            g.split_strip_inplace_dev(d_in.ptr, n_in, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8,
+                                      d_tab.ptr + cap * 16, d_tab.ptr + cap * 24, cap, d_res.ptr,
+                                      base=rank * n_in, edge=edge)
+        else:
+            g.split_strip_dev(d_in.ptr, n_in, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8, d_tab.ptr + cap * 16,
+                              cap, d_res.ptr, base=rank * n_in, edge=edge)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -396,7 +405,7 @@ def main():
                        "start_codes": "3/4-byte mixed, 0-2 trailing zeros on 1/4 of NALs",
                        "l2": "input %.1f GiB >> 126 MB L2, no flush needed" % (n_in / 2**30),
                        "parallelism": "byte-range shards, 1 per GPU, host merge, no collective",
-                       "kernel": SCAN_KERNEL_NAME(),
+                       "kernel": SCAN_KERNEL_NAME(args.scan_gen),
                        "gen_seconds": round(gen_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -113,6 +113,29 @@ H264GPU_API int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in,
 					void *stream);
 
 /*
+ * The same scan + strip with the RBSP of every NAL written IN PLACE: NAL k's RBSP is
+ * d_rbsp[d_nal_rbsp[k] .. d_nal_rbsp[k] + d_nal_rbsp_len[k]) with d_nal_rbsp[k] =
+ * d_nal_start[k] - base, i.e. where the NAL's first byte is in d_in; the bytes of d_rbsp
+ * between two NALs' RBSPs are unspecified.  d_rbsp needs len bytes.  Same reference behaviour
+ * per NAL (h264_find_nalu bounds, src/h264_bitstream.c:159-184; the byte sequence
+ * h264_bs_read_bits(8) yields, include/h264/h264_bitstream.h:168-218), but a byte's output
+ * position depends only on its own NAL, which removes the stream-long dependency chain of the
+ * packed form.  result->rbsp_bytes = sum of the RBSP lengths; the bytes a shard
+ * holds before its first boundary event (a NAL continued from the previous shard) are written
+ * at d_rbsp[0 .. head_bytes).  The last NAL's length runs to the shard end when end_open.
+ * result->reserved != 0: more boundary events than the workspace holds (4 x nal_cap + 4096),
+ * the table is incomplete -> pass a larger nal_cap.
+ */
+H264GPU_API int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *d_in,
+						uint64_t len, uint64_t base,
+						const struct h264gpu_shard_edge *edge,
+						uint8_t *d_rbsp, uint64_t *d_nal_start,
+						uint64_t *d_nal_end, uint64_t *d_nal_rbsp,
+						uint64_t *d_nal_rbsp_len, uint64_t nal_cap,
+						struct h264gpu_scan_result *d_result,
+						void *stream);
+
+/*
  * Host-side merge of per-shard results (byte-range shards of one stream, in
  * stream order: chunks of the host pipeline, or one shard per GPU).  No device
  * work and no collective: each shard contributes its small result struct and
@@ -143,6 +166,18 @@ H264GPU_API int h264gpu_merge_shard(struct h264gpu_merge *m,
 				    uint64_t *tab_rbsp, uint64_t tab_cap,
 				    uint64_t shard_nals_copied, uint64_t *rbsp_skip,
 				    uint64_t *rbsp_take);
+/*
+ * Merge step for shards scanned by h264gpu_split_strip_inplace_dev.  RBSP offsets stay
+ * shard-relative (NAL k's RBSP is in the d_rbsp of the shard its start lies in); what crosses a
+ * seam is the NAL left open by the earlier shards: its length grows by this shard's head
+ * bytes (*carry_len, found at the start of this shard's d_rbsp, or at offset nal_start - base
+ * when the NAL's start code straddles the seam) and its end becomes this
+ * shard's first boundary event.  tab_end / tab_rbsp_len: the merged tables so far.
+ */
+H264GPU_API int h264gpu_merge_shard_inplace(struct h264gpu_merge *m,
+					    const struct h264gpu_scan_result *r,
+					    uint64_t *tab_end, uint64_t *tab_rbsp_len,
+					    uint64_t tab_cap, uint64_t *carry_len);
 H264GPU_API int h264gpu_merge_finish(struct h264gpu_merge *m, uint64_t stream_len,
 				     uint64_t *tab_end, uint64_t tab_cap,
 				     uint64_t *final_off);

@@ -78,7 +78,7 @@ GPU_SYMBOLS = [
     "h264gpu_device_count", "h264gpu_create", "h264gpu_destroy", "h264gpu_device",
     "h264gpu_version", "h264gpu_launch_count", "h264gpu_malloc", "h264gpu_free",
     "h264gpu_host_alloc", "h264gpu_host_free", "h264gpu_memcpy_h2d", "h264gpu_memcpy_d2h",
-    "h264gpu_sync", "h264gpu_split_strip_dev", "h264gpu_merge_init", "h264gpu_merge_shard",
+    "h264gpu_sync", "h264gpu_split_strip_dev", "h264gpu_split_strip_inplace_dev", "h264gpu_merge_init", "h264gpu_merge_shard", "h264gpu_merge_shard_inplace",
     "h264gpu_merge_finish", "h264gpu_split_strip_host", "h264gpu_frame_dev",
     "h264gpu_frame_host", "h264gpu_timer_create", "h264gpu_timer_destroy",
     "h264gpu_timer_start", "h264gpu_timer_stop", "h264gpu_timer_elapsed_ms",
@@ -110,9 +110,11 @@ def load_gpu_lib():
         lib.h264gpu_sync.argtypes = [vp, vp]
         lib.h264gpu_split_strip_dev.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, u64, vp, vp]
         lib.h264gpu_split_strip_host.argtypes = [vp, vp, u64, vp, vp, vp, vp, u64p, u64p, u64p]
+        lib.h264gpu_split_strip_inplace_dev.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, u64, vp, vp]
         lib.h264gpu_merge_init.restype = None
         lib.h264gpu_merge_init.argtypes = [vp]
         lib.h264gpu_merge_shard.argtypes = [vp, vp, vp, vp, vp, u64, u64, u64p, u64p]
+        lib.h264gpu_merge_shard_inplace.argtypes = [vp, vp, vp, vp, u64, u64p]
         lib.h264gpu_merge_finish.argtypes = [vp, u64, vp, u64, u64p]
         lib.h264gpu_frame_dev.argtypes = [vp, vp, vp, u64, i, vp, u64, vp, vp, vp]
         lib.h264gpu_frame_host.argtypes = [vp, vp, vp, u64, i, vp, u64, vp, u64p]
@@ -245,6 +247,50 @@ class Gpu:
             C.c_void_p(d_rbsp) if d_rbsp else None, C.c_void_p(d_start), C.c_void_p(d_end),
             C.c_void_p(d_rb) if d_rb else None, cap, C.c_void_p(d_result), stream),
             "h264gpu_split_strip_dev")
+
+    def split_strip_inplace_dev(self, d_in, length, d_rbsp, d_start, d_end, d_rb, d_rblen, cap, d_result,
+                                base=0, edge=None, stream=None):
+        """Scan + strip with every NAL's RBSP written in place (include/h264gpu.h)."""
+        _check(self.lib.h264gpu_split_strip_inplace_dev(
+            self.h, C.c_void_p(d_in), length, base, C.byref(edge) if edge is not None else None,
+            C.c_void_p(d_rbsp) if d_rbsp else None, C.c_void_p(d_start), C.c_void_p(d_end),
+            C.c_void_p(d_rb) if d_rb else None, C.c_void_p(d_rblen) if d_rblen else None, cap,
+            C.c_void_p(d_result), stream), "h264gpu_split_strip_inplace_dev")
+
+    def split_strip_inplace(self, buf, want_rbsp=True, cap=None, edge=None, base=0):
+        """Host convenience over split_strip_inplace_dev (upload, run, download): the per-NAL
+        view dict(start, end, rbsp_off, rbsp_len, nal_rbsp=[bytes per NAL], body, res)."""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        n = len(buf)
+        cap = (n // 3 + 2) if cap is None else cap
+        d_in = self.alloc(n + 16)
+        d_out = self.alloc(n + 16 + 128) if want_rbsp else None
+        d_tab = self.alloc(cap * 32)
+        d_res = self.alloc(C.sizeof(ScanResult))
+        try:
+            d_in.upload(buf)
+            if want_rbsp:
+                d_out.upload(np.full(n + 16 + 128, 0xAA, np.uint8))
+            self.split_strip_inplace_dev(d_in.ptr, n, d_out.ptr + 64 if want_rbsp else None, d_tab.ptr,
+                                         d_tab.ptr + cap * 8, d_tab.ptr + cap * 16, d_tab.ptr + cap * 24,
+                                         cap, d_res.ptr, base=base, edge=edge)
+            self.sync()
+            res = ScanResult.from_buffer_copy(d_res.download().tobytes())
+            k = min(int(res.n_nal), cap)
+            tab = d_tab.download(dtype=np.uint64)
+            start, end = tab[:k].copy(), tab[cap:cap + k].copy()
+            rb, rl = tab[2 * cap:2 * cap + k].copy(), tab[3 * cap:3 * cap + k].copy()
+            body, per_nal = None, None
+            if want_rbsp:
+                raw = d_out.download()
+                assert (raw[:64] == 0xAA).all() and (raw[64 + n:] == 0xAA).all(), "write outside d_rbsp"
+                body = raw[64:64 + n]
+                per_nal = [body[int(rb[i]):int(rb[i]) + int(rl[i])] for i in range(k)]
+            return dict(start=start, end=end, rbsp_off=rb, rbsp_len=rl, nal_rbsp=per_nal, body=body, res=res)
+        finally:
+            for d in (d_in, d_out, d_tab, d_res):
+                if d is not None:
+                    d.free()
 
     def split_strip_host(self, buf, want_rbsp=True, cap=None, out=None):
         """buf: uint8 numpy array (host).  Returns dict(start,end,rbsp_off,rbsp,final_off)."""

@@ -54,6 +54,11 @@ struct ScanArgs {
 	uint8_t right[2];
 	uint8_t has_right;
 	uint8_t init_in;
+	uint64_t *trace; /* diagnostics (H264GPU_SCAN_TRACE): 8 timestamps per tile, or NULL */
+	/* gen 5 (in-place RBSP, annexb_scan5.cuh): boundary-event append buffer */
+	uint32_t *ev_cursor; /* pre-set to 0xffffffff */
+	uint64_t *evbuf;
+	uint64_t ev_cap;
 };
 
 /* 0x80 in every byte of x that is zero, exact */

@@ -35,6 +35,20 @@ using annexb::ScanArgs;
 using annexb::SlowMasks;
 using annexb::kInvalid;
 
+/* phase timestamps of a tile (diagnostics only; a.trace is NULL in normal runs) */
+__device__ __forceinline__ void trace_mark(const ScanArgs &a, uint32_t t, int k)
+{
+#ifndef H264_EMU
+	if (a.trace != nullptr) {
+		uint64_t ns;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+		a.trace[(uint64_t)t * 8 + k] = ns;
+	}
+#else
+	(void)a; (void)t; (void)k;
+#endif
+}
+
 constexpr int kT = 256;
 constexpr int kW = kT / 32;
 
@@ -474,6 +488,8 @@ __global__ void __launch_bounds__(kT, MINB) scan2_kernel(const ScanArgs a)
 	__syncthreads();
 
 	const uint32_t t = s.tile;
+	if (tid == 0)
+		trace_mark(a, t, 0);
 	const uint64_t tile_off = (uint64_t)t * C::TILE;
 	const uint64_t rem = a.len - tile_off;
 	const bool full = rem >= (uint64_t)C::TILE;
@@ -500,6 +516,8 @@ __global__ void __launch_bounds__(kT, MINB) scan2_kernel(const ScanArgs a)
 		}
 	}
 	__syncthreads();
+	if (tid == 0)
+		trace_mark(a, t, 1);
 
 	/* ---- P1: classify every chunk: delete mask (EPB, start-code bytes, bytes
 	 * past the end) and the "owns a boundary event" flag ---- */
@@ -671,10 +689,13 @@ __global__ void __launch_bounds__(kT, MINB) scan2_kernel(const ScanArgs a)
 		uint64_t kept_in, nnal_in;
 		bool sc_in, any_in;
 		const uint32_t fl = s.tflags;
+		if (lane == 0)
+			trace_mark(a, t, 2);
 		lookback(a, t, lane, H, B, s.tn, fl & 1, (fl >> 1) & 1, kept_in, nnal_in, sc_in, any_in);
 		if (lane == 0) {
 			s.pin[0] = kept_in | (uint64_t)(sc_in ? 1 : 0) << 62 | (uint64_t)(any_in ? 1 : 0) << 61;
 			s.pin[1] = nnal_in;
+			trace_mark(a, t, 3);
 		}
 	}
 	__syncthreads();
@@ -774,6 +795,8 @@ __global__ void __launch_bounds__(kT, MINB) scan2_kernel(const ScanArgs a)
 	}
 	} /* STRIP && tile_kept */
 
+	if (tid == 0)
+		trace_mark(a, t, 4);
 	/* ---- P8 (last warp, only with events): NAL table entries; nothing waits on it ---- */
 	if (warp == kW - 1 && s.anyev) {
 		bool cur_seen = false, cur_sc = false;

@@ -17,6 +17,7 @@ static inline uint32_t ldg_u32(const void *p) { return *(const uint32_t *)p; }
 static inline uint64_t ld_relaxed_u64(const uint64_t *p) { return *(const volatile uint64_t *)p; }
 static inline void st_relaxed_u64(uint64_t *p, uint64_t v) { *(volatile uint64_t *)p = v; }
 static inline void stg_stream16(void *p, uint4 v) { *(uint4 *)p = v; }
+static inline void stg_stream16_free(void *p, uint4 v) { *(uint4 *)p = v; }
 static inline void bulk_load_start(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
 	(void)bar;
@@ -64,6 +65,13 @@ __device__ __forceinline__ void stg_stream16(void *p, uint4 v)
 	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p),
 		     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
 		     : "memory");
+}
+/* the same without the compiler-level memory barrier: output bytes nobody in this kernel reads
+ * back, so loads of the next iterations may be hoisted above the store */
+__device__ __forceinline__ void stg_stream16_free(void *p, uint4 v)
+{
+	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+		     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 /* loads that bypass the (non-coherent) L1: data another CTA wrote */
 __device__ __forceinline__ uint4 ldcg16(const void *p)

@@ -8,6 +8,7 @@
 
 #include "annexb_scan.cuh"
 #include "annexb_scan2.cuh"
+#include "annexb_scan5.cuh"
 
 extern "C" {
 
@@ -349,6 +350,14 @@ extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, ui
 	}
 	cudaError_t ce;
 	const bool strip = d_rbsp != NULL;
+	/* diagnostics: per-tile phase timestamps dumped to the file named by H264GPU_SCAN_TRACE */
+	const char *trace_path = getenv("H264GPU_SCAN_TRACE");
+	uint64_t *d_trace = NULL;
+	if (trace_path != NULL && items >= 100) {
+		CU_TRY(cudaMalloc(&d_trace, ntiles * 64));
+		CU_TRY(cudaMemsetAsync(d_trace, 0, ntiles * 64, st));
+		a.trace = d_trace;
+	}
 	if (items == 108)
 		ce = launch_scan2<8, 4>(a, strip, st);
 	else if (items == 118)
@@ -365,6 +374,159 @@ extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, ui
 		ce = launch_scan<4>(a, strip, st);
 	CU_TRY(ce);
 	ctx->launches++;
+	if (d_trace != NULL) {
+		uint64_t *h = (uint64_t *)malloc(ntiles * 64);
+		CU_TRY(cudaStreamSynchronize(st));
+		CU_TRY(cudaMemcpy(h, d_trace, ntiles * 64, cudaMemcpyDeviceToHost));
+		FILE *f = fopen(trace_path, "wb");
+		if (f != NULL) {
+			fwrite(h, 64, ntiles, f);
+			fclose(f);
+		}
+		free(h);
+		cudaFree(d_trace);
+	}
+	return 0;
+}
+
+/* ---- scan + strip, RBSP in place (gen 5) ----------------------------------- */
+
+extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len,
+					       uint64_t base, const struct h264gpu_shard_edge *edge,
+					       uint8_t *d_rbsp, uint64_t *d_nal_start, uint64_t *d_nal_end,
+					       uint64_t *d_nal_rbsp, uint64_t *d_nal_rbsp_len,
+					       uint64_t nal_cap, struct h264gpu_scan_result *d_result,
+					       void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (d_in == NULL || d_result == NULL || (nal_cap && (!d_nal_start || !d_nal_end)))
+		return -EINVAL;
+	if (((uintptr_t)d_in & 15) || ((uintptr_t)d_rbsp & 15))
+		return -EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (len == 0) {
+		CU_TRY(cudaMemsetAsync(d_result, 0, sizeof(*d_result), st));
+		return 0;
+	}
+	if (len >= (1ull << 40))
+		return -E2BIG;
+	/* tile shape: 84 = 8 chunks/thread, 4 CTAs/SM (default); 45 / 46 = 4 chunks, 5 / 6 CTAs */
+	int shape = 84;
+	{
+		const char *e = getenv("H264GPU_SCAN5_SHAPE");
+		if (e != NULL && (atoi(e) == 45 || atoi(e) == 46 || atoi(e) == 85))
+			shape = atoi(e);
+	}
+	const int CPT = shape / 10;
+	const uint64_t tile = (uint64_t)annexb5::kT * CPT * 16;
+	const uint64_t ntiles = (len + tile - 1) / tile;
+	/* events: a start code and at most a few terminators per NAL in real streams */
+	uint64_t ev_cap = 4 * nal_cap + 4096;
+	if (ev_cap > len / 3 + 2)
+		ev_cap = len / 3 + 2;
+	if (ev_cap >= 0xffffffffull)
+		ev_cap = 0xfffffffeull;
+	/* workspace: [256 control][32 B per tile][2 words per tile][events][ordered events] */
+	const size_t desc_end = 256 + (size_t)ntiles * 32;
+	const size_t pre_off = (desc_end + 255) & ~(size_t)255;
+	const size_t ev_off = pre_off + (size_t)ntiles * 16;
+	const size_t ord_off = ev_off + (size_t)ev_cap * 8;
+	const size_t tot_off = ord_off + (size_t)ev_cap * 24;
+	const size_t need = tot_off + 64;
+	r = h264gpu_ws_reserve(ctx, need);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaMemsetAsync(ctx->ws, 0xff, desc_end, st));
+
+	annexb::ScanArgs a;
+	memset(&a, 0, sizeof(a));
+	a.in = d_in;
+	a.len = len;
+	a.base = base;
+	a.rbsp = d_rbsp;
+	a.ticket = (uint32_t *)ctx->ws;
+	a.ev_cursor = (uint32_t *)((uint8_t *)ctx->ws + 8);
+	a.desc = (uint64_t *)((uint8_t *)ctx->ws + 256);
+	a.evbuf = (uint64_t *)((uint8_t *)ctx->ws + ev_off);
+	a.ev_cap = ev_cap;
+	a.result = d_result;
+	a.num_tiles = (uint32_t)ntiles;
+	a.halo_left = 0xffffffffu;
+	a.right[0] = a.right[1] = 0xff;
+	int assume_in = 0;
+	if (edge != NULL) {
+		if (edge->has_left)
+			a.halo_left = 0xffffu | (uint32_t)edge->left[0] << 16 | (uint32_t)edge->left[1] << 24;
+		a.has_right = edge->has_right ? 1 : 0;
+		a.right[0] = edge->right[0];
+		a.right[1] = edge->right[1];
+		assume_in = edge->assume_in ? 1 : 0;
+	}
+	const char *trace_path = getenv("H264GPU_SCAN_TRACE");
+	uint64_t *d_trace = NULL;
+	if (trace_path != NULL) {
+		CU_TRY(cudaMalloc(&d_trace, ntiles * 64));
+		CU_TRY(cudaMemsetAsync(d_trace, 0, ntiles * 64, st));
+		a.trace = d_trace;
+	}
+#define SCAN5_LAUNCH(C, S, B)                                                                 \
+	do {                                                                                  \
+		cudaFuncSetAttribute(annexb5::scan5_kernel<C, S, B>,                          \
+				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
+		annexb5::scan5_kernel<C, S, B><<<(uint32_t)ntiles, annexb5::kT, 0, st>>>(a);  \
+	} while (0)
+	const bool strip5 = d_rbsp != NULL;
+	if (shape == 45) {
+		if (strip5) SCAN5_LAUNCH(4, true, 5); else SCAN5_LAUNCH(4, false, 5);
+	} else if (shape == 46) {
+		if (strip5) SCAN5_LAUNCH(4, true, 6); else SCAN5_LAUNCH(4, false, 6);
+	} else if (shape == 85) {
+		if (strip5) SCAN5_LAUNCH(8, true, 5); else SCAN5_LAUNCH(8, false, 5);
+	} else {
+		if (strip5) SCAN5_LAUNCH(8, true, 4); else SCAN5_LAUNCH(8, false, 4);
+	}
+#undef SCAN5_LAUNCH
+	CU_TRY(cudaGetLastError());
+
+	annexb5::FinArgs f;
+	memset(&f, 0, sizeof(f));
+	f.desc = a.desc;
+	f.num_tiles = (uint32_t)ntiles;
+	f.tile_bytes = (uint32_t)tile;
+	f.evbuf = a.evbuf;
+	f.ev_cap = ev_cap;
+	f.ordered = (uint64_t *)((uint8_t *)ctx->ws + ord_off);
+	f.tile_pre = (uint64_t *)((uint8_t *)ctx->ws + pre_off);
+	f.totals = (uint64_t *)((uint8_t *)ctx->ws + tot_off);
+	f.len = len;
+	f.base = base;
+	f.nal_start = d_nal_start;
+	f.nal_end = d_nal_end;
+	f.nal_rbsp = d_nal_rbsp;
+	f.nal_rbsp_len = d_nal_rbsp_len;
+	f.nal_cap = nal_cap;
+	f.result = d_result;
+	f.has_right = a.has_right;
+	f.strip = d_rbsp != NULL ? 1 : 0;
+	f.assume_in = (uint32_t)assume_in;
+	/* the table kernel is sized for the events the workspace can hold; in the common case
+	 * (few events per NAL) most of its threads exit at once */
+	CU_TRY(annexb5::launch_finalize(f, nal_cap * 2 + 4096 < ev_cap ? nal_cap * 2 + 4096 : ev_cap, st));
+	ctx->launches += 5;
+	if (d_trace != NULL) {
+		uint64_t *h = (uint64_t *)malloc(ntiles * 64);
+		CU_TRY(cudaStreamSynchronize(st));
+		CU_TRY(cudaMemcpy(h, d_trace, ntiles * 64, cudaMemcpyDeviceToHost));
+		FILE *fp = fopen(trace_path, "wb");
+		if (fp != NULL) {
+			fwrite(h, 64, ntiles, fp);
+			fclose(fp);
+		}
+		free(h);
+		cudaFree(d_trace);
+	}
 	return 0;
 }
 
@@ -406,6 +568,34 @@ extern "C" int h264gpu_merge_shard(struct h264gpu_merge *m, const struct h264gpu
 		*rbsp_skip = skip;
 	if (rbsp_take)
 		*rbsp_take = take;
+	return 0;
+}
+
+extern "C" int h264gpu_merge_shard_inplace(struct h264gpu_merge *m, const struct h264gpu_scan_result *r,
+					   uint64_t *tab_end, uint64_t *tab_rbsp_len, uint64_t tab_cap,
+					   uint64_t *carry_len)
+{
+	if (m == NULL || r == NULL)
+		return -EINVAL;
+	/* every shard but the first reported the bytes before its first event as the head of an
+	 * open NAL; they count only if a NAL really is open */
+	const int assumed_in = m->shards > 0;
+	const int actual_in = m->shards > 0 && m->open;
+	const uint64_t head = assumed_in ? r->head_bytes : 0;
+	const uint64_t carry = actual_in ? head : 0;
+	if (m->open && m->n_nal >= 1 && m->n_nal - 1 < tab_cap) {
+		if (tab_rbsp_len != NULL)
+			tab_rbsp_len[m->n_nal - 1] += carry;
+		if (r->any_event)
+			tab_end[m->n_nal - 1] = r->first_event_pos;
+	}
+	m->n_nal += r->n_nal;
+	m->rbsp_bytes += r->rbsp_bytes - (head - carry);
+	if (r->any_event)
+		m->open = r->end_open ? 1 : 0;
+	m->shards++;
+	if (carry_len)
+		*carry_len = carry;
 	return 0;
 }
 

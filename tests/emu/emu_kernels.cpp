@@ -5,6 +5,7 @@
  */
 #include "annexb_scan.cuh"
 #include "annexb_scan2.cuh"
+#include "annexb_scan5.cuh"
 #include "annexb_frame.cuh"
 
 #include <vector>
@@ -75,6 +76,91 @@ extern "C" int emu_split_strip(const uint8_t *in, uint64_t len, uint64_t base,
 		else if (items == 2) EMU_LAUNCH((scan_kernel<2, false>), grid, block, a);
 		else EMU_LAUNCH((scan_kernel<4, false>), grid, block, a);
 	}
+	free(buf);
+	return 0;
+}
+
+/* gen 5: in-place RBSP (annexb_scan5.cuh).  cpt = 16-byte chunks per thread (1, 2 or 8). */
+extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t base,
+				       const struct h264gpu_shard_edge *edge, uint8_t *rbsp,
+				       uint64_t *nal_start, uint64_t *nal_end, uint64_t *nal_rbsp,
+				       uint64_t *nal_rbsp_len, uint64_t nal_cap,
+				       struct h264gpu_scan_result *result, int cpt, uint64_t ev_cap)
+{
+	using namespace annexb;
+	if (len == 0)
+		return -1;
+	const uint64_t tile = (uint64_t)annexb5::kT * cpt * 16;
+	const uint32_t ntiles = (uint32_t)((len + tile - 1) / tile);
+	std::vector<uint64_t> desc((size_t)ntiles * 4, ~0ull), pre((size_t)ntiles * 2, 0);
+	std::vector<uint64_t> evbuf(ev_cap ? ev_cap : 1, 0), ordered(3 * (ev_cap ? ev_cap : 1), 0);
+	uint64_t totals[4] = {0, 0, 0, 0};
+	uint32_t ctrl[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+	memset(result, 0xff, sizeof(*result));
+	uint8_t *buf = (uint8_t *)aligned_alloc(16, (len + 15) & ~15ull);
+	memcpy(buf, in, len);
+	ScanArgs a;
+	memset(&a, 0, sizeof(a));
+	a.in = buf;
+	a.len = len;
+	a.base = base;
+	a.rbsp = rbsp;
+	a.desc = desc.data();
+	a.ticket = &ctrl[0];
+	a.ev_cursor = &ctrl[2];
+	a.evbuf = evbuf.data();
+	a.ev_cap = ev_cap;
+	a.result = result;
+	a.num_tiles = ntiles;
+	a.halo_left = 0xffffffffu;
+	a.right[0] = a.right[1] = 0xff;
+	int assume_in = 0;
+	if (edge) {
+		if (edge->has_left)
+			a.halo_left = 0xffffu | (uint32_t)edge->left[0] << 16 | (uint32_t)edge->left[1] << 24;
+		a.has_right = edge->has_right;
+		a.right[0] = edge->right[0];
+		a.right[1] = edge->right[1];
+		assume_in = edge->assume_in;
+	}
+	dim3 grid(ntiles), block(annexb5::kT);
+	if (rbsp) {
+		if (cpt == 1) EMU_LAUNCH((annexb5::scan5_kernel<1, true, 1>), grid, block, a);
+		else if (cpt == 2) EMU_LAUNCH((annexb5::scan5_kernel<2, true, 1>), grid, block, a);
+		else EMU_LAUNCH((annexb5::scan5_kernel<8, true, 1>), grid, block, a);
+	} else {
+		if (cpt == 1) EMU_LAUNCH((annexb5::scan5_kernel<1, false, 1>), grid, block, a);
+		else if (cpt == 2) EMU_LAUNCH((annexb5::scan5_kernel<2, false, 1>), grid, block, a);
+		else EMU_LAUNCH((annexb5::scan5_kernel<8, false, 1>), grid, block, a);
+	}
+	annexb5::FinArgs f;
+	memset(&f, 0, sizeof(f));
+	f.desc = desc.data();
+	f.num_tiles = ntiles;
+	f.tile_bytes = (uint32_t)tile;
+	f.evbuf = evbuf.data();
+	f.ev_cap = ev_cap;
+	f.ordered = ordered.data();
+	f.tile_pre = pre.data();
+	f.totals = totals;
+	f.len = len;
+	f.base = base;
+	f.nal_start = nal_start;
+	f.nal_end = nal_end;
+	f.nal_rbsp = nal_rbsp;
+	f.nal_rbsp_len = nal_rbsp_len;
+	f.nal_cap = nal_cap;
+	f.result = result;
+	f.has_right = a.has_right;
+	f.strip = rbsp ? 1 : 0;
+	f.assume_in = (uint32_t)assume_in;
+	dim3 g1(1), b1(annexb5::kFinT), b256(256), one(1);
+	EMU_LAUNCH((annexb5::fin_tiles), g1, b1, f);
+	dim3 gt((ntiles + 255) / 256);
+	EMU_LAUNCH((annexb5::fin_order), gt, b256, f);
+	EMU_LAUNCH((annexb5::fin_head), g1, one, f);
+	dim3 ge((uint32_t)((ev_cap + 255) / 256 ? (ev_cap + 255) / 256 : 1));
+	EMU_LAUNCH((annexb5::fin_table), ge, b256, f);
 	free(buf);
 	return 0;
 }

@@ -307,6 +307,44 @@ def slice_params_from_trace(ev):
     return np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
 
 
+def emu_split_strip_inplace(buf, strip=True, cpt=8, edge=None, base=0, ev_cap=None):
+    """Gen-5 kernel + finalize on the emulator.  Returns the per-NAL view: start, end, rbsp_off,
+    rbsp_len, nal_rbsp (list of per-NAL byte arrays), the raw output buffer and the result."""
+    lib = emu()
+    lib.emu_split_strip_inplace.restype = C.c_int
+    lib.emu_split_strip_inplace.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                            C.c_void_p, C.c_int, C.c_uint64]
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    cap = len(buf) // 3 + 2
+    s = np.full(cap, NONE64, np.uint64)
+    e = np.full(cap, NONE64, np.uint64)
+    r = np.full(cap, NONE64, np.uint64)
+    rl = np.full(cap, NONE64, np.uint64)
+    guard = 64
+    out = np.full(len(buf) + 2 * guard, 0xAA, np.uint8) if strip else None
+    res = ScanResult()
+    if strip:  # the kernel wants a 16-byte aligned output base: carve one out of the guarded buffer
+        addr = out.ctypes.data
+        lead = (-(addr + guard)) % 16 + guard
+        out_ptr = C.c_void_p(addr + lead)
+    else:
+        lead, out_ptr = 0, None
+    rc = lib.emu_split_strip_inplace(ptr(buf), len(buf), base, C.byref(edge) if edge else None, out_ptr,
+                                     ptr(s), ptr(e), ptr(r), ptr(rl), cap, C.byref(res), cpt,
+                                     cap if ev_cap is None else ev_cap)
+    assert rc == 0
+    n = res.n_nal
+    body = out[lead:lead + len(buf)] if strip else None
+    if strip:  # nothing may be written outside [0, len)
+        assert (out[:lead] == 0xAA).all() and (out[lead + len(buf):] == 0xAA).all(), "write outside d_rbsp"
+    per_nal = None
+    if strip:
+        per_nal = [body[int(r[k]):int(r[k]) + int(rl[k])].copy() for k in range(min(n, cap))]
+    return dict(start=s[:n].copy(), end=e[:n].copy(), rbsp_off=r[:n].copy(), rbsp_len=rl[:n].copy(),
+                nal_rbsp=per_nal, body=body, res=res)
+
+
 def emu_cavlc_parse(stream, params, n_records):
     lib = emu()
     lib.emu_cavlc_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]

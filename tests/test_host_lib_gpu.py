@@ -43,9 +43,41 @@ def test_bulk_parse_mixed_and_damaged():
     hdrs = T.gen(lib, T.REF, 321, rounds=4)            # SEI/AUD/filler/CABAC/FMO headers in between
     s = np.concatenate([hdrs, video, hdrs[:300], video])
     T.assert_same_trace(T.trace(lib, T.OURS, s, 1, 0), T.trace(lib, T.REF, s, 1, 0), "mixed")
+    excused = 0
     for it in range(6):
         d = video.copy()
         for p in rng.integers(40, len(d), 4):
             d[p] ^= 1 << int(rng.integers(0, 8))
         a, b = T.trace(lib, T.OURS, d, 1, 0), T.trace(lib, T.REF, d, 1, 0)
-        T.assert_same_trace(a, b, "damaged %d" % it)
+        excused += assert_same_trace_outside_ub(a, b, "damaged %d" % it)
+    assert excused <= 6  # at most one such slice per damaged stream here
+
+
+T_NALU_BEGIN, T_SD_MB = 1, 9
+
+
+def assert_same_trace_outside_ub(a, b, what):
+    """Equal traces, except for ONE documented case (SURVEY.md §8c "validity domain"): inside a
+    damaged slice the reference can place a coefficient past the end of a 15-entry block
+    (`coeffLevel[startIdx + coeffNum]`, src/h264_syntax_slice_data.h:226, unchecked) and keeps
+    parsing on undefined behaviour; the GPU parse stops that slice with -EIO.  There the
+    reference's extra slice_data_mb callbacks are skipped and the comparison resumes at the
+    next NAL.  Returns how often that happened."""
+    ea, eb = T.split_log(a), T.split_log(b)
+    i = j = excused = 0
+    while i < len(ea) and j < len(eb):
+        if ea[i] == eb[j]:
+            i += 1
+            j += 1
+            continue
+        # ours ended the slice (next event belongs to what follows the macroblocks) while the
+        # reference still delivers macroblocks of the same slice
+        assert eb[j][0] == T_SD_MB and ea[i][0] != T_SD_MB, \
+            "%s: event %d/%d differs: tag %d/%d" % (what, i, j, ea[i][0], eb[j][0])
+        excused += 1
+        while i < len(ea) and ea[i][0] != T_NALU_BEGIN:
+            i += 1
+        while j < len(eb) and eb[j][0] != T_NALU_BEGIN:
+            j += 1
+    assert (i == len(ea)) == (j == len(eb)), what
+    return excused
