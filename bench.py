@@ -136,11 +136,15 @@ def SCAN_KERNEL_NAME(gen=2):
         ("annexb::scan_kernel<%d,strip>" % it)
 
 
-def mb_parse_leg(g, L, frames, steps, warmup, rank, with_cpu):
-    """Slice-parallel CAVLC macroblock parse (1080p High, 16 slices/frame): macroblocks/s
-    device-resident, end-to-end from host buffers, and the reference reader on the host cores."""
-    stream, nmb, nsl, params = L.synth_video(frames=frames, want_params=True,
-                                             **dict(MB_CFG, seed=MB_CFG["seed"] + rank))
+def mb_parse_leg(g, L, frames, steps, warmup, rank, with_cpu, cabac=False):
+    """Slice-parallel macroblock parse (1080p, 16 slices/frame; CAVLC High or, cabac=True, the
+    CABAC kernel on BASELINE config 3's shape): macroblocks/s device-resident, end-to-end from
+    host buffers, and the reference reader on the host cores (CAVLC only: the reference parses
+    no CABAC slice data)."""
+    cfg = dict(MB_CFG, seed=MB_CFG["seed"] + rank)
+    if cabac:
+        cfg.update(profile_idc=77, transform_8x8=0, entropy_cabac=1)
+    stream, nmb, nsl, params = L.synth_video(frames=frames, want_params=True, **cfg)
     d_stream = g.alloc(len(stream) + 16)
     d_stream.upload(stream)
     d_params = g.alloc(len(params))
@@ -148,8 +152,11 @@ def mb_parse_leg(g, L, frames, steps, warmup, rank, with_cpu):
     d_rec = g.alloc(nmb * 16 + 16)
     d_res = g.alloc(nsl * 16)
 
+    parse_dev = g.cabac_parse_dev if cabac else g.cavlc_parse_dev
+    parse_host = g.cabac_parse_host if cabac else g.cavlc_parse_host
+
     def step():
-        g.cavlc_parse_dev(d_stream.ptr, len(stream), d_params.ptr, nsl, d_rec.ptr, d_res.ptr)
+        parse_dev(d_stream.ptr, len(stream), d_params.ptr, nsl, d_rec.ptr, d_res.ptr)
 
     for _ in range(warmup):
         step()
@@ -163,14 +170,19 @@ def mb_parse_leg(g, L, frames, steps, warmup, rank, with_cpu):
     res = d_res.download(dtype=np.uint8).view(L.SLICE_RESULT)
     ok = bool((res["status"] == 0).all() and int(res["mb_count"].sum()) == nmb)
     t1 = time.perf_counter()
-    recs, res2 = g.cavlc_parse_host(stream, params, nmb)
+    recs, res2 = parse_host(stream, params, nmb)
     e2e_s = time.perf_counter() - t1
-    out = {"workload": "CAVLC 1080p High, 16 slices/frame, %d frames (%d slices, %d MBs, %.1f MB stream)"
-                       % (frames, nsl, nmb, len(stream) / 1e6),
+    out = {"workload": "%s, 16 slices/frame, %d frames (%d slices, %d MBs, %.1f MB stream)"
+                       % ("CABAC 1080p Main (BASELINE config 3 shape)" if cabac else "CAVLC 1080p High",
+                          frames, nsl, nmb, len(stream) / 1e6),
+           "kernel": "cabac::cabac_parse_kernel" if cabac else "cavlc::cavlc_parse_kernel",
            "macroblocks_per_s": nmb / (ms / 1e3), "ms_per_step": ms, "parity_counts_ok": ok,
            "e2e_macroblocks_per_s": nmb / e2e_s,
-           "e2e_note": "h264gpu_cavlc_parse_host: H2D stream+params, kernel, D2H 16 B/MB records"}
-    if with_cpu:
+           "e2e_note": "h264gpu_%s_parse_host: H2D stream+params, kernel, D2H 16 B/MB records"
+                       % ("cabac" if cabac else "cavlc")}
+    if cabac:
+        out["cpu_baseline"] = None  # the reference has no CABAC slice-data parser
+    if with_cpu and not cabac:
         lib, kind = ref_lib()
         if lib is not None:
             lib.ref_mt_parse.restype = C.c_double
@@ -190,6 +202,43 @@ def mb_parse_leg(g, L, frames, steps, warmup, rank, with_cpu):
                                              "reader per thread (%d threads, %d MBs total), best of 2" %
                                              (cores, mbs.value)}
     for d in (d_stream, d_params, d_rec, d_res):
+        d.free()
+    return out
+
+
+def frame_leg(g, L, size, steps, warmup, rank):
+    """Writer side (BASELINE config 5): EPB insertion + 4-byte start-code framing of `size` bytes
+    of synthetic RBSP payloads, device-resident; GB/s of payload, roofline on N_rbsp + N_out."""
+    offs = L.synth_offsets(SEED + 100 + rank, size)
+    rbsp = L.synth_payloads(SEED + 100 + rank, offs)
+    n = len(offs) - 1
+    cap = len(rbsp) + len(rbsp) // 2 + 4 * n + 64
+    d_r = g.alloc(len(rbsp) + 16)
+    d_r.upload(rbsp)
+    d_o = g.alloc(len(offs) * 8)
+    d_o.upload(offs)
+    d_out = g.alloc(cap + 16)
+    d_oo = g.alloc((n + 2) * 8)
+
+    def step():
+        g.frame_dev(d_r.ptr, d_o.ptr, n, 4, d_out.ptr, cap, d_oo.ptr, d_oo.ptr + (n + 1) * 8)
+
+    for _ in range(warmup):
+        step()
+    g.sync()
+    tm = g.timer()
+    g.timer_start(tm)
+    for _ in range(steps):
+        step()
+    g.timer_stop(tm)
+    ms = g.timer_ms(tm) / steps
+    total = int(d_oo.download(dtype=np.uint64)[n + 1])
+    peak, _ = measured_peak()
+    out = {"workload": "EPB insert + framing of %.0f MiB RBSP in %d payloads (BASELINE config 5)" % (size / 2**20, n),
+           "kernel": "frame::frame_prepass + frame::frame_kernel<4>",
+           "gb_per_s": len(rbsp) / (ms / 1e3) / 1e9, "ms_per_step": ms, "out_bytes": total,
+           "roofline_frac": (len(rbsp) + total + 8 * (n + 1)) / (ms / 1e3) / 1e9 / peak}
+    for d in (d_r, d_o, d_out, d_oo):
         d.free()
     return out
 
@@ -238,7 +287,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scan-gen", type=int, default=5, choices=[2, 5],
                     help="5: RBSP in place per NAL (h264gpu_split_strip_inplace_dev); 2: packed RBSP")
-    ap.add_argument("--mb-frames", type=int, default=250, help="frames of the macroblock-parse workload")
+    ap.add_argument("--mb-frames", type=int, default=1000, help="frames of the macroblock-parse workload")
+    ap.add_argument("--cabac-frames", type=int, default=250,
+                    help="frames of the CABAC macroblock-parse workload (0 = skip)")
+    ap.add_argument("--frame-mb", type=int, default=1024,
+                    help="MiB of RBSP payloads for the writer leg (BASELINE config 5; 0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -389,9 +442,16 @@ def main():
         d.free()
     mb = mb_parse_leg(g, L, args.mb_frames, max(3, args.steps // 4), 2, rank,
                       with_cpu=(rank == 0 and world == 1 and not args.no_cpu))
+    mbc = mb_parse_leg(g, L, args.cabac_frames, 3, 1, rank, with_cpu=False, cabac=True) \
+        if args.cabac_frames > 0 else None
+    fr = frame_leg(g, L, args.frame_mb << 20, 5, 2, rank) if args.frame_mb > 0 else None
     if world > 1:
         mb["macroblocks_per_s"] = sum_over_ranks(mb["macroblocks_per_s"])
         mb["e2e_macroblocks_per_s"] = sum_over_ranks(mb["e2e_macroblocks_per_s"])
+        if mbc:
+            mbc["macroblocks_per_s"] = sum_over_ranks(mbc["macroblocks_per_s"])
+        if fr:
+            fr["gb_per_s"] = sum_over_ranks(fr["gb_per_s"])
 
     if rank == 0:
         line = {
@@ -417,7 +477,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
-            "extra": {"macroblocks_per_s": mb["macroblocks_per_s"], "mb_parse": mb},
+            "extra": {"macroblocks_per_s": mb["macroblocks_per_s"], "mb_parse": mb,
+                      "mb_parse_cabac": mbc, "writer_frame": fr},
         }
         print(json.dumps(line))
     if dist is not None:

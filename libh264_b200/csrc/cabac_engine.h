@@ -23,6 +23,11 @@
 #ifndef CABAC_HD
 #define CABAC_HD
 #endif
+/* hot, many-call-site routines stay real functions on the device (code size: the fully
+ * inlined kernel does not fit the instruction cache) */
+#ifndef CABAC_OUTLINE
+#define CABAC_OUTLINE CABAC_HD
+#endif
 
 namespace cabac {
 
@@ -76,7 +81,7 @@ struct Dec {
 	CABAC_HD bool failed() const { return bad; }
 
 	/* next RBSP byte (emulation prevention bytes dropped) */
-	CABAC_HD uint32_t fetch()
+	CABAC_OUTLINE uint32_t fetch()
 	{
 		if (pos >= len) {
 			bad = true;
@@ -132,7 +137,7 @@ struct Dec {
 	/* raw bit position in the NAL of the next unread bit */
 	CABAC_HD uint64_t raw_bitpos() const { return (uint64_t)pos * 8 - (uint64_t)nbits; }
 
-	CABAC_HD uint32_t bin(uint32_t ctx, uint32_t)
+	CABAC_OUTLINE uint32_t bin(uint32_t ctx, uint32_t)
 	{
 		uint8_t *sp = st + ctx * stride;
 		const uint32_t s = *sp;
@@ -160,7 +165,7 @@ struct Dec {
 		return b;
 	}
 
-	CABAC_HD uint32_t byp(uint32_t)
+	CABAC_OUTLINE uint32_t byp(uint32_t)
 	{
 		offset = (offset << 1) | get(1);
 		if (offset >= range) {

@@ -19,6 +19,7 @@
 #include "h264gpu_slice.h"
 
 #define CABAC_HD __device__
+#define CABAC_OUTLINE __device__ __noinline__
 #define CABAC_CONST __device__ const
 #include "cabac_engine.h"
 #include "cabac_syntax.h"
@@ -50,10 +51,19 @@ struct CabacArgs {
 };
 
 constexpr uint32_t kTabBytes = 256 + 64 + 64;
+/* per-slice working set kept in SHARED memory (walker state + the macroblock being decoded):
+ * as thread-local data it would live in lane-interleaved local memory, where a warp that runs
+ * one or a few slices still occupies 32 lanes' worth of cache lines and thrashes L1 */
+constexpr uint32_t kSlotBytes = (uint32_t)((sizeof(Walk<Dec>) + sizeof(Mb) + 15) & ~(size_t)15) + 16;
+
+__host__ __device__ inline uint32_t smem_bytes(uint32_t slices_per_block)
+{
+	return ((kTabBytes + kNumCtx * slices_per_block + 15) & ~15u) + slices_per_block * kSlotBytes;
+}
 
 __device__ __forceinline__ void parse_slice(const uint8_t *stream, const h264gpu_slice_params &sp, Nb *ring,
 					     h264gpu_mb_record *rec, h264gpu_slice_result &res, uint8_t *ctx_states,
-					     uint32_t ctx_stride, const uint8_t *tabs)
+					     uint32_t ctx_stride, const uint8_t *tabs, uint8_t *slot)
 {
 	res.status = 0;
 	res.mb_count = 0;
@@ -67,7 +77,8 @@ __device__ __forceinline__ void parse_slice(const uint8_t *stream, const h264gpu
 		res.status = -ENOSYS;
 		return;
 	}
-	Walk<Dec> w;
+	Walk<Dec> &w = *reinterpret_cast<Walk<Dec> *>(slot);
+	Mb &m = *reinterpret_cast<Mb *>(slot + ((sizeof(Walk<Dec>) + 7) & ~(size_t)7));
 	w.begin_slice(&sp, ring);
 	w.c.st = ctx_states;
 	w.c.stride = ctx_stride;
@@ -85,7 +96,6 @@ __device__ __forceinline__ void parse_slice(const uint8_t *stream, const h264gpu
 			status = -ENOBUFS;
 			break;
 		}
-		Mb m;
 		bool skipped = false, end = false;
 		if (!w.mb_step(cur, skipped, m, end)) {
 			status = -EIO;
@@ -107,7 +117,7 @@ __device__ __forceinline__ void parse_slice(const uint8_t *stream, const h264gpu
 /*
  * Like K4, slices diverge completely, so few slices are spread one per warp and only packed
  * into the lanes of a warp once there are more slices than resident warps.  Dynamic shared
- * memory: [384 B tables][460 x (slices per block) context bytes].
+ * memory: [384 B tables][460 x (slices per block) context bytes][slices x working set].
  */
 __global__ void __launch_bounds__(128) cabac_parse_kernel(const CabacArgs a)
 {
@@ -135,8 +145,9 @@ __global__ void __launch_bounds__(128) cabac_parse_kernel(const CabacArgs a)
 		a.results[i] = res;
 		return;
 	}
+	uint8_t *slots = smem + ((kTabBytes + kNumCtx * per_block + 15) & ~15u);
 	parse_slice(a.stream, sp, a.ring + (uint64_t)i * a.ring_stride, a.records + sp.mb_out_off, res,
-		    smem + kTabBytes + slot, per_block, smem);
+		    smem + kTabBytes + slot, per_block, smem, slots + (size_t)slot * kSlotBytes);
 	a.results[i] = res;
 }
 

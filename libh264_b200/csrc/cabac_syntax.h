@@ -28,6 +28,9 @@
 #ifndef CABAC_HD
 #define CABAC_HD
 #endif
+#ifndef CABAC_OUTLINE
+#define CABAC_OUTLINE CABAC_HD
+#endif
 
 namespace cabac {
 
@@ -309,7 +312,7 @@ template <class Coder> struct Walk {
 	}
 
 	/* ref_idx of the partition whose top-left 8x8 block is b8 (0..3) */
-	CABAC_HD uint32_t ref_idx(uint32_t list, uint32_t b8, uint32_t v)
+	CABAC_OUTLINE uint32_t ref_idx(uint32_t list, uint32_t b8, uint32_t v)
 	{
 		const uint32_t x = b8 & 1, y = b8 >> 1;
 		uint32_t a, b;
@@ -349,7 +352,7 @@ template <class Coder> struct Walk {
 	}
 
 	/* 9.3.2.3 UEG3, signedValFlag 1, uCoff 9 */
-	CABAC_HD int32_t mvd_comp(uint32_t list, uint32_t comp, uint32_t bx, uint32_t by, int32_t v)
+	CABAC_OUTLINE int32_t mvd_comp(uint32_t list, uint32_t comp, uint32_t bx, uint32_t by, int32_t v)
 	{
 		const uint32_t sum = mvd_sum(list, comp, bx, by);
 		const uint32_t base = comp ? 47 : 40;
@@ -410,7 +413,7 @@ template <class Coder> struct Walk {
 	 * macroblock); self_bit: where to record this block's flag.  Returns the number of
 	 * non-zero coefficients; coef[0..n) holds the levels in scan order.
 	 */
-	CABAC_HD uint32_t residual_block(uint32_t blkcat, uint32_t n, bool chroma_word, bool in_a, uint32_t bit_a,
+	CABAC_OUTLINE uint32_t residual_block(uint32_t blkcat, uint32_t n, bool chroma_word, bool in_a, uint32_t bit_a,
 					 bool in_b, uint32_t bit_b, uint32_t self_bit, uint32_t field, uint32_t idx_base)
 	{
 		/* levels to code (encoder): already in coef[]; count them */

@@ -73,7 +73,7 @@ struct BitReader {
 	bool err;
 };
 
-__device__ __forceinline__ void br_refill(BitReader &b)
+__device__ __noinline__ void br_refill(BitReader &b)
 {
 	while (b.nbits <= 56 && b.pos < b.len) {
 		/* up to 5 raw bytes in flight at once (independent loads), then the EPB
@@ -165,7 +165,7 @@ __device__ __forceinline__ uint32_t br_get(BitReader &b, int n)
 
 /* 9.1 Exp-Golomb; same result as h264_bs_read_bits_ue for codes the reference
  * handles without undefined behaviour (fewer than 32 leading zeros) */
-__device__ __forceinline__ uint32_t br_ue(BitReader &b)
+__device__ __noinline__ uint32_t br_ue(BitReader &b)
 {
 	uint32_t top = br_peek(b, 32);
 	if (top == 0) {
@@ -207,7 +207,7 @@ __device__ __forceinline__ uint64_t br_raw_bitpos(const BitReader &b)
 }
 
 /* h264_bs_more_rbsp_data, src/h264_bitstream.c:325-355 */
-__device__ __forceinline__ bool br_more_rbsp_data(BitReader &b)
+__device__ __noinline__ bool br_more_rbsp_data(BitReader &b)
 {
 	if (b.nbits < 8)
 		br_refill(b);
@@ -273,7 +273,7 @@ __device__ __forceinline__ uint8_t *ring_slot(SliceCtx &s, uint32_t mb)
 }
 
 /* 6.4.11.4 / 6.4.11.5: total_coeff of the left and upper 4x4 neighbours -> nC */
-__device__ __forceinline__ uint32_t calc_nc(SliceCtx &s, uint32_t comp, uint32_t blk, bool chroma_ac)
+__device__ __noinline__ uint32_t calc_nc(SliceCtx &s, uint32_t comp, uint32_t blk, bool chroma_ac)
 {
 	uint32_t nA = 0, nB = 0;
 	bool aA, aB;
@@ -321,7 +321,7 @@ __device__ __forceinline__ uint32_t calc_nc(SliceCtx &s, uint32_t comp, uint32_t
  * 4:2:2.  Coefficient i of the block contributes to the checksum as
  * (field, idx_base + startIdx + position).  Returns total_coeff.
  */
-__device__ __forceinline__ uint32_t residual_block(SliceCtx &s, uint32_t tab, uint32_t max_num_coeff,
+__device__ __noinline__ uint32_t residual_block(SliceCtx &s, uint32_t tab, uint32_t max_num_coeff,
 						    uint32_t field, uint32_t idx_base)
 {
 	BitReader &b = s.br;

@@ -39,16 +39,18 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	a.ring = (uint8_t *)ctx->ws;
 	a.ring_stride = ring_stride;
 	a.ring_w = ring_w;
-	/* slices per warp: 1 until there are more slices than ~48 warps per SM can hold */
+	/* Slices per warp.  Slices diverge completely, so a warp runs its lanes one after the
+	 * other: one slice per warp is best while the warps fit the machine, and lanes are packed
+	 * only beyond ~32 warps per SM (measured, profiles/r01_slice_lane_packing.txt: 4000 slices
+	 * -> 1 per warp, 16000 slices -> 4 per warp). */
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-	const uint64_t warp_slots = (uint64_t)sms * 48;
 	uint32_t lanes_log2 = 0;
 	const char *env = getenv("H264GPU_CAVLC_LANES_LOG2");
 	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
 		lanes_log2 = (uint32_t)atoi(env);
 	} else {
-		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > warp_slots)
+		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > (uint64_t)sms * 32)
 			lanes_log2++;
 	}
 	a.lanes_log2 = lanes_log2;
@@ -166,23 +168,23 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	a.ring = (cabac::Nb *)ctx->ws;
 	a.ring_stride = ring_stride;
 	a.ring_w = ring_w;
-	/* slices per warp: 1 until there are more slices than ~48 warps per SM can hold */
+	/* slices per warp: same rule as the CAVLC parse; one warp per block so that a block's
+	 * shared memory (tables + 1.1 KB per slice) stays small and many blocks fit an SM */
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-	const uint64_t warp_slots = (uint64_t)sms * 48;
 	uint32_t lanes_log2 = 0;
 	const char *env = getenv("H264GPU_CABAC_LANES_LOG2");
 	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
 		lanes_log2 = (uint32_t)atoi(env);
 	} else {
-		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > warp_slots)
+		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > (uint64_t)sms * 32)
 			lanes_log2++;
 	}
 	a.lanes_log2 = lanes_log2;
-	const uint32_t threads = 128; /* 4 warps per block */
+	const uint32_t threads = 32; /* one warp per block */
 	const uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
 	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
-	const size_t smem = cabac::kTabBytes + (size_t)cabac::kNumCtx * ((threads / 32) << lanes_log2);
+	const size_t smem = cabac::smem_bytes((threads / 32) << lanes_log2);
 	static size_t smem_set = 0;
 	if (smem > smem_set) {
 		CU_TRY(cudaFuncSetAttribute(cabac::cabac_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -10,11 +10,13 @@ echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tai
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/${TAG}_smoke.log
 echo "== bench"; timeout 900 python bench.py 2> gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err; cut -c1-400 gpurun_out/${TAG}_bench.json
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2> gpurun_out/${TAG}_bench_ref.err > gpurun_out/${TAG}_bench_ref.json; cut -c1-400 gpurun_out/${TAG}_bench_ref.json
-SHORT="--size-mb 1024 --steps 3 --warmup 3 --e2e-steps 1 --no-cpu --mb-frames 60"
+SHORT="--size-mb 1024 --steps 3 --warmup 3 --e2e-steps 1 --no-cpu --mb-frames 120 --cabac-frames 60 --frame-mb 256"
 echo "== ncu launch list"
 timeout 600 python bench.py $SHORT > gpurun_out/${TAG}_plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py $SHORT > gpurun_out/${TAG}_ncu_launches.log 2>&1
-echo "== ncu full: scan, cavlc"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan2_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_scan python bench.py $SHORT > gpurun_out/${TAG}_ncu_scan.log 2>&1
+echo "== ncu full: scan, cavlc, cabac, frame"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan5_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_scan python bench.py $SHORT > gpurun_out/${TAG}_ncu_scan.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:cavlc_parse -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_cavlc python bench.py $SHORT > gpurun_out/${TAG}_ncu_cavlc.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:cabac_parse -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_cabac python bench.py $SHORT > gpurun_out/${TAG}_ncu_cabac.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:frame_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_frame python bench.py $SHORT > gpurun_out/${TAG}_ncu_frame.log 2>&1
 ls -la gpurun_out/${TAG}_*
