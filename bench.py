@@ -44,6 +44,20 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(kernel_name, n_in):
+    """DRAM bytes (read + write) of the dominant kernel per launch from the committed ncu
+    capture of this very workload (profiles/r01_traffic.json, written by scripts/gpu_session.sh);
+    None when no capture matches the kernel and input size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("bytes_in") == int(n_in) and t.get("kernel", "").split("<")[0] in kernel_name:
+            return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def make_workload(L, size_bytes, seed, out=None, nthreads=None):
     """Config-2 stream: NAL sizes log-uniform 64 B..256 KiB, P(00)=3/16, escaped, mixed
     3/4-byte start codes, 0-2 trailing zero bytes on a quarter of the NALs."""
@@ -130,7 +144,7 @@ MB_CFG = dict(width_mbs=120, height_mbs=68, slices_per_frame=16, profile_idc=100
 
 def SCAN_KERNEL_NAME(gen=2):
     if gen == 5:
-        return "annexb5::scan5_kernel<8,strip> + scan5_finalize (RBSP in place per NAL)"
+        return "annexb5::scan5_kernel<8,strip> + fin_tiles/fin_order/fin_head/fin_table (RBSP in place per NAL)"
     it = int(os.environ.get("H264GPU_SCAN_ITEMS", "108"))
     return ("annexb2::scan2_kernel<%d,strip>" % (it % 10)) if it >= 100 else \
         ("annexb::scan_kernel<%d,strip>" % it)
@@ -468,7 +482,9 @@ def main():
                        "kernel": SCAN_KERNEL_NAME(args.scan_gen),
                        "gen_seconds": round(gen_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": measured_traffic(SCAN_KERNEL_NAME(args.scan_gen), n_in) if world == 1 else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes),
                          "note": "duration = CUDA-event step time (kernel + two tiny memsets) on the launch stream"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n_in),

@@ -61,7 +61,9 @@ template <int CPT> struct Cfg {
 	static constexpr int TILE = NCH * 16;
 	static constexpr int UPT = CPT + 1;
 	static constexpr int NUCAP = kT * UPT;
-	static constexpr int LIST_CAP = NCH / 4;
+	/* deleting chunks / dirty units listed per tile (~9 % of the chunks at P(00) = 3/16);
+	 * denser tiles take the unlisted paths.  Sized so that five CTAs fit an SM. */
+	static constexpr int LIST_CAP = NCH / 8 < 64 ? 64 : NCH / 8;
 };
 
 template <int CPT> struct __align__(128) Smem {
@@ -884,9 +886,11 @@ __global__ void __launch_bounds__(kT, MINB) scan5_kernel(const ScanArgs a)
  * Finalize: order the event records by tile, pair every start code with the next event, derive
  * the RBSP lengths from the prefix of per-tile EPB counts, fill the NAL table and the result.
  * Three small kernels (~1 % of the scan):
- *   fin_tiles   one CTA: exclusive prefix over the tiles of (events, start codes, EPBs)
- *   fin_order   a thread per tile: its events -> ordered array, with NAL index and EPB prefix
- *   fin_table   a thread per ordered event: table entries; thread 0 of block 0: the result
+ *   fin_tiles   a tile per thread: block-local exclusive prefix of (events, start codes, EPBs)
+ *   fin_order   a tile per thread: + earlier blocks' totals; events -> ordered array with NAL
+ *               index and EPB prefix
+ *   fin_head    totals and the result fields that need no reduction
+ *   fin_table   a thread per ordered event: table entries, RBSP byte sum
  */
 struct FinArgs {
 	const uint64_t *desc; /* 4 words per tile */
@@ -896,7 +900,8 @@ struct FinArgs {
 	uint64_t ev_cap;
 	uint64_t *ordered;  /* 3 words per event: record, EPB prefix, NAL index */
 	uint64_t *tile_pre; /* 2 words per tile: ev_off | sc_off << 32, EPB prefix */
-	uint64_t *totals;   /* 4 words: events, start codes, EPBs, RBSP byte sum */
+	uint64_t *totals;   /* 4 words: events, start codes, EPBs, spare */
+	uint64_t *blk_tot;  /* 3 words per fin_tiles block */
 	uint64_t len, base;
 	uint64_t *nal_start, *nal_end, *nal_rbsp, *nal_rbsp_len;
 	uint64_t nal_cap;
@@ -906,19 +911,18 @@ struct FinArgs {
 
 constexpr int kFinT = 1024;
 
+/* a tile per thread, kFinT tiles per block: block-local exclusive prefix + block totals */
 __global__ void __launch_bounds__(kFinT, 1) fin_tiles(const FinArgs f)
 {
 	__shared__ uint64_t sh[kFinT][3];
 	const uint32_t tid = threadIdx.x;
-	const uint32_t per = (f.num_tiles + kFinT - 1) / kFinT;
-	const uint32_t t0 = tid * per < f.num_tiles ? tid * per : f.num_tiles;
-	const uint32_t t1 = t0 + per < f.num_tiles ? t0 + per : f.num_tiles;
+	const uint64_t t = (uint64_t)blockIdx.x * kFinT + tid;
 	uint64_t nev = 0, nsc = 0, epb = 0;
-	for (uint32_t t = t0; t < t1; t++) {
-		const uint64_t ev = f.desc[(uint64_t)t * 4 + 2];
-		nev += (ev >> 32) & 0xffffu;
-		nsc += (ev >> 48) & 0x7fffu;
-		epb += f.desc[(uint64_t)t * 4 + 3] & 0xffffffffull;
+	if (t < f.num_tiles) {
+		const uint64_t ev = f.desc[t * 4 + 2];
+		nev = (ev >> 32) & 0xffffu;
+		nsc = (ev >> 48) & 0x7fffu;
+		epb = f.desc[t * 4 + 3] & 0xffffffffull;
 	}
 	sh[tid][0] = nev;
 	sh[tid][1] = nsc;
@@ -937,26 +941,44 @@ __global__ void __launch_bounds__(kFinT, 1) fin_tiles(const FinArgs f)
 		sh[tid][2] += x2;
 		__syncthreads();
 	}
-	uint64_t e = sh[tid][0] - nev, c = sh[tid][1] - nsc, g = sh[tid][2] - epb;
-	for (uint32_t t = t0; t < t1; t++) {
-		const uint64_t ev = f.desc[(uint64_t)t * 4 + 2];
-		f.tile_pre[2 * (uint64_t)t] = e | c << 32;
-		f.tile_pre[2 * (uint64_t)t + 1] = g;
-		e += (ev >> 32) & 0xffffu;
-		c += (ev >> 48) & 0x7fffu;
-		g += f.desc[(uint64_t)t * 4 + 3] & 0xffffffffull;
+	if (t < f.num_tiles) {
+		f.tile_pre[2 * t] = (sh[tid][0] - nev) | (sh[tid][1] - nsc) << 32;
+		f.tile_pre[2 * t + 1] = sh[tid][2] - epb;
 	}
 	if (tid == kFinT - 1) {
-		f.totals[0] = sh[tid][0];
-		f.totals[1] = sh[tid][1];
-		f.totals[2] = sh[tid][2];
-		f.totals[3] = 0;
+		f.blk_tot[3 * (uint64_t)blockIdx.x] = sh[tid][0];
+		f.blk_tot[3 * (uint64_t)blockIdx.x + 1] = sh[tid][1];
+		f.blk_tot[3 * (uint64_t)blockIdx.x + 2] = sh[tid][2];
 	}
 }
 
+/* a tile per thread (256 per block, all inside one fin_tiles block): add the totals of the
+ * earlier fin_tiles blocks, then write the tile's events to their ordered places */
 __global__ void __launch_bounds__(256) fin_order(const FinArgs f)
 {
+	__shared__ uint64_t grp[3];
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t g = (blockIdx.x * blockDim.x) / kFinT; /* earlier fin_tiles blocks */
+	if (threadIdx.x < 32) {
+		uint64_t a0 = 0, a1 = 0, a2 = 0;
+		for (uint32_t j = threadIdx.x; j < g; j += 32) {
+			a0 += f.blk_tot[3 * (uint64_t)j];
+			a1 += f.blk_tot[3 * (uint64_t)j + 1];
+			a2 += f.blk_tot[3 * (uint64_t)j + 2];
+		}
+#pragma unroll
+		for (int d = 16; d >= 1; d >>= 1) {
+			a0 += __shfl_xor_sync(FULL_MASK, a0, d);
+			a1 += __shfl_xor_sync(FULL_MASK, a1, d);
+			a2 += __shfl_xor_sync(FULL_MASK, a2, d);
+		}
+		if (threadIdx.x == 0) {
+			grp[0] = a0;
+			grp[1] = a1;
+			grp[2] = a2;
+		}
+	}
+	__syncthreads();
 	if (t >= f.num_tiles)
 		return;
 	const uint64_t ev = f.desc[(uint64_t)t * 4 + 2];
@@ -965,14 +987,14 @@ __global__ void __launch_bounds__(256) fin_order(const FinArgs f)
 		return;
 	const uint64_t basei = ev & 0xffffffffull;
 	const uint64_t pre = f.tile_pre[2 * (uint64_t)t];
-	const uint64_t e = pre & 0xffffffffull, g = f.tile_pre[2 * (uint64_t)t + 1];
-	uint64_t k = pre >> 32;
+	const uint64_t e = (pre & 0xffffffffull) + grp[0], gp = f.tile_pre[2 * (uint64_t)t + 1] + grp[2];
+	uint64_t k = (pre >> 32) + grp[1];
 	for (uint32_t i = 0; i < n; i++) {
 		if (e + i >= f.ev_cap || basei + i >= f.ev_cap)
 			break;
 		const uint64_t rec = f.evbuf[basei + i];
 		f.ordered[3 * (e + i)] = rec;
-		f.ordered[3 * (e + i) + 1] = g + ((rec >> 40) & 0x3fffffu);
+		f.ordered[3 * (e + i) + 1] = gp + ((rec >> 40) & 0x3fffffu);
 		f.ordered[3 * (e + i) + 2] = k;
 		k += (rec >> 62) & 1;
 	}
@@ -1028,7 +1050,17 @@ __global__ void __launch_bounds__(256) fin_table(const FinArgs f)
 /* result fields that need no reduction; runs before fin_table (which adds the RBSP sum) */
 __global__ void fin_head(const FinArgs f)
 {
-	const uint64_t total_ev = f.totals[0], total_sc = f.totals[1], total_epb = f.totals[2];
+	uint64_t total_ev = 0, total_sc = 0, total_epb = 0;
+	const uint32_t nblk = (f.num_tiles + kFinT - 1) / kFinT;
+	for (uint32_t j = 0; j < nblk; j++) {
+		total_ev += f.blk_tot[3 * (uint64_t)j];
+		total_sc += f.blk_tot[3 * (uint64_t)j + 1];
+		total_epb += f.blk_tot[3 * (uint64_t)j + 2];
+	}
+	f.totals[0] = total_ev;
+	f.totals[1] = total_sc;
+	f.totals[2] = total_epb;
+	f.totals[3] = 0;
 	const uint64_t nordered = total_ev < f.ev_cap ? total_ev : f.ev_cap;
 	struct h264gpu_scan_result r;
 	r.n_nal = total_sc;
@@ -1063,7 +1095,7 @@ __global__ void fin_head(const FinArgs f)
 #ifndef H264_EMU
 static inline cudaError_t launch_finalize(const FinArgs &f, uint64_t ev_bound, cudaStream_t st)
 {
-	fin_tiles<<<1, kFinT, 0, st>>>(f);
+	fin_tiles<<<(f.num_tiles + kFinT - 1) / kFinT, kFinT, 0, st>>>(f);
 	fin_order<<<(f.num_tiles + 255) / 256, 256, 0, st>>>(f);
 	fin_head<<<1, 1, 0, st>>>(f);
 	const uint64_t nb = (ev_bound + 255) / 256;

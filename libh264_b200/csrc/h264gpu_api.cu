@@ -412,11 +412,11 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 	}
 	if (len >= (1ull << 40))
 		return -E2BIG;
-	/* tile shape: 84 = 8 chunks/thread, 4 CTAs/SM (default); 45 / 46 = 4 chunks, 5 / 6 CTAs */
-	int shape = 84;
+	/* tile shape: 85 = 8 chunks/thread, 5 CTAs/SM (default); 84: 4 CTAs; 45 / 46 = 4 chunks, 5 / 6 CTAs */
+	int shape = 85;
 	{
 		const char *e = getenv("H264GPU_SCAN5_SHAPE");
-		if (e != NULL && (atoi(e) == 45 || atoi(e) == 46 || atoi(e) == 85))
+		if (e != NULL && (atoi(e) == 45 || atoi(e) == 46 || atoi(e) == 84))
 			shape = atoi(e);
 	}
 	const int CPT = shape / 10;
@@ -434,7 +434,8 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 	const size_t ev_off = pre_off + (size_t)ntiles * 16;
 	const size_t ord_off = ev_off + (size_t)ev_cap * 8;
 	const size_t tot_off = ord_off + (size_t)ev_cap * 24;
-	const size_t need = tot_off + 64;
+	const size_t blk_off = tot_off + 64;
+	const size_t need = blk_off + ((size_t)ntiles / annexb5::kFinT + 1) * 24;
 	r = h264gpu_ws_reserve(ctx, need);
 	if (r < 0)
 		return r;
@@ -482,10 +483,10 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 		if (strip5) SCAN5_LAUNCH(4, true, 5); else SCAN5_LAUNCH(4, false, 5);
 	} else if (shape == 46) {
 		if (strip5) SCAN5_LAUNCH(4, true, 6); else SCAN5_LAUNCH(4, false, 6);
-	} else if (shape == 85) {
-		if (strip5) SCAN5_LAUNCH(8, true, 5); else SCAN5_LAUNCH(8, false, 5);
-	} else {
+	} else if (shape == 84) {
 		if (strip5) SCAN5_LAUNCH(8, true, 4); else SCAN5_LAUNCH(8, false, 4);
+	} else {
+		if (strip5) SCAN5_LAUNCH(8, true, 5); else SCAN5_LAUNCH(8, false, 5);
 	}
 #undef SCAN5_LAUNCH
 	CU_TRY(cudaGetLastError());
@@ -500,6 +501,7 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 	f.ordered = (uint64_t *)((uint8_t *)ctx->ws + ord_off);
 	f.tile_pre = (uint64_t *)((uint8_t *)ctx->ws + pre_off);
 	f.totals = (uint64_t *)((uint8_t *)ctx->ws + tot_off);
+	f.blk_tot = (uint64_t *)((uint8_t *)ctx->ws + blk_off);
 	f.len = len;
 	f.base = base;
 	f.nal_start = d_nal_start;

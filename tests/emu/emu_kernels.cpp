@@ -95,6 +95,7 @@ extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t
 	std::vector<uint64_t> desc((size_t)ntiles * 4, ~0ull), pre((size_t)ntiles * 2, 0);
 	std::vector<uint64_t> evbuf(ev_cap ? ev_cap : 1, 0), ordered(3 * (ev_cap ? ev_cap : 1), 0);
 	uint64_t totals[4] = {0, 0, 0, 0};
+	std::vector<uint64_t> blk_tot(3 * ((size_t)ntiles / annexb5::kFinT + 1), 0);
 	uint32_t ctrl[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
 	memset(result, 0xff, sizeof(*result));
 	uint8_t *buf = (uint8_t *)aligned_alloc(16, (len + 15) & ~15ull);
@@ -143,6 +144,7 @@ extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t
 	f.ordered = ordered.data();
 	f.tile_pre = pre.data();
 	f.totals = totals;
+	f.blk_tot = blk_tot.data();
 	f.len = len;
 	f.base = base;
 	f.nal_start = nal_start;
@@ -155,7 +157,8 @@ extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t
 	f.strip = rbsp ? 1 : 0;
 	f.assume_in = (uint32_t)assume_in;
 	dim3 g1(1), b1(annexb5::kFinT), b256(256), one(1);
-	EMU_LAUNCH((annexb5::fin_tiles), g1, b1, f);
+	dim3 gft((ntiles + annexb5::kFinT - 1) / annexb5::kFinT);
+	EMU_LAUNCH((annexb5::fin_tiles), gft, b1, f);
 	dim3 gt((ntiles + 255) / 256);
 	EMU_LAUNCH((annexb5::fin_order), gt, b256, f);
 	EMU_LAUNCH((annexb5::fin_head), g1, one, f);

@@ -46,5 +46,26 @@ def main():
         print(name, len(stream), "bytes", nmb, "mbs", nsl, "slices")
 
 
+def main_cabac():
+    """CABAC twins: a CAVLC stream parsed by the reference, its ctx->mb syntax elements re-coded
+    as CABAC (tests/test_cabac.py make_twin); the fixture holds the CABAC blob, the parameter
+    blocks and the REFERENCE's records, so the parse is checked against reference output even
+    where oracle/_ref is not available."""
+    import test_cabac as TC
+    cases = {
+        "main_b": dict(width_mbs=8, height_mbs=6, frames=6, slices_per_frame=2, profile_idc=77, transform_8x8=0,
+                       b_frames=1, num_ref_frames=2, idr_period=3, pct_skip=30, coef_density=40, seed=41),
+        "high_t8_pcm": dict(width_mbs=7, height_mbs=5, frames=6, slices_per_frame=1, profile_idc=100,
+                            transform_8x8=1, b_frames=1, num_ref_frames=3, idr_period=3, pct_skip=20,
+                            coef_density=50, pct_pcm=40, seed=42),
+    }
+    for name, cfg in cases.items():
+        blob, params, ref_mbs = TC.make_twin(cfg)
+        np.savez_compressed(os.path.join(HERE, "cabac_twin_%s.npz" % name), blob=blob,
+                            params=params.view(np.uint8), mbs=ref_mbs)
+        print("cabac twin", name, len(blob), "bytes", len(ref_mbs), "mbs", len(params), "slices")
+
+
 if __name__ == "__main__":
     main()
+    main_cabac()

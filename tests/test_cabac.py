@@ -223,6 +223,22 @@ def test_twin_stream_matches_reference_records(cfg):
     assert (res["end_bit"] > (params["nal_len"].astype(np.uint64) - 1) * 8).all()
 
 
+GOLDEN = ["main_b", "high_t8_pcm"]
+
+
+def load_golden_twin(name):
+    g = np.load(os.path.join(HERE, "golden", "cabac_twin_%s.npz" % name))
+    return g["blob"], g["params"], g["mbs"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_twin_fixture(name):
+    """Committed fixture (tests/golden/make_golden.py): CABAC blob + the reference's records."""
+    blob, params, ref_mbs = load_golden_twin(name)
+    recs, res = cpu_decode(blob, params, len(ref_mbs))
+    assert (res["status"] == 0).all() and np.array_equal(recs, ref_mbs)
+
+
 # ---- 4. generator round trip ------------------------------------------------------------------
 
 @pytest.mark.parametrize("cfg", CFGS, ids=lambda c: "seed%d" % c["seed"])
@@ -281,6 +297,14 @@ def test_gpu_twin_stream_matches_reference_records(gpu, cfg):
     recs, res = gpu.cabac_parse_host(blob, params.view(np.uint8), len(ref_mbs))
     assert (res["status"] == 0).all()
     assert np.array_equal(recs, ref_mbs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN)
+def test_gpu_golden_twin_fixture(gpu, name):
+    blob, params, ref_mbs = load_golden_twin(name)
+    recs, res = gpu.cabac_parse_host(blob, params, len(ref_mbs))
+    assert (res["status"] == 0).all() and np.array_equal(recs, ref_mbs)
 
 
 @pytest.mark.gpu

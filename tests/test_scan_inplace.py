@@ -78,6 +78,14 @@ def test_emu_long_nal_crosses_many_tiles():
     run_emu(buf, 1, "long")
 
 
+def test_emu_more_tiles_than_one_finalize_block():
+    """> 1024 tiles: the tile prefix of the finalize step spans several blocks."""
+    rng = np.random.default_rng(9)
+    buf = S.gen_annexb(rng, 1500, lo=64, hi=20000)
+    assert len(buf) > 1100 * 4096
+    run_emu(buf, 1, "finalize blocks")
+
+
 def test_emu_seams_at_every_offset():
     """A start code / EPB / terminator sliding over a tile seam (4 KiB tiles)."""
     for pat in ([0, 0, 1, 0x65, 0, 0, 3, 1], [0, 0, 0, 1, 0x41], [0, 0, 3, 0, 0, 3], [0, 0, 0, 0, 0, 1, 5]):
