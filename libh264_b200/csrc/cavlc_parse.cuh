@@ -156,7 +156,7 @@ __device__ __forceinline__ void br_skip(BitReader &b, int n)
 	b.nbits -= n;
 }
 
-__device__ __forceinline__ uint32_t br_get(BitReader &b, int n)
+__device__ __noinline__ uint32_t br_get(BitReader &b, int n)
 {
 	uint32_t v = br_peek(b, n);
 	br_skip(b, n);
@@ -179,13 +179,13 @@ __device__ __noinline__ uint32_t br_ue(BitReader &b)
 	return br_get(b, lz + 1) - 1;
 }
 
-__device__ __forceinline__ int32_t br_se(BitReader &b)
+__device__ __noinline__ int32_t br_se(BitReader &b)
 {
 	uint32_t u = br_ue(b);
 	return (u & 1) ? (int32_t)((u + 1) >> 1) : -(int32_t)(u >> 1);
 }
 
-__device__ __forceinline__ uint32_t br_te(BitReader &b, uint32_t max)
+__device__ __noinline__ uint32_t br_te(BitReader &b, uint32_t max)
 {
 	if (max == 1)
 		return br_get(b, 1) ^ 1;
@@ -258,7 +258,7 @@ struct SliceCtx {
 	uint64_t hash;
 };
 
-__device__ __forceinline__ void hash_add(SliceCtx &s, uint32_t field, uint32_t idx, int64_t v)
+__device__ __noinline__ void hash_add(SliceCtx &s, uint32_t field, uint32_t idx, int64_t v)
 {
 	/* device-side twin of h264gpu_mb_hash_term (include/h264gpu_slice.h) */
 	if (v != 0) {
