@@ -158,7 +158,25 @@ def mb_parse_leg(g, L, frames, steps, warmup, rank, with_cpu, cabac=False):
     cfg = dict(MB_CFG, seed=MB_CFG["seed"] + rank)
     if cabac:
         cfg.update(profile_idc=77, transform_8x8=0, entropy_cabac=1)
+    reps = 1
+    if cabac and frames > 250:
+        # the CABAC generator is single-threaded (~0.08 s per frame): generate 250 frames and lay
+        # `reps` copies of them end to end (separate memory, separate slices; said in "workload")
+        reps, frames = (frames + 249) // 250, 250
     stream, nmb, nsl, params = L.synth_video(frames=frames, want_params=True, **cfg)
+    if reps > 1:
+        P = np.frombuffer(params, L.SLICE_PARAMS)
+        pad = (-len(stream)) % 16
+        one = np.concatenate([stream, np.zeros(pad, np.uint8)])
+        allp = []
+        for k in range(reps):
+            q = P.copy()
+            q["nal_off"] += k * len(one)
+            q["mb_out_off"] += k * nmb
+            allp.append(q)
+        stream = np.tile(one, reps)
+        params = np.concatenate(allp).view(np.uint8)
+        nmb, nsl, frames = nmb * reps, nsl * reps, frames * reps
     d_stream = g.alloc(len(stream) + 16)
     d_stream.upload(stream)
     d_params = g.alloc(len(params))
@@ -186,9 +204,10 @@ def mb_parse_leg(g, L, frames, steps, warmup, rank, with_cpu, cabac=False):
     t1 = time.perf_counter()
     recs, res2 = parse_host(stream, params, nmb)
     e2e_s = time.perf_counter() - t1
-    out = {"workload": "%s, 16 slices/frame, %d frames (%d slices, %d MBs, %.1f MB stream)"
+    out = {"workload": "%s, 16 slices/frame, %d frames%s (%d slices, %d MBs, %.1f MB stream)"
                        % ("CABAC 1080p Main (BASELINE config 3 shape)" if cabac else "CAVLC 1080p High",
-                          frames, nsl, nmb, len(stream) / 1e6),
+                          frames, " = %d copies of 250 generated frames" % reps if reps > 1 else "",
+                          nsl, nmb, len(stream) / 1e6),
            "kernel": "cabac::cabac_parse_kernel" if cabac else "cavlc::cavlc_parse_kernel",
            "macroblocks_per_s": nmb / (ms / 1e3), "ms_per_step": ms, "parity_counts_ok": ok,
            "e2e_macroblocks_per_s": nmb / e2e_s,
@@ -280,7 +299,7 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "annexb_scan_strip", "sample_mib": len(stream) >> 20,
+        "config": {"workload": "annexb_scan_strip (BASELINE config 2)", "sample_mib": len(stream) >> 20,
                    "full_size_mib_per_gpu": args.size_mb, "nal_bytes": "loguniform[64,262144]",
                    "p_zero": 0.1875},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
@@ -302,7 +321,7 @@ def main():
     ap.add_argument("--scan-gen", type=int, default=5, choices=[2, 5],
                     help="5: RBSP in place per NAL (h264gpu_split_strip_inplace_dev); 2: packed RBSP")
     ap.add_argument("--mb-frames", type=int, default=1000, help="frames of the macroblock-parse workload")
-    ap.add_argument("--cabac-frames", type=int, default=250,
+    ap.add_argument("--cabac-frames", type=int, default=1000,
                     help="frames of the CABAC macroblock-parse workload (0 = skip)")
     ap.add_argument("--frame-mb", type=int, default=1024,
                     help="MiB of RBSP payloads for the writer leg (BASELINE config 5; 0 = skip)")
