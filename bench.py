@@ -143,6 +143,8 @@ MB_CFG = dict(width_mbs=120, height_mbs=68, slices_per_frame=16, profile_idc=100
 
 
 def SCAN_KERNEL_NAME(gen=2):
+    if gen == 6:
+        return "annexb6::scan6_kernel<8,strip> + fin_tiles/fin_order/fin_head/fin_table (RBSP in place per NAL, warp-autonomous tiles)"
     if gen == 5:
         return "annexb5::scan5_kernel<8,strip> + fin_tiles/fin_order/fin_head/fin_table (RBSP in place per NAL)"
     it = int(os.environ.get("H264GPU_SCAN_ITEMS", "108"))
@@ -318,14 +320,17 @@ def main():
     ap.add_argument("--size-mb", type=int, default=4096, help="input MiB per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--scan-gen", type=int, default=5, choices=[2, 5],
-                    help="5: RBSP in place per NAL (h264gpu_split_strip_inplace_dev); 2: packed RBSP")
+    ap.add_argument("--scan-gen", type=int, default=6, choices=[2, 5, 6],
+                    help="6 / 5: RBSP in place per NAL (h264gpu_split_strip_inplace_dev; 6 = warp-autonomous "
+                         "tiles, 5 = block-wide unit binning); 2: packed RBSP")
     ap.add_argument("--mb-frames", type=int, default=1000, help="frames of the macroblock-parse workload")
     ap.add_argument("--cabac-frames", type=int, default=1000,
                     help="frames of the CABAC macroblock-parse workload (0 = skip)")
     ap.add_argument("--frame-mb", type=int, default=1024,
                     help="MiB of RBSP payloads for the writer leg (BASELINE config 5; 0 = skip)")
     args = ap.parse_args()
+    if args.scan_gen >= 5:
+        os.environ["H264GPU_INPLACE_GEN"] = str(args.scan_gen)
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -402,7 +407,7 @@ def main():
             edge.has_right, edge.right[0], edge.right[1] = 1, int(allh[rank + 1][0]), int(allh[rank + 1][1])
 
     def step():
-        if args.scan_gen == 5:
+        if args.scan_gen >= 5:
             g.split_strip_inplace_dev(d_in.ptr, n_in, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8,
                                       d_tab.ptr + cap * 16, d_tab.ptr + cap * 24, cap, d_res.ptr,
                                       base=rank * n_in, edge=edge)

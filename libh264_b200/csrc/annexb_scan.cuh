@@ -59,6 +59,7 @@ struct ScanArgs {
 	uint32_t *ev_cursor; /* pre-set to 0xffffffff */
 	uint64_t *evbuf;
 	uint64_t ev_cap;
+	uint32_t flags; /* gen 6 tuning: 1 = one tile per CTA (grid = tiles), 2 = no L2 prefetch */
 };
 
 /* 0x80 in every byte of x that is zero, exact */

@@ -24,6 +24,14 @@ static inline void bulk_load_start(void *sdst, const void *gsrc, uint32_t bytes,
 	memcpy(sdst, gsrc, bytes);
 }
 static inline void bulk_load_wait(uint64_t *bar) { (void)bar; }
+static inline void bulk_bar_init(uint64_t *bar) { (void)bar; }
+static inline void bulk_load_issue(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+	(void)bar;
+	memcpy(sdst, gsrc, bytes);
+}
+static inline void bulk_load_wait_parity(uint64_t *bar, uint32_t parity) { (void)bar; (void)parity; }
+static inline void l2_prefetch(const void *gsrc, uint32_t bytes) { (void)gsrc; (void)bytes; }
 static inline void spin_pause(unsigned ns) { (void)ns; }
 static inline uint4 ldcg16(const void *p) { return *(const uint4 *)p; }
 static inline uint32_t ldcg_u32(const void *p) { return *(const volatile uint32_t *)p; }
@@ -139,8 +147,60 @@ __device__ __forceinline__ void bulk_load_wait(uint64_t *bar)
 		     "}" ::"r"(b)
 		     : "memory");
 }
+/* the same split up for a barrier that is reused tile after tile (persistent CTAs): init once,
+ * then arm + copy per tile and wait on the phase parity (0, 1, 0, ...) */
+__device__ __forceinline__ void bulk_bar_init(uint64_t *bar)
+{
+	const uint32_t b = smem_u32(bar);
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_issue(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+	const uint32_t b = smem_u32(bar), d = smem_u32(sdst);
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes)
+		     : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+		     "[%0], [%1], %2, [%3];" ::"r"(d),
+		     "l"(gsrc), "r"(bytes), "r"(b)
+		     : "memory");
+}
+__device__ __forceinline__ void bulk_load_wait_parity(uint64_t *bar, uint32_t parity)
+{
+	const uint32_t b = smem_u32(bar);
+	asm volatile("{\n"
+		     ".reg .pred p;\n"
+		     "BULK_WAITP:\n"
+		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		     "@p bra BULK_DONEP;\n"
+		     "bra BULK_WAITP;\n"
+		     "BULK_DONEP:\n"
+		     "}" ::"r"(b),
+		     "r"(parity)
+		     : "memory");
+}
+/* pull a range of global memory into L2 ahead of its bulk load */
+__device__ __forceinline__ void l2_prefetch(const void *gsrc, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 #endif
 
 #define FULL_MASK 0xffffffffu
+
+/* OR of a value over the warp (all lanes take part) */
+#ifdef H264_EMU
+static inline uint32_t warp_or(uint32_t v)
+{
+	for (int d = 16; d >= 1; d >>= 1)
+		v |= __shfl_xor_sync(FULL_MASK, v, d);
+	return v;
+}
+#else
+__device__ __forceinline__ uint32_t warp_or(uint32_t v)
+{
+	return __reduce_or_sync(FULL_MASK, v);
+}
+#endif
 
 #endif /* H264GPU_COMPAT_H */

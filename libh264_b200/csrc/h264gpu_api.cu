@@ -9,6 +9,7 @@
 #include "annexb_scan.cuh"
 #include "annexb_scan2.cuh"
 #include "annexb_scan5.cuh"
+#include "annexb_scan6.cuh"
 
 extern "C" {
 
@@ -419,9 +420,18 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 		if (e != NULL && (atoi(e) == 45 || atoi(e) == 46 || atoi(e) == 84))
 			shape = atoi(e);
 	}
+	/* kernel generation: 6 = warp-autonomous tiles (annexb_scan6.cuh, default), 5 = block-wide
+	 * unit binning (annexb_scan5.cuh, kept as the A/B baseline) */
+	int gen = 6;
+	{
+		const char *e = getenv("H264GPU_INPLACE_GEN");
+		if (e != NULL && atoi(e) == 5)
+			gen = 5;
+	}
 	const int CPT = shape / 10;
-	const uint64_t tile = (uint64_t)annexb5::kT * CPT * 16;
-	const uint64_t ntiles = (len + tile - 1) / tile;
+	const uint64_t tile = gen == 6 ? (uint64_t)annexb6::Cfg<8>::TILE : (uint64_t)annexb5::kT * CPT * 16;
+	/* gen 6 owns a boundary event by its third byte: the launch covers the two edge bytes too */
+	const uint64_t ntiles = ((gen == 6 ? len + 2 : len) + tile - 1) / tile;
 	/* events: a start code and at most a few terminators per NAL in real streams */
 	uint64_t ev_cap = 4 * nal_cap + 4096;
 	if (ev_cap > len / 3 + 2)
@@ -479,7 +489,38 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 		annexb5::scan5_kernel<C, S, B><<<(uint32_t)ntiles, annexb5::kT, 0, st>>>(a);  \
 	} while (0)
 	const bool strip5 = d_rbsp != NULL;
-	if (shape == 45) {
+	if (gen == 6) {
+		/* persistent CTAs: one wave, every CTA takes tiles by ticket */
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+		auto grid6 = [](uint64_t nt, int cap) { return (uint32_t)(nt < (uint64_t)cap ? nt : (uint64_t)cap); };
+		{
+			const char *e = getenv("H264GPU_SCAN6_FLAGS");
+			a.flags = e != NULL ? (uint32_t)atoi(e) : 0u;
+			if (a.flags & 1u)
+				sms = 1 << 24; /* one tile per CTA */
+		}
+		int minb = 5;
+		{
+			const char *e = getenv("H264GPU_SCAN6_CTAS");
+			if (e != NULL && (atoi(e) == 4 || atoi(e) == 3))
+				minb = atoi(e);
+		}
+#define SCAN6_LAUNCH(S, B)                                                                    \
+	do {                                                                                  \
+		cudaFuncSetAttribute(annexb6::scan6_kernel<8, S, B>,                          \
+				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
+		annexb6::scan6_kernel<8, S, B><<<grid6(ntiles, sms * B), annexb6::kT, 0, st>>>(a); \
+	} while (0)
+		if (minb == 5) {
+			if (strip5) SCAN6_LAUNCH(true, 5); else SCAN6_LAUNCH(false, 5);
+		} else if (minb == 4) {
+			if (strip5) SCAN6_LAUNCH(true, 4); else SCAN6_LAUNCH(false, 4);
+		} else {
+			if (strip5) SCAN6_LAUNCH(true, 3); else SCAN6_LAUNCH(false, 3);
+		}
+#undef SCAN6_LAUNCH
+	} else if (shape == 45) {
 		if (strip5) SCAN5_LAUNCH(4, true, 5); else SCAN5_LAUNCH(4, false, 5);
 	} else if (shape == 46) {
 		if (strip5) SCAN5_LAUNCH(4, true, 6); else SCAN5_LAUNCH(4, false, 6);

@@ -17,7 +17,8 @@ n = len(stream); cap = len(offs) + 1024
 d_in = g.alloc(n + 16); d_in.upload(stream)
 d_rbsp = g.alloc(n + 16); d_tab = g.alloc(cap * 32); d_res = g.alloc(C.sizeof(L.ScanResult))
 for rep in range(3):
-    if gen == 5:
+    if gen >= 5:
+        os.environ["H264GPU_INPLACE_GEN"] = str(gen)
         g.split_strip_inplace_dev(d_in.ptr, n, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8, d_tab.ptr + cap * 16,
                                   d_tab.ptr + cap * 24, cap, d_res.ptr)
     else:
@@ -31,6 +32,13 @@ for k in range(4):
     d = (t[:, k + 1] - t[:, k]) / 1e3
     print("%-26s mean %7.2f  p10 %7.2f  p50 %7.2f  p90 %7.2f  p99 %7.2f us" %
           (names[k], d.mean(), *np.percentile(d, [10, 50, 90, 99])))
+if gen == 6:
+    # marks: 0 ticket, 1 loaded, 5 classified, 6 prefix + event walk, 2 after barrier 2, 3 look-back
+    # done, 7 row loop done (warp 0), 4 end
+    for nm, x, y in (("load wait", 0, 1), ("classify (warp 0)", 1, 5), ("prefix + walk (warp 0)", 5, 6), ("emit (warp 0)", 3, 4),
+                     ("barrier 2 wait", 6, 2), ("aggregate + look-back", 2, 3)):
+        d = (t[:, y] - t[:, x]) / 1e3
+        print("  %-26s mean %7.2f  p50 %7.2f  p90 %7.2f us" % (nm, d.mean(), *np.percentile(d, [50, 90])))
 if gen == 5:
     for nm, x, y in (("seg table+premark+bin", 3, 5), ("T scan", 5, 6), ("clean copy (tid 0)", 6, 7), ("dirty+edges (tid 0)", 7, 4)):
         d = (t[:, y] - t[:, x]) / 1e3

@@ -6,6 +6,7 @@
 #include "annexb_scan.cuh"
 #include "annexb_scan2.cuh"
 #include "annexb_scan5.cuh"
+#include "annexb_scan6.cuh"
 #include "annexb_frame.cuh"
 
 #include <vector>
@@ -90,8 +91,11 @@ extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t
 	using namespace annexb;
 	if (len == 0)
 		return -1;
-	const uint64_t tile = (uint64_t)annexb5::kT * cpt * 16;
-	const uint32_t ntiles = (uint32_t)((len + tile - 1) / tile);
+	/* cpt 6x selects the sixth-generation kernel with x 512-byte rows per warp */
+	const bool gen6 = cpt >= 60;
+	const int rows = cpt % 10;
+	const uint64_t tile = gen6 ? (uint64_t)annexb6::kT * rows * 16 : (uint64_t)annexb5::kT * cpt * 16;
+	const uint32_t ntiles = (uint32_t)(((gen6 ? len + 2 : len) + tile - 1) / tile);
 	std::vector<uint64_t> desc((size_t)ntiles * 4, ~0ull), pre((size_t)ntiles * 2, 0);
 	std::vector<uint64_t> evbuf(ev_cap ? ev_cap : 1, 0), ordered(3 * (ev_cap ? ev_cap : 1), 0);
 	uint64_t totals[4] = {0, 0, 0, 0};
@@ -125,7 +129,20 @@ extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t
 		assume_in = edge->assume_in;
 	}
 	dim3 grid(ntiles), block(annexb5::kT);
-	if (rbsp) {
+	if (gen6) {
+		/* persistent CTAs: a few of them share the tiles (the emulator runs them one after
+		 * the other, so the first takes every ticket and the others find none) */
+		grid = dim3(ntiles < 3 ? ntiles : 3);
+		if (rbsp) {
+			if (rows == 1) EMU_LAUNCH((annexb6::scan6_kernel<1, true, 1>), grid, block, a);
+			else if (rows == 2) EMU_LAUNCH((annexb6::scan6_kernel<2, true, 1>), grid, block, a);
+			else EMU_LAUNCH((annexb6::scan6_kernel<8, true, 1>), grid, block, a);
+		} else {
+			if (rows == 1) EMU_LAUNCH((annexb6::scan6_kernel<1, false, 1>), grid, block, a);
+			else if (rows == 2) EMU_LAUNCH((annexb6::scan6_kernel<2, false, 1>), grid, block, a);
+			else EMU_LAUNCH((annexb6::scan6_kernel<8, false, 1>), grid, block, a);
+		}
+	} else if (rbsp) {
 		if (cpt == 1) EMU_LAUNCH((annexb5::scan5_kernel<1, true, 1>), grid, block, a);
 		else if (cpt == 2) EMU_LAUNCH((annexb5::scan5_kernel<2, true, 1>), grid, block, a);
 		else EMU_LAUNCH((annexb5::scan5_kernel<8, true, 1>), grid, block, a);

@@ -39,7 +39,7 @@ def run_emu(buf, cpt, what):
     assert np.array_equal(g["start"], exp["start"]) and np.array_equal(g["end"], exp["end"])
 
 
-@pytest.mark.parametrize("cpt", [1, 2, 8])
+@pytest.mark.parametrize("cpt", [1, 2, 8, 61, 62, 68])
 def test_emu_random_streams(cpt):
     rng = np.random.default_rng(100 + cpt)
     for it in range(12):
@@ -49,7 +49,7 @@ def test_emu_random_streams(cpt):
         run_emu(buf, cpt, ("random", cpt, it))
 
 
-@pytest.mark.parametrize("cpt", [1, 8])
+@pytest.mark.parametrize("cpt", [1, 8, 61, 68])
 def test_emu_pathological_streams(cpt):
     rng = np.random.default_rng(7)
     for it in range(20):
@@ -68,38 +68,43 @@ def test_emu_pathological_streams(cpt):
         run_emu(buf, cpt, ("patho", cpt, it))
 
 
-def test_emu_long_nal_crosses_many_tiles():
+@pytest.mark.parametrize("cpt", [1, 61])
+def test_emu_long_nal_crosses_many_tiles(cpt):
     """One NAL over > 32 tiles: the look-back has to walk more than one window, and tiles
     without a start code chain their shifts."""
     rng = np.random.default_rng(3)
     body = rng.choice(np.array([0, 0, 3, 7, 9], np.uint8), 4096 * 70)
     buf = np.concatenate([np.array([9, 9, 0, 0, 1, 0x65], np.uint8), S.oracle_insert(body),
                           np.array([0, 0, 0, 1, 0x41, 1, 2, 3], np.uint8)])
-    run_emu(buf, 1, "long")
+    run_emu(buf, cpt, "long")
 
 
-def test_emu_more_tiles_than_one_finalize_block():
+@pytest.mark.parametrize("cpt", [1, 61])
+def test_emu_more_tiles_than_one_finalize_block(cpt):
     """> 1024 tiles: the tile prefix of the finalize step spans several blocks."""
     rng = np.random.default_rng(9)
     buf = S.gen_annexb(rng, 1500, lo=64, hi=20000)
     assert len(buf) > 1100 * 4096
-    run_emu(buf, 1, "finalize blocks")
+    run_emu(buf, cpt, "finalize blocks")
 
 
-def test_emu_seams_at_every_offset():
-    """A start code / EPB / terminator sliding over a tile seam (4 KiB tiles)."""
+@pytest.mark.parametrize("cpt", [1, 61, 62])
+def test_emu_seams_at_every_offset(cpt):
+    """A start code / EPB / terminator sliding over a tile seam (4 KiB tiles; for gen 6 also a
+    warp-span seam and, with 62, a row seam inside a span)."""
     for pat in ([0, 0, 1, 0x65, 0, 0, 3, 1], [0, 0, 0, 1, 0x41], [0, 0, 3, 0, 0, 3], [0, 0, 0, 0, 0, 1, 5]):
         for shift in range(0, 12):
             buf = np.full(4096 * 2 + 64, 0x55, np.uint8)
             buf[:4] = [0, 0, 1, 0x67]
             pos = 4096 - 8 + shift
             buf[pos:pos + len(pat)] = pat
-            run_emu(buf, 1, (pat, shift))
+            run_emu(buf, cpt, (pat, shift))
 
 
-def test_emu_event_buffer_overflow_is_reported():
+@pytest.mark.parametrize("cpt", [1, 61])
+def test_emu_event_buffer_overflow_is_reported(cpt):
     buf = np.tile(np.array([0, 0, 1, 7], np.uint8), 400)
-    g = S.emu_split_strip_inplace(buf, cpt=1, ev_cap=16)
+    g = S.emu_split_strip_inplace(buf, cpt=cpt, ev_cap=16)
     assert g["res"].n_nal == 400 and g["res"].reserved == 1
 
 
@@ -156,9 +161,10 @@ def check_merged(g, o, what):
     assert g["final_off"] == o["final_off"] and g["rbsp_bytes"] == len(o["rbsp"]), what
 
 
-def test_emu_sharded_scan_merges_to_whole():
+@pytest.mark.parametrize("cpt", [1, 61])
+def test_emu_sharded_scan_merges_to_whole(cpt):
     rng = np.random.default_rng(5)
-    run = lambda buf, e, lo: S.emu_split_strip_inplace(buf, cpt=1, edge=e, base=lo)
+    run = lambda buf, e, lo: S.emu_split_strip_inplace(buf, cpt=cpt, edge=e, base=lo)
     for it in range(12):
         b = S.gen_annexb(rng, 30, 1, 3000) if it % 2 else rng.choice(ALPHA, int(rng.integers(200, 20000)))
         n = len(b)
@@ -169,6 +175,39 @@ def test_emu_sharded_scan_merges_to_whole():
     body = rng.choice(np.array([0, 0, 3, 7], np.uint8), 9000)
     b = np.concatenate([np.array([0, 0, 1, 0x65], np.uint8), S.oracle_insert(body), np.array([0, 0, 1, 9], np.uint8)])
     check_merged(_merge_shards(run, b, [2048, 4096, 6000 // 16 * 16]), S.oracle_split_strip(b), "through")
+
+
+def test_emu_gen6_row_and_span_seams_and_shard_ends():
+    """Gen 6 specifics: patterns sliding over a row seam inside a span (62: rows of 512 B, spans of
+    1 KiB, tiles of 8 KiB), streams ending within +-3 bytes of a tile multiple (the launch covers
+    len + 2 bytes because events are owned by their third byte), and a shard cut exactly at a
+    tile multiple with the start code straddling it."""
+    pats = ([0, 0, 1, 0x65, 0, 0, 3, 1], [0, 0, 0, 1, 0x41], [0, 0, 3, 0, 0, 3, 0, 0, 3, 0, 0, 3], [0, 0, 0, 0, 0, 1, 5])
+    for pat in pats:
+        for seam in (512, 1024):
+            for shift in range(0, 14):
+                buf = np.full(8192 + 100, 0x55, np.uint8)
+                buf[:4] = [0, 0, 1, 0x67]
+                buf[100:106] = [0, 0, 3, 0, 0, 3]  # a non-zero shift before the seam
+                pos = seam - 10 + shift
+                buf[pos:pos + len(pat)] = pat
+                run_emu(buf, 62, (pat, seam, shift))
+    rng = np.random.default_rng(21)
+    for tail in ([0, 0, 1], [0, 0, 0], [0, 0, 3], [0, 0, 1, 9], [0, 0], [7, 0, 0, 3, 0]):
+        for d in range(-3, 4):
+            n = 4096 * 2 + d
+            buf = S.oracle_insert(rng.choice(np.array([0, 0, 3, 7, 9], np.uint8), n))[:n - len(tail) - 4]
+            buf = np.concatenate([np.array([0, 0, 1, 0x65], np.uint8), buf, np.array(tail, np.uint8)])
+            assert len(buf) == n
+            run_emu(buf, 61, (tail, d))
+    run = lambda b, e, lo: S.emu_split_strip_inplace(b, cpt=61, edge=e, base=lo)
+    for shift in range(0, 8):
+        b = np.full(4096 * 3, 0x33, np.uint8)
+        b[:4] = [0, 0, 1, 0x67]
+        b[200:206] = [0, 0, 3, 0, 0, 3]
+        b[4096 - 4 + shift:4096 - 4 + shift + 5] = [0, 0, 0, 1, 0x41]
+        b[8192 - 3 + shift % 4:8192 - 3 + shift % 4 + 3] = [0, 0, 3]
+        check_merged(_merge_shards(run, b, [4096, 8192]), S.oracle_split_strip(b), ("cut at tile", shift))
 
 
 # ---- GPU ------------------------------------------------------------------------------------
