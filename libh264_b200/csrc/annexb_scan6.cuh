@@ -23,7 +23,12 @@
  *
  * Start codes are rare (one per NAL): the 512-byte row a reset point falls in, the row the
  * shard ends in, and nothing else, is written byte by byte; the units next to such a row or to
- * the tile seam are cut at the seam (each side writes its own bytes).
+ * the tile seam are cut at the seam (each side writes its own bytes).  The byte-exact work
+ * (listed chunks, chunks of byte-wise rows) is shared out over the whole block, one item per
+ * thread, so that no warp holds the tile back with a second pass.
+ *
+ * CTAs are persistent (148 x 5, tiles by ticket, taken only when the CTA is ready: a ticket held
+ * back delays every later tile's look-back) and pull the tile one grid ahead into L2.
  *
  * Boundary events are owned by the position t = q + 2 of their THIRD byte here (the chunk
  * needs no look-ahead then); the record still carries q.  The launch therefore covers
@@ -62,12 +67,13 @@ template <int ROWS> struct Cfg {
 };
 
 template <int ROWS> struct __align__(128) Smem {
-	uint8_t raw[16 + Cfg<ROWS>::TILE + 48]; /* [left halo pad][tile][pad] */
-	uint16_t M[Cfg<ROWS>::NCH + 16];        /* delete mask per chunk (bit j = byte j is an EPB) */
+	uint8_t raw[16 + Cfg<ROWS>::TILE + 32]; /* [left halo pad][tile][pad] */
+	uint16_t M[Cfg<ROWS>::NCH + 8];         /* delete mask per chunk (bit j = byte j is an EPB) */
 	uint16_t E[Cfg<ROWS>::NCH];             /* EPBs of the span before the chunk; candidate list before that */
 	uint8_t dl[Cfg<ROWS>::NCH];             /* per span: chunks that take the byte-exact path */
 	int32_t rbrel[kW][ROWS];                /* shift at the row start minus E, rows after a reset */
-	uint32_t sp_etail[kW], sp_etot[kW], sp_nev[kW], sp_nsc[kW];
+	uint64_t sp_d0[kW];                     /* shift at the span start */
+	uint32_t sp_etail[kW], sp_etot[kW], sp_nev[kW], sp_nsc[kW], sp_nd[kW];
 	uint8_t sp_has[kW], sp_rbhas[kW], sp_bw[kW];
 	uint64_t bar;
 	uint64_t b0; /* shift at the tile start */
@@ -233,7 +239,7 @@ __device__ __forceinline__ void emit_span(Smem<ROWS> &s, uint32_t warp, uint32_t
 			basep = out_tile - (int64_t)r;
 		}
 		if (!LEAN && ((bwl >> (i + 1)) & 1)) {
-			/* a row with a reset point or the shard end: byte by byte */
+			/* a row with a reset point or the shard end goes byte by byte */
 			const uint4 v = *(const uint4 *)(raw32 + 4 * c);
 			const uint32_t rm = reset_mask(raw32[4 * (int)c - 1], v.x, v.y, v.z, v.w) & valid16(p0, nvalid);
 			const uint32_t bal = __ballot_sync(FULL_MASK, rm != 0);
@@ -241,21 +247,10 @@ __device__ __forceinline__ void emit_span(Smem<ROWS> &s, uint32_t warp, uint32_t
 			const uint32_t e_last = e + (uint32_t)__popc(m & ((1u << top) - 1u));
 			const uint32_t below = bal & ltmask;
 			const uint32_t e_prev = __shfl_sync(FULL_MASK, e_last, below ? 31 - __clz((int)below) : 0);
-			/* out = basec + p0 + j - cur, cur = EPBs since the last reset */
-			uint8_t *basec = below ? out_tile : basep;
-			uint32_t cur = below ? e - e_prev : e;
-			const uint32_t nv = p0 >= nvalid ? 0u : (nvalid - p0 >= 16u ? 16u : nvalid - p0);
-			for (uint32_t j = 0; j < nv; j++) {
-				if ((rm >> j) & 1) {
-					cur = 0;
-					basec = out_tile;
-				}
-				if ((m >> j) & 1) {
-					cur++;
-					continue;
-				}
-				basec[p0 + j - cur] = rawb[p0 + j];
-			}
+			/* the bytes themselves are written in the block-wide pass (one thread per chunk);
+			 * leave it the chunk's shift: EPBs since the last reset of the row below the
+			 * chunk (bit 15), or the span's count as for any other row */
+			s.E[c] = (uint16_t)(below ? ((e - e_prev) | 0x8000u) : e);
 			continue;
 		}
 		const uint32_t mn = s.M[c + 1];
@@ -293,19 +288,71 @@ __device__ __forceinline__ void emit_span(Smem<ROWS> &s, uint32_t warp, uint32_t
 			dlist[ndirty + (uint32_t)__popc(bal & ltmask)] = (uint8_t)(i * 32 + lane);
 		ndirty += (uint32_t)__popc(bal);
 	}
-	__syncwarp();
-	for (uint32_t j = lane; j < ndirty; j += 32) {
-		const uint32_t cr = dlist[j];
-		const uint32_t i = cr >> 5;
-		uint32_t shlo = (uint32_t)d0;
-		uint8_t *basep = out_tile - d0;
-		if (!LEAN && ((rbhas >> i) & 1)) {
-			const int32_t r = s.rbrel[warp][i];
-			shlo = (uint32_t)r;
-			basep = out_tile - (int64_t)r;
+	if (lane == 0)
+		s.sp_nd[warp] = ndirty;
+}
+
+/* shift base of row R (low bits of the shift at E = 0, where tile position 0 goes at E = 0) */
+template <int ROWS>
+__device__ __forceinline__ void row_base(const Smem<ROWS> &s, uint32_t R, uint8_t *out_tile, uint32_t &shlo,
+					 uint8_t *&basep)
+{
+	const uint32_t w = R / ROWS, i = R % ROWS;
+	if ((s.sp_rbhas[w] >> i) & 1) {
+		const int32_t r = s.rbrel[w][i];
+		shlo = (uint32_t)r;
+		basep = out_tile - (int64_t)r;
+	} else {
+		const uint64_t d0 = s.sp_d0[w];
+		shlo = (uint32_t)d0;
+		basep = out_tile - d0;
+	}
+}
+
+/* the byte-exact path for chunk c of the tile: shift base and seam from the span's tables */
+template <int ROWS>
+__device__ __forceinline__ void dirty_of_tile(const Smem<ROWS> &s, uint32_t c, uint8_t *out_tile)
+{
+	const uint32_t R = c >> 5;
+	uint32_t shlo;
+	uint8_t *basep;
+	row_base<ROWS>(s, R, out_tile, shlo, basep);
+	const bool nextlim =
+		R == (uint32_t)Cfg<ROWS>::NROW - 1 || ((s.sp_bw[(R + 1) / ROWS] >> ((R + 1) % ROWS)) & 1);
+	const uint32_t limit = nextlim ? (R + 1) * 512u : (uint32_t)Cfg<ROWS>::TILE + 64u;
+	dirty_chunk<ROWS>(s, c, shlo, basep, limit);
+}
+
+/* chunk c of a byte-wise row (a reset point in the row, or the shard ends in it): every byte to
+ * its place, the shift restarting at each reset point; E[c] holds the shift at the chunk start
+ * as left by emit_span */
+template <int ROWS>
+__device__ __forceinline__ void bytewise_chunk(const Smem<ROWS> &s, uint32_t c, uint8_t *out_tile, uint32_t nvalid)
+{
+	const uint32_t *raw32 = (const uint32_t *)(s.raw + 16);
+	const uint8_t *rawb = s.raw + 16;
+	const uint32_t p0 = c * 16;
+	uint32_t shlo;
+	uint8_t *basep;
+	row_base<ROWS>(s, c >> 5, out_tile, shlo, basep);
+	const uint32_t enc = s.E[c];
+	const uint32_t m = s.M[c];
+	const uint4 v = *(const uint4 *)(raw32 + 4 * c);
+	const uint32_t rm = reset_mask(raw32[4 * (int)c - 1], v.x, v.y, v.z, v.w) & valid16(p0, nvalid);
+	/* out = basec + p0 + j - cur, cur = EPBs since the last reset */
+	uint8_t *basec = (enc & 0x8000u) ? out_tile : basep;
+	uint32_t cur = enc & 0x7fffu;
+	const uint32_t nv = p0 >= nvalid ? 0u : (nvalid - p0 >= 16u ? 16u : nvalid - p0);
+	for (uint32_t j = 0; j < nv; j++) {
+		if ((rm >> j) & 1) {
+			cur = 0;
+			basec = out_tile;
 		}
-		const uint32_t limit = ((bwl >> (i + 2)) & 1) ? (c0 + (i + 1) * 32) * 16 : (uint32_t)Cfg<ROWS>::TILE + 64u;
-		dirty_chunk<ROWS>(s, c0 + cr, shlo, basep, limit);
+		if ((m >> j) & 1) {
+			cur++;
+			continue;
+		}
+		basec[p0 + j - cur] = rawb[p0 + j];
 	}
 }
 
@@ -348,8 +395,8 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 		uint4 *m4 = (uint4 *)(s.M + c0);
 		for (uint32_t i = lane; i < (uint32_t)C::SPAN_CH / 8; i += 32)
 			m4[i] = make_uint4(0, 0, 0, 0);
-		if (warp == kW - 1 && lane < 2)
-			((uint4 *)(s.M + C::NCH))[lane] = make_uint4(0, 0, 0, 0);
+		if (warp == kW - 1 && lane == 0)
+			*(uint4 *)(s.M + C::NCH) = make_uint4(0, 0, 0, 0);
 	}
 	__syncthreads();
 	if (s.tile >= a.num_tiles)
@@ -597,12 +644,11 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 			const uint32_t fr = s.first_r;
 			const uint32_t r0 = (t == 0 && fr < 3) ? fr : 0u;
 			st_relaxed_u64(dt + 3, (uint64_t)total | (uint64_t)r0 << 32);
-			uint32_t evbase = 0;
-			if (nev_t)
-				evbase = atomicAdd(a.ev_cursor, nev_t) + 1u;
-			s.evbase = evbase;
-			dt[2] = (uint64_t)evbase | (uint64_t)nev_t << 32 | (uint64_t)nsc_t << 48;
 		}
+		/* the slot of the tile's event records: asked for now, needed after the look-back */
+		uint32_t evprev = 0xffffffffu;
+		if (lane == 0 && nev_t)
+			evprev = atomicAdd(a.ev_cursor, nev_t);
 		if (t > 0) {
 			if (STRIP) {
 				const uint64_t b0 = annexb5::lookback(a, t, lane);
@@ -615,38 +661,17 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 				st_relaxed_u64(dt + 1, 0);
 			}
 		}
+		if (lane == 0) {
+			const uint32_t evbase = evprev + 1u;
+			s.evbase = evbase;
+			dt[2] = (uint64_t)evbase | (uint64_t)nev_t << 32 | (uint64_t)nsc_t << 48;
+		}
 	}
 	if (tid == 0)
 		trace_mark(a, t, 3);
 	__syncthreads();
 
-	/* ---- P4 (per warp): emit ---- */
-	if (STRIP) {
-		uint64_t d0 = 0;
-		{
-			bool found = false;
-			for (int j = (int)warp - 1; j >= 0; j--) {
-				d0 += s.sp_etail[j];
-				if (s.sp_has[j]) {
-					found = true;
-					break;
-				}
-			}
-			if (!found)
-				d0 += s.b0;
-		}
-		/* seams around and inside the span */
-		uint32_t bwl = (uint32_t)s.sp_bw[warp] << 1;
-		bwl |= warp == 0 ? 1u : ((uint32_t)s.sp_bw[warp - 1] >> (ROWS - 1)) & 1u;
-		bwl |= (warp == kW - 1 ? 1u : (uint32_t)s.sp_bw[warp + 1] & 1u) << (ROWS + 1);
-		uint8_t *const out_tile = a.rbsp + tile_off;
-		if (rbhas == 0 && (bwl & (((1u << ROWS) - 1u) << 1)) == 0)
-			emit_span<ROWS, true>(s, warp, lane, bwl, 0, d0, out_tile, nvalid);
-		else
-			emit_span<ROWS, false>(s, warp, lane, bwl, rbhas, d0, out_tile, nvalid);
-	}
-
-	/* ---- P5 (spans with events): event records; nothing waits on them ---- */
+	/* ---- P5 (spans with events): event records (before the emit pass reuses E of byte-wise rows) ---- */
 	if (nev) {
 		uint32_t idx0 = s.evbase, epb0 = 0;
 		for (uint32_t j = 0; j < warp; j++) {
@@ -679,6 +704,70 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 					a.evbuf[idx] = pack_event(tile_off + p0 + j - 2, eb, (m.sc16 >> j) & 1);
 			}
 			idx0 += __shfl_sync(FULL_MASK, einc, 31);
+		}
+	}
+	/* ---- P4: emit.  Every warp its span's rows; the chunks that need the byte-exact path are
+	 * listed per span and then shared out over the whole block (a span has 28 +- 6 of them:
+	 * alone, one warp in four would need a second pass and the rest of the tile would wait) ---- */
+	if (STRIP) {
+		uint64_t d0 = 0;
+		{
+			bool found = false;
+			for (int j = (int)warp - 1; j >= 0; j--) {
+				d0 += s.sp_etail[j];
+				if (s.sp_has[j]) {
+					found = true;
+					break;
+				}
+			}
+			if (!found)
+				d0 += s.b0;
+		}
+		if (lane == 0)
+			s.sp_d0[warp] = d0;
+		/* seams around and inside the span */
+		uint32_t bwl = (uint32_t)s.sp_bw[warp] << 1;
+		bwl |= warp == 0 ? 1u : ((uint32_t)s.sp_bw[warp - 1] >> (ROWS - 1)) & 1u;
+		bwl |= (warp == kW - 1 ? 1u : (uint32_t)s.sp_bw[warp + 1] & 1u) << (ROWS + 1);
+		uint8_t *const out_tile = a.rbsp + tile_off;
+		if (rbhas == 0 && (bwl & (((1u << ROWS) - 1u) << 1)) == 0)
+			emit_span<ROWS, true>(s, warp, lane, bwl, 0, d0, out_tile, nvalid);
+		else
+			emit_span<ROWS, false>(s, warp, lane, bwl, rbhas, d0, out_tile, nvalid);
+		if (tid == 0)
+			trace_mark(a, t, 7);
+		__syncthreads();
+		uint32_t pre[kW + 1];
+		pre[0] = 0;
+#pragma unroll
+		for (int j = 0; j < kW; j++)
+			pre[j + 1] = pre[j] + s.sp_nd[j];
+		uint64_t BW = 0;
+#pragma unroll
+		for (int j = 0; j < kW; j++)
+			BW |= (uint64_t)s.sp_bw[j] << (j * ROWS);
+		const uint32_t nitems = pre[kW] + 32u * (uint32_t)__popcll(BW);
+		for (uint32_t g = tid; g < nitems; g += kT) {
+			if (g >= pre[kW]) {
+				/* chunk (g % 32) of the byte-wise row number (g / 32) */
+				const uint32_t k = (g - pre[kW]) >> 5;
+				uint64_t x = BW;
+				for (uint32_t n = 0; n < k; n++)
+					x &= x - 1;
+				const uint32_t R = (uint32_t)__ffsll((long long)x) - 1;
+				bytewise_chunk<ROWS>(s, R * 32 + ((g - pre[kW]) & 31u), out_tile, nvalid);
+				continue;
+			}
+			uint32_t w = 0;
+#pragma unroll
+			for (int j = 1; j < kW; j++)
+				w += g >= pre[j] ? 1u : 0u;
+			uint32_t pw = 0;
+#pragma unroll
+			for (int j = 1; j < kW; j++)
+				pw = g >= pre[j] ? pre[j] : pw;
+			const uint32_t c = w * (uint32_t)C::SPAN_CH + s.dl[w * (uint32_t)C::SPAN_CH + (g - pw)];
+			dirty_of_tile<ROWS>(s, c, out_tile);
 		}
 	}
 	if (tid == 0)

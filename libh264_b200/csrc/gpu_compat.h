@@ -188,6 +188,23 @@ __device__ __forceinline__ void l2_prefetch(const void *gsrc, uint32_t bytes)
 
 #define FULL_MASK 0xffffffffu
 
+/* atomic add on a shared-memory word (the generic-address form costs a space check and a loop) */
+#ifdef H264_EMU
+static inline uint32_t smem_atomic_add(uint32_t *p, uint32_t v)
+{
+	const uint32_t o = *p;
+	*p = o + v;
+	return o;
+}
+#else
+__device__ __forceinline__ uint32_t smem_atomic_add(uint32_t *p, uint32_t v)
+{
+	uint32_t o;
+	asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(smem_u32(p)), "r"(v) : "memory");
+	return o;
+}
+#endif
+
 /* OR of a value over the warp (all lanes take part) */
 #ifdef H264_EMU
 static inline uint32_t warp_or(uint32_t v)
