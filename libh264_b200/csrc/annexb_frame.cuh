@@ -127,8 +127,8 @@ __device__ __forceinline__ void insert03(uint32_t d[5], uint32_t j)
 	}
 }
 
-template <int ITEMS>
-__global__ void __launch_bounds__(kBlock) frame_kernel(const FrameArgs a)
+template <int ITEMS, int MINB = 4>
+__global__ void __launch_bounds__(kBlock, MINB) frame_kernel(const FrameArgs a)
 {
 	constexpr int WARP_BYTES = ITEMS * 512;
 	constexpr int TILE = kBlock * ITEMS * 16;

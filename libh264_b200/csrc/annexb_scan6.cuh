@@ -356,7 +356,7 @@ __device__ __forceinline__ void bytewise_chunk(const Smem<ROWS> &s, uint32_t c, 
 	}
 }
 
-template <int ROWS, bool STRIP, int MINB = 4>
+template <int ROWS, bool STRIP, int MINB = 4, bool TRACE = false>
 __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 {
 	using C = Cfg<ROWS>;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 											   : (uint32_t)(a.len - tile_off));
 	const bool full = nvalid == (uint32_t)C::TILE;
 
-	if (tid == 0)
+	if (TRACE && tid == 0)
 		trace_mark(a, t, 0);
 	if (tid == 0)
 		raw32[-1] = tile_off == 0 ? a.halo_left
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 		__syncthreads();
 	}
 
-	if (tid == 0)
+	if (TRACE && tid == 0)
 		trace_mark(a, t, 1);
 
 	/* ---- P1 (per warp): classify.  A chunk matters only if some byte <= 3 follows two zero
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 			}
 		}
 	}
-	if (tid == 0)
+	if (TRACE && tid == 0)
 		trace_mark(a, t, 5);
 	/* a start code ending just before the span resets at its first byte */
 	const uint8_t *rawb = s.raw + 16;
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 			if ((c0 + (uint32_t)(i + 1) * 32) * 16 > nvalid)
 				bw |= 1u << i;
 	}
-	if (tid == 0)
+	if (TRACE && tid == 0)
 		trace_mark(a, t, 6);
 	if (lane == 0) {
 		s.sp_etail[warp] = has ? (uint32_t)((int32_t)etot + cur_rel) : etot;
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 
 	/* ---- P3 (warp 0): tile aggregate, published at once; shift at the tile start by the
 	 * short look-back of gen 5 ---- */
-	if (tid == 0)
+	if (TRACE && tid == 0)
 		trace_mark(a, t, 2);
 	if (warp == 0) {
 		uint32_t total = 0, e_tail = 0, nev_t = 0, nsc_t = 0;
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 			dt[2] = (uint64_t)evbase | (uint64_t)nev_t << 32 | (uint64_t)nsc_t << 48;
 		}
 	}
-	if (tid == 0)
+	if (TRACE && tid == 0)
 		trace_mark(a, t, 3);
 	__syncthreads();
 
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 			emit_span<ROWS, true>(s, warp, lane, bwl, 0, d0, out_tile, nvalid);
 		else
 			emit_span<ROWS, false>(s, warp, lane, bwl, rbhas, d0, out_tile, nvalid);
-		if (tid == 0)
+		if (TRACE && tid == 0)
 			trace_mark(a, t, 7);
 		__syncthreads();
 		uint32_t pre[kW + 1];
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 			dirty_of_tile<ROWS>(s, c, out_tile);
 		}
 	}
-	if (tid == 0)
+	if (TRACE && tid == 0)
 		trace_mark(a, t, 4);
 	if (a.flags & 1u)
 		break;

@@ -512,7 +512,12 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
 		annexb6::scan6_kernel<8, S, B><<<grid6(ntiles, sms * B), annexb6::kT, 0, st>>>(a); \
 	} while (0)
-		if (minb == 5) {
+		if (a.trace != NULL && strip5) {
+			/* diagnostics build of the same kernel: per-tile phase timestamps */
+			cudaFuncSetAttribute(annexb6::scan6_kernel<8, true, 5, true>,
+					     cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+			annexb6::scan6_kernel<8, true, 5, true><<<grid6(ntiles, sms * 5), annexb6::kT, 0, st>>>(a);
+		} else if (minb == 5) {
 			if (strip5) SCAN6_LAUNCH(true, 5); else SCAN6_LAUNCH(false, 5);
 		} else if (minb == 4) {
 			if (strip5) SCAN6_LAUNCH(true, 4); else SCAN6_LAUNCH(false, 4);
@@ -807,7 +812,18 @@ static cudaError_t launch_frame(const frame::FrameArgs &a, cudaStream_t st)
 	const uint32_t pthreads = 128;
 	const uint32_t pblocks = (a.num_tiles + 1 + pthreads - 1) / pthreads;
 	frame::frame_prepass<ITEMS><<<pblocks, pthreads, 0, st>>>(a);
-	frame::frame_kernel<ITEMS><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
+	/* resident CTAs per SM the kernel is compiled for (register budget): 4 (64 registers), 5 or 6 */
+	static int minb = 0;
+	if (minb == 0) {
+		const char *e = getenv("H264GPU_FRAME_CTAS");
+		minb = (e != NULL && (atoi(e) == 4 || atoi(e) == 6)) ? atoi(e) : 5;
+	}
+	if (minb == 4)
+		frame::frame_kernel<ITEMS, 4><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
+	else if (minb == 6)
+		frame::frame_kernel<ITEMS, 6><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
+	else
+		frame::frame_kernel<ITEMS, 5><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
 	return cudaGetLastError();
 }
 
