@@ -143,6 +143,8 @@ MB_CFG = dict(width_mbs=120, height_mbs=68, slices_per_frame=16, profile_idc=100
 
 
 def SCAN_KERNEL_NAME(gen=2):
+    if gen == 7:
+        return "annexb6::scan6p_kernel<4,strip> + fin_tiles/fin_order/fin_head/fin_table (RBSP in place per NAL, two tiles per CTA in flight)"
     if gen == 6:
         return "annexb6::scan6_kernel<8,strip> + fin_tiles/fin_order/fin_head/fin_table (RBSP in place per NAL, warp-autonomous tiles)"
     if gen == 5:
@@ -320,7 +322,7 @@ def main():
     ap.add_argument("--size-mb", type=int, default=4096, help="input MiB per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--scan-gen", type=int, default=6, choices=[2, 5, 6],
+    ap.add_argument("--scan-gen", type=int, default=6, choices=[2, 5, 6, 7],
                     help="6 / 5: RBSP in place per NAL (h264gpu_split_strip_inplace_dev; 6 = warp-autonomous "
                          "tiles, 5 = block-wide unit binning); 2: packed RBSP")
     ap.add_argument("--mb-frames", type=int, default=1000, help="frames of the macroblock-parse workload")

@@ -74,10 +74,12 @@ template <int ROWS> struct __align__(128) Smem {
 	int32_t rbrel[kW][ROWS];                /* shift at the row start minus E, rows after a reset */
 	uint64_t sp_d0[kW];                     /* shift at the span start */
 	uint32_t sp_etail[kW], sp_etot[kW], sp_nev[kW], sp_nsc[kW], sp_nd[kW];
-	uint8_t sp_has[kW], sp_rbhas[kW], sp_bw[kW];
+	uint8_t sp_has[kW], sp_rbhas[kW], sp_bw[kW], sp_evrows[kW];
 	uint64_t bar;
 	uint64_t b0; /* shift at the tile start */
 	uint32_t tile, evbase, first_r;
+	/* the tile aggregate, kept from its publication to the look-back (pipelined kernel) */
+	uint32_t ag_total, ag_nev, ag_nsc, ag_has, ag_evprev;
 };
 
 struct TMasks {
@@ -356,25 +358,19 @@ __device__ __forceinline__ void bytewise_chunk(const Smem<ROWS> &s, uint32_t c, 
 	}
 }
 
-template <int ROWS, bool STRIP, int MINB = 4, bool TRACE = false>
-__global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
+/* P0 of a tile into buffer s: ticket, bulk load, L2 prefetch one grid ahead, cleared tables */
+template <int ROWS, bool STRIP>
+__device__ __forceinline__ void stage_take(Smem<ROWS> &s, const ScanArgs &a)
 {
 	using C = Cfg<ROWS>;
-	__shared__ Smem<ROWS> s;
-
 	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31, warp = tid >> 5;
 	const uint32_t ltmask = (1u << lane) - 1u;
 	uint32_t *raw32 = (uint32_t *)(s.raw + 16);
 	const uint32_t c0 = warp * (uint32_t)C::SPAN_CH;
-
-	/* persistent CTAs: tiles are taken by ticket until none is left (a ticket is taken only when
-	 * the CTA is ready for it: a tile held back delays every later tile's look-back).  The tile
-	 * one grid ahead, which some CTA will take about a tile's life from now, is pulled into L2. */
-	uint32_t parity = 0;
-	if (tid == 0)
-		bulk_bar_init(&s.bar);
-	for (;;) {
+	(void)ltmask;
+	(void)raw32;
+	(void)c0;
 	/* ---- P0: ticket, bulk load, clear the span's delete masks ---- */
 	if (tid == 0) {
 		const uint32_t t0 = atomicAdd(a.ticket, 1u) + 1u;
@@ -398,16 +394,32 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 		if (warp == kW - 1 && lane == 0)
 			*(uint4 *)(s.M + C::NCH) = make_uint4(0, 0, 0, 0);
 	}
-	__syncthreads();
-	if (s.tile >= a.num_tiles)
-		break;
+}
 
+/*
+ * Stage 1 of a tile (buffer s, tile id in s.tile, bulk load under way): wait for the bytes,
+ * classify, per-span prefix and events, tile aggregate published.  Ends with every warp past
+ * the aggregate barrier; the look-back and everything that needs it is stage 2.
+ */
+template <int ROWS, bool STRIP, bool TRACE>
+__device__ __forceinline__ void stage_classify(Smem<ROWS> &s, const ScanArgs &a, uint32_t parity)
+{
+	using C = Cfg<ROWS>;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t lane = tid & 31, warp = tid >> 5;
+	const uint32_t ltmask = (1u << lane) - 1u;
+	uint32_t *raw32 = (uint32_t *)(s.raw + 16);
+	const uint32_t c0 = warp * (uint32_t)C::SPAN_CH;
+	(void)ltmask;
+	(void)raw32;
+	(void)c0;
 	const uint32_t t = s.tile;
 	const uint64_t tile_off = (uint64_t)t * C::TILE;
 	const uint32_t nvalid = tile_off >= a.len ? 0u
 						  : (a.len - tile_off >= (uint64_t)C::TILE ? (uint32_t)C::TILE
 											   : (uint32_t)(a.len - tile_off));
 	const bool full = nvalid == (uint32_t)C::TILE;
+	(void)full;
 
 	if (TRACE && tid == 0)
 		trace_mark(a, t, 0);
@@ -417,7 +429,6 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 							       : annexb::edge_word(a, tile_off - 4));
 	if (full) {
 		bulk_load_wait_parity(&s.bar, parity);
-		parity ^= 1u;
 		__syncwarp();
 	} else {
 		for (uint32_t c = tid; c < (uint32_t)C::NCH; c += kT) {
@@ -612,6 +623,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 		s.sp_has[warp] = has ? 1 : 0;
 		s.sp_rbhas[warp] = (uint8_t)rbhas;
 		s.sp_bw[warp] = (uint8_t)bw;
+		s.sp_evrows[warp] = (uint8_t)evrows;
 		if (warp == 0)
 			s.first_r = first_r;
 	}
@@ -646,9 +658,44 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 			st_relaxed_u64(dt + 3, (uint64_t)total | (uint64_t)r0 << 32);
 		}
 		/* the slot of the tile's event records: asked for now, needed after the look-back */
-		uint32_t evprev = 0xffffffffu;
-		if (lane == 0 && nev_t)
-			evprev = atomicAdd(a.ev_cursor, nev_t);
+		if (lane == 0) {
+			s.ag_total = total;
+			s.ag_nev = nev_t;
+			s.ag_nsc = nsc_t;
+			s.ag_has = has_t ? 1u : 0u;
+			s.ag_evprev = nev_t ? atomicAdd(a.ev_cursor, nev_t) : 0xffffffffu;
+		}
+	}
+}
+
+/*
+ * Stage 2 of a tile: shift at the tile start (look-back by warp 0), event records, rows, the
+ * byte-exact pass.  Leaves with the tile's output written; the caller's next barrier frees s.
+ */
+template <int ROWS, bool STRIP, bool TRACE>
+__device__ __forceinline__ void stage_emit(Smem<ROWS> &s, const ScanArgs &a)
+{
+	using C = Cfg<ROWS>;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t lane = tid & 31, warp = tid >> 5;
+	const uint32_t ltmask = (1u << lane) - 1u;
+	uint32_t *raw32 = (uint32_t *)(s.raw + 16);
+	const uint32_t c0 = warp * (uint32_t)C::SPAN_CH;
+	(void)ltmask;
+	(void)raw32;
+	(void)c0;
+	const uint32_t t = s.tile;
+	const uint64_t tile_off = (uint64_t)t * C::TILE;
+	const uint32_t nvalid = tile_off >= a.len ? 0u
+						  : (a.len - tile_off >= (uint64_t)C::TILE ? (uint32_t)C::TILE
+											   : (uint32_t)(a.len - tile_off));
+	const bool full = nvalid == (uint32_t)C::TILE;
+	(void)full;
+	if (warp == 0) {
+		__syncwarp();
+		const uint32_t total = s.ag_total, nev_t = s.ag_nev, nsc_t = s.ag_nsc;
+		const bool has_t = s.ag_has != 0;
+		uint64_t *dt = a.desc + (uint64_t)t * 4;
 		if (t > 0) {
 			if (STRIP) {
 				const uint64_t b0 = annexb5::lookback(a, t, lane);
@@ -662,7 +709,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 			}
 		}
 		if (lane == 0) {
-			const uint32_t evbase = evprev + 1u;
+			const uint32_t evbase = s.ag_evprev + 1u;
 			s.evbase = evbase;
 			dt[2] = (uint64_t)evbase | (uint64_t)nev_t << 32 | (uint64_t)nsc_t << 48;
 		}
@@ -672,6 +719,7 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 	__syncthreads();
 
 	/* ---- P5 (spans with events): event records (before the emit pass reuses E of byte-wise rows) ---- */
+	const uint32_t nev = s.sp_nev[warp], evrows = s.sp_evrows[warp], rbhas = s.sp_rbhas[warp];
 	if (nev) {
 		uint32_t idx0 = s.evbase, epb0 = 0;
 		for (uint32_t j = 0; j < warp; j++) {
@@ -772,10 +820,69 @@ __global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
 	}
 	if (TRACE && tid == 0)
 		trace_mark(a, t, 4);
-	if (a.flags & 1u)
-		break;
-	__syncthreads(); /* the tile's shared memory is reused */
-	} /* tiles */
+}
+
+template <int ROWS, bool STRIP, int MINB = 4, bool TRACE = false>
+__global__ void __launch_bounds__(kT, MINB) scan6_kernel(const ScanArgs a)
+{
+	__shared__ Smem<ROWS> s;
+	/* persistent CTAs: tiles are taken by ticket until none is left (a ticket is taken only when
+	 * the CTA is ready for it: a tile held back delays every later tile's look-back).  The tile
+	 * one grid ahead, which some CTA will take about a tile's life from now, is pulled into L2. */
+	uint32_t parity = 0;
+	if (threadIdx.x == 0)
+		bulk_bar_init(&s.bar);
+	for (;;) {
+		stage_take<ROWS, STRIP>(s, a);
+		__syncthreads();
+		if (s.tile >= a.num_tiles)
+			break;
+		stage_classify<ROWS, STRIP, TRACE>(s, a, parity);
+		if ((uint64_t)s.tile * Cfg<ROWS>::TILE + Cfg<ROWS>::TILE <= a.len)
+			parity ^= 1u;
+		stage_emit<ROWS, STRIP, TRACE>(s, a);
+		if (a.flags & 1u)
+			break;
+		__syncthreads(); /* the tile's shared memory is reused */
+	}
+}
+
+/*
+ * The same stages, two tiles per CTA in flight: tile B is taken, loaded and classified (its
+ * aggregate published) BEFORE tile A's look-back, so that the look-back finds its predecessors'
+ * aggregates already there instead of waiting for their timing jitter (20 % of warp time in the
+ * single-buffer kernel).  The ticket of a tile is still taken right before its load and
+ * classification (no tile is held back).  Two buffers of half the size: ROWS = 4, 16 KiB tiles.
+ */
+template <int ROWS, bool STRIP, int MINB = 4, bool TRACE = false>
+__global__ void __launch_bounds__(kT, MINB) scan6p_kernel(const ScanArgs a)
+{
+	__shared__ Smem<ROWS> sb[2];
+	uint32_t parity[2] = {0, 0};
+	if (threadIdx.x == 0) {
+		bulk_bar_init(&sb[0].bar);
+		bulk_bar_init(&sb[1].bar);
+	}
+	uint32_t cur = 0;
+	bool pending = false;
+	for (;;) {
+		Smem<ROWS> &s = sb[cur];
+		stage_take<ROWS, STRIP>(s, a);
+		__syncthreads();
+		const bool valid = s.tile < a.num_tiles;
+		if (valid) {
+			stage_classify<ROWS, STRIP, TRACE>(s, a, parity[cur]);
+			if ((uint64_t)s.tile * Cfg<ROWS>::TILE + Cfg<ROWS>::TILE <= a.len)
+				parity[cur] ^= 1u;
+		}
+		if (pending)
+			stage_emit<ROWS, STRIP, TRACE>(sb[cur ^ 1], a);
+		if (!valid)
+			break;
+		pending = true;
+		cur ^= 1;
+		__syncthreads(); /* the older tile's buffer is free for the next ticket */
+	}
 }
 
 } /* namespace annexb6 */

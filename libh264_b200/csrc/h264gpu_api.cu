@@ -425,11 +425,15 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 	int gen = 6;
 	{
 		const char *e = getenv("H264GPU_INPLACE_GEN");
-		if (e != NULL && atoi(e) == 5)
-			gen = 5;
+		if (e != NULL && (atoi(e) == 5 || atoi(e) == 7))
+			gen = atoi(e);
 	}
+	const bool piped = gen == 7; /* gen 6 stages, two 16 KiB tiles per CTA in flight */
+	if (piped)
+		gen = 6;
 	const int CPT = shape / 10;
-	const uint64_t tile = gen == 6 ? (uint64_t)annexb6::Cfg<8>::TILE : (uint64_t)annexb5::kT * CPT * 16;
+	const uint64_t tile = piped ? (uint64_t)annexb6::Cfg<4>::TILE
+			    : (gen == 6 ? (uint64_t)annexb6::Cfg<8>::TILE : (uint64_t)annexb5::kT * CPT * 16);
 	/* gen 6 owns a boundary event by its third byte: the launch covers the two edge bytes too */
 	const uint64_t ntiles = ((gen == 6 ? len + 2 : len) + tile - 1) / tile;
 	/* events: a start code and at most a few terminators per NAL in real streams */
@@ -512,7 +516,18 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
 		annexb6::scan6_kernel<8, S, B><<<grid6(ntiles, sms * B), annexb6::kT, 0, st>>>(a); \
 	} while (0)
-		if (a.trace != NULL && strip5) {
+		if (piped) {
+#define SCAN6P_LAUNCH(S, T)                                                                   \
+	do {                                                                                  \
+		cudaFuncSetAttribute(annexb6::scan6p_kernel<4, S, 5, T>,                      \
+				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
+		annexb6::scan6p_kernel<4, S, 5, T><<<grid6(ntiles, sms * 5), annexb6::kT, 0, st>>>(a); \
+	} while (0)
+			if (a.trace != NULL && strip5) SCAN6P_LAUNCH(true, true);
+			else if (strip5) SCAN6P_LAUNCH(true, false);
+			else SCAN6P_LAUNCH(false, false);
+#undef SCAN6P_LAUNCH
+		} else if (a.trace != NULL && strip5) {
 			/* diagnostics build of the same kernel: per-tile phase timestamps */
 			cudaFuncSetAttribute(annexb6::scan6_kernel<8, true, 5, true>,
 					     cudaFuncAttributePreferredSharedMemoryCarveout, 100);

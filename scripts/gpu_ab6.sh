@@ -4,7 +4,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-ab6}
-echo "== pytest gpu (in-place scan)"; timeout 600 python -m pytest tests/test_scan_inplace.py tests/test_gpu_annexb.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.log
+echo "== pytest gpu (in-place scan)"; H264GPU_INPLACE_GEN=${PYGEN:-6} timeout 600 python -m pytest tests/test_scan_inplace.py tests/test_gpu_annexb.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.log
 Q="--steps 10 --warmup 3 --e2e-steps 1 --no-cpu --mb-frames 2 --cabac-frames 0 --frame-mb 0"
 for v in ${VARIANTS:-6:5 5:5}; do
   set -- ${v//:/ }

@@ -32,7 +32,7 @@ for k in range(4):
     d = (t[:, k + 1] - t[:, k]) / 1e3
     print("%-26s mean %7.2f  p10 %7.2f  p50 %7.2f  p90 %7.2f  p99 %7.2f us" %
           (names[k], d.mean(), *np.percentile(d, [10, 50, 90, 99])))
-if gen == 6:
+if gen >= 6:
     # marks: 0 ticket, 1 loaded, 5 classified, 6 prefix + event walk, 2 after barrier 2, 3 look-back
     # done, 7 row loop done (warp 0), 4 end
     for nm, x, y in (("load wait", 0, 1), ("classify (warp 0)", 1, 5), ("prefix + walk (warp 0)", 5, 6), ("emit (warp 0)", 3, 4),

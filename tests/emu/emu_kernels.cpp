@@ -91,8 +91,10 @@ extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t
 	using namespace annexb;
 	if (len == 0)
 		return -1;
-	/* cpt 6x selects the sixth-generation kernel with x 512-byte rows per warp */
+	/* cpt 6x selects the sixth-generation kernel with x 512-byte rows per warp, 7x its pipelined
+	 * form (two tiles per CTA in flight) */
 	const bool gen6 = cpt >= 60;
+	const bool piped = cpt >= 70;
 	const int rows = cpt % 10;
 	const uint64_t tile = gen6 ? (uint64_t)annexb6::kT * rows * 16 : (uint64_t)annexb5::kT * cpt * 16;
 	const uint32_t ntiles = (uint32_t)(((gen6 ? len + 2 : len) + tile - 1) / tile);
@@ -133,7 +135,17 @@ extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t
 		/* persistent CTAs: a few of them share the tiles (the emulator runs them one after
 		 * the other, so the first takes every ticket and the others find none) */
 		grid = dim3(ntiles < 3 ? ntiles : 3);
-		if (rbsp) {
+		if (piped) {
+			if (rbsp) {
+				if (rows == 1) EMU_LAUNCH((annexb6::scan6p_kernel<1, true, 1>), grid, block, a);
+				else if (rows == 2) EMU_LAUNCH((annexb6::scan6p_kernel<2, true, 1>), grid, block, a);
+				else EMU_LAUNCH((annexb6::scan6p_kernel<4, true, 1>), grid, block, a);
+			} else {
+				if (rows == 1) EMU_LAUNCH((annexb6::scan6p_kernel<1, false, 1>), grid, block, a);
+				else if (rows == 2) EMU_LAUNCH((annexb6::scan6p_kernel<2, false, 1>), grid, block, a);
+				else EMU_LAUNCH((annexb6::scan6p_kernel<4, false, 1>), grid, block, a);
+			}
+		} else if (rbsp) {
 			if (rows == 1) EMU_LAUNCH((annexb6::scan6_kernel<1, true, 1>), grid, block, a);
 			else if (rows == 2) EMU_LAUNCH((annexb6::scan6_kernel<2, true, 1>), grid, block, a);
 			else EMU_LAUNCH((annexb6::scan6_kernel<8, true, 1>), grid, block, a);

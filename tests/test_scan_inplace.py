@@ -39,7 +39,7 @@ def run_emu(buf, cpt, what):
     assert np.array_equal(g["start"], exp["start"]) and np.array_equal(g["end"], exp["end"])
 
 
-@pytest.mark.parametrize("cpt", [1, 2, 8, 61, 62, 68])
+@pytest.mark.parametrize("cpt", [1, 2, 8, 61, 62, 68, 71, 74])
 def test_emu_random_streams(cpt):
     rng = np.random.default_rng(100 + cpt)
     for it in range(12):
@@ -49,7 +49,7 @@ def test_emu_random_streams(cpt):
         run_emu(buf, cpt, ("random", cpt, it))
 
 
-@pytest.mark.parametrize("cpt", [1, 8, 61, 68])
+@pytest.mark.parametrize("cpt", [1, 8, 61, 68, 74])
 def test_emu_pathological_streams(cpt):
     rng = np.random.default_rng(7)
     for it in range(20):
@@ -68,7 +68,7 @@ def test_emu_pathological_streams(cpt):
         run_emu(buf, cpt, ("patho", cpt, it))
 
 
-@pytest.mark.parametrize("cpt", [1, 61])
+@pytest.mark.parametrize("cpt", [1, 61, 71])
 def test_emu_long_nal_crosses_many_tiles(cpt):
     """One NAL over > 32 tiles: the look-back has to walk more than one window, and tiles
     without a start code chain their shifts."""
@@ -88,7 +88,7 @@ def test_emu_more_tiles_than_one_finalize_block(cpt):
     run_emu(buf, cpt, "finalize blocks")
 
 
-@pytest.mark.parametrize("cpt", [1, 61, 62])
+@pytest.mark.parametrize("cpt", [1, 61, 62, 71])
 def test_emu_seams_at_every_offset(cpt):
     """A start code / EPB / terminator sliding over a tile seam (4 KiB tiles; for gen 6 also a
     warp-span seam and, with 62, a row seam inside a span)."""
@@ -161,7 +161,7 @@ def check_merged(g, o, what):
     assert g["final_off"] == o["final_off"] and g["rbsp_bytes"] == len(o["rbsp"]), what
 
 
-@pytest.mark.parametrize("cpt", [1, 61])
+@pytest.mark.parametrize("cpt", [1, 61, 71])
 def test_emu_sharded_scan_merges_to_whole(cpt):
     rng = np.random.default_rng(5)
     run = lambda buf, e, lo: S.emu_split_strip_inplace(buf, cpt=cpt, edge=e, base=lo)
