@@ -272,7 +272,8 @@ def frame_leg(g, L, size, steps, warmup, rank):
     total = int(d_oo.download(dtype=np.uint64)[n + 1])
     peak, _ = measured_peak()
     out = {"workload": "EPB insert + framing of %.0f MiB RBSP in %d payloads (BASELINE config 5)" % (size / 2**20, n),
-           "kernel": "frame::frame_prepass + frame::frame_kernel<4>",
+           "kernel": ("frame::frame_prepass + frame::frame_kernel<4>" if os.environ.get("H264GPU_FRAME_GEN") == "1"
+                      else "frame::frame_prepass<8> + frame6::frame6_kernel<8> (persistent CTAs, 32 KiB tiles)"),
            "gb_per_s": len(rbsp) / (ms / 1e3) / 1e9, "ms_per_step": ms, "out_bytes": total,
            "roofline_frac": (len(rbsp) + total + 8 * (n + 1)) / (ms / 1e3) / 1e9 / peak}
     for d in (d_r, d_o, d_out, d_oo):

@@ -1,0 +1,606 @@
+/*
+ * annexb_frame6.cuh — K3 second generation: writer-side emulation-prevention-byte insertion and
+ * start-code framing with the tile organisation of the gen-6 scan kernel (annexb_scan6.cuh).
+ *
+ * Why: frame_kernel (annexb_frame.cuh) spends ~20 k warp-instructions per 16 KiB tile
+ * (profiles/r01_frame_kernel_raw.csv): exact zero-run bookkeeping for every chunk, a byte shifter
+ * per inserted 03, a swizzled shared staging buffer and a copy-out pass; 0.14 of the HBM peak.
+ *
+ * Here the source tile (32 KiB) is staged once with a bulk copy and the OUTPUT is produced in
+ * aligned 16-byte units straight from it.  A source byte at absolute position x goes to
+ *
+ *     out(x) = x + INS(x) + sc_len * K(x)
+ *
+ * INS(x) = 03 bytes inserted before x (look-back prefix over tiles + the span prefix E),
+ * K(x) = number of payloads starting at or before x (closed form: a search in off[], no chain).
+ * Inside a row without a payload start the output ranges of consecutive 16-byte source chunks
+ * partition the output; chunk c, with k inserted bytes, covers 16 + k >= 16 output bytes and
+ * therefore always holds the unit boundary b = (-out(16c)) & 15 bytes into its output.  A chunk
+ * without an insert whose successor has none before its byte b copies source bytes
+ * [16c + b, 16c + b + 16) with one funnel-shifted aligned store (~85 % of the chunks); the others
+ * build their one or two units with a 128-bit byte shifter (block-shared pass, one item per
+ * thread).  Rows that contain a payload start (start code, zero-run reset, out_off[k]) or the
+ * end of the input go byte by byte, one thread per chunk; units next to such a row or to the
+ * tile seam are cut at the seam (each side writes its own bytes).
+ *
+ * Classification: an insert needs `00 00 [<= 3]`; one SIMD-in-register test per chunk finds the
+ * candidate chunks (~10 %), only they get the exact parity-of-the-zero-run evaluation
+ * (insert before byte i  <=>  r[i] <= 3, z(i) >= 2, z(i) even).
+ *
+ * Reference behaviour reproduced bit-exactly (Parrot-Developers/libh264):
+ *   h264_bs_flush        src/h264_bitstream.c:54-81
+ *   h264_bs_write_bits   src/h264_bitstream.c:211-239
+ *   start code           src/h264.c:251-272
+ * The pre-pass (per-tile first payload and trailing zero run) is frame::frame_prepass.
+ */
+#ifndef ANNEXB_FRAME6_CUH
+#define ANNEXB_FRAME6_CUH
+
+#include "annexb_frame.cuh"
+
+namespace frame6 {
+
+using annexb::kInvalid;
+using annexb::zmask4;
+using frame::FrameArgs;
+using frame::count_le;
+using frame::kPrefix;
+using frame::kValueMask;
+
+constexpr int kT = 256;
+constexpr int kW = kT / 32;
+
+template <int ROWS> struct Cfg {
+	static constexpr int SPAN_CH = 32 * ROWS; /* 16-byte chunks per warp span */
+	static constexpr int NCH = kW * SPAN_CH;  /* chunks per tile */
+	static constexpr int TILE = NCH * 16;     /* bytes per tile */
+	static constexpr int NROW = kW * ROWS;    /* 512-byte rows per tile (<= 64) */
+};
+
+template <int ROWS> struct __align__(128) Smem {
+	uint8_t raw[16 + Cfg<ROWS>::TILE + 32]; /* [left halo pad][tile][pad] */
+	uint16_t M[Cfg<ROWS>::NCH + 8];         /* insert mask per chunk (bit j = 03 before byte j) */
+	uint16_t E[Cfg<ROWS>::NCH];             /* inserts of the span before the chunk; candidate list before that */
+	uint8_t dl[Cfg<ROWS>::NCH];             /* per span: chunks that take the byte-exact path */
+	uint32_t krow[Cfg<ROWS>::NROW];         /* payload starts of the tile at or before the row start */
+	uint32_t sp_etot[kW], sp_nd[kW];
+	uint32_t bw32[2];                       /* byte-wise rows */
+	uint64_t bar;
+	uint64_t pin; /* inserts before the tile */
+	uint32_t tile, zt;
+};
+
+__device__ __forceinline__ uint32_t valid16(uint32_t p0, uint32_t nvalid)
+{
+	const uint32_t nv = p0 >= nvalid ? 0u : (nvalid - p0 >= 16u ? 16u : nvalid - p0);
+	return (1u << nv) - 1u;
+}
+
+/* one byte / one 16-byte unit to the output, never past its capacity */
+__device__ __forceinline__ void put_byte(uint8_t *p, uint8_t v, const uint8_t *capend)
+{
+	if (p < capend)
+		*p = v;
+}
+
+__device__ __forceinline__ void put_unit(uint8_t *p, uint64_t q0, uint64_t q1, const uint8_t *capend)
+{
+	if (p + 16 <= capend) {
+		stg_stream16(p, make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32)));
+	} else {
+		for (uint32_t n = 0; n < 16; n++)
+			put_byte(p + n, (uint8_t)((n < 8 ? q0 >> (8 * n) : q1 >> (8 * (n - 8))) & 0xff), capend);
+	}
+}
+
+/* bytes [from, to) of chunk c's own output sequence (its 03s included), byte stores; dst = where
+ * output offset 0 of the chunk goes */
+template <int ROWS>
+__device__ __forceinline__ void chunk_bytes(const Smem<ROWS> &s, uint32_t c, uint32_t from, uint32_t to, uint8_t *dst,
+					    const uint8_t *capend)
+{
+	const uint8_t *rawb = s.raw + 16 + c * 16;
+	const uint32_t m = s.M[c];
+	uint32_t o = 0;
+	for (uint32_t j = 0; j < 16 && o < to; j++) {
+		if ((m >> j) & 1) {
+			if (o >= from)
+				put_byte(dst + o, 3, capend);
+			o++;
+			if (o >= to)
+				break;
+		}
+		if (o >= from)
+			put_byte(dst + o, rawb[j], capend);
+		o++;
+	}
+}
+
+/* the aligned unit that starts ub bytes into chunk c's output (ub < 16 + inserts of c): 16 output
+ * bytes from the source window that starts at the byte (or at the 03 before the byte) found there */
+template <int ROWS>
+__device__ __forceinline__ void gen_unit(const Smem<ROWS> &s, uint32_t c, uint32_t ub, uint8_t *dst, const uint8_t *capend)
+{
+	const uint32_t m = s.M[c];
+	/* smallest source byte j of the chunk whose output offset j + inserts(<= j) is >= ub */
+	uint32_t j = ub < 15u ? ub : 15u;
+	while (j > 0) {
+		const uint32_t jj = j - 1;
+		if (jj + (uint32_t)__popc(m & ((2u << jj) - 1u)) >= ub)
+			j = jj;
+		else
+			break;
+	}
+	const uint32_t idx = j + (uint32_t)__popc(m & ((2u << j) - 1u));
+	uint32_t dm = (m | (uint32_t)s.M[c + 1] << 16) >> j;
+	if (idx == ub)
+		dm &= ~1u; /* the 03 before byte j, if any, belongs to the unit before */
+	dm &= 0xffffu;
+	const uint32_t S = c * 16 + j;
+	const uint32_t *raw32 = (const uint32_t *)(s.raw + 16);
+	const uint32_t wi = S >> 2, sh = (S & 3) * 8;
+	const uint32_t y0 = raw32[wi], y1 = raw32[wi + 1], y2 = raw32[wi + 2], y3 = raw32[wi + 3], y4 = raw32[wi + 4];
+	uint64_t q0 = (uint64_t)__funnelshift_r(y0, y1, sh) | (uint64_t)__funnelshift_r(y1, y2, sh) << 32;
+	uint64_t q1 = (uint64_t)__funnelshift_r(y2, y3, sh) | (uint64_t)__funnelshift_r(y3, y4, sh) << 32;
+	uint32_t added = 0;
+	while (dm) {
+		const uint32_t pos = (uint32_t)__ffs((int)dm) - 1 + added;
+		if (pos >= 16)
+			break;
+		dm &= dm - 1;
+		added++;
+		if (pos < 8) {
+			const uint64_t lo = (1ull << (8 * pos)) - 1;
+			const uint64_t carry = q0 >> 56;
+			q0 = (q0 & lo) | (3ull << (8 * pos)) | ((q0 & ~lo) << 8);
+			q1 = (q1 << 8) | carry;
+		} else {
+			const uint32_t pp = pos - 8;
+			const uint64_t lo = (1ull << (8 * pp)) - 1;
+			q1 = (q1 & lo) | (3ull << (8 * pp)) | ((q1 & ~lo) << 8);
+		}
+	}
+	put_unit(dst, q0, q1, capend);
+}
+
+/* where source position 0 of the tile goes for the chunks of row R at E = 0 */
+template <int ROWS>
+__device__ __forceinline__ uint64_t row_shift(const Smem<ROWS> &s, const FrameArgs &a, uint32_t R, uint64_t k_lo,
+					      bool has_b)
+{
+	uint64_t d = s.pin + a.sc_len * (k_lo + (has_b ? s.krow[R] : 0u));
+	const uint32_t w = R / ROWS;
+	for (uint32_t j = 0; j < w; j++)
+		d += s.sp_etot[j];
+	return d;
+}
+
+/* chunk c of a byte-wise row: payload starts (out_off, start code), 03s and bytes one by one */
+template <int ROWS>
+__device__ __forceinline__ void bytewise_chunk(const Smem<ROWS> &s, const FrameArgs &a, uint32_t c, uint64_t tile_off,
+					       uint32_t nvalid, uint64_t k_lo, uint64_t k_hi)
+{
+	const uint32_t p0 = c * 16;
+	if (p0 >= nvalid)
+		return;
+	const uint32_t nv = nvalid - p0 >= 16u ? 16u : nvalid - p0;
+	const uint64_t x = tile_off + p0;
+	const bool has_b = k_hi > k_lo;
+	/* payloads that started before the chunk */
+	uint64_t next = k_lo + ((has_b && x) ? count_le(a.off, k_lo, k_hi, x - 1) : 0u);
+	uint64_t d = s.pin + (uint64_t)s.E[c];
+	const uint32_t w = c / (uint32_t)Cfg<ROWS>::SPAN_CH;
+	for (uint32_t j = 0; j < w; j++)
+		d += s.sp_etot[j];
+	uint64_t pos = x + d + a.sc_len * next;
+	const uint8_t *capend = a.out + a.out_cap;
+	const uint8_t *rawb = s.raw + 16 + p0;
+	const uint32_t m = s.M[c];
+	uint64_t noff = next < k_hi ? a.off[next] : ~0ull;
+	for (uint32_t j = 0; j < nv; j++) {
+		while (noff == x + j) {
+			a.out_off[next] = pos;
+			for (uint32_t b = 0; b < a.sc_len; b++)
+				put_byte(a.out + pos + b, b + 1 == a.sc_len ? 1 : 0, capend);
+			pos += a.sc_len;
+			next++;
+			noff = next < k_hi ? a.off[next] : ~0ull;
+		}
+		if ((m >> j) & 1)
+			put_byte(a.out + pos++, 3, capend);
+		put_byte(a.out + pos++, rawb[j], capend);
+	}
+}
+
+template <int ROWS, int MINB = 5>
+__global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
+{
+	using C = Cfg<ROWS>;
+	__shared__ Smem<ROWS> s;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t lane = tid & 31, warp = tid >> 5;
+	const uint32_t ltmask = (1u << lane) - 1u;
+	uint32_t *raw32 = (uint32_t *)(s.raw + 16);
+	const uint8_t *rawb = s.raw + 16;
+	const uint32_t c0 = warp * (uint32_t)C::SPAN_CH;
+	const uint8_t *capend = a.out + a.out_cap;
+	uint32_t parity = 0;
+	if (tid == 0)
+		bulk_bar_init(&s.bar);
+
+	for (;;) {
+		/* ---- P0: ticket, bulk load, L2 prefetch one grid ahead, cleared masks ---- */
+		if (tid == 0) {
+			const uint32_t t0 = atomicAdd(a.ticket, 1u) + 1u;
+			s.tile = t0;
+			if (t0 < a.num_tiles) {
+				const uint64_t off = (uint64_t)t0 * C::TILE;
+				if (off + (uint64_t)C::TILE <= a.len)
+					bulk_load_issue(s.raw + 16, a.rbsp + off, C::TILE, &s.bar);
+				const uint64_t noff = off + (uint64_t)gridDim.x * C::TILE;
+				if (noff + (uint64_t)C::TILE <= a.len)
+					l2_prefetch(a.rbsp + noff, C::TILE);
+			}
+		}
+		{
+			uint4 *m4 = (uint4 *)(s.M + c0);
+			for (uint32_t i = lane; i < (uint32_t)C::SPAN_CH / 8; i += 32)
+				m4[i] = make_uint4(0, 0, 0, 0);
+			if (warp == kW - 1 && lane == 0)
+				*(uint4 *)(s.M + C::NCH) = make_uint4(0, 0, 0, 0);
+		}
+		__syncthreads();
+		const uint32_t t = s.tile;
+		if (t >= a.num_tiles)
+			break;
+		const uint64_t tile_off = (uint64_t)t * C::TILE;
+		const uint32_t nvalid = tile_off >= a.len ? 0u
+							  : (a.len - tile_off >= (uint64_t)C::TILE ? (uint32_t)C::TILE
+												   : (uint32_t)(a.len - tile_off));
+		const bool full = nvalid == (uint32_t)C::TILE;
+		const uint64_t k_lo = a.first[t], k_hi = a.first[t + 1];
+		const bool has_b = k_hi > k_lo;
+
+		/* ---- P0b: the zero run before the tile, payload counts and byte-wise rows ---- */
+		if (tid == kT - 1) {
+			/* parity-faithful code: 0, 1, 2 = even >= 2, 3 = odd >= 3 */
+			uint32_t zt = 0;
+			if (t > 0 && !(has_b && a.off[k_lo] == tile_off)) {
+				uint64_t z = 0;
+				for (int64_t tt = (int64_t)t - 1;; tt--) {
+					const uint32_t ti = a.tail[tt];
+					z += ti & 0x7fffffffu;
+					if (!(ti >> 31) || tt == 0)
+						break;
+				}
+				zt = z < 2 ? (uint32_t)z : 2u + (uint32_t)(z & 1);
+			}
+			s.zt = zt;
+			raw32[-1] = tile_off == 0 ? 0xffffffffu : ldg_u32(a.rbsp + tile_off - 4);
+		}
+		if (warp < 2) {
+			const uint32_t R = tid;
+			bool bwr = false;
+			if (R < (uint32_t)C::NROW) {
+				const uint64_t rs = tile_off + (uint64_t)R * 512;
+				uint32_t kr = 0;
+				if (has_b) {
+					kr = count_le(a.off, k_lo, k_hi, rs);
+					const uint32_t below = rs ? count_le(a.off, k_lo, k_hi, rs - 1) : 0u;
+					bwr = count_le(a.off, k_lo, k_hi, rs + 511) > below;
+				}
+				s.krow[R] = kr;
+				if ((R + 1) * 512u > nvalid)
+					bwr = true;
+			}
+			const uint32_t bal = __ballot_sync(FULL_MASK, bwr);
+			if (lane == 0)
+				s.bw32[warp] = bal;
+		}
+		if (!full) {
+			for (uint32_t c = tid; c < (uint32_t)C::NCH; c += kT) {
+				const uint64_t o = tile_off + (uint64_t)c * 16;
+				uint4 v;
+				if (o + 16 <= a.len) {
+					v = ldg_stream16(a.rbsp + o);
+				} else {
+					uint32_t w[4] = {0, 0, 0, 0};
+					for (int b = 0; b < 16; b++)
+						if (o + b < a.len)
+							w[b >> 2] |= (uint32_t)a.rbsp[o + b] << (8 * (b & 3));
+					v = make_uint4(w[0], w[1], w[2], w[3]);
+				}
+				*(uint4 *)(raw32 + 4 * c) = v;
+			}
+		}
+		__syncthreads();
+		if (full) {
+			bulk_load_wait_parity(&s.bar, parity);
+			parity ^= 1u;
+			__syncwarp();
+		}
+		const uint64_t BW = (uint64_t)s.bw32[0] | (uint64_t)s.bw32[1] << 32;
+		const uint32_t zt = s.zt;
+
+		/* ---- P1 (per warp): candidates (some byte <= 3 after two zero bytes), then the exact
+		 * insert mask for them ---- */
+		{
+			const uint32_t k1 = 0x01010101u, kfc = 0xfcfcfcfcu;
+			uint16_t *cand = s.E + c0;
+			uint32_t ntot = 0;
+#pragma unroll 2
+			for (int i = 0; i < ROWS; i++) {
+				const uint32_t c = c0 + i * 32 + lane;
+				const uint4 v = *(const uint4 *)(raw32 + 4 * c);
+				const uint32_t pw = raw32[4 * (int)c - 1];
+				const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+				const uint32_t X0 = __funnelshift_l(pw, w0, 16) | __funnelshift_l(pw, w0, 8) | (w0 & kfc);
+				const uint32_t X1 = __funnelshift_l(w0, w1, 16) | __funnelshift_l(w0, w1, 8) | (w1 & kfc);
+				const uint32_t X2 = __funnelshift_l(w1, w2, 16) | __funnelshift_l(w1, w2, 8) | (w2 & kfc);
+				const uint32_t X3 = __funnelshift_l(w2, w3, 16) | __funnelshift_l(w2, w3, 8) | (w3 & kfc);
+				const uint32_t acc = ((X0 - k1) & ~X0) | ((X1 - k1) & ~X1) | ((X2 - k1) & ~X2) | ((X3 - k1) & ~X3);
+				const bool hit = (acc & 0x80808080u) != 0;
+				const uint32_t bal = __ballot_sync(FULL_MASK, hit);
+				if (hit)
+					cand[ntot + (uint32_t)__popc(bal & ltmask)] = (uint16_t)c;
+				ntot += (uint32_t)__popc(bal);
+			}
+			__syncwarp();
+			for (uint32_t q = lane; q < ntot; q += 32) {
+				const uint32_t c = cand[q];
+				const uint32_t p0 = c * 16;
+				const uint32_t R = c >> 5;
+				const uint32_t vm = full ? 0xffffu : valid16(p0, nvalid);
+				/* payload starts: the last one at or before the chunk, those inside it */
+				uint32_t B16 = 0;
+				int32_t lim = -1;
+				if (has_b) {
+					uint32_t cnt0 = s.krow[R];
+					if ((BW >> R) & 1) {
+						cnt0 = count_le(a.off, k_lo, k_hi, tile_off + p0);
+						const uint32_t cnt1 = count_le(a.off, k_lo, k_hi, tile_off + p0 + 15);
+						for (uint32_t n = cnt0; n < cnt1; n++)
+							B16 |= 1u << (uint32_t)(a.off[k_lo + n] - tile_off - p0);
+					}
+					if (cnt0)
+						lim = (int32_t)(a.off[k_lo + cnt0 - 1] - tile_off);
+				}
+				/* zero run that reaches the chunk from the left */
+				const uint32_t lo = lim >= 0 ? (uint32_t)lim : 0u;
+				uint32_t p = p0;
+				while (p >= lo + 16) {
+					const uint4 u = *(const uint4 *)(raw32 + (p >> 2) - 4);
+					if (u.x | u.y | u.z | u.w)
+						break;
+					p -= 16;
+				}
+				while (p > lo && rawb[p - 1] == 0)
+					p--;
+				uint32_t zin = p0 - p;
+				if (p == 0 && lim < 0)
+					zin += zt;
+				const uint4 v = *(const uint4 *)(raw32 + 4 * c);
+				const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+				uint32_t ins16 = 0;
+				if (B16 == 0) {
+					const uint32_t kfc2 = 0xfcfcfcfcu;
+					const uint32_t Z16 = zmask4(w0) | zmask4(w1) << 4 | zmask4(w2) << 8 | zmask4(w3) << 12;
+					const uint32_t L16 = zmask4(w0 & kfc2) | zmask4(w1 & kfc2) << 4 | zmask4(w2 & kfc2) << 8 |
+							     zmask4(w3 & kfc2) << 12;
+					const uint32_t Zext = Z16 << 2 | (zin >= 1 ? 2u : 0u) | (zin >= 2 ? 1u : 0u);
+					uint32_t pc = L16 & (Zext >> 1) & Zext & 0xffffu;
+					while (pc) {
+						const uint32_t j = (uint32_t)__ffs((int)pc) - 1;
+						pc &= pc - 1;
+						const uint32_t n1 = (uint32_t)__clz((int)~(Zext << (30 - j)));
+						const uint32_t z = n1 < j + 2 ? n1 : j + zin;
+						if (!(z & 1))
+							ins16 |= 1u << j;
+					}
+				} else {
+					uint32_t z = zin;
+					const uint32_t wv[4] = {w0, w1, w2, w3};
+					for (uint32_t j = 0; j < 16; j++) {
+						if ((B16 >> j) & 1)
+							z = 0;
+						const uint32_t cb = (wv[j >> 2] >> (8 * (j & 3))) & 0xff;
+						if (cb <= 3 && z >= 2 && !(z & 1))
+							ins16 |= 1u << j;
+						z = cb == 0 ? z + 1 : 0;
+					}
+				}
+				ins16 &= vm;
+				if (ins16)
+					s.M[c] = (uint16_t)ins16;
+			}
+			__syncwarp();
+		}
+
+		/* ---- P2 (per warp): inserts of the span before every chunk ---- */
+		{
+			uint32_t ex[ROWS];
+			uint32_t run = 0;
+			const uint16_t *mp = s.M + c0 + lane * ROWS;
+#pragma unroll
+			for (int k = 0; k < ROWS; k++) {
+				ex[k] = run;
+				run += (uint32_t)__popc(mp[k]);
+			}
+			uint32_t inc = run;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+				if (lane >= (uint32_t)d)
+					inc += o;
+			}
+			const uint32_t etot = __shfl_sync(FULL_MASK, inc, 31);
+			const uint32_t base = inc - run;
+			uint16_t *ep = s.E + c0 + lane * ROWS;
+#pragma unroll
+			for (int k = 0; k < ROWS; k++)
+				ep[k] = (uint16_t)(base + ex[k]);
+			if (lane == 0)
+				s.sp_etot[warp] = etot;
+		}
+		__syncthreads();
+
+		/* ---- P3 (warp 0): tile aggregate published at once, look-back over sums ---- */
+		if (warp == 0) {
+			uint32_t tile_total = 0;
+#pragma unroll
+			for (int j = 0; j < kW; j++)
+				tile_total += s.sp_etot[j];
+			uint64_t pin = 0;
+			if (t > 0) {
+				if (lane == 0)
+					st_relaxed_u64(a.desc + t, (uint64_t)tile_total);
+				int64_t j0 = (int64_t)t - 1;
+				for (bool done = false; !done;) {
+					const int64_t j = j0 - lane;
+					const bool need = j >= 0;
+					uint64_t d = kInvalid;
+					uint32_t pm;
+					for (;;) {
+						if (need)
+							d = ld_relaxed_u64(a.desc + j);
+						pm = __ballot_sync(FULL_MASK, need && !(d & kInvalid) && (d & kPrefix));
+						const uint32_t ok = __ballot_sync(FULL_MASK, !need || !(d & kInvalid));
+						const uint32_t upto = pm ? ((pm & (0u - pm)) << 1) - 1u : 0xffffffffu;
+						if ((ok & upto) == upto)
+							break;
+						spin_pause(20);
+					}
+					const int fp = pm ? __ffs((int)pm) - 1 : 32;
+					uint64_t val = (need && (int)lane <= fp) ? (d & kValueMask) : 0;
+#pragma unroll
+					for (int dd = 16; dd >= 1; dd >>= 1)
+						val += __shfl_xor_sync(FULL_MASK, val, dd);
+					pin += val;
+					if (fp < 32)
+						done = true;
+					else
+						j0 -= 32;
+				}
+			}
+			const uint64_t pout = pin + tile_total;
+			if (lane == 0) {
+#ifdef H264_EMU
+				/* test hook: withhold most prefixes so look-back must sum aggregates */
+				if (t == 0 || annexb::emu_prefix_every <= 1 || t % annexb::emu_prefix_every == 0)
+#endif
+					st_relaxed_u64(a.desc + t, pout | kPrefix);
+				s.pin = pin;
+				if (t == a.num_tiles - 1) {
+					/* payloads that start at len (empty, at the very end) and the total */
+					for (uint64_t k = k_hi; k < a.n; k++) {
+						const uint64_t pos = a.len + pout + a.sc_len * k;
+						a.out_off[k] = pos;
+						for (uint32_t b = 0; b < a.sc_len; b++)
+							put_byte(a.out + pos + b, b + 1 == a.sc_len ? 1 : 0, capend);
+					}
+					const uint64_t end = a.len + pout + a.sc_len * a.n;
+					a.out_off[a.n] = end;
+					*a.total = end;
+				}
+			}
+		}
+		__syncthreads();
+
+		/* ---- P4: emit.  Every warp its span's rows; chunks that need the byte-exact path are
+		 * listed per span and shared out over the block afterwards ---- */
+		{
+			uint64_t d0 = s.pin;
+			for (uint32_t j = 0; j < warp; j++)
+				d0 += s.sp_etot[j];
+			uint8_t *dl = s.dl + c0;
+			uint32_t ndirty = 0;
+#pragma unroll 2
+			for (int i = 0; i < ROWS; i++) {
+				const uint32_t R = warp * ROWS + i;
+				if ((BW >> R) & 1)
+					continue;
+				const bool seam_before = R == 0 || ((BW >> (R - 1)) & 1);
+				const bool seam_after = R == (uint32_t)C::NROW - 1 || ((BW >> (R + 1)) & 1);
+				const uint64_t rd = d0 + a.sc_len * (k_lo + (has_b ? s.krow[R] : 0u));
+				const uint32_t c = c0 + i * 32 + lane;
+				const uint32_t p0 = c * 16;
+				const uint32_t e = s.E[c];
+				const uint32_t m = s.M[c];
+				const uint32_t mn = s.M[c + 1];
+				uint8_t *o = a.out + (tile_off + rd + p0 + e); /* the chunk's first output byte */
+				const uint32_t b = (0u - ((uint32_t)rd + e)) & 15u;
+				if (seam_before && lane == 0 && b)
+					chunk_bytes<ROWS>(s, c, 0, b, o, capend);
+				uint32_t bad = m | (mn & ((1u << b) - 1u));
+				if (seam_after && lane == 31 && (b | m))
+					bad = 1; /* the unit runs over a seam */
+				if (!bad) {
+					const uint32_t S = p0 + b;
+					const uint32_t wi = S >> 2, sh = (S & 3) * 8;
+					const uint32_t y0 = raw32[wi], y1 = raw32[wi + 1], y2 = raw32[wi + 2];
+					const uint32_t y3 = raw32[wi + 3], y4 = raw32[wi + 4];
+					const uint4 val = make_uint4(__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh),
+								     __funnelshift_r(y2, y3, sh), __funnelshift_r(y3, y4, sh));
+					if (o + b + 16 <= capend)
+						stg_stream16_free(o + b, val);
+					else
+						put_unit(o + b, (uint64_t)val.x | (uint64_t)val.y << 32,
+							 (uint64_t)val.z | (uint64_t)val.w << 32, capend);
+				}
+				const uint32_t bal = __ballot_sync(FULL_MASK, bad != 0);
+				if (bad)
+					dl[ndirty + (uint32_t)__popc(bal & ltmask)] = (uint8_t)(i * 32 + lane);
+				ndirty += (uint32_t)__popc(bal);
+			}
+			if (lane == 0)
+				s.sp_nd[warp] = ndirty;
+		}
+		__syncthreads();
+		{
+			uint32_t pre[kW + 1];
+			pre[0] = 0;
+#pragma unroll
+			for (int j = 0; j < kW; j++)
+				pre[j + 1] = pre[j] + s.sp_nd[j];
+			const uint32_t nitems = pre[kW] + 32u * (uint32_t)__popcll(BW);
+			for (uint32_t g = tid; g < nitems; g += kT) {
+				if (g >= pre[kW]) {
+					/* chunk (g % 32) of the byte-wise row number (g / 32) */
+					const uint32_t k = (g - pre[kW]) >> 5;
+					uint64_t x = BW;
+					for (uint32_t n = 0; n < k; n++)
+						x &= x - 1;
+					const uint32_t R = (uint32_t)__ffsll((long long)x) - 1;
+					bytewise_chunk<ROWS>(s, a, R * 32 + ((g - pre[kW]) & 31u), tile_off, nvalid, k_lo, k_hi);
+					continue;
+				}
+				uint32_t w = 0, pw = 0;
+#pragma unroll
+				for (int j = 1; j < kW; j++) {
+					w += g >= pre[j] ? 1u : 0u;
+					pw = g >= pre[j] ? pre[j] : pw;
+				}
+				const uint32_t c = w * (uint32_t)C::SPAN_CH + s.dl[w * (uint32_t)C::SPAN_CH + (g - pw)];
+				const uint32_t R = c >> 5;
+				const uint64_t rd = row_shift<ROWS>(s, a, R, k_lo, has_b);
+				const uint32_t e = s.E[c];
+				const uint32_t kins = (uint32_t)__popc(s.M[c]);
+				uint8_t *o = a.out + (tile_off + rd + (uint64_t)c * 16 + e);
+				const uint32_t b = (0u - ((uint32_t)rd + e)) & 15u;
+				const bool seam_after = (c & 31u) == 31u && (R == (uint32_t)C::NROW - 1 || ((BW >> (R + 1)) & 1));
+				if (seam_after) {
+					chunk_bytes<ROWS>(s, c, b, 16 + kins, o, capend);
+				} else {
+					gen_unit<ROWS>(s, c, b, o + b, capend);
+					if (b < kins)
+						gen_unit<ROWS>(s, c, b + 16, o + b + 16, capend);
+				}
+			}
+		}
+		__syncthreads(); /* the tile's shared memory is reused */
+	}
+}
+
+} /* namespace frame6 */
+
+#endif /* ANNEXB_FRAME6_CUH */

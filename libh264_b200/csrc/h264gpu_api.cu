@@ -820,6 +820,42 @@ extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, u
 /* ---- writer side: EPB insert + framing --------------------------------------- */
 
 #include "annexb_frame.cuh"
+#include "annexb_frame6.cuh"
+
+/* K3 generation: 6 = frame6_kernel (persistent CTAs, units straight from the staged source tile,
+ * the default), 1 = frame_kernel (A/B baseline); H264GPU_FRAME_GEN */
+static int frame_gen(void)
+{
+	static int gen = 0;
+	if (gen == 0) {
+		const char *e = getenv("H264GPU_FRAME_GEN");
+		gen = (e != NULL && atoi(e) == 1) ? 1 : 6;
+	}
+	return gen;
+}
+
+template <int ROWS>
+static cudaError_t launch_frame6(const frame::FrameArgs &a, cudaStream_t st)
+{
+	const uint32_t pthreads = 128;
+	const uint32_t pblocks = (a.num_tiles + 1 + pthreads - 1) / pthreads;
+	frame::frame_prepass<ROWS><<<pblocks, pthreads, 0, st>>>(a);
+	static int sms = 0;
+	if (sms == 0) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (sms <= 0)
+			sms = 148;
+	}
+	constexpr int B = ROWS == 8 ? 5 : 4;
+	cudaFuncSetAttribute(frame6::frame6_kernel<ROWS, B>, cudaFuncAttributePreferredSharedMemoryCarveout,
+			     cudaSharedmemCarveoutMaxShared);
+	const uint32_t cap = (uint32_t)sms * B;
+	const uint32_t grid = a.num_tiles < cap ? a.num_tiles : cap;
+	frame6::frame6_kernel<ROWS, B><<<grid, frame6::kT, 0, st>>>(a);
+	return cudaGetLastError();
+}
 
 template <int ITEMS>
 static cudaError_t launch_frame(const frame::FrameArgs &a, cudaStream_t st)
@@ -862,7 +898,8 @@ extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const 
 	CU_TRY(cudaStreamSynchronize(st));
 	if (len && d_rbsp == NULL)
 		return -EINVAL;
-	const int items = ctx->scan_items >= 100 ? 4 : ctx->scan_items;
+	const int gen = frame_gen();
+	const int items = ctx->scan_items >= 100 ? (gen == 6 ? 8 : 4) : ctx->scan_items;
 	const uint64_t tile = (uint64_t)annexb::kBlock * items * 16;
 	uint64_t ntiles = (len + tile - 1) / tile;
 	if (ntiles == 0)
@@ -896,7 +933,12 @@ extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const 
 	a.tail = (uint32_t *)((uint8_t *)ctx->ws + tail_off);
 	a.num_tiles = (uint32_t)ntiles;
 	cudaError_t ce;
-	if (items == 1)
+	if (gen == 6)
+		ce = items == 1 ? launch_frame6<1>(a, st)
+		   : items == 2 ? launch_frame6<2>(a, st)
+		   : items == 4 ? launch_frame6<4>(a, st)
+				: launch_frame6<8>(a, st);
+	else if (items == 1)
 		ce = launch_frame<1>(a, st);
 	else if (items == 2)
 		ce = launch_frame<2>(a, st);

@@ -8,6 +8,7 @@
 #include "annexb_scan5.cuh"
 #include "annexb_scan6.cuh"
 #include "annexb_frame.cuh"
+#include "annexb_frame6.cuh"
 
 #include <vector>
 
@@ -202,6 +203,10 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 			 uint64_t *total, int items)
 {
 	using namespace frame;
+	/* items 1/2/4: frame_kernel; 61/62/64/68: frame6_kernel with 1/2/4/8 rows per warp */
+	const bool gen6 = items > 60;
+	if (gen6)
+		items -= 60;
 	const uint64_t tile = (uint64_t)kBlock * items * 16;
 	uint32_t ntiles = (uint32_t)((len + tile - 1) / tile);
 	if (ntiles == 0)
@@ -228,7 +233,23 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 	a.tail = tail.data();
 	a.num_tiles = ntiles;
 	dim3 pgrid((ntiles + 1 + 127) / 128), pblock(128), grid(ntiles), block(kBlock);
-	if (items == 1) {
+	if (gen6) {
+		/* persistent CTAs: a few of them share the tiles */
+		dim3 g6(ntiles < 3 ? ntiles : 3);
+		if (items == 1) {
+			EMU_LAUNCH((frame_prepass<1>), pgrid, pblock, a);
+			EMU_LAUNCH((frame6::frame6_kernel<1, 1>), g6, block, a);
+		} else if (items == 2) {
+			EMU_LAUNCH((frame_prepass<2>), pgrid, pblock, a);
+			EMU_LAUNCH((frame6::frame6_kernel<2, 1>), g6, block, a);
+		} else if (items == 4) {
+			EMU_LAUNCH((frame_prepass<4>), pgrid, pblock, a);
+			EMU_LAUNCH((frame6::frame6_kernel<4, 1>), g6, block, a);
+		} else {
+			EMU_LAUNCH((frame_prepass<8>), pgrid, pblock, a);
+			EMU_LAUNCH((frame6::frame6_kernel<8, 1>), g6, block, a);
+		}
+	} else if (items == 1) {
 		EMU_LAUNCH((frame_prepass<1>), pgrid, pblock, a);
 		EMU_LAUNCH((frame_kernel<1>), grid, block, a);
 	} else if (items == 2) {

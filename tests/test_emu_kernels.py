@@ -216,6 +216,80 @@ def test_emu_frame_random_and_adversarial():
     check_frame(np.zeros(0, np.uint8), np.array([0], np.uint64), 4, 1, "no payloads")
 
 
+# ---- K3 gen 6 (frame6_kernel): items 61/62/64/68 = 1/2/4/8 rows per warp -------------------
+
+def test_emu_frame6_known_answer():
+    p = KA.hx(KA.INSERT_IN)
+    for items in (61, 68):
+        out, oo, tot = emu_frame(p, np.array([0, len(p)], np.uint64), 0, items)
+        assert bytes(out[:tot]) == bytes(KA.hx(KA.INSERT_OUT))
+
+
+def test_emu_frame6_random_and_adversarial():
+    lib = S.emu()
+    rng = np.random.default_rng(55)
+    g6 = [61, 62, 64, 68]
+    try:
+        for every in (1, 3, 50):
+            lib.emu_set_prefix_every(every)
+            for it in range(4):
+                data, offs = S.gen_payloads(rng, int(rng.integers(1, 60)), 1, 5000)
+                check_frame(data, offs, 4 if it % 2 else 3, int(rng.choice(g6)), ("rand6", every, it))
+            for it in range(8):
+                tot = int(rng.integers(0, 40000))
+                data = rng.choice(np.array([0, 0, 0, 0, 1, 2, 3, 4, 0xFF], np.uint8), tot)
+                n = int(rng.integers(0, 30))
+                cuts = np.sort(rng.integers(0, tot + 1, n)) if n else np.zeros(0, np.int64)
+                offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+                check_frame(data, offs, int(rng.choice([0, 3, 4])), int(rng.choice(g6)), ("adv6", every, it))
+            for it in range(3):  # zero runs spanning whole rows, spans and tiles
+                tot = int(rng.integers(9000, 70000))
+                data = np.zeros(tot, np.uint8)
+                for p in rng.integers(0, tot, 3):
+                    data[p] = rng.choice([1, 3, 7])
+                check_frame(data, np.array([0, tot // 3, tot // 3, tot], np.uint64), 4, int(rng.choice([61, 68])),
+                            ("zeros6", every, it))
+    finally:
+        lib.emu_set_prefix_every(1)
+    for items in (61, 68):
+        check_frame(np.zeros(0, np.uint8), np.array([0, 0, 0], np.uint64), 4, items, "empty payloads only")
+        check_frame(np.zeros(0, np.uint8), np.array([0], np.uint64), 4, items, "no payloads")
+
+
+def test_emu_frame6_stream_shaped_and_dense_starts():
+    rng = np.random.default_rng(56)
+    for it in range(3):  # the bench's byte statistics, a handful of payloads over several 32 KiB tiles
+        tot = int(rng.integers(100000, 250000))
+        data = rng.integers(0, 256, tot).astype(np.uint8)
+        data[rng.random(tot) < 0.1875] = 0
+        cuts = np.sort(rng.integers(0, tot + 1, int(rng.integers(1, 8))))
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        check_frame(data, offs, 4, 68, ("stream6", it))
+        check_frame(data, offs, 3, 62, ("stream6", it))
+    for it in range(3):  # payloads of a few bytes: every row goes byte by byte
+        tot = int(rng.integers(3000, 20000))
+        data = rng.choice(np.array([0, 0, 0, 1, 3, 0xFF], np.uint8), tot)
+        cuts = np.sort(rng.integers(0, tot + 1, tot // 3))
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        check_frame(data, offs, 4, int(rng.choice([61, 64])), ("dense6", it))
+
+
+def test_emu_frame6_output_capacity_is_respected():
+    """Nothing is written past out_cap (the C-ABI reports -ENOBUFS from the total)."""
+    lib = S.emu()
+    rng = np.random.default_rng(57)
+    data = rng.choice(np.array([0, 0, 0, 1, 3, 0xFF], np.uint8), 20000)
+    offs = np.array([0, 7000, 20000], np.uint64)
+    exp, eoo = S.oracle_frame(data, offs, 4)
+    for cap in (0, 5, 4099, len(exp) - 1):
+        out = np.full(len(exp) + 64, 0xAA, np.uint8)
+        oo = np.full(3, S.NONE64, np.uint64)
+        tot = C.c_uint64(0)
+        lib.emu_frame(S.ptr(data), len(data), S.ptr(offs), 2, 4, S.ptr(out), cap, S.ptr(oo), C.byref(tot), 62)
+        assert tot.value == len(exp)
+        assert np.array_equal(out[:cap], exp[:cap]) and (out[cap:] == 0xAA).all(), cap
+
+
 def test_emu_frame_then_scan_round_trip():
     rng = np.random.default_rng(8)
     data, offs = S.gen_payloads(rng, 50, 2, 3000)

@@ -219,6 +219,35 @@ def test_frame_random_and_adversarial(gpu):
     assert bytes(out) == bytes([0, 0, 0, 1, 0, 0, 0, 1])
 
 
+def test_frame_small_tiles_and_capacity():
+    """frame6_kernel with 1/2/4 rows per warp (4-16 KiB tiles: many tiles, seams and look-back on
+    small inputs), sparse and zero-heavy bytes."""
+    rng = np.random.default_rng(58)
+    old = os.environ.get("H264GPU_SCAN_ITEMS")
+    try:
+        for items in ("1", "2", "4"):
+            os.environ["H264GPU_SCAN_ITEMS"] = items
+            g = L.Gpu(0)
+            try:
+                for it in range(4):
+                    tot = int(rng.integers(1000, 300000))
+                    data = rng.integers(0, 256, tot).astype(np.uint8)
+                    data[rng.random(tot) < (0.1875 if it % 2 else 0.6)] = 0
+                    n = int(rng.integers(0, 40))
+                    cuts = np.sort(rng.integers(0, tot + 1, n)) if n else np.zeros(0, np.int64)
+                    offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+                    exp, eoo = S.oracle_frame(data, offs, 4)
+                    out, oo = g.frame_host(data, offs, sc_len=4)
+                    assert np.array_equal(out, exp) and np.array_equal(oo, eoo), (items, it)
+            finally:
+                g.close()
+    finally:
+        if old is None:
+            os.environ.pop("H264GPU_SCAN_ITEMS", None)
+        else:
+            os.environ["H264GPU_SCAN_ITEMS"] = old
+
+
 def test_writer_round_trip_full_size(gpu):
     """Config 5 shape at 64 MiB: frame on the GPU, then the reference-side reader
     semantics (GPU scan+strip, itself oracle-checked above) give back the payloads."""
