@@ -62,9 +62,9 @@ template <int ROWS> struct __align__(128) Smem {
 	uint16_t M[Cfg<ROWS>::NCH + 8];         /* insert mask per chunk (bit j = 03 before byte j) */
 	uint16_t E[Cfg<ROWS>::NCH];             /* inserts of the span before the chunk; candidate list before that */
 	uint8_t dl[Cfg<ROWS>::NCH];             /* per span: chunks that take the byte-exact path */
-	uint32_t krow[Cfg<ROWS>::NROW];         /* payload starts of the tile at or before the row start */
+	uint32_t krow[Cfg<ROWS>::NROW + 1];     /* payload starts of the tile before the row start */
 	uint32_t sp_etot[kW], sp_nd[kW];
-	uint32_t bw32[2];                       /* byte-wise rows */
+	uint64_t sp_base[kW];                   /* inserts before the span + sc_len * payloads before the tile */
 	uint64_t bar;
 	uint64_t pin; /* inserts before the tile */
 	uint32_t tile, zt;
@@ -83,20 +83,26 @@ __device__ __forceinline__ void put_byte(uint8_t *p, uint8_t v, const uint8_t *c
 		*p = v;
 }
 
+/* a unit that does not fit whole: byte by byte (only next to the end of the output buffer) */
+__device__ __noinline__ void put_unit_bytes(uint8_t *p, uint64_t q0, uint64_t q1, const uint8_t *capend)
+{
+#pragma unroll 1
+	for (uint32_t n = 0; n < 16; n++)
+		put_byte(p + n, (uint8_t)((n < 8 ? q0 >> (8 * n) : q1 >> (8 * (n - 8))) & 0xff), capend);
+}
+
 __device__ __forceinline__ void put_unit(uint8_t *p, uint64_t q0, uint64_t q1, const uint8_t *capend)
 {
-	if (p + 16 <= capend) {
+	if (p + 16 <= capend)
 		stg_stream16(p, make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32)));
-	} else {
-		for (uint32_t n = 0; n < 16; n++)
-			put_byte(p + n, (uint8_t)((n < 8 ? q0 >> (8 * n) : q1 >> (8 * (n - 8))) & 0xff), capend);
-	}
+	else
+		put_unit_bytes(p, q0, q1, capend);
 }
 
 /* bytes [from, to) of chunk c's own output sequence (its 03s included), byte stores; dst = where
  * output offset 0 of the chunk goes */
 template <int ROWS>
-__device__ __forceinline__ void chunk_bytes(const Smem<ROWS> &s, uint32_t c, uint32_t from, uint32_t to, uint8_t *dst,
+__device__ __noinline__ void chunk_bytes(const Smem<ROWS> &s, uint32_t c, uint32_t from, uint32_t to, uint8_t *dst,
 					    const uint8_t *capend)
 {
 	const uint8_t *rawb = s.raw + 16 + c * 16;
@@ -163,21 +169,9 @@ __device__ __forceinline__ void gen_unit(const Smem<ROWS> &s, uint32_t c, uint32
 	put_unit(dst, q0, q1, capend);
 }
 
-/* where source position 0 of the tile goes for the chunks of row R at E = 0 */
-template <int ROWS>
-__device__ __forceinline__ uint64_t row_shift(const Smem<ROWS> &s, const FrameArgs &a, uint32_t R, uint64_t k_lo,
-					      bool has_b)
-{
-	uint64_t d = s.pin + a.sc_len * (k_lo + (has_b ? s.krow[R] : 0u));
-	const uint32_t w = R / ROWS;
-	for (uint32_t j = 0; j < w; j++)
-		d += s.sp_etot[j];
-	return d;
-}
-
 /* chunk c of a byte-wise row: payload starts (out_off, start code), 03s and bytes one by one */
 template <int ROWS>
-__device__ __forceinline__ void bytewise_chunk(const Smem<ROWS> &s, const FrameArgs &a, uint32_t c, uint64_t tile_off,
+__device__ __noinline__ void bytewise_chunk(const Smem<ROWS> &s, const FrameArgs &a, uint32_t c, uint64_t tile_off,
 					       uint32_t nvalid, uint64_t k_lo, uint64_t k_hi)
 {
 	const uint32_t p0 = c * 16;
@@ -188,11 +182,9 @@ __device__ __forceinline__ void bytewise_chunk(const Smem<ROWS> &s, const FrameA
 	const bool has_b = k_hi > k_lo;
 	/* payloads that started before the chunk */
 	uint64_t next = k_lo + ((has_b && x) ? count_le(a.off, k_lo, k_hi, x - 1) : 0u);
-	uint64_t d = s.pin + (uint64_t)s.E[c];
-	const uint32_t w = c / (uint32_t)Cfg<ROWS>::SPAN_CH;
-	for (uint32_t j = 0; j < w; j++)
-		d += s.sp_etot[j];
-	uint64_t pos = x + d + a.sc_len * next;
+	/* sp_base holds sc_len * k_lo already */
+	const uint64_t d = s.sp_base[c / (uint32_t)Cfg<ROWS>::SPAN_CH] + (uint64_t)s.E[c];
+	uint64_t pos = x + d + a.sc_len * (next - k_lo);
 	const uint8_t *capend = a.out + a.out_cap;
 	const uint8_t *rawb = s.raw + 16 + p0;
 	const uint32_t m = s.M[c];
@@ -210,6 +202,62 @@ __device__ __forceinline__ void bytewise_chunk(const Smem<ROWS> &s, const FrameA
 			put_byte(a.out + pos++, 3, capend);
 		put_byte(a.out + pos++, rawb[j], capend);
 	}
+}
+
+/*
+ * P4: the rows of a span.  bwl: bit 0 = the row before the span is a seam (byte-wise row or tile
+ * start), bits 1..ROWS = own rows that go byte by byte, bit ROWS + 1 = the row after the span is a
+ * seam.  LEAN (most spans): no byte-wise row, hence no payload start, in the span: one start-code
+ * offset for all rows and seams only at the two ends.  base = where source position 0 of the
+ * tile goes for this span at E = 0 without the start codes of the tile, shl = its low bits.
+ */
+template <int ROWS, bool LEAN>
+__device__ __forceinline__ void emit_span(Smem<ROWS> &s, const FrameArgs &a, uint32_t warp, uint32_t lane, uint32_t bwl,
+					  uint8_t *base, uint32_t shl, bool has_b, bool safe, const uint8_t *capend)
+{
+	const uint32_t c0 = warp * (uint32_t)Cfg<ROWS>::SPAN_CH;
+	const uint32_t ltmask = (1u << lane) - 1u;
+	const uint32_t *raw32 = (const uint32_t *)(s.raw + 16);
+	uint8_t *dl = s.dl + c0;
+	uint32_t ndirty = 0;
+	const uint32_t koff0 = has_b ? a.sc_len * s.krow[warp * ROWS] : 0u;
+#pragma unroll(LEAN ? ROWS : 1)
+	for (int i = 0; i < ROWS; i++) {
+		if (!LEAN && ((bwl >> (i + 1)) & 1))
+			continue;
+		const uint32_t koff = LEAN ? koff0 : (has_b ? a.sc_len * s.krow[warp * ROWS + i] : 0u);
+		const uint32_t c = c0 + i * 32 + lane;
+		const uint32_t p0 = c * 16;
+		const uint32_t e = s.E[c];
+		const uint32_t m = s.M[c];
+		const uint32_t mn = s.M[c + 1];
+		uint8_t *o = base + (p0 + e + koff); /* the chunk's first output byte */
+		const uint32_t b = (0u - (shl + e + koff)) & 15u;
+		if ((i == 0 || !LEAN) && ((bwl >> i) & 1) && lane == 0 && b)
+			chunk_bytes<ROWS>(s, c, 0, b, o, capend);
+		uint32_t bad = m | (mn & ((1u << b) - 1u));
+		if ((i == ROWS - 1 || !LEAN) && ((bwl >> (i + 2)) & 1) && lane == 31 && (b | m))
+			bad = 1; /* the unit runs over a seam */
+		if (!bad) {
+			const uint32_t S = p0 + b;
+			const uint32_t wi = S >> 2, sh = (S & 3) * 8;
+			const uint32_t y0 = raw32[wi], y1 = raw32[wi + 1], y2 = raw32[wi + 2];
+			const uint32_t y3 = raw32[wi + 3], y4 = raw32[wi + 4];
+			const uint4 val = make_uint4(__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh),
+						     __funnelshift_r(y2, y3, sh), __funnelshift_r(y3, y4, sh));
+			if (safe || o + b + 16 <= capend)
+				stg_stream16_free(o + b, val);
+			else
+				put_unit(o + b, (uint64_t)val.x | (uint64_t)val.y << 32, (uint64_t)val.z | (uint64_t)val.w << 32,
+					 capend);
+		}
+		const uint32_t bal = __ballot_sync(FULL_MASK, bad != 0);
+		if (bad)
+			dl[ndirty + (uint32_t)__popc(bal & ltmask)] = (uint8_t)(i * 32 + lane);
+		ndirty += (uint32_t)__popc(bal);
+	}
+	if (lane == 0)
+		s.sp_nd[warp] = ndirty;
 }
 
 template <int ROWS, int MINB = 5>
@@ -278,24 +326,10 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 			s.zt = zt;
 			raw32[-1] = tile_off == 0 ? 0xffffffffu : ldg_u32(a.rbsp + tile_off - 4);
 		}
-		if (warp < 2) {
-			const uint32_t R = tid;
-			bool bwr = false;
-			if (R < (uint32_t)C::NROW) {
-				const uint64_t rs = tile_off + (uint64_t)R * 512;
-				uint32_t kr = 0;
-				if (has_b) {
-					kr = count_le(a.off, k_lo, k_hi, rs);
-					const uint32_t below = rs ? count_le(a.off, k_lo, k_hi, rs - 1) : 0u;
-					bwr = count_le(a.off, k_lo, k_hi, rs + 511) > below;
-				}
-				s.krow[R] = kr;
-				if ((R + 1) * 512u > nvalid)
-					bwr = true;
-			}
-			const uint32_t bal = __ballot_sync(FULL_MASK, bwr);
-			if (lane == 0)
-				s.bw32[warp] = bal;
+		if (tid <= (uint32_t)C::NROW) {
+			/* payload starts of the tile before row `tid` (entry NROW: all of them) */
+			const uint64_t rs = tile_off + (uint64_t)tid * 512;
+			s.krow[tid] = (has_b && rs) ? count_le(a.off, k_lo, k_hi, rs - 1) : 0u;
 		}
 		if (!full) {
 			for (uint32_t c = tid; c < (uint32_t)C::NCH; c += kT) {
@@ -319,7 +353,14 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 			parity ^= 1u;
 			__syncwarp();
 		}
-		const uint64_t BW = (uint64_t)s.bw32[0] | (uint64_t)s.bw32[1] << 32;
+		/* byte-wise rows: a payload start inside, or the input ends in (or before) the row */
+		uint64_t BW;
+		{
+			const uint32_t r0 = lane, r1 = lane + 32;
+			const bool b0 = r0 < (uint32_t)C::NROW && (s.krow[r0 + 1] > s.krow[r0] || (r0 + 1) * 512u > nvalid);
+			const bool b1 = r1 < (uint32_t)C::NROW && (s.krow[r1 + 1] > s.krow[r1] || (r1 + 1) * 512u > nvalid);
+			BW = (uint64_t)__ballot_sync(FULL_MASK, b0) | (uint64_t)__ballot_sync(FULL_MASK, b1) << 32;
+		}
 		const uint32_t zt = s.zt;
 
 		/* ---- P1 (per warp): candidates (some byte <= 3 after two zero bytes), then the exact
@@ -508,72 +549,45 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 
 		/* ---- P4: emit.  Every warp its span's rows; chunks that need the byte-exact path are
 		 * listed per span and shared out over the block afterwards ---- */
+		const uint64_t pin = s.pin;
+		/* the tile's whole output, with a unit of slack, inside the capacity: no store needs a check */
+		const bool safe = tile_off + (uint64_t)(C::TILE + C::TILE / 2 + 32) + pin + a.sc_len * k_hi <= a.out_cap;
 		{
-			uint64_t d0 = s.pin;
+			uint64_t d0 = pin + a.sc_len * k_lo;
 			for (uint32_t j = 0; j < warp; j++)
 				d0 += s.sp_etot[j];
-			uint8_t *dl = s.dl + c0;
-			uint32_t ndirty = 0;
-#pragma unroll 2
-			for (int i = 0; i < ROWS; i++) {
-				const uint32_t R = warp * ROWS + i;
-				if ((BW >> R) & 1)
-					continue;
-				const bool seam_before = R == 0 || ((BW >> (R - 1)) & 1);
-				const bool seam_after = R == (uint32_t)C::NROW - 1 || ((BW >> (R + 1)) & 1);
-				const uint64_t rd = d0 + a.sc_len * (k_lo + (has_b ? s.krow[R] : 0u));
-				const uint32_t c = c0 + i * 32 + lane;
-				const uint32_t p0 = c * 16;
-				const uint32_t e = s.E[c];
-				const uint32_t m = s.M[c];
-				const uint32_t mn = s.M[c + 1];
-				uint8_t *o = a.out + (tile_off + rd + p0 + e); /* the chunk's first output byte */
-				const uint32_t b = (0u - ((uint32_t)rd + e)) & 15u;
-				if (seam_before && lane == 0 && b)
-					chunk_bytes<ROWS>(s, c, 0, b, o, capend);
-				uint32_t bad = m | (mn & ((1u << b) - 1u));
-				if (seam_after && lane == 31 && (b | m))
-					bad = 1; /* the unit runs over a seam */
-				if (!bad) {
-					const uint32_t S = p0 + b;
-					const uint32_t wi = S >> 2, sh = (S & 3) * 8;
-					const uint32_t y0 = raw32[wi], y1 = raw32[wi + 1], y2 = raw32[wi + 2];
-					const uint32_t y3 = raw32[wi + 3], y4 = raw32[wi + 4];
-					const uint4 val = make_uint4(__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh),
-								     __funnelshift_r(y2, y3, sh), __funnelshift_r(y3, y4, sh));
-					if (o + b + 16 <= capend)
-						stg_stream16_free(o + b, val);
-					else
-						put_unit(o + b, (uint64_t)val.x | (uint64_t)val.y << 32,
-							 (uint64_t)val.z | (uint64_t)val.w << 32, capend);
-				}
-				const uint32_t bal = __ballot_sync(FULL_MASK, bad != 0);
-				if (bad)
-					dl[ndirty + (uint32_t)__popc(bal & ltmask)] = (uint8_t)(i * 32 + lane);
-				ndirty += (uint32_t)__popc(bal);
-			}
 			if (lane == 0)
-				s.sp_nd[warp] = ndirty;
+				s.sp_base[warp] = d0;
+			/* seams: bit 0 = the row before the span, bits 1..ROWS = own byte-wise rows, bit ROWS + 1 =
+			 * the row after the span */
+			uint32_t bwl = ((uint32_t)(BW >> (warp * ROWS)) & ((1u << ROWS) - 1u)) << 1;
+			bwl |= warp == 0 ? 1u : (uint32_t)(BW >> (warp * ROWS - 1)) & 1u;
+			bwl |= (warp == kW - 1 ? 1u : (uint32_t)(BW >> ((warp + 1) * ROWS)) & 1u) << (ROWS + 1);
+			uint8_t *base = a.out + (tile_off + d0);
+			if ((bwl & (((1u << ROWS) - 1u) << 1)) == 0)
+				emit_span<ROWS, true>(s, a, warp, lane, bwl, base, (uint32_t)d0, has_b, safe, capend);
+			else
+				emit_span<ROWS, false>(s, a, warp, lane, bwl, base, (uint32_t)d0, has_b, safe, capend);
 		}
 		__syncthreads();
 		{
+			/* byte-wise rows first and on the last warps: they are the long items (searches in
+			 * off[], byte stores) and must not share a warp's pass with the listed chunks */
+			const uint32_t nbwi = 32u * (uint32_t)__popcll(BW);
+			for (uint32_t g = kT - 1 - tid; g < nbwi; g += kT) {
+				uint64_t x = BW;
+				for (uint32_t n = 0; n < (g >> 5); n++)
+					x &= x - 1;
+				const uint32_t R = (uint32_t)__ffsll((long long)x) - 1;
+				bytewise_chunk<ROWS>(s, a, R * 32 + (g & 31u), tile_off, nvalid, k_lo, k_hi);
+			}
 			uint32_t pre[kW + 1];
 			pre[0] = 0;
 #pragma unroll
 			for (int j = 0; j < kW; j++)
 				pre[j + 1] = pre[j] + s.sp_nd[j];
-			const uint32_t nitems = pre[kW] + 32u * (uint32_t)__popcll(BW);
-			for (uint32_t g = tid; g < nitems; g += kT) {
-				if (g >= pre[kW]) {
-					/* chunk (g % 32) of the byte-wise row number (g / 32) */
-					const uint32_t k = (g - pre[kW]) >> 5;
-					uint64_t x = BW;
-					for (uint32_t n = 0; n < k; n++)
-						x &= x - 1;
-					const uint32_t R = (uint32_t)__ffsll((long long)x) - 1;
-					bytewise_chunk<ROWS>(s, a, R * 32 + ((g - pre[kW]) & 31u), tile_off, nvalid, k_lo, k_hi);
-					continue;
-				}
+			const uint8_t *cap2 = safe ? (const uint8_t *)~(uintptr_t)0 : capend;
+			for (uint32_t g = tid; g < pre[kW]; g += kT) {
 				uint32_t w = 0, pw = 0;
 #pragma unroll
 				for (int j = 1; j < kW; j++) {
@@ -582,7 +596,7 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 				}
 				const uint32_t c = w * (uint32_t)C::SPAN_CH + s.dl[w * (uint32_t)C::SPAN_CH + (g - pw)];
 				const uint32_t R = c >> 5;
-				const uint64_t rd = row_shift<ROWS>(s, a, R, k_lo, has_b);
+				const uint64_t rd = s.sp_base[w] + (has_b ? a.sc_len * s.krow[R] : 0u);
 				const uint32_t e = s.E[c];
 				const uint32_t kins = (uint32_t)__popc(s.M[c]);
 				uint8_t *o = a.out + (tile_off + rd + (uint64_t)c * 16 + e);
@@ -591,9 +605,9 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 				if (seam_after) {
 					chunk_bytes<ROWS>(s, c, b, 16 + kins, o, capend);
 				} else {
-					gen_unit<ROWS>(s, c, b, o + b, capend);
+					gen_unit<ROWS>(s, c, b, o + b, cap2);
 					if (b < kins)
-						gen_unit<ROWS>(s, c, b + 16, o + b + 16, capend);
+						gen_unit<ROWS>(s, c, b + 16, o + b + 16, cap2);
 				}
 			}
 		}

@@ -848,12 +848,24 @@ static cudaError_t launch_frame6(const frame::FrameArgs &a, cudaStream_t st)
 		if (sms <= 0)
 			sms = 148;
 	}
-	constexpr int B = ROWS == 8 ? 5 : 4;
-	cudaFuncSetAttribute(frame6::frame6_kernel<ROWS, B>, cudaFuncAttributePreferredSharedMemoryCarveout,
-			     cudaSharedmemCarveoutMaxShared);
-	const uint32_t cap = (uint32_t)sms * B;
-	const uint32_t grid = a.num_tiles < cap ? a.num_tiles : cap;
-	frame6::frame6_kernel<ROWS, B><<<grid, frame6::kT, 0, st>>>(a);
+	/* resident CTAs per SM the 32 KiB-tile kernel is compiled for: 5 (48 registers, the default) or
+	 * 4 (64 registers); H264GPU_FRAME_CTAS */
+	static int minb = 0;
+	if (minb == 0) {
+		const char *e = getenv("H264GPU_FRAME_CTAS");
+		minb = (e != NULL && atoi(e) == 4) ? 4 : 5;
+	}
+	if (ROWS == 8 && minb == 5) {
+		cudaFuncSetAttribute(frame6::frame6_kernel<ROWS, 5>, cudaFuncAttributePreferredSharedMemoryCarveout,
+				     cudaSharedmemCarveoutMaxShared);
+		const uint32_t cap = (uint32_t)sms * 5;
+		frame6::frame6_kernel<ROWS, 5><<<a.num_tiles < cap ? a.num_tiles : cap, frame6::kT, 0, st>>>(a);
+	} else {
+		cudaFuncSetAttribute(frame6::frame6_kernel<ROWS, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+				     cudaSharedmemCarveoutMaxShared);
+		const uint32_t cap = (uint32_t)sms * 4;
+		frame6::frame6_kernel<ROWS, 4><<<a.num_tiles < cap ? a.num_tiles : cap, frame6::kT, 0, st>>>(a);
+	}
 	return cudaGetLastError();
 }
 

@@ -8,8 +8,8 @@ TAG=${1:-f6}
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
 echo "== pytest (writer + scan)"; timeout 600 python -m pytest tests/test_gpu_annexb.py -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/${TAG}_pytest.log
 Q="--size-mb 256 --steps 3 --warmup 3 --e2e-steps 1 --no-cpu --mb-frames 2 --cabac-frames 0 --frame-mb 1024"
-for gen in 1 6 6; do
-  H264GPU_FRAME_GEN=$gen timeout 300 python bench.py $Q > gpurun_out/${TAG}_g$gen.json 2> gpurun_out/${TAG}_g$gen.err
+for gen in 1 6 64; do
+  H264GPU_FRAME_CTAS=$((gen == 64 ? 4 : 5)) H264GPU_FRAME_GEN=$((gen == 1 ? 1 : 6)) timeout 300 python bench.py $Q > gpurun_out/${TAG}_g$gen.json 2> gpurun_out/${TAG}_g$gen.err
   python -c "
 import json
 d=json.loads(open('gpurun_out/${TAG}_g$gen.json').read())
