@@ -49,6 +49,8 @@ using frame::kValueMask;
 
 constexpr int kT = 256;
 constexpr int kW = kT / 32;
+constexpr int kLbW = 1;   /* look-back: windows of 32 tile descriptors fetched per round trip (4 measured: no gain, the wait is for aggregates, not depth) */
+constexpr int kSoff = 64; /* payload starts of a tile staged in shared memory (more: searched in off[]) */
 
 template <int ROWS> struct Cfg {
 	static constexpr int SPAN_CH = 32 * ROWS; /* 16-byte chunks per warp span */
@@ -63,6 +65,7 @@ template <int ROWS> struct __align__(128) Smem {
 	uint16_t E[Cfg<ROWS>::NCH];             /* inserts of the span before the chunk; candidate list before that */
 	uint8_t dl[Cfg<ROWS>::NCH];             /* per span: chunks that take the byte-exact path */
 	uint32_t krow[Cfg<ROWS>::NROW + 1];     /* payload starts of the tile before the row start */
+	uint32_t soff[kSoff];                   /* the tile's first payload starts, relative to the tile */
 	uint32_t sp_etot[kW], sp_nd[kW];
 	uint64_t sp_base[kW];                   /* inserts before the span + sc_len * payloads before the tile */
 	uint64_t bar;
@@ -74,6 +77,34 @@ __device__ __forceinline__ uint32_t valid16(uint32_t p0, uint32_t nvalid)
 {
 	const uint32_t nv = p0 >= nvalid ? 0u : (nvalid - p0 >= 16u ? 16u : nvalid - p0);
 	return (1u << nv) - 1u;
+}
+
+/* payload starts of the tile (off[k_lo .. k_hi), nb of them) at or before tile position x; from
+ * the staged copy when they all fit */
+template <int ROWS>
+__device__ __forceinline__ uint32_t starts_le(const Smem<ROWS> &s, const FrameArgs &a, uint64_t tile_off, uint64_t k_lo,
+					      uint64_t k_hi, uint32_t x)
+{
+	const uint32_t nb = (uint32_t)(k_hi - k_lo);
+	if (k_hi - k_lo > (uint64_t)kSoff)
+		return count_le(a.off, k_lo, k_hi, tile_off + x);
+	uint32_t lo = 0, hi = nb;
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (s.soff[mid] <= x)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	return lo;
+}
+
+/* tile position of the tile's payload start number i */
+template <int ROWS>
+__device__ __forceinline__ uint32_t start_at(const Smem<ROWS> &s, const FrameArgs &a, uint64_t tile_off, uint64_t k_lo,
+					     uint64_t k_hi, uint32_t i)
+{
+	return k_hi - k_lo > (uint64_t)kSoff ? (uint32_t)(a.off[k_lo + i] - tile_off) : s.soff[i];
 }
 
 /* one byte / one 16-byte unit to the output, never past its capacity */
@@ -178,25 +209,24 @@ __device__ __noinline__ void bytewise_chunk(const Smem<ROWS> &s, const FrameArgs
 	if (p0 >= nvalid)
 		return;
 	const uint32_t nv = nvalid - p0 >= 16u ? 16u : nvalid - p0;
-	const uint64_t x = tile_off + p0;
-	const bool has_b = k_hi > k_lo;
-	/* payloads that started before the chunk */
-	uint64_t next = k_lo + ((has_b && x) ? count_le(a.off, k_lo, k_hi, x - 1) : 0u);
+	const uint32_t nb = (uint32_t)(k_hi - k_lo);
+	/* payloads of the tile that started before the chunk */
+	uint32_t next = (nb && p0) ? starts_le<ROWS>(s, a, tile_off, k_lo, k_hi, p0 - 1) : 0u;
 	/* sp_base holds sc_len * k_lo already */
 	const uint64_t d = s.sp_base[c / (uint32_t)Cfg<ROWS>::SPAN_CH] + (uint64_t)s.E[c];
-	uint64_t pos = x + d + a.sc_len * (next - k_lo);
+	uint64_t pos = tile_off + p0 + d + a.sc_len * next;
 	const uint8_t *capend = a.out + a.out_cap;
 	const uint8_t *rawb = s.raw + 16 + p0;
 	const uint32_t m = s.M[c];
-	uint64_t noff = next < k_hi ? a.off[next] : ~0ull;
+	uint32_t noff = next < nb ? start_at<ROWS>(s, a, tile_off, k_lo, k_hi, next) : 0xffffffffu;
 	for (uint32_t j = 0; j < nv; j++) {
-		while (noff == x + j) {
-			a.out_off[next] = pos;
+		while (noff == p0 + j) {
+			a.out_off[k_lo + next] = pos;
 			for (uint32_t b = 0; b < a.sc_len; b++)
 				put_byte(a.out + pos + b, b + 1 == a.sc_len ? 1 : 0, capend);
 			pos += a.sc_len;
 			next++;
-			noff = next < k_hi ? a.off[next] : ~0ull;
+			noff = next < nb ? start_at<ROWS>(s, a, tile_off, k_lo, k_hi, next) : 0xffffffffu;
 		}
 		if ((m >> j) & 1)
 			put_byte(a.out + pos++, 3, capend);
@@ -233,9 +263,9 @@ __device__ __forceinline__ void emit_span(Smem<ROWS> &s, const FrameArgs &a, uin
 		const uint32_t mn = s.M[c + 1];
 		uint8_t *o = base + (p0 + e + koff); /* the chunk's first output byte */
 		const uint32_t b = (0u - (shl + e + koff)) & 15u;
-		if ((i == 0 || !LEAN) && ((bwl >> i) & 1) && lane == 0 && b)
-			chunk_bytes<ROWS>(s, c, 0, b, o, capend);
 		uint32_t bad = m | (mn & ((1u << b) - 1u));
+		if ((i == 0 || !LEAN) && ((bwl >> i) & 1) && lane == 0 && b)
+			bad = 1; /* the bytes before the row's first unit: written in the byte-exact pass */
 		if ((i == ROWS - 1 || !LEAN) && ((bwl >> (i + 2)) & 1) && lane == 31 && (b | m))
 			bad = 1; /* the unit runs over a seam */
 		if (!bad) {
@@ -326,6 +356,8 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 			s.zt = zt;
 			raw32[-1] = tile_off == 0 ? 0xffffffffu : ldg_u32(a.rbsp + tile_off - 4);
 		}
+		if (tid >= kT - 32 - kSoff && tid < kT - 32 && k_lo + (tid - (kT - 32 - kSoff)) < k_hi)
+			s.soff[tid - (kT - 32 - kSoff)] = (uint32_t)(a.off[k_lo + (tid - (kT - 32 - kSoff))] - tile_off);
 		if (tid <= (uint32_t)C::NROW) {
 			/* payload starts of the tile before row `tid` (entry NROW: all of them) */
 			const uint64_t rs = tile_off + (uint64_t)tid * 512;
@@ -398,13 +430,13 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 				if (has_b) {
 					uint32_t cnt0 = s.krow[R];
 					if ((BW >> R) & 1) {
-						cnt0 = count_le(a.off, k_lo, k_hi, tile_off + p0);
-						const uint32_t cnt1 = count_le(a.off, k_lo, k_hi, tile_off + p0 + 15);
+						cnt0 = starts_le<ROWS>(s, a, tile_off, k_lo, k_hi, p0);
+						const uint32_t cnt1 = starts_le<ROWS>(s, a, tile_off, k_lo, k_hi, p0 + 15);
 						for (uint32_t n = cnt0; n < cnt1; n++)
-							B16 |= 1u << (uint32_t)(a.off[k_lo + n] - tile_off - p0);
+							B16 |= 1u << (start_at<ROWS>(s, a, tile_off, k_lo, k_hi, n) - p0);
 					}
 					if (cnt0)
-						lim = (int32_t)(a.off[k_lo + cnt0 - 1] - tile_off);
+						lim = (int32_t)start_at<ROWS>(s, a, tile_off, k_lo, k_hi, cnt0 - 1);
 				}
 				/* zero run that reaches the chunk from the left */
 				const uint32_t lo = lim >= 0 ? (uint32_t)lim : 0u;
@@ -495,32 +527,39 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 			if (t > 0) {
 				if (lane == 0)
 					st_relaxed_u64(a.desc + t, (uint64_t)tile_total);
+				/* the inserts of every tile before this one: aggregates summed back to the nearest
+				 * tile with an inclusive prefix, kLbW windows of 32 descriptors per round trip
+				 * (tile -1 reads as a prefix of 0 and ends the walk) */
 				int64_t j0 = (int64_t)t - 1;
 				for (bool done = false; !done;) {
-					const int64_t j = j0 - lane;
-					const bool need = j >= 0;
-					uint64_t d = kInvalid;
-					uint32_t pm;
-					for (;;) {
-						if (need)
-							d = ld_relaxed_u64(a.desc + j);
-						pm = __ballot_sync(FULL_MASK, need && !(d & kInvalid) && (d & kPrefix));
-						const uint32_t ok = __ballot_sync(FULL_MASK, !need || !(d & kInvalid));
-						const uint32_t upto = pm ? ((pm & (0u - pm)) << 1) - 1u : 0xffffffffu;
-						if ((ok & upto) == upto)
-							break;
-						spin_pause(20);
-					}
-					const int fp = pm ? __ffs((int)pm) - 1 : 32;
-					uint64_t val = (need && (int)lane <= fp) ? (d & kValueMask) : 0;
+					uint64_t d[kLbW];
 #pragma unroll
-					for (int dd = 16; dd >= 1; dd >>= 1)
-						val += __shfl_xor_sync(FULL_MASK, val, dd);
-					pin += val;
-					if (fp < 32)
-						done = true;
-					else
+					for (int k = 0; k < kLbW; k++) {
+						const int64_t j = j0 - 32 * k - (int64_t)lane;
+						d[k] = j >= 0 ? ld_relaxed_u64(a.desc + j) : kPrefix;
+					}
+#pragma unroll
+					for (int k = 0; k < kLbW; k++) {
+						const bool valid = !(d[k] & kInvalid);
+						const uint32_t pm = __ballot_sync(FULL_MASK, valid && (d[k] & kPrefix));
+						const uint32_t ok = __ballot_sync(FULL_MASK, valid);
+						const uint32_t upto = pm ? ((pm & (0u - pm)) << 1) - 1u : 0xffffffffu;
+						if ((ok & upto) != upto) {
+							spin_pause(20); /* an aggregate is not there yet: fetch again from this window on */
+							break;
+						}
+						const int fp = pm ? __ffs((int)pm) - 1 : 32;
+						uint64_t val = (int)lane <= fp ? (d[k] & kValueMask) : 0;
+#pragma unroll
+						for (int dd = 16; dd >= 1; dd >>= 1)
+							val += __shfl_xor_sync(FULL_MASK, val, dd);
+						pin += val;
+						if (fp < 32) {
+							done = true;
+							break;
+						}
 						j0 -= 32;
+					}
 				}
 			}
 			const uint64_t pout = pin + tile_total;
@@ -602,6 +641,8 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 				uint8_t *o = a.out + (tile_off + rd + (uint64_t)c * 16 + e);
 				const uint32_t b = (0u - ((uint32_t)rd + e)) & 15u;
 				const bool seam_after = (c & 31u) == 31u && (R == (uint32_t)C::NROW - 1 || ((BW >> (R + 1)) & 1));
+				if ((c & 31u) == 0 && b && (R == 0 || ((BW >> (R - 1)) & 1)))
+					chunk_bytes<ROWS>(s, c, 0, b, o, capend); /* the unit began on the other side of a seam */
 				if (seam_after) {
 					chunk_bytes<ROWS>(s, c, b, 16 + kins, o, capend);
 				} else {
