@@ -354,8 +354,11 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 				zt = z < 2 ? (uint32_t)z : 2u + (uint32_t)(z & 1);
 			}
 			s.zt = zt;
-			raw32[-1] = tile_off == 0 ? 0xffffffffu : ldg_u32(a.rbsp + tile_off - 4);
 		}
+		/* the four bytes before the tile, for the candidate test of its first chunk */
+		uint32_t halo = 0xffffffffu;
+		if (tid == 0 && tile_off)
+			halo = ldg_u32(a.rbsp + tile_off - 4);
 		if (tid >= kT - 32 - kSoff && tid < kT - 32 && k_lo + (tid - (kT - 32 - kSoff)) < k_hi)
 			s.soff[tid - (kT - 32 - kSoff)] = (uint32_t)(a.off[k_lo + (tid - (kT - 32 - kSoff))] - tile_off);
 		if (tid <= (uint32_t)C::NROW) {
@@ -379,21 +382,14 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 				*(uint4 *)(raw32 + 4 * c) = v;
 			}
 		}
-		__syncthreads();
 		if (full) {
 			bulk_load_wait_parity(&s.bar, parity);
 			parity ^= 1u;
 			__syncwarp();
+		} else {
+			__syncthreads();
 		}
-		/* byte-wise rows: a payload start inside, or the input ends in (or before) the row */
 		uint64_t BW;
-		{
-			const uint32_t r0 = lane, r1 = lane + 32;
-			const bool b0 = r0 < (uint32_t)C::NROW && (s.krow[r0 + 1] > s.krow[r0] || (r0 + 1) * 512u > nvalid);
-			const bool b1 = r1 < (uint32_t)C::NROW && (s.krow[r1 + 1] > s.krow[r1] || (r1 + 1) * 512u > nvalid);
-			BW = (uint64_t)__ballot_sync(FULL_MASK, b0) | (uint64_t)__ballot_sync(FULL_MASK, b1) << 32;
-		}
-		const uint32_t zt = s.zt;
 
 		/* ---- P1 (per warp): candidates (some byte <= 3 after two zero bytes), then the exact
 		 * insert mask for them ---- */
@@ -405,7 +401,7 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 			for (int i = 0; i < ROWS; i++) {
 				const uint32_t c = c0 + i * 32 + lane;
 				const uint4 v = *(const uint4 *)(raw32 + 4 * c);
-				const uint32_t pw = raw32[4 * (int)c - 1];
+				const uint32_t pw = c ? raw32[4 * (int)c - 1] : halo;
 				const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
 				const uint32_t X0 = __funnelshift_l(pw, w0, 16) | __funnelshift_l(pw, w0, 8) | (w0 & kfc);
 				const uint32_t X1 = __funnelshift_l(w0, w1, 16) | __funnelshift_l(w0, w1, 8) | (w1 & kfc);
@@ -418,7 +414,17 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 					cand[ntot + (uint32_t)__popc(bal & ltmask)] = (uint16_t)c;
 				ntot += (uint32_t)__popc(bal);
 			}
-			__syncwarp();
+			/* the searches of P0b (payload counts, staged offsets, zero run before the tile) ran
+			 * under the bulk load and the candidate test: only the exact evaluation needs them */
+			__syncthreads();
+			{
+				/* byte-wise rows: a payload start inside, or the input ends in (or before) the row */
+				const uint32_t r0 = lane, r1 = lane + 32;
+				const bool b0 = r0 < (uint32_t)C::NROW && (s.krow[r0 + 1] > s.krow[r0] || (r0 + 1) * 512u > nvalid);
+				const bool b1 = r1 < (uint32_t)C::NROW && (s.krow[r1 + 1] > s.krow[r1] || (r1 + 1) * 512u > nvalid);
+				BW = (uint64_t)__ballot_sync(FULL_MASK, b0) | (uint64_t)__ballot_sync(FULL_MASK, b1) << 32;
+			}
+			const uint32_t zt = s.zt;
 			for (uint32_t q = lane; q < ntot; q += 32) {
 				const uint32_t c = cand[q];
 				const uint32_t p0 = c * 16;

@@ -227,7 +227,7 @@ __device__ __forceinline__ void emit_span(Smem<ROWS> &s, uint32_t warp, uint32_t
 	const uint8_t *rawb = s.raw + 16;
 	uint8_t *dlist = s.dl + c0;
 	uint32_t ndirty = 0;
-#pragma unroll
+#pragma unroll(LEAN ? ROWS : 1)
 	for (int i = 0; i < ROWS; i++) {
 		const uint32_t c = c0 + i * 32 + lane;
 		const uint32_t p0 = c * 16;
@@ -329,7 +329,7 @@ __device__ __forceinline__ void dirty_of_tile(const Smem<ROWS> &s, uint32_t c, u
  * its place, the shift restarting at each reset point; E[c] holds the shift at the chunk start
  * as left by emit_span */
 template <int ROWS>
-__device__ __forceinline__ void bytewise_chunk(const Smem<ROWS> &s, uint32_t c, uint8_t *out_tile, uint32_t nvalid)
+__device__ __noinline__ void bytewise_chunk(const Smem<ROWS> &s, uint32_t c, uint8_t *out_tile, uint32_t nvalid)
 {
 	const uint32_t *raw32 = (const uint32_t *)(s.raw + 16);
 	const uint8_t *rawb = s.raw + 16;
