@@ -219,7 +219,23 @@ def test_frame_random_and_adversarial(gpu):
     assert bytes(out) == bytes([0, 0, 0, 1, 0, 0, 0, 1])
 
 
-def test_frame_small_tiles_and_capacity():
+def test_writer_round_trip_config5_size(gpu):
+    """BASELINE config 5 at its full size (1 GiB of RBSP payloads): the GPU writer's output is
+    byte-identical to the CPU writer's, and the GPU reader gives the payloads back."""
+    seed = 11
+    offs = L.synth_offsets(seed, 1 << 30)
+    rbsp = L.synth_payloads(seed, offs)
+    out, oo = gpu.frame_host(rbsp, offs, sc_len=4)
+    exp, eoo = L.synth_annexb(seed, rbsp, offs, mixed_sc=False, trailing=False)
+    assert len(out) == len(exp) and np.array_equal(oo, eoo)
+    assert np.array_equal(out, exp)
+    del exp
+    back = gpu.split_strip_host(out)
+    assert np.array_equal(back["rbsp_off"], offs[:-1])
+    assert np.array_equal(back["rbsp"], rbsp)
+
+
+def test_frame_small_tiles():
     """frame6_kernel with 1/2/4 rows per warp (4-16 KiB tiles: many tiles, seams and look-back on
     small inputs), sparse and zero-heavy bytes."""
     rng = np.random.default_rng(58)
