@@ -257,6 +257,36 @@ def test_gpu_config2_shape_against_oracle_and_packed_kernel(gpu):
 
 
 @pytest.mark.gpu
+def test_gpu_config2_full_size_properties(gpu):
+    """BASELINE config 2 at its full size (4 GiB of synthetic Annex-B): too big for the oracle in
+    the test budget, so size-independent properties: strip(escape(x)) == x NAL by NAL against the
+    generator's payloads, the NAL table against the generator's offsets, ordering, nothing written
+    outside the output buffer (checked by the wrapper)."""
+    seed = 0x264
+    offs = L.synth_offsets(seed, int((4 << 30) * 0.992))
+    rbsp = L.synth_payloads(seed, offs)
+    stream, nal_off = L.synth_annexb(seed, rbsp, offs)
+    n = len(offs) - 1
+    got = gpu.split_strip_inplace(stream, cap=n + 64)
+    assert got["res"].n_nal == n
+    # the generator's own table: NAL k starts right after its 3- or 4-byte start code
+    sc = got["start"].astype(np.int64) - np.asarray(nal_off[:n], np.int64)
+    assert ((sc == 3) | (sc == 4)).all()
+    assert (got["end"] >= got["start"]).all() and (got["start"][1:] >= got["end"][:-1] + 3).all()
+    assert np.array_equal(got["rbsp_off"], got["start"])  # in place: the RBSP begins where the NAL does
+    want_len = np.diff(offs.astype(np.int64))
+    tz = int(got["rbsp_len"][-1]) - int(want_len[-1])  # zero bytes after the last NAL stay with it
+    assert 0 <= tz <= 2
+    assert np.array_equal(got["rbsp_len"][:-1].astype(np.int64), want_len[:-1])
+    body = got["body"]
+    for k in range(n):
+        a, b = int(offs[k]), int(offs[k + 1])
+        o = int(got["rbsp_off"][k])
+        assert np.array_equal(body[o:o + (b - a)], rbsp[a:b]), k
+    assert not body[int(got["rbsp_off"][-1]) + int(want_len[-1]):][:tz].any()
+
+
+@pytest.mark.gpu
 def test_gpu_sharded_merge(gpu):
     rng = np.random.default_rng(17)
     run = lambda buf, e, lo: gpu.split_strip_inplace(buf, edge=e, base=lo)
