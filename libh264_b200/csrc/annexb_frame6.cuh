@@ -652,9 +652,10 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 				if (seam_after) {
 					chunk_bytes<ROWS>(s, c, b, 16 + kins, o, capend);
 				} else {
-					gen_unit<ROWS>(s, c, b, o + b, cap2);
-					if (b < kins)
-						gen_unit<ROWS>(s, c, b + 16, o + b + 16, cap2);
+					/* one unit, or two when the inserts push a second boundary into the chunk */
+#pragma unroll 1
+					for (uint32_t ub = b; ub < 16 + kins; ub += 16)
+						gen_unit<ROWS>(s, c, ub, o + ub, cap2);
 				}
 			}
 		}
