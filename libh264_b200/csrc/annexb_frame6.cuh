@@ -234,6 +234,60 @@ __device__ __noinline__ void bytewise_chunk(const Smem<ROWS> &s, const FrameArgs
 	}
 }
 
+/* the tile the input ends in (once per launch): plain loads, zero fill past the end */
+template <int ROWS>
+__device__ __noinline__ void load_partial_tile(Smem<ROWS> &s, const FrameArgs &a, uint64_t tile_off)
+{
+	uint32_t *raw32 = (uint32_t *)(s.raw + 16);
+	for (uint32_t c = threadIdx.x; c < (uint32_t)Cfg<ROWS>::NCH; c += kT) {
+		const uint64_t o = tile_off + (uint64_t)c * 16;
+		uint4 v;
+		if (o + 16 <= a.len) {
+			v = ldg_stream16(a.rbsp + o);
+		} else {
+			uint32_t w[4] = {0, 0, 0, 0};
+			for (int b = 0; b < 16; b++)
+				if (o + b < a.len)
+					w[b >> 2] |= (uint32_t)a.rbsp[o + b] << (8 * (b & 3));
+			v = make_uint4(w[0], w[1], w[2], w[3]);
+		}
+		*(uint4 *)(raw32 + 4 * c) = v;
+	}
+}
+
+/* insert mask of a chunk with payload starts inside (bits of B16): byte by byte, the zero run
+ * restarting at every start */
+__device__ __noinline__ uint32_t inserts_with_starts(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t B16,
+						     uint32_t zin)
+{
+	uint32_t ins16 = 0, z = zin;
+	const uint32_t wv[4] = {w0, w1, w2, w3};
+	for (uint32_t j = 0; j < 16; j++) {
+		if ((B16 >> j) & 1)
+			z = 0;
+		const uint32_t cb = (wv[j >> 2] >> (8 * (j & 3))) & 0xff;
+		if (cb <= 3 && z >= 2 && !(z & 1))
+			ins16 |= 1u << j;
+		z = cb == 0 ? z + 1 : 0;
+	}
+	return ins16;
+}
+
+/* last tile: payloads that start at len (empty, at the very end) and the total */
+__device__ __noinline__ void finish_output(const FrameArgs &a, uint64_t k_hi, uint64_t pout)
+{
+	const uint8_t *capend = a.out + a.out_cap;
+	for (uint64_t k = k_hi; k < a.n; k++) {
+		const uint64_t pos = a.len + pout + a.sc_len * k;
+		a.out_off[k] = pos;
+		for (uint32_t b = 0; b < a.sc_len; b++)
+			put_byte(a.out + pos + b, b + 1 == a.sc_len ? 1 : 0, capend);
+	}
+	const uint64_t end = a.len + pout + a.sc_len * a.n;
+	a.out_off[a.n] = end;
+	*a.total = end;
+}
+
 /*
  * P4: the rows of a span.  bwl: bit 0 = the row before the span is a seam (byte-wise row or tile
  * start), bits 1..ROWS = own rows that go byte by byte, bit ROWS + 1 = the row after the span is a
@@ -366,22 +420,8 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 			const uint64_t rs = tile_off + (uint64_t)tid * 512;
 			s.krow[tid] = (has_b && rs) ? count_le(a.off, k_lo, k_hi, rs - 1) : 0u;
 		}
-		if (!full) {
-			for (uint32_t c = tid; c < (uint32_t)C::NCH; c += kT) {
-				const uint64_t o = tile_off + (uint64_t)c * 16;
-				uint4 v;
-				if (o + 16 <= a.len) {
-					v = ldg_stream16(a.rbsp + o);
-				} else {
-					uint32_t w[4] = {0, 0, 0, 0};
-					for (int b = 0; b < 16; b++)
-						if (o + b < a.len)
-							w[b >> 2] |= (uint32_t)a.rbsp[o + b] << (8 * (b & 3));
-					v = make_uint4(w[0], w[1], w[2], w[3]);
-				}
-				*(uint4 *)(raw32 + 4 * c) = v;
-			}
-		}
+		if (!full)
+			load_partial_tile<ROWS>(s, a, tile_off);
 		if (full) {
 			bulk_load_wait_parity(&s.bar, parity);
 			parity ^= 1u;
@@ -477,16 +517,7 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 							ins16 |= 1u << j;
 					}
 				} else {
-					uint32_t z = zin;
-					const uint32_t wv[4] = {w0, w1, w2, w3};
-					for (uint32_t j = 0; j < 16; j++) {
-						if ((B16 >> j) & 1)
-							z = 0;
-						const uint32_t cb = (wv[j >> 2] >> (8 * (j & 3))) & 0xff;
-						if (cb <= 3 && z >= 2 && !(z & 1))
-							ins16 |= 1u << j;
-						z = cb == 0 ? z + 1 : 0;
-					}
+					ins16 = inserts_with_starts(w0, w1, w2, w3, B16, zin);
 				}
 				ins16 &= vm;
 				if (ins16)
@@ -576,18 +607,8 @@ __global__ void __launch_bounds__(kT, MINB) frame6_kernel(const FrameArgs a)
 #endif
 					st_relaxed_u64(a.desc + t, pout | kPrefix);
 				s.pin = pin;
-				if (t == a.num_tiles - 1) {
-					/* payloads that start at len (empty, at the very end) and the total */
-					for (uint64_t k = k_hi; k < a.n; k++) {
-						const uint64_t pos = a.len + pout + a.sc_len * k;
-						a.out_off[k] = pos;
-						for (uint32_t b = 0; b < a.sc_len; b++)
-							put_byte(a.out + pos + b, b + 1 == a.sc_len ? 1 : 0, capend);
-					}
-					const uint64_t end = a.len + pout + a.sc_len * a.n;
-					a.out_off[a.n] = end;
-					*a.total = end;
-				}
+				if (t == a.num_tiles - 1)
+					finish_output(a, k_hi, pout);
 			}
 		}
 		__syncthreads();
