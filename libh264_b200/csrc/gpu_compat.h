@@ -32,7 +32,8 @@ static inline void bulk_load_issue(void *sdst, const void *gsrc, uint32_t bytes,
 }
 static inline void bulk_load_wait_parity(uint64_t *bar, uint32_t parity) { (void)bar; (void)parity; }
 static inline void l2_prefetch(const void *gsrc, uint32_t bytes) { (void)gsrc; (void)bytes; }
-static inline void spin_pause(unsigned ns) { (void)ns; }
+/* a polling loop gives the other fibers (warps of the CTA) a turn */
+static inline void spin_pause(unsigned ns) { (void)ns; emu::yield(); }
 static inline uint4 ldcg16(const void *p) { return *(const uint4 *)p; }
 static inline uint32_t ldcg_u32(const void *p) { return *(const volatile uint32_t *)p; }
 static inline uint32_t ld_relaxed_u32(const uint32_t *p) { return *(const volatile uint32_t *)p; }
@@ -217,6 +218,21 @@ static inline uint32_t warp_or(uint32_t v)
 __device__ __forceinline__ uint32_t warp_or(uint32_t v)
 {
 	return __reduce_or_sync(FULL_MASK, v);
+}
+#endif
+
+/* sum of a 32-bit value over the warp (all lanes take part) */
+#ifdef H264_EMU
+static inline uint32_t warp_add(uint32_t v)
+{
+	for (int d = 16; d >= 1; d >>= 1)
+		v += __shfl_xor_sync(FULL_MASK, v, d);
+	return v;
+}
+#else
+__device__ __forceinline__ uint32_t warp_add(uint32_t v)
+{
+	return __reduce_add_sync(FULL_MASK, v);
 }
 #endif
 

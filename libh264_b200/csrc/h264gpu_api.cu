@@ -10,6 +10,7 @@
 #include "annexb_scan2.cuh"
 #include "annexb_scan5.cuh"
 #include "annexb_scan6.cuh"
+#include "annexb_scan7.cuh"
 
 extern "C" {
 
@@ -95,6 +96,7 @@ int h264gpu_destroy(h264gpu_ctx *ctx)
 	cudaDeviceSynchronize();
 	free_pipeline(ctx);
 	cudaFree(ctx->ws);
+	cudaFree(ctx->ws7);
 	free(ctx);
 	return 0;
 }
@@ -390,6 +392,153 @@ extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, ui
 	return 0;
 }
 
+/* ---- scan + strip, RBSP in place: gen 7 (annexb_scan7.cuh) ------------------------ */
+
+/* the scan's own workspace: control words are zero at allocation and re-armed by the last
+ * finalize block of every launch; chain words carry the launch epoch, so nothing is cleared
+ * between launches */
+static int ws7_reserve(h264gpu_ctx *ctx, size_t bytes)
+{
+	if (bytes <= ctx->ws7_bytes)
+		return 0;
+	CU_TRY(cudaDeviceSynchronize());
+	if (ctx->ws7)
+		CU_TRY(cudaFree(ctx->ws7));
+	ctx->ws7 = NULL;
+	ctx->ws7_bytes = 0;
+	const size_t want = (bytes + (bytes >> 3) + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+	CU_TRY(cudaMalloc(&ctx->ws7, want));
+	CU_TRY(cudaMemset(ctx->ws7, 0, want));
+	ctx->ws7_bytes = want;
+	return 0;
+}
+
+static int device_sms(h264gpu_ctx *ctx)
+{
+	if (ctx->sms == 0) {
+		int sms = 0;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+		ctx->sms = sms > 0 ? sms : 148;
+	}
+	return ctx->sms;
+}
+
+static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uint64_t base,
+			const struct h264gpu_shard_edge *edge, uint8_t *d_rbsp, uint64_t *d_nal_start,
+			uint64_t *d_nal_end, uint64_t *d_nal_rbsp, uint64_t *d_nal_rbsp_len, uint64_t nal_cap,
+			struct h264gpu_scan_result *d_result, cudaStream_t st)
+{
+	constexpr int ROWS = 8;
+	const uint64_t span = (uint64_t)annexb7::Cfg<ROWS>::SPAN;
+	/* a boundary event is owned by its third byte: the launch covers the two edge bytes too */
+	const uint64_t nspans = (len + 2 + span - 1) / span;
+	if (nspans > 0x7fffffffull)
+		return -E2BIG;
+	/* events: a start code and at most a few terminators per NAL in real streams */
+	uint64_t ev_cap = 4 * nal_cap + 4096;
+	if (ev_cap > len / 3 + 2)
+		ev_cap = len / 3 + 2;
+	if (ev_cap >= 0xffffffffull)
+		ev_cap = 0xfffffffeull;
+	const uint64_t nblk = (nspans + annexb7::kFinT - 1) / annexb7::kFinT;
+	/* [256 control][chain][fin][span_pre][blk: 2 per fin block][totals][events][ordered events] */
+	const size_t chain_off = 256;
+	const size_t fin_off = chain_off + (size_t)nspans * 8;
+	const size_t pre_off = fin_off + (size_t)nspans * 8;
+	const size_t blk_off = pre_off + (size_t)nspans * 8;
+	const size_t tot_off = blk_off + (size_t)nblk * 16;
+	const size_t ev_off = tot_off + 64;
+	const size_t ord_off = ev_off + (size_t)ev_cap * 16;
+	const size_t need = ord_off + (size_t)ev_cap * 24;
+	const size_t had = ctx->ws7_bytes;
+	int r = ws7_reserve(ctx, need);
+	if (r < 0)
+		return r;
+	if (ctx->ws7_bytes != had)
+		ctx->epoch7 = 0; /* fresh zeroed buffer */
+	if (++ctx->epoch7 > 0xffffu) {
+		/* epoch wrap: stale chain words of 65535 launches ago could look valid */
+		CU_TRY(cudaMemsetAsync((uint8_t *)ctx->ws7 + chain_off, 0, (size_t)nspans * 8, st));
+		ctx->epoch7 = 1;
+	}
+	uint8_t *ws = (uint8_t *)ctx->ws7;
+
+	annexb7::Scan7Args a;
+	memset(&a, 0, sizeof(a));
+	a.in = d_in;
+	a.len = len;
+	a.rbsp = d_rbsp;
+	a.chain = (uint64_t *)(ws + chain_off);
+	a.fin = (uint64_t *)(ws + fin_off);
+	a.ctrl = (uint32_t *)ws;
+	a.evbuf = (uint64_t *)(ws + ev_off);
+	a.ev_cap = ev_cap;
+	a.num_spans = (uint32_t)nspans;
+	a.halo_left = 0xffffffffu;
+	a.epoch = ctx->epoch7;
+	a.right[0] = a.right[1] = 0xff;
+	int assume_in = 0;
+	if (edge != NULL) {
+		if (edge->has_left)
+			a.halo_left = 0xffffu | (uint32_t)edge->left[0] << 16 | (uint32_t)edge->left[1] << 24;
+		a.has_right = edge->has_right ? 1 : 0;
+		a.right[0] = edge->right[0];
+		a.right[1] = edge->right[1];
+		assume_in = edge->assume_in ? 1 : 0;
+	}
+	const int sms = device_sms(ctx);
+	const uint64_t ctas_needed = (nspans + annexb7::kW - 1) / annexb7::kW;
+	if (d_rbsp != NULL) {
+		const uint32_t grid = (uint32_t)(ctas_needed < (uint64_t)sms * 5 ? ctas_needed : (uint64_t)sms * 5);
+		a.pf_dist = getenv("H264GPU_SCAN7_NOPF") ? 0u : grid * annexb7::kW;
+		if (!(ctx->attr_set & 1u)) {
+			cudaFuncSetAttribute(annexb7::scan7_kernel<ROWS, 5>, cudaFuncAttributePreferredSharedMemoryCarveout,
+					     cudaSharedmemCarveoutMaxShared);
+			ctx->attr_set |= 1u;
+		}
+		annexb7::scan7_kernel<ROWS, 5><<<grid, annexb7::kT, 0, st>>>(a);
+	} else {
+		const uint32_t grid = (uint32_t)(ctas_needed < (uint64_t)sms * 4 ? ctas_needed : (uint64_t)sms * 4);
+		annexb7::scan7_only_kernel<ROWS, 4><<<grid, annexb7::kT, 0, st>>>(a);
+	}
+	CU_TRY(cudaGetLastError());
+
+	annexb7::Fin7Args f;
+	memset(&f, 0, sizeof(f));
+	f.fin = a.fin;
+	f.chain = a.chain;
+	f.num_spans = (uint32_t)nspans;
+	f.nblk = (uint32_t)nblk;
+	f.evbuf = a.evbuf;
+	f.ev_cap = ev_cap;
+	f.ordered = (uint64_t *)(ws + ord_off);
+	f.span_pre = (uint64_t *)(ws + pre_off);
+	f.blk = (uint64_t *)(ws + blk_off);
+	f.totals = (uint64_t *)(ws + tot_off);
+	f.ctrl = a.ctrl;
+	f.len = len;
+	f.base = base;
+	f.nal_start = d_nal_start;
+	f.nal_end = d_nal_end;
+	f.nal_rbsp = d_nal_rbsp;
+	f.nal_rbsp_len = d_nal_rbsp_len;
+	f.nal_cap = nal_cap;
+	f.result = d_result;
+	f.has_right = a.has_right;
+	f.strip = d_rbsp != NULL ? 1 : 0;
+	f.assume_in = (uint32_t)assume_in;
+	annexb7::fin7_spans<<<(uint32_t)nblk, annexb7::kFinT, 0, st>>>(f);
+	annexb7::fin7_order<<<(uint32_t)((nspans + 255) / 256), 256, 0, st>>>(f);
+	/* grid-stride over the ordered events: any grid covers them all */
+	uint64_t tb = (ev_cap + 255) / 256;
+	if (tb > (uint64_t)sms * 8)
+		tb = (uint64_t)sms * 8;
+	annexb7::fin7_table<<<(uint32_t)(tb ? tb : 1), 256, 0, st>>>(f);
+	CU_TRY(cudaGetLastError());
+	ctx->launches += 4;
+	return 0;
+}
+
 /* ---- scan + strip, RBSP in place (gen 5) ----------------------------------- */
 
 extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len,
@@ -413,6 +562,14 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 	}
 	if (len >= (1ull << 40))
 		return -E2BIG;
+	{
+		/* kernel generation: 7 = warp-autonomous spans (annexb_scan7.cuh, default); 6 / 5 = the
+		 * block-wide tile kernels kept for A/B runs (H264GPU_INPLACE_GEN) */
+		const char *e = getenv("H264GPU_INPLACE_GEN");
+		if (e == NULL || atoi(e) == 7 || atoi(e) == 0)
+			return scan7_launch(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp,
+					    d_nal_rbsp_len, nal_cap, d_result, st);
+	}
 	/* tile shape: 85 = 8 chunks/thread, 5 CTAs/SM (default); 84: 4 CTAs; 45 / 46 = 4 chunks, 5 / 6 CTAs */
 	int shape = 85;
 	{

@@ -19,6 +19,12 @@ struct h264gpu_ctx {
 	/* scan/frame workspace: [256 B control][tile descriptors / tile tables] */
 	void *ws;
 	size_t ws_bytes;
+	/* gen-7 scan workspace (own buffer: zeroed once, re-armed by the finalize kernels) */
+	void *ws7;
+	size_t ws7_bytes;
+	uint32_t epoch7;
+	uint32_t attr_set; /* per-context (= per-device) cudaFuncSetAttribute done: bit 0 scan7 */
+	int sms;
 	/* host-buffer pipeline */
 	cudaStream_t s_in, s_out, s_tab;
 	uint8_t *d_chunk_in[2];

@@ -1,0 +1,8 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+CMD="python scripts/scan_ab.py --size-mb 1024 --gens 7 --steps 2 --warmup 1"
+timeout 300 $CMD > gpurun_out/r2b_plain.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan7_kernel -s 1 -c 1 -f -o gpurun_out/r2b_prof_scan7 $CMD > gpurun_out/r2b_ncu.log 2>&1
+tail -3 gpurun_out/r2b_plain.log; tail -3 gpurun_out/r2b_ncu.log

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""A/B of the in-place scan kernels on one GPU: same buffer, device resident, CUDA events.
+   python scripts/scan_ab.py [--size-mb 4096] [--gens 6,7] [--steps 10]"""
+import argparse, ctypes as C, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import libh264_b200 as L
+from bench import make_workload, SEED
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--size-mb", type=int, default=4096)
+ap.add_argument("--gens", default="6,7")
+ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
+args = ap.parse_args()
+g = L.Gpu(0)
+size = args.size_mb << 20
+pin = g.pinned(size + 4096)
+stream, rbsp_ref, offs = make_workload(L, size, SEED, out=pin.array, nthreads=min(os.cpu_count() or 1, 64))
+n_in, n_nal = len(stream), len(offs) - 1
+tz = 0
+while stream[n_in - 1 - tz] == 0:
+    tz += 1
+n_rbsp = len(rbsp_ref) + tz
+cap = n_nal + 1024
+d_in, d_rbsp = g.alloc(n_in + 16), g.alloc(n_in + 16)
+d_tab, d_res = g.alloc(cap * 32), g.alloc(C.sizeof(L.ScanResult))
+d_in.upload(stream)
+g.sync()
+out = {}
+for strip in (True, False):
+    for gen in [int(x) for x in args.gens.split(",")]:
+        os.environ["H264GPU_INPLACE_GEN"] = str(gen)
+        def step():
+            g.split_strip_inplace_dev(d_in.ptr, n_in, d_rbsp.ptr if strip else 0, d_tab.ptr, d_tab.ptr + cap * 8,
+                                      d_tab.ptr + cap * 16, d_tab.ptr + cap * 24, cap, d_res.ptr)
+        for _ in range(args.warmup):
+            step()
+        g.sync()
+        tm = g.timer()
+        g.timer_start(tm)
+        for _ in range(args.steps):
+            step()
+        g.timer_stop(tm)
+        ms = g.timer_ms(tm) / args.steps
+        res = L.ScanResult.from_buffer_copy(d_res.download().tobytes())
+        ok = res.n_nal == n_nal and (not strip or res.rbsp_bytes == n_rbsp) and res.reserved == 0
+        key = "gen%d_%s" % (gen, "strip" if strip else "scan_only")
+        out[key] = {"ms": ms, "GBps": n_in / ms / 1e6, "ok": bool(ok), "n_nal": int(res.n_nal),
+                    "rbsp_bytes": int(res.rbsp_bytes)}
+        print(key, out[key], flush=True)
+print(json.dumps(out))

@@ -7,6 +7,7 @@
 #include "annexb_scan2.cuh"
 #include "annexb_scan5.cuh"
 #include "annexb_scan6.cuh"
+#include "annexb_scan7.cuh"
 #include "annexb_frame.cuh"
 #include "annexb_frame6.cuh"
 
@@ -82,6 +83,106 @@ extern "C" int emu_split_strip(const uint8_t *in, uint64_t len, uint64_t base,
 	return 0;
 }
 
+/* gen 7: warp-autonomous spans (annexb_scan7.cuh); rows = 512-byte rows per span (1, 2 or 8).
+ * `epoch` and a dirty (non-zero, stale-epoch) chain buffer check that nothing needs clearing. */
+template <int ROWS>
+static void emu_scan7_run(const annexb7::Scan7Args &a, const annexb7::Fin7Args &f, bool strip, uint64_t ev_cap)
+{
+	const uint32_t nctas = (a.num_spans + annexb7::kW - 1) / annexb7::kW;
+	dim3 grid(nctas < 3 ? nctas : 3), block(annexb7::kT);
+	if (strip)
+		EMU_LAUNCH((annexb7::scan7_kernel<ROWS, 1>), grid, block, a);
+	else
+		EMU_LAUNCH((annexb7::scan7_only_kernel<ROWS, 1>), grid, block, a);
+	dim3 gs(f.nblk), bs(annexb7::kFinT), b256(256);
+	EMU_LAUNCH((annexb7::fin7_spans), gs, bs, f);
+	dim3 go((a.num_spans + 255) / 256);
+	EMU_LAUNCH((annexb7::fin7_order), go, b256, f);
+	uint64_t tb = (ev_cap + 255) / 256;
+	if (tb > 5)
+		tb = 5; /* fewer blocks than events: the grid-stride loop is exercised */
+	dim3 gt((uint32_t)(tb ? tb : 1));
+	EMU_LAUNCH((annexb7::fin7_table), gt, b256, f);
+}
+
+static int emu_scan7(const uint8_t *buf, uint64_t len, uint64_t base, const struct h264gpu_shard_edge *edge,
+		     uint8_t *rbsp, uint64_t *nal_start, uint64_t *nal_end, uint64_t *nal_rbsp,
+		     uint64_t *nal_rbsp_len, uint64_t nal_cap, struct h264gpu_scan_result *result, int rows,
+		     uint64_t ev_cap)
+{
+	using namespace annexb7;
+	const uint64_t span = (uint64_t)rows * 512;
+	const uint32_t nspans = (uint32_t)((len + 2 + span - 1) / span);
+	const uint32_t nblk = (nspans + kFinT - 1) / kFinT;
+	static uint32_t epoch = 0;
+	static std::vector<uint64_t> chain; /* kept across launches: they see each other's stale words */
+	if (++epoch > 0xffffu) {
+		std::fill(chain.begin(), chain.end(), 0);
+		epoch = 1;
+	}
+	if (chain.size() < nspans)
+		chain.resize(nspans, 0);
+	std::vector<uint64_t> fin(nspans, ~0ull), pre(nspans, ~0ull), blk(2 * (size_t)nblk, ~0ull);
+	std::vector<uint64_t> evbuf(2 * (ev_cap ? ev_cap : 1), 0), ordered(3 * (ev_cap ? ev_cap : 1), 0);
+	uint64_t totals[8] = {0};
+	static uint32_t ctrl[64] = {0}; /* zero once; the finalize kernels re-arm it */
+	Scan7Args a;
+	memset(&a, 0, sizeof(a));
+	a.in = buf;
+	a.len = len;
+	a.rbsp = rbsp;
+	a.chain = chain.data();
+	a.fin = fin.data();
+	a.ctrl = ctrl;
+	a.evbuf = evbuf.data();
+	a.ev_cap = ev_cap;
+	a.num_spans = nspans;
+	a.halo_left = 0xffffffffu;
+	a.epoch = epoch;
+	a.pf_dist = 24;
+	a.right[0] = a.right[1] = 0xff;
+	int assume_in = 0;
+	if (edge) {
+		if (edge->has_left)
+			a.halo_left = 0xffffu | (uint32_t)edge->left[0] << 16 | (uint32_t)edge->left[1] << 24;
+		a.has_right = edge->has_right;
+		a.right[0] = edge->right[0];
+		a.right[1] = edge->right[1];
+		assume_in = edge->assume_in;
+	}
+	Fin7Args f;
+	memset(&f, 0, sizeof(f));
+	f.fin = fin.data();
+	f.chain = chain.data();
+	f.num_spans = nspans;
+	f.nblk = nblk;
+	f.evbuf = evbuf.data();
+	f.ev_cap = ev_cap;
+	f.ordered = ordered.data();
+	f.span_pre = pre.data();
+	f.blk = blk.data();
+	f.totals = totals;
+	f.ctrl = ctrl;
+	f.len = len;
+	f.base = base;
+	f.nal_start = nal_start;
+	f.nal_end = nal_end;
+	f.nal_rbsp = nal_rbsp;
+	f.nal_rbsp_len = nal_rbsp_len;
+	f.nal_cap = nal_cap;
+	f.result = result;
+	f.has_right = a.has_right;
+	f.strip = rbsp ? 1 : 0;
+	f.assume_in = (uint32_t)assume_in;
+	if (rows == 1) emu_scan7_run<1>(a, f, rbsp != NULL, ev_cap);
+	else if (rows == 2) emu_scan7_run<2>(a, f, rbsp != NULL, ev_cap);
+	else emu_scan7_run<8>(a, f, rbsp != NULL, ev_cap);
+	for (int i = 0; i < 5; i++)
+		if (ctrl[i] != 0)
+			return -2; /* control words not re-armed */
+	return 0;
+}
+
 /* gen 5: in-place RBSP (annexb_scan5.cuh).  cpt = 16-byte chunks per thread (1, 2 or 8). */
 extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t base,
 				       const struct h264gpu_shard_edge *edge, uint8_t *rbsp,
@@ -107,6 +208,12 @@ extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t
 	memset(result, 0xff, sizeof(*result));
 	uint8_t *buf = (uint8_t *)aligned_alloc(16, (len + 15) & ~15ull);
 	memcpy(buf, in, len);
+	if (cpt >= 80) {
+		const int rc = emu_scan7(buf, len, base, edge, rbsp, nal_start, nal_end, nal_rbsp, nal_rbsp_len,
+					 nal_cap, result, cpt % 10, ev_cap);
+		free(buf);
+		return rc;
+	}
 	ScanArgs a;
 	memset(&a, 0, sizeof(a));
 	a.in = buf;

@@ -39,7 +39,7 @@ def run_emu(buf, cpt, what):
     assert np.array_equal(g["start"], exp["start"]) and np.array_equal(g["end"], exp["end"])
 
 
-@pytest.mark.parametrize("cpt", [1, 2, 8, 61, 62, 68, 71, 74])
+@pytest.mark.parametrize("cpt", [1, 2, 8, 61, 62, 68, 71, 74, 81, 82, 88])
 def test_emu_random_streams(cpt):
     rng = np.random.default_rng(100 + cpt)
     for it in range(12):
@@ -49,7 +49,7 @@ def test_emu_random_streams(cpt):
         run_emu(buf, cpt, ("random", cpt, it))
 
 
-@pytest.mark.parametrize("cpt", [1, 8, 61, 68, 74])
+@pytest.mark.parametrize("cpt", [1, 8, 61, 68, 74, 81, 82, 88])
 def test_emu_pathological_streams(cpt):
     rng = np.random.default_rng(7)
     for it in range(20):
@@ -68,7 +68,7 @@ def test_emu_pathological_streams(cpt):
         run_emu(buf, cpt, ("patho", cpt, it))
 
 
-@pytest.mark.parametrize("cpt", [1, 61, 71])
+@pytest.mark.parametrize("cpt", [1, 61, 71, 81, 88])
 def test_emu_long_nal_crosses_many_tiles(cpt):
     """One NAL over > 32 tiles: the look-back has to walk more than one window, and tiles
     without a start code chain their shifts."""
@@ -79,7 +79,7 @@ def test_emu_long_nal_crosses_many_tiles(cpt):
     run_emu(buf, cpt, "long")
 
 
-@pytest.mark.parametrize("cpt", [1, 61])
+@pytest.mark.parametrize("cpt", [1, 61, 81, 88])
 def test_emu_more_tiles_than_one_finalize_block(cpt):
     """> 1024 tiles: the tile prefix of the finalize step spans several blocks."""
     rng = np.random.default_rng(9)
@@ -88,7 +88,7 @@ def test_emu_more_tiles_than_one_finalize_block(cpt):
     run_emu(buf, cpt, "finalize blocks")
 
 
-@pytest.mark.parametrize("cpt", [1, 61, 62, 71])
+@pytest.mark.parametrize("cpt", [1, 61, 62, 71, 81, 82, 88])
 def test_emu_seams_at_every_offset(cpt):
     """A start code / EPB / terminator sliding over a tile seam (4 KiB tiles; for gen 6 also a
     warp-span seam and, with 62, a row seam inside a span)."""
@@ -101,7 +101,7 @@ def test_emu_seams_at_every_offset(cpt):
             run_emu(buf, cpt, (pat, shift))
 
 
-@pytest.mark.parametrize("cpt", [1, 61])
+@pytest.mark.parametrize("cpt", [1, 61, 81])
 def test_emu_event_buffer_overflow_is_reported(cpt):
     buf = np.tile(np.array([0, 0, 1, 7], np.uint8), 400)
     g = S.emu_split_strip_inplace(buf, cpt=cpt, ev_cap=16)
@@ -161,7 +161,7 @@ def check_merged(g, o, what):
     assert g["final_off"] == o["final_off"] and g["rbsp_bytes"] == len(o["rbsp"]), what
 
 
-@pytest.mark.parametrize("cpt", [1, 61, 71])
+@pytest.mark.parametrize("cpt", [1, 61, 71, 81, 88])
 def test_emu_sharded_scan_merges_to_whole(cpt):
     rng = np.random.default_rng(5)
     run = lambda buf, e, lo: S.emu_split_strip_inplace(buf, cpt=cpt, edge=e, base=lo)
@@ -177,8 +177,9 @@ def test_emu_sharded_scan_merges_to_whole(cpt):
     check_merged(_merge_shards(run, b, [2048, 4096, 6000 // 16 * 16]), S.oracle_split_strip(b), "through")
 
 
-def test_emu_gen6_row_and_span_seams_and_shard_ends():
-    """Gen 6 specifics: patterns sliding over a row seam inside a span (62: rows of 512 B, spans of
+@pytest.mark.parametrize("gen", [6, 8])
+def test_emu_gen6_row_and_span_seams_and_shard_ends(gen):
+    """Gen 6 / gen 7 (cpt 8x) specifics: patterns sliding over a row seam inside a span (62: rows of 512 B, spans of
     1 KiB, tiles of 8 KiB), streams ending within +-3 bytes of a tile multiple (the launch covers
     len + 2 bytes because events are owned by their third byte), and a shard cut exactly at a
     tile multiple with the start code straddling it."""
@@ -191,7 +192,7 @@ def test_emu_gen6_row_and_span_seams_and_shard_ends():
                 buf[100:106] = [0, 0, 3, 0, 0, 3]  # a non-zero shift before the seam
                 pos = seam - 10 + shift
                 buf[pos:pos + len(pat)] = pat
-                run_emu(buf, 62, (pat, seam, shift))
+                run_emu(buf, gen * 10 + 2, (pat, seam, shift))
     rng = np.random.default_rng(21)
     for tail in ([0, 0, 1], [0, 0, 0], [0, 0, 3], [0, 0, 1, 9], [0, 0], [7, 0, 0, 3, 0]):
         for d in range(-3, 4):
@@ -199,8 +200,8 @@ def test_emu_gen6_row_and_span_seams_and_shard_ends():
             buf = S.oracle_insert(rng.choice(np.array([0, 0, 3, 7, 9], np.uint8), n))[:n - len(tail) - 4]
             buf = np.concatenate([np.array([0, 0, 1, 0x65], np.uint8), buf, np.array(tail, np.uint8)])
             assert len(buf) == n
-            run_emu(buf, 61, (tail, d))
-    run = lambda b, e, lo: S.emu_split_strip_inplace(b, cpt=61, edge=e, base=lo)
+            run_emu(buf, gen * 10 + 1, (tail, d))
+    run = lambda b, e, lo: S.emu_split_strip_inplace(b, cpt=gen * 10 + 1, edge=e, base=lo)
     for shift in range(0, 8):
         b = np.full(4096 * 3, 0x33, np.uint8)
         b[:4] = [0, 0, 1, 0x67]
