@@ -11,6 +11,24 @@
  * and runs its own byte-exact pass.  A warp that waits (bulk load, look-back) costs one of the
  * forty resident warps of the SM, not a whole CTA, and there is no __syncthreads in the kernel.
  *
+ * TICKETS GO ROUND ROBIN OVER K REGIONS of the stream.  With tickets in stream order a span's
+ * look-back needs the words of ~16 predecessors that took their tickets within nanoseconds of
+ * it, i.e. it waits for the slowest of them: 4.8 us of a 12.8 us span life
+ * (profiles/r02_scan7_phase_trace.txt).  With ticket -> (region tk % K, index tk / K) the
+ * predecessor of a span was taken K tickets earlier (K = 1480: ~3 us, the time from a ticket to
+ * its chain word), so the look-back finds it published, usually already as a PFX.  The spans at
+ * the head of a region (up to its first start code) would have to wait for the END of the
+ * region before them: their look-back does not block but defers them to a second, small launch
+ * of the same kernel over the deferred list (~17 spans per region), by which time every chain
+ * word exists.  1719 -> 2136 GB/s at 4 GiB.
+ *
+ * Measured and NOT kept: a CTA-level ticket pool (spans
+ * reserved early are published late: 1636 GB/s), 3 KiB spans at 48 warps per SM (1687), two
+ * 16-byte loads + word select instead of five conflicting 4-byte loads (no change: the kernel is
+ * not bound by a pipe), and running the emit phase one loop iteration after the classify phase
+ * with the masks parked in L2 (look-back wait 0.95 us, but the second read of the span misses
+ * L2 59 % of the time and the larger code misses the instruction cache: 1760 GB/s).
+ *
  * Chain descriptors are ONE 64-bit word per span, tagged with a 16-bit epoch of the launch
  * (nothing to clear between launches):  epoch << 48 | pfx << 41 | value.
  *   AGG (pfx = 0)  value = EPBs of the span (a span without a reset point)
@@ -57,17 +75,38 @@ struct Scan7Args {
 	uint8_t *rbsp;
 	uint64_t *chain; /* one word per span (strip only) */
 	uint64_t *fin;   /* one word per span: event slot | events << 32 | start codes << 48 */
-	uint32_t *ctrl;  /* [0] span ticket  [1] event cursor  [2] r0  [3],[4] finalize block counters */
+	uint32_t *ctrl;  /* [0] span ticket  [1] event cursor  [2] r0  [3],[4] finalize block counters
+			  * [5] deferred spans  [6] ticket of the second pass */
 	uint64_t *evbuf; /* 2 words per event: position | start code << 62, shift */
 	uint64_t ev_cap;
 	uint32_t num_spans;
 	uint32_t halo_left; /* bytes -4..-1 as a little-endian word, 0xff = none */
 	uint32_t epoch;     /* 1..65535 */
 	uint32_t pf_dist;   /* L2 prefetch distance in spans, 0 = off */
+	uint32_t nap_max;   /* longest sleep of a look-back poll, ns */
+	uint32_t regions;   /* K: tickets go round robin over K regions of region_len spans */
+	uint32_t region_len;
+	uint32_t pass2;     /* 1: the launch works off the deferred list */
+	uint32_t *deferred; /* spans whose look-back would cross a region start before the region before it is done */
 	uint8_t right[2];
 	uint8_t has_right;
 	uint8_t pad;
+	uint64_t *trace; /* diagnostics (H264GPU_SCAN_TRACE): 8 timestamps per span, or NULL */
 };
+
+/* phase timestamps of a span (diagnostics build of the kernel only) */
+template <bool TRACE> __device__ __forceinline__ void trace_mark(const Scan7Args &a, uint32_t t, uint32_t lane, int k)
+{
+#ifndef H264_EMU
+	if (TRACE && lane == 0) {
+		uint64_t ns;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+		a.trace[(uint64_t)t * 8 + k] = ns;
+	}
+#else
+	(void)a; (void)t; (void)lane; (void)k;
+#endif
+}
 
 /* the slice of shared memory a warp owns */
 template <int ROWS> struct __align__(128) WSmem {
@@ -184,27 +223,40 @@ __device__ __forceinline__ uint64_t chain_word(uint32_t epoch, bool pfx, uint64_
  * Shift at the start of span t = EPBs since the last reset point before it: fold the
  * predecessors' words back to the nearest PFX.  Whole warp, 32 predecessors per probe.
  */
-__device__ __forceinline__ uint64_t lookback(const Scan7Args &a, uint32_t t, uint32_t lane)
+constexpr uint64_t kDefer = ~0ull;
+
+/*
+ * rstart: first span of the region t lies in.  Words inside the region are waited for (their
+ * spans were taken earlier and are running); a word BEFORE the region that is not there yet
+ * belongs to a span that is taken late (the end of the previous region): the span is deferred
+ * to the second pass instead of waiting (kDefer).
+ */
+__device__ __forceinline__ uint64_t lookback(const Scan7Args &a, uint32_t t, uint32_t rstart, uint32_t lane)
 {
 	uint64_t acc = 0;
 	int64_t j0 = (int64_t)t - 1;
-	const uint64_t ep = (uint64_t)a.epoch;
-	uint32_t nap = 64; /* a waiting warp sleeps (the warps it waits for need the issue slots) */
+	const uint32_t ep = a.epoch;
+	uint32_t nap = 128; /* a waiting warp sleeps (the warps it waits for need the issue slots) */
 	for (;;) {
 		const int64_t jl = j0 - (int64_t)lane;
-		uint64_t w;
+		const uint64_t *p = a.chain + jl;
+		uint64_t w = (uint64_t)ep << 48 | kPfxBit; /* before the shard: shift 0 */
 		uint32_t stop;
 		for (;;) {
-			w = jl >= 0 ? ld_relaxed_u64(a.chain + jl) : (ep << 48 | kPfxBit); /* before the shard: shift 0 */
-			const bool valid = (w >> 48) == ep;
-			const bool ends = valid && (w & kPfxBit);
-			stop = __ballot_sync(FULL_MASK, ends);
+			if (jl >= 0)
+				w = ld_relaxed_u64(p);
+			const uint32_t hi = (uint32_t)(w >> 32);
+			const bool valid = (hi >> 16) == ep;
+			stop = __ballot_sync(FULL_MASK, valid && (hi & (uint32_t)(kPfxBit >> 32)));
 			const uint32_t ok = __ballot_sync(FULL_MASK, valid);
 			const uint32_t upto = stop ? ((stop & (0u - stop)) << 1) - 1u : 0xffffffffu;
-			if ((ok & upto) == upto)
+			const uint32_t missing = ~ok & upto;
+			if (!missing)
 				break;
+			if (missing & __ballot_sync(FULL_MASK, jl < (int64_t)rstart))
+				return kDefer;
 			spin_pause(nap);
-			nap = nap < 512 ? nap * 2 : 512;
+			nap = nap * 2 < a.nap_max ? nap * 2 : a.nap_max;
 		}
 		const int fs = stop ? __ffs((int)stop) - 1 : 32;
 		/* AGG values are small (<= SPAN / 3): one 32-bit warp sum; the PFX word has 40 bits */
@@ -449,9 +501,9 @@ __device__ __forceinline__ uint32_t emit_span(WSmem<ROWS> &s, uint32_t lane, uin
 }
 
 /* one span, all of it, by one warp */
-template <int ROWS>
-__device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint32_t t, uint32_t lane,
-					uint32_t &parity)
+template <int ROWS, bool TRACE>
+__device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint32_t t, uint32_t rstart,
+					uint32_t lane, uint32_t &parity, uint32_t &next)
 {
 	using C = Cfg<ROWS>;
 	const uint32_t ltmask = (1u << lane) - 1u;
@@ -463,10 +515,12 @@ __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint
 											   : (uint32_t)(a.len - span_off));
 	const bool full = nvalid == (uint32_t)C::SPAN;
 
+	trace_mark<TRACE>(a, t, lane, 0);
 	/* ---- P0: bulk load into the warp's slice, L2 prefetch ahead, cleared delete masks ---- */
 	if (lane == 0) {
 		if (full)
 			bulk_load_issue(s.raw + 16, a.in + span_off, C::SPAN, &s.bar);
+		/* the span that follows in the region is taken `regions` tickets from now */
 		const uint64_t noff = span_off + (uint64_t)a.pf_dist * C::SPAN;
 		if (a.pf_dist && noff + (uint64_t)C::SPAN <= a.len)
 			l2_prefetch(a.in + noff, C::SPAN);
@@ -492,6 +546,7 @@ __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint
 		}
 	}
 	__syncwarp();
+	trace_mark<TRACE>(a, t, lane, 1);
 
 	/* ---- P1: classify.  A chunk matters only if some byte <= 3 follows two zero bytes (an EPB
 	 * or the third byte of a boundary event): one SIMD-in-register test per chunk finds the
@@ -556,6 +611,7 @@ __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint
 	ecnt = warp_add(ecnt);
 	if (!any_ev && lane == 0)
 		st_relaxed_u64(a.chain + t, chain_word(a.epoch, t == 0, ecnt));
+	trace_mark<TRACE>(a, t, lane, 2);
 
 	/* ---- P2: EPBs of the span before every chunk (a lane sums ROWS consecutive chunks) ---- */
 	uint32_t etot;
@@ -655,24 +711,34 @@ __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint
 	/* ---- P3: the span's chain word, published at once; event slot asked for; then the shift
 	 * at the span start by the look-back ---- */
 	const uint32_t e_tail = has ? (uint32_t)((int32_t)etot + cur_rel) : etot;
+	if (lane == 0 && any_ev)
+		st_relaxed_u64(a.chain + t, chain_word(a.epoch, has || t == 0, e_tail));
+	uint64_t d0 = 0;
+	trace_mark<TRACE>(a, t, lane, 3);
+	if (t > 0) {
+		d0 = lookback(a, t, rstart, lane);
+		if (d0 == kDefer) {
+			/* the shift depends on the region before, which is not done: second pass */
+			if (lane == 0) {
+				a.deferred[atomicAdd(a.ctrl + 5, 1u)] = t;
+				next = atomicAdd(a.ctrl + (a.pass2 ? 6 : 0), 1u);
+			}
+			__syncwarp();
+			return;
+		}
+		if (!has && lane == 0)
+			st_relaxed_u64(a.chain + t, chain_word(a.epoch, true, d0 + (uint64_t)etot));
+	}
 	uint32_t evbase = 0;
 	if (lane == 0) {
-		if (any_ev)
-			st_relaxed_u64(a.chain + t, chain_word(a.epoch, has || t == 0, e_tail));
 		if (nev)
 			evbase = atomicAdd(a.ctrl + 1, nev);
 		if (t == 0)
 			a.ctrl[2] = first_r < 3 ? first_r : 0u;
-	}
-	uint64_t d0 = 0;
-	if (t > 0) {
-		d0 = lookback(a, t, lane);
-		if (!has && lane == 0)
-			st_relaxed_u64(a.chain + t, chain_word(a.epoch, true, d0 + (uint64_t)etot));
-	}
-	if (lane == 0)
 		a.fin[t] = (uint64_t)evbase | (uint64_t)nev << 32 | (uint64_t)nsc << 48;
+	}
 	__syncwarp(); /* rbrel written by lane 0 */
+	trace_mark<TRACE>(a, t, lane, 4);
 
 	/* ---- P5 (spans with events): event records with the shift at the event (before the emit
 	 * pass reuses E of byte-wise rows) ---- */
@@ -743,6 +809,11 @@ __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint
 		else
 			ndirty = emit_span<ROWS, false>(s, lane, bwl, rbhas, d0, out_span, nvalid);
 		__syncwarp();
+		trace_mark<TRACE>(a, t, lane, 5);
+		/* the next span's ticket is asked for here: its round trip (the one contended word of
+		 * the kernel, ~1.7 us under load) hides behind the byte-exact pass */
+		if (lane == 0)
+			next = atomicAdd(a.ctrl + (a.pass2 ? 6 : 0), 1u);
 		for (uint32_t g = lane; g < ndirty; g += 32) {
 			const uint32_t c = s.dl[g];
 			const uint32_t R = c >> 5;
@@ -756,9 +827,10 @@ __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint
 			bytewise_chunk<ROWS>(s, ((uint32_t)__ffs((int)x) - 1) * 32 + lane, rbhas, d0, out_span, nvalid);
 	}
 	__syncwarp(); /* the slice is reused by the next span */
+	trace_mark<TRACE>(a, t, lane, 6);
 }
 
-template <int ROWS, int MINB>
+template <int ROWS, int MINB, bool TRACE = false>
 __global__ void __launch_bounds__(kT, MINB) scan7_kernel(const Scan7Args a)
 {
 	__shared__ WSmem<ROWS> sm[kW];
@@ -768,14 +840,32 @@ __global__ void __launch_bounds__(kT, MINB) scan7_kernel(const Scan7Args a)
 		bulk_bar_init(&s.bar);
 	__syncwarp();
 	uint32_t parity = 0;
+	uint32_t next = 0;
+	uint32_t *const tick = a.ctrl + (a.pass2 ? 6 : 0);
+	if (lane == 0)
+		next = atomicAdd(tick, 1u);
+	/* first pass: ticket -> (region, index): consecutive spans of the stream are taken `regions`
+	 * tickets apart, so a span's predecessors published their chain words microseconds ago;
+	 * second pass: the spans the first one deferred */
+	const uint32_t limit = a.pass2 ? *(volatile uint32_t *)(a.ctrl + 5) : a.regions * a.region_len;
 	for (;;) {
-		uint32_t t = 0;
-		if (lane == 0)
-			t = atomicAdd(a.ctrl, 1u);
-		t = __shfl_sync(FULL_MASK, t, 0);
-		if (t >= a.num_spans)
+		const uint32_t tk = __shfl_sync(FULL_MASK, next, 0);
+		if (tk >= limit)
 			break;
-		do_span<ROWS>(s, a, t, lane, parity);
+		uint32_t t, rstart = 0;
+		if (a.pass2) {
+			t = a.deferred[tk];
+		} else {
+			const uint32_t i = tk / a.regions, r = tk - i * a.regions;
+			rstart = r * a.region_len;
+			t = rstart + i;
+			if (t >= a.num_spans) { /* the last regions are ragged */
+				if (lane == 0)
+					next = atomicAdd(tick, 1u);
+				continue;
+			}
+		}
+		do_span<ROWS, TRACE>(s, a, t, rstart, lane, parity, next);
 	}
 }
 
@@ -1105,6 +1195,8 @@ __global__ void __launch_bounds__(256) fin7_table(const Fin7Args f)
 	f.ctrl[1] = 0;
 	f.ctrl[2] = 0;
 	f.ctrl[4] = 0;
+	f.ctrl[5] = 0;
+	f.ctrl[6] = 0;
 }
 
 } /* namespace annexb7 */

@@ -423,12 +423,12 @@ static int device_sms(h264gpu_ctx *ctx)
 	return ctx->sms;
 }
 
-static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uint64_t base,
-			const struct h264gpu_shard_edge *edge, uint8_t *d_rbsp, uint64_t *d_nal_start,
-			uint64_t *d_nal_end, uint64_t *d_nal_rbsp, uint64_t *d_nal_rbsp_len, uint64_t nal_cap,
-			struct h264gpu_scan_result *d_result, cudaStream_t st)
+template <int ROWS, int CTAS>
+static int scan7_launch_t(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uint64_t base,
+			  const struct h264gpu_shard_edge *edge, uint8_t *d_rbsp, uint64_t *d_nal_start,
+			  uint64_t *d_nal_end, uint64_t *d_nal_rbsp, uint64_t *d_nal_rbsp_len, uint64_t nal_cap,
+			  struct h264gpu_scan_result *d_result, cudaStream_t st)
 {
-	constexpr int ROWS = 8;
 	const uint64_t span = (uint64_t)annexb7::Cfg<ROWS>::SPAN;
 	/* a boundary event is owned by its third byte: the launch covers the two edge bytes too */
 	const uint64_t nspans = (len + 2 + span - 1) / span;
@@ -449,7 +449,8 @@ static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uin
 	const size_t tot_off = blk_off + (size_t)nblk * 16;
 	const size_t ev_off = tot_off + 64;
 	const size_t ord_off = ev_off + (size_t)ev_cap * 16;
-	const size_t need = ord_off + (size_t)ev_cap * 24;
+	const size_t def_off = ord_off + (size_t)ev_cap * 24;
+	const size_t need = def_off + (size_t)nspans * 4;
 	const size_t had = ctx->ws7_bytes;
 	int r = ws7_reserve(ctx, need);
 	if (r < 0)
@@ -473,6 +474,7 @@ static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uin
 	a.ctrl = (uint32_t *)ws;
 	a.evbuf = (uint64_t *)(ws + ev_off);
 	a.ev_cap = ev_cap;
+	a.deferred = (uint32_t *)(ws + def_off);
 	a.num_spans = (uint32_t)nspans;
 	a.halo_left = 0xffffffffu;
 	a.epoch = ctx->epoch7;
@@ -489,14 +491,73 @@ static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uin
 	const int sms = device_sms(ctx);
 	const uint64_t ctas_needed = (nspans + annexb7::kW - 1) / annexb7::kW;
 	if (d_rbsp != NULL) {
-		const uint32_t grid = (uint32_t)(ctas_needed < (uint64_t)sms * 5 ? ctas_needed : (uint64_t)sms * 5);
-		a.pf_dist = getenv("H264GPU_SCAN7_NOPF") ? 0u : grid * annexb7::kW;
-		if (!(ctx->attr_set & 1u)) {
-			cudaFuncSetAttribute(annexb7::scan7_kernel<ROWS, 5>, cudaFuncAttributePreferredSharedMemoryCarveout,
-					     cudaSharedmemCarveoutMaxShared);
-			ctx->attr_set |= 1u;
+		const uint32_t grid = (uint32_t)(ctas_needed < (uint64_t)sms * CTAS ? ctas_needed : (uint64_t)sms * CTAS);
+		/* tickets go round robin over K regions: a span's predecessor was taken K tickets
+		 * (K x ~2 ns) before it.  K = a quarter of the resident warps gives ~3 us of lead, the
+		 * time a span needs from its ticket to its chain word; every region start defers ~17
+		 * spans (up to the first start code) to the second pass, so K is also kept below 1/128
+		 * of the spans.  Measured at 4 GiB: K = 1 1719, 370 2068, 740 2108, 1480 2136, 5920 2116 GB/s */
+		uint32_t K = grid * annexb7::kW / 4;
+		{
+			const char *e = getenv("H264GPU_SCAN7_REGIONS");
+			if (e != NULL && atoi(e) > 0)
+				K = (uint32_t)atoi(e);
 		}
-		annexb7::scan7_kernel<ROWS, 5><<<grid, annexb7::kT, 0, st>>>(a);
+		if (K > nspans / 128)
+			K = (uint32_t)(nspans / 128);
+		if (K < 1)
+			K = 1;
+		a.regions = K;
+		a.region_len = (uint32_t)((nspans + K - 1) / K);
+		a.pf_dist = 1; /* the next span of the region: taken K tickets from now */
+		{
+			const char *e = getenv("H264GPU_SCAN7_PF");
+			if (e != NULL)
+				a.pf_dist = (uint32_t)atoi(e);
+		}
+		{
+			const char *e = getenv("H264GPU_SCAN7_NAP");
+			a.nap_max = e != NULL && atoi(e) > 0 ? (uint32_t)atoi(e) : 512u;
+		}
+		if (!(ctx->attr_set & (1u << ROWS))) {
+			cudaFuncSetAttribute(annexb7::scan7_kernel<ROWS, CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+					     cudaSharedmemCarveoutMaxShared);
+			ctx->attr_set |= 1u << ROWS;
+		}
+		const char *trace_path = getenv("H264GPU_SCAN_TRACE");
+		if (trace_path != NULL) {
+			/* diagnostics build of the same kernel: per-span phase timestamps to a file */
+			uint64_t *d_trace = NULL;
+			CU_TRY(cudaMalloc(&d_trace, nspans * 64));
+			CU_TRY(cudaMemsetAsync(d_trace, 0, nspans * 64, st));
+			a.trace = d_trace;
+			cudaFuncSetAttribute(annexb7::scan7_kernel<ROWS, CTAS, true>,
+					     cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+			annexb7::scan7_kernel<ROWS, CTAS, true><<<grid, annexb7::kT, 0, st>>>(a);
+			uint64_t *h = (uint64_t *)malloc(nspans * 64);
+			CU_TRY(cudaStreamSynchronize(st));
+			CU_TRY(cudaMemcpy(h, d_trace, nspans * 64, cudaMemcpyDeviceToHost));
+			FILE *fp = fopen(trace_path, "wb");
+			if (fp != NULL) {
+				fwrite(h, 64, nspans, fp);
+				fclose(fp);
+			}
+			free(h);
+			cudaFree(d_trace);
+		} else {
+			annexb7::scan7_kernel<ROWS, CTAS><<<grid, annexb7::kT, 0, st>>>(a);
+		}
+		if (K > 1) {
+			/* second pass: the spans deferred at region starts (every chain word is there now) */
+			annexb7::Scan7Args b = a;
+			b.pass2 = 1;
+			b.regions = 1;
+			b.trace = NULL;
+			const uint64_t est = (uint64_t)K * 4; /* CTAs worth launching: ~17 spans per region */
+			const uint32_t g2 = (uint32_t)(est < grid ? est : grid);
+			annexb7::scan7_kernel<ROWS, CTAS><<<g2 ? g2 : 1, annexb7::kT, 0, st>>>(b);
+			ctx->launches++;
+		}
 	} else {
 		const uint32_t grid = (uint32_t)(ctas_needed < (uint64_t)sms * 4 ? ctas_needed : (uint64_t)sms * 4);
 		annexb7::scan7_only_kernel<ROWS, 4><<<grid, annexb7::kT, 0, st>>>(a);
@@ -537,6 +598,20 @@ static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uin
 	CU_TRY(cudaGetLastError());
 	ctx->launches += 4;
 	return 0;
+}
+
+static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uint64_t base,
+			const struct h264gpu_shard_edge *edge, uint8_t *d_rbsp, uint64_t *d_nal_start,
+			uint64_t *d_nal_end, uint64_t *d_nal_rbsp, uint64_t *d_nal_rbsp_len, uint64_t nal_cap,
+			struct h264gpu_scan_result *d_result, cudaStream_t st)
+{
+	/* span shape: 8 rows (4 KiB, 5 CTAs per SM) or 6 rows (3 KiB, 6 CTAs per SM) */
+	const char *e = getenv("H264GPU_SCAN7_ROWS");
+	if (e != NULL && atoi(e) == 6)
+		return scan7_launch_t<6, 6>(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp,
+					    d_nal_rbsp_len, nal_cap, d_result, st);
+	return scan7_launch_t<8, 5>(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp,
+				    d_nal_rbsp_len, nal_cap, d_result, st);
 }
 
 /* ---- scan + strip, RBSP in place (gen 5) ----------------------------------- */

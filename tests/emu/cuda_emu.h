@@ -349,6 +349,14 @@ template <class T> static inline T atomicExch(T *p, T v)
 	*p = v;
 	return o;
 }
+template <class T> static inline T atomicCAS(T *p, T cmp, T v)
+{
+	T o = *p;
+	if (o == cmp)
+		*p = v;
+	return o;
+}
+static inline void __threadfence_block() {}
 template <class T> static inline T atomicOr(T *p, T v)
 {
 	T o = *p;

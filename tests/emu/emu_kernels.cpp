@@ -90,9 +90,15 @@ static void emu_scan7_run(const annexb7::Scan7Args &a, const annexb7::Fin7Args &
 {
 	const uint32_t nctas = (a.num_spans + annexb7::kW - 1) / annexb7::kW;
 	dim3 grid(nctas < 3 ? nctas : 3), block(annexb7::kT);
-	if (strip)
+	if (strip) {
 		EMU_LAUNCH((annexb7::scan7_kernel<ROWS, 1>), grid, block, a);
-	else
+		if (a.regions > 1) {
+			annexb7::Scan7Args b = a;
+			b.pass2 = 1;
+			b.regions = 1;
+			EMU_LAUNCH((annexb7::scan7_kernel<ROWS, 1>), grid, block, b);
+		}
+	} else
 		EMU_LAUNCH((annexb7::scan7_only_kernel<ROWS, 1>), grid, block, a);
 	dim3 gs(f.nblk), bs(annexb7::kFinT), b256(256);
 	EMU_LAUNCH((annexb7::fin7_spans), gs, bs, f);
@@ -139,7 +145,17 @@ static int emu_scan7(const uint8_t *buf, uint64_t len, uint64_t base, const stru
 	a.num_spans = nspans;
 	a.halo_left = 0xffffffffu;
 	a.epoch = epoch;
-	a.pf_dist = 24;
+	a.pf_dist = 1;
+	a.nap_max = 256;
+	/* regions: 1, 3, 5, 7 in turn (small streams get regions of a few spans: lots of deferrals) */
+	static uint32_t kreg = 0;
+	kreg = (kreg + 1) % 4;
+	a.regions = 2 * kreg + 1;
+	if (a.regions > nspans)
+		a.regions = nspans;
+	a.region_len = (nspans + a.regions - 1) / a.regions;
+	std::vector<uint32_t> deferred(nspans + 1, 0);
+	a.deferred = deferred.data();
 	a.right[0] = a.right[1] = 0xff;
 	int assume_in = 0;
 	if (edge) {
@@ -176,8 +192,9 @@ static int emu_scan7(const uint8_t *buf, uint64_t len, uint64_t base, const stru
 	f.assume_in = (uint32_t)assume_in;
 	if (rows == 1) emu_scan7_run<1>(a, f, rbsp != NULL, ev_cap);
 	else if (rows == 2) emu_scan7_run<2>(a, f, rbsp != NULL, ev_cap);
+	else if (rows == 6) emu_scan7_run<6>(a, f, rbsp != NULL, ev_cap);
 	else emu_scan7_run<8>(a, f, rbsp != NULL, ev_cap);
-	for (int i = 0; i < 5; i++)
+	for (int i = 0; i < 7; i++)
 		if (ctrl[i] != 0)
 			return -2; /* control words not re-armed */
 	return 0;

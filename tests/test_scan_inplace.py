@@ -39,7 +39,7 @@ def run_emu(buf, cpt, what):
     assert np.array_equal(g["start"], exp["start"]) and np.array_equal(g["end"], exp["end"])
 
 
-@pytest.mark.parametrize("cpt", [1, 2, 8, 61, 62, 68, 71, 74, 81, 82, 88])
+@pytest.mark.parametrize("cpt", [1, 2, 8, 61, 62, 68, 71, 74, 81, 82, 86, 88])
 def test_emu_random_streams(cpt):
     rng = np.random.default_rng(100 + cpt)
     for it in range(12):
@@ -49,7 +49,7 @@ def test_emu_random_streams(cpt):
         run_emu(buf, cpt, ("random", cpt, it))
 
 
-@pytest.mark.parametrize("cpt", [1, 8, 61, 68, 74, 81, 82, 88])
+@pytest.mark.parametrize("cpt", [1, 8, 61, 68, 74, 81, 82, 86, 88])
 def test_emu_pathological_streams(cpt):
     rng = np.random.default_rng(7)
     for it in range(20):
