@@ -73,8 +73,36 @@ struct BitReader {
 	bool err;
 };
 
+/* 4 raw bytes at p (any alignment) as a big-endian word; reads the two aligned words around them */
+__device__ __forceinline__ uint32_t load_be32(const uint8_t *p)
+{
+#ifdef H264_EMU
+	return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+#else
+	const uintptr_t a = (uintptr_t)p;
+	const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+	const uint32_t v = __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+	return __byte_perm(v, 0, 0x0123);
+#endif
+}
+
 __device__ __noinline__ void br_refill(BitReader &b)
 {
+	/* word at a time: a word without a 03 byte holds no emulation prevention byte, whatever came
+	 * before it (8 bytes of the NAL must be left so that the aligned loads stay inside it) */
+	while (b.nbits <= 32 && b.pos + 8 <= b.len) {
+		const uint32_t w = load_be32(b.p + b.pos);
+		const uint32_t x = w ^ 0x03030303u;
+		if ((x - 0x01010101u) & ~x & 0x80808080u)
+			break; /* a 03 byte: the byte path decides */
+		b.cache |= (uint64_t)w << (32 - b.nbits);
+		b.nbits += 32;
+		b.pos += 4;
+		b.epbq <<= 4;
+		b.zeros = (w & 0xffffu) == 0 ? 2u : ((w & 0xffu) == 0 ? 1u : 0u);
+	}
+	if (b.nbits > 32)
+		return; /* no reader asks for more than 32 bits at once */
 	while (b.nbits <= 56 && b.pos < b.len) {
 		/* up to 5 raw bytes in flight at once (independent loads), then the EPB
 		 * state machine runs on registers */
@@ -258,7 +286,7 @@ struct SliceCtx {
 	uint64_t hash;
 };
 
-__device__ __noinline__ void hash_add(SliceCtx &s, uint32_t field, uint32_t idx, int64_t v)
+__device__ __forceinline__ void hash_add(SliceCtx &s, uint32_t field, uint32_t idx, int64_t v)
 {
 	/* device-side twin of h264gpu_mb_hash_term (include/h264gpu_slice.h) */
 	if (v != 0) {
@@ -415,49 +443,73 @@ __device__ __forceinline__ uint32_t tab_for_nc(uint32_t nc)
 	return nc < 2 ? 0 : nc < 4 ? 1 : nc < 8 ? 2 : 3;
 }
 
-/* residual_luma for component comp (0 Y, 1 Cb, 2 Cr): src/h264_syntax_slice_data.h:247-331 */
-__device__ __forceinline__ void residual_luma(SliceCtx &s, uint32_t comp, bool i16, uint32_t cbp_luma)
+/*
+ * The residual blocks of a macroblock as a bit mask of SLOTS, in the order residual() reads them
+ * (src/h264_syntax_slice_data.h:334-419, residual_luma :247-331):
+ *   17 * c + 0        Intra16x16 DC of colour component c (c > 0 only with ChromaArrayType 3)
+ *   17 * c + 1 + blk  4x4 block blk of component c (AC only for Intra16x16)
+ *   17, 18            chroma DC Cb, Cr            (ChromaArrayType 1, 2)
+ *   19 + 8 * ic + blk chroma AC block             (ChromaArrayType 1, 2)
+ * A lane walks its mask lowest bit first; the k-th coded block of every lane of a warp goes
+ * through the same residual_block code together.
+ */
+__device__ __forceinline__ uint64_t residual_slots(const SliceCtx &s, bool i16, uint32_t cbp_luma,
+						    uint32_t cbp_chroma)
 {
-	if (i16) {
-		uint32_t tc = residual_block(s, tab_for_nc(calc_nc(s, comp, 0, false)), 16,
-					     H264GPU_F_I16_DC + 3 * comp, 0);
-		s.nz[comp * 16] = (uint8_t)tc;
+	uint64_t luma = i16 ? 1u : 0u;
+#pragma unroll
+	for (uint32_t q = 0; q < 4; q++)
+		if (cbp_luma & (1u << q))
+			luma |= 0xfull << (1 + 4 * q);
+	uint64_t m = luma;
+	if (s.cat == 3) {
+		m |= luma << 17 | luma << 34;
+	} else if (s.cat == 1 || s.cat == 2) {
+		const uint64_t blks = s.cat == 1 ? 0xfull : 0xffull;
+		if (cbp_chroma & 3)
+			m |= 3ull << 17;
+		if (cbp_chroma & 2)
+			m |= blks << 19 | blks << 27;
 	}
-	for (uint32_t blk = 0; blk < 16 && !s.br.err; blk++) {
-		if (!(cbp_luma & (1u << (blk >> 2))))
-			continue;
-		uint32_t tab = tab_for_nc(calc_nc(s, comp, blk, false));
-		uint32_t tc = i16 ? residual_block(s, tab, 15, H264GPU_F_I16_AC + 3 * comp, blk * 16)
-				  : residual_block(s, tab, 16, H264GPU_F_LEVEL4X4 + 3 * comp, blk * 16);
-		s.nz[comp * 16 + blk] = (uint8_t)tc;
-	}
+	return m;
 }
 
-/* residual(): src/h264_syntax_slice_data.h:334-419 */
-__device__ __forceinline__ void residual(SliceCtx &s, bool i16, uint32_t cbp_luma, uint32_t cbp_chroma)
+__device__ __forceinline__ void residual_slot(SliceCtx &s, bool i16, uint32_t slot)
 {
-	residual_luma(s, 0, i16, cbp_luma);
-	if (s.cat == 1 || s.cat == 2) {
-		const uint32_t nblk = s.cat == 1 ? 4 : 8;
-		if (cbp_chroma & 3) {
-			for (uint32_t ic = 0; ic < 2 && !s.br.err; ic++) {
-				uint32_t tc = residual_block(s, s.cat == 1 ? 4 : 5, nblk, H264GPU_F_CHROMA_DC, ic * 16);
-				s.nz[(1 + ic) * 16] = (uint8_t)tc;
-			}
+	uint32_t tab, maxc, field, idx, out;
+	if (s.cat == 3 || slot < 17) {
+		const uint32_t comp = slot / 17, k = slot - 17 * comp;
+		if (k == 0) {
+			tab = tab_for_nc(calc_nc(s, comp, 0, false));
+			maxc = 16;
+			field = H264GPU_F_I16_DC + 3 * comp;
+			idx = 0;
+			out = comp * 16;
+		} else {
+			const uint32_t blk = k - 1;
+			tab = tab_for_nc(calc_nc(s, comp, blk, false));
+			maxc = i16 ? 15 : 16;
+			field = (i16 ? H264GPU_F_I16_AC : H264GPU_F_LEVEL4X4) + 3 * comp;
+			idx = blk * 16;
+			out = comp * 16 + blk;
 		}
-		if (cbp_chroma & 2) {
-			for (uint32_t ic = 0; ic < 2; ic++)
-				for (uint32_t blk = 0; blk < nblk && !s.br.err; blk++) {
-					uint32_t tab = tab_for_nc(calc_nc(s, 1 + ic, blk, true));
-					uint32_t tc = residual_block(s, tab, 15, H264GPU_F_CHROMA_AC,
-								     (ic * 16 + blk) * 16);
-					s.nz[(1 + ic) * 16 + blk] = (uint8_t)tc;
-				}
-		}
-	} else if (s.cat == 3) {
-		residual_luma(s, 1, i16, cbp_luma);
-		residual_luma(s, 2, i16, cbp_luma);
+	} else if (slot < 19) {
+		const uint32_t ic = slot - 17;
+		tab = s.cat == 1 ? 4 : 5;
+		maxc = s.cat == 1 ? 4 : 8;
+		field = H264GPU_F_CHROMA_DC;
+		idx = ic * 16;
+		out = (1 + ic) * 16;
+	} else {
+		const uint32_t jj = slot - 19, ic = jj >> 3, blk = jj & 7;
+		tab = tab_for_nc(calc_nc(s, 1 + ic, blk, true));
+		maxc = 15;
+		field = H264GPU_F_CHROMA_AC;
+		idx = (ic * 16 + blk) * 16;
+		out = (1 + ic) * 16 + blk;
 	}
+	const uint32_t tc = residual_block(s, tab, maxc, field, idx);
+	s.nz[out] = (uint8_t)tc;
 }
 
 /* B mb_type 4..21: prediction modes of the two partitions (src/h264_slice_data.c:847-866) */
@@ -562,12 +614,14 @@ __device__ __forceinline__ bool decode_mb_type(SliceCtx &s, MbInfo &m, uint32_t 
 }
 
 /* macroblock_layer: src/h264_syntax_slice_data.h:604-696 */
-__device__ __forceinline__ bool macroblock_layer(SliceCtx &s, uint32_t &mb_type_out)
+__device__ __forceinline__ bool macroblock_layer(SliceCtx &s, uint32_t &mb_type_out, uint64_t &slots, bool &i16_out)
 {
 	BitReader &b = s.br;
 	const h264gpu_slice_params &sp = *s.sp;
 	MbInfo m;
 	uint32_t cbp_luma = 0, cbp_chroma = 0;
+	slots = 0;
+	i16_out = false;
 	if (!decode_mb_type(s, m, cbp_luma, cbp_chroma) || b.err)
 		return false;
 	mb_type_out = m.mb_type;
@@ -718,101 +772,172 @@ __device__ __forceinline__ bool macroblock_layer(SliceCtx &s, uint32_t &mb_type_
 
 	if (cbp_luma > 0 || cbp_chroma > 0 || m.pm[0] == PM_I16) {
 		hash_add(s, H264GPU_F_MB_QP_DELTA, 0, br_se(b));
-		residual(s, m.pm[0] == PM_I16, cbp_luma, cbp_chroma);
+		i16_out = m.pm[0] == PM_I16;
+		slots = residual_slots(s, i16_out, cbp_luma, cbp_chroma);
 	}
 	return !b.err;
 }
 
-/* one slice: src/h264_syntax_slice_data.h:701-787 */
-__device__ __forceinline__ void parse_slice(const uint8_t *stream, const h264gpu_slice_params &sp,
-					     uint8_t *ring, h264gpu_mb_record *rec,
-					     h264gpu_slice_result &res)
+/*
+ * One slice (src/h264_syntax_slice_data.h:701-787) as three steps per macroblock, so that the
+ * lanes of a warp (one slice each) can take every step together:
+ *   mb_begin   skip run + macroblock header up to the residual -> the slots to decode
+ *   residual_slot x popcount(slots)
+ *   mb_end     context ring, record, end-of-slice test
+ */
+struct SliceRun {
+	SliceCtx s;
+	h264gpu_mb_record *rec;
+	uint32_t pic_size, first, cur, count, mb_type;
+	int status;
+	bool inter, done, i16;
+};
+
+__device__ __forceinline__ void slice_begin(SliceRun &r, const uint8_t *stream, uint64_t stream_len,
+					     const h264gpu_slice_params &sp, uint8_t *ring, h264gpu_mb_record *rec)
 {
-	res.status = 0;
-	res.mb_count = 0;
-	res.end_bit = 0;
+	r.status = 0;
+	r.count = 0;
+	r.done = true;
+	r.rec = rec;
+	r.s.sp = &sp;
+	r.s.br.p = stream;
+	r.s.br.len = r.s.br.pos = 0;
+	r.s.br.nbits = 0;
+	r.s.br.cache = 0;
+	r.s.br.epbq = 0;
 	if (sp.entropy_coding_mode_flag) {
-		res.status = H264GPU_SLICE_SKIPPED;
+		r.status = H264GPU_SLICE_SKIPPED;
 		return;
 	}
 	if (sp.mbaff_frame_flag || sp.num_slice_groups_minus1 != 0 || sp.pic_width_in_mbs == 0) {
-		res.status = -ENOSYS;
+		r.status = -ENOSYS;
 		return;
 	}
-	SliceCtx s;
-	s.sp = &sp;
+	/* a parameter block that points outside the stream must not be followed */
+	if ((uint64_t)sp.nal_off + sp.nal_len > stream_len || sp.data_bit_off >= 8ull * sp.nal_len) {
+		r.status = -22; /* -EINVAL */
+		return;
+	}
+	SliceCtx &s = r.s;
 	s.W = sp.pic_width_in_mbs;
 	s.cat = sp.chroma_array_type;
 	s.mbw_c4 = s.cat == 0 ? 0 : (s.cat == 3 ? 4 : 2);
 	s.mbh_c4 = s.cat == 0 ? 0 : (s.cat == 1 ? 2 : 4);
 	s.ring = ring;
 	br_init(s.br, stream + sp.nal_off, sp.nal_len, sp.data_bit_off);
-	const uint32_t pic_size = (uint32_t)sp.pic_width_in_mbs * sp.pic_height_in_mbs;
-	const uint32_t first = sp.first_mb_in_slice;
-	const bool inter = sp.slice_type != ST_I && sp.slice_type != ST_SI;
-	uint32_t cur = first, count = 0;
-	int status = 0;
+	r.pic_size = (uint32_t)sp.pic_width_in_mbs * sp.pic_height_in_mbs;
+	r.first = sp.first_mb_in_slice;
+	r.inter = sp.slice_type != ST_I && sp.slice_type != ST_SI;
+	r.cur = r.first;
+	r.done = false;
+}
 
-	for (;;) {
-		if (inter) {
-			uint32_t run = br_ue(s.br);
-			if (s.br.err) {
-				status = -EIO;
-				break;
+/* returns the residual slots of the macroblock; r.done set when the slice ends here */
+__device__ __forceinline__ uint64_t mb_begin(SliceRun &r)
+{
+	SliceCtx &s = r.s;
+	const h264gpu_slice_params &sp = *s.sp;
+	if (r.inter) {
+		const uint32_t run = br_ue(s.br);
+		if (s.br.err) {
+			r.status = -EIO;
+			r.done = true;
+			return 0;
+		}
+		for (uint32_t i = 0; i < run; i++) {
+			if (r.count >= sp.mb_out_cap || r.cur >= r.pic_size) {
+				r.status = -ENOBUFS;
+				r.done = true;
+				return 0;
 			}
-			for (uint32_t i = 0; i < run; i++) {
-				if (count >= sp.mb_out_cap || cur >= pic_size) {
-					status = -ENOBUFS;
-					break;
-				}
-				uint32_t *slot = (uint32_t *)ring_slot(s, cur);
-				for (int k = 0; k < 12; k++)
-					slot[k] = 0;
-				rec[count].mb_addr = cur;
-				rec[count].mb_type = sp.slice_type == ST_B ? MB_B_SKIP : MB_P_SKIP;
-				rec[count].hash = 0;
-				count++;
-				cur++;
-			}
-			if (status)
-				break;
-			if (run > 0 && !br_more_rbsp_data(s.br))
-				break;
+			uint32_t *slot = (uint32_t *)ring_slot(s, r.cur);
+			for (int k = 0; k < 12; k++)
+				slot[k] = 0;
+			r.rec[r.count].mb_addr = r.cur;
+			r.rec[r.count].mb_type = sp.slice_type == ST_B ? MB_B_SKIP : MB_P_SKIP;
+			r.rec[r.count].hash = 0;
+			r.count++;
+			r.cur++;
 		}
-		if (count >= sp.mb_out_cap || cur >= pic_size) {
-			status = -ENOBUFS;
-			break;
+		if (run > 0 && !br_more_rbsp_data(s.br)) {
+			r.done = true;
+			return 0;
 		}
-		s.cur = cur;
-		s.availA = cur >= first + 1 && cur % s.W != 0;
-		s.availB = cur >= first + s.W;
-		for (int k = 0; k < 48; k++)
-			s.nz[k] = 0;
-		s.hash = 0;
-		uint32_t mb_type = MB_UNKNOWN;
-		if (!macroblock_layer(s, mb_type)) {
-			status = -EIO;
-			break;
-		}
-		uint32_t *slot = (uint32_t *)ring_slot(s, cur);
-		for (int k = 0; k < 12; k++)
-			slot[k] = (uint32_t)s.nz[4 * k] | (uint32_t)s.nz[4 * k + 1] << 8 |
-				  (uint32_t)s.nz[4 * k + 2] << 16 | (uint32_t)s.nz[4 * k + 3] << 24;
-		rec[count].mb_addr = cur;
-		rec[count].mb_type = mb_type;
-		rec[count].hash = s.hash;
-		count++;
-		cur++;
-		if (!br_more_rbsp_data(s.br))
-			break;
 	}
-	res.status = status;
-	res.mb_count = count;
-	res.end_bit = br_raw_bitpos(s.br);
+	if (r.count >= sp.mb_out_cap || r.cur >= r.pic_size) {
+		r.status = -ENOBUFS;
+		r.done = true;
+		return 0;
+	}
+	s.cur = r.cur;
+	s.availA = r.cur >= r.first + 1 && r.cur % s.W != 0;
+	s.availB = r.cur >= r.first + s.W;
+	for (int k = 0; k < 48; k++)
+		s.nz[k] = 0;
+	s.hash = 0;
+	r.mb_type = MB_UNKNOWN;
+	uint64_t slots = 0;
+	if (!macroblock_layer(s, r.mb_type, slots, r.i16)) {
+		r.status = -EIO;
+		r.done = true;
+		return 0;
+	}
+	return slots;
+}
+
+__device__ __forceinline__ void mb_end(SliceRun &r)
+{
+	SliceCtx &s = r.s;
+	if (s.br.err) {
+		r.status = -EIO;
+		r.done = true;
+		return;
+	}
+	uint32_t *slot = (uint32_t *)ring_slot(s, r.cur);
+	for (int k = 0; k < 12; k++)
+		slot[k] = (uint32_t)s.nz[4 * k] | (uint32_t)s.nz[4 * k + 1] << 8 |
+			  (uint32_t)s.nz[4 * k + 2] << 16 | (uint32_t)s.nz[4 * k + 3] << 24;
+	r.rec[r.count].mb_addr = r.cur;
+	r.rec[r.count].mb_type = r.mb_type;
+	r.rec[r.count].hash = s.hash;
+	r.count++;
+	r.cur++;
+	if (!br_more_rbsp_data(s.br))
+		r.done = true;
+}
+
+__device__ __forceinline__ void slice_end(const SliceRun &r, h264gpu_slice_result &res)
+{
+	res.status = r.status;
+	res.mb_count = r.count;
+	res.end_bit = (r.status == 0 || r.status == -EIO || r.status == -ENOBUFS) && r.s.br.len ? br_raw_bitpos(r.s.br) : 0;
+}
+
+/* the serial form (emulator harness, one slice per call) */
+__device__ __forceinline__ void parse_slice(const uint8_t *stream, uint64_t stream_len,
+					     const h264gpu_slice_params &sp, uint8_t *ring, h264gpu_mb_record *rec,
+					     h264gpu_slice_result &res)
+{
+	SliceRun r;
+	slice_begin(r, stream, stream_len, sp, ring, rec);
+	while (!r.done) {
+		uint64_t slots = mb_begin(r);
+		if (r.done)
+			break;
+		while (slots && !r.s.br.err) {
+			const uint32_t slot = (uint32_t)__ffsll((long long)slots) - 1;
+			slots &= slots - 1;
+			residual_slot(r.s, r.i16, slot);
+		}
+		mb_end(r);
+	}
+	slice_end(r, res);
 }
 
 struct CavlcArgs {
 	const uint8_t *stream;
+	uint64_t stream_len;
 	const h264gpu_slice_params *params;
 	uint32_t n_slices;
 	h264gpu_mb_record *records;
@@ -824,33 +949,52 @@ struct CavlcArgs {
 };
 
 /*
- * Slices diverge completely (every lane is at a different point of a different
- * macroblock), so a warp runs its lanes one after the other.  Few slices are
- * therefore spread over MANY warps (down to one slice per warp) to fill the SMs'
- * issue slots, and only packed into the lanes of a warp once there are more slices
- * than resident warps.
+ * Warp-synchronous: every lane of a warp carries one slice and the warp takes the macroblock
+ * steps together.  Left alone, the lanes of a warp never meet again after the first divergent
+ * branch of a slice (round 1: 1.00 active threads per instruction, packing slices into lanes
+ * made it slower).  Here the warp re-converges at every macroblock (the loop condition is a warp
+ * vote), the header paths diverge only by macroblock type, and the residual blocks -- where the
+ * bits are -- run in lock-step: iteration k of the slot loop decodes the k-th coded block of
+ * every lane through the same code.  Few slices are still spread over more warps
+ * (lanes_log2 < 5) so that the SMs have warps to switch between.
  */
 __global__ void __launch_bounds__(128) cavlc_parse_kernel(const CavlcArgs a)
 {
 	const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t step = 32u >> a.lanes_log2; /* active lanes are multiples of this */
-	if (lane & (step - 1))
-		return;
 	const uint32_t i = (gwarp << a.lanes_log2) + lane / step;
-	if (i >= a.n_slices)
-		return;
-	const h264gpu_slice_params sp = a.params[i];
-	h264gpu_slice_result res;
-	if (sp.pic_width_in_mbs > a.ring_w) {
-		res.status = -7; /* -E2BIG */
-		res.mb_count = 0;
-		res.end_bit = 0;
-		a.results[i] = res;
-		return;
+	const bool mine = !(lane & (step - 1)) && i < a.n_slices;
+	SliceRun r;
+	r.done = true;
+	r.status = 0;
+	r.count = 0;
+	r.s.br.len = 0;
+	if (mine) {
+		const h264gpu_slice_params &sp = a.params[i];
+		if (sp.pic_width_in_mbs > a.ring_w)
+			r.status = -7; /* -E2BIG */
+		else
+			slice_begin(r, a.stream, a.stream_len, sp, a.ring + (uint64_t)i * a.ring_stride,
+				    a.records + sp.mb_out_off);
 	}
-	parse_slice(a.stream, sp, a.ring + (uint64_t)i * a.ring_stride, a.records + sp.mb_out_off, res);
-	a.results[i] = res;
+	while (__any_sync(FULL_MASK, !r.done)) {
+		uint64_t slots = 0;
+		if (!r.done)
+			slots = mb_begin(r);
+		while (slots && !r.s.br.err) {
+			const uint32_t slot = (uint32_t)__ffsll((long long)slots) - 1;
+			slots &= slots - 1;
+			residual_slot(r.s, r.i16, slot);
+		}
+		if (!r.done)
+			mb_end(r);
+	}
+	if (mine) {
+		h264gpu_slice_result res;
+		slice_end(r, res);
+		a.results[i] = res;
+	}
 }
 
 } /* namespace cavlc */

@@ -20,7 +20,6 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 		return 0;
 	if (d_stream == NULL || d_params == NULL || d_records == NULL || d_results == NULL)
 		return -EINVAL;
-	(void)stream_len;
 	cudaStream_t st = (cudaStream_t)stream;
 	/* nC context ring per slice: (PicWidthInMbs + 1) macroblocks x 48 counts, sized
 	 * for pictures up to 8192 luma samples wide (512 MBs); wider slices get -E2BIG. */
@@ -32,6 +31,7 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 		return r;
 	cavlc::CavlcArgs a;
 	a.stream = d_stream;
+	a.stream_len = stream_len;
 	a.params = d_params;
 	a.n_slices = n_slices;
 	a.records = d_records;

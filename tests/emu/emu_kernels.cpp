@@ -394,11 +394,10 @@ extern "C" int emu_cavlc_parse(const uint8_t *stream, uint64_t stream_len,
 			       const struct h264gpu_slice_params *params, uint32_t n_slices,
 			       struct h264gpu_mb_record *records, struct h264gpu_slice_result *results)
 {
-	(void)stream_len;
 	for (uint32_t i = 0; i < n_slices; i++) {
 		const h264gpu_slice_params &sp = params[i];
 		std::vector<uint8_t> ring(((size_t)sp.pic_width_in_mbs + 1) * 48 + 64, 0xEE);
-		cavlc::parse_slice(stream, sp, ring.data(), records + sp.mb_out_off, results[i]);
+		cavlc::parse_slice(stream, stream_len, sp, ring.data(), records + sp.mb_out_off, results[i]);
 	}
 	return 0;
 }
