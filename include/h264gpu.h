@@ -28,6 +28,11 @@
  * Device pointers ("d_*") must come from the same device the context was made
  * on and be 16-byte aligned.  All *_dev calls are asynchronous on `stream`
  * (a cudaStream_t passed as void*, NULL = the legacy default stream).
+ *
+ * Concurrency: a context owns ONE set of workspaces (tickets, chain words, event buffers,
+ * context rings) shared by all its entry points, so at most one operation may be in flight
+ * per context; use one context per stream / thread for concurrent work (contexts are cheap:
+ * workspaces are allocated on first use and grow only).
  */
 #ifndef H264GPU_H
 #define H264GPU_H
@@ -195,6 +200,24 @@ H264GPU_API int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in,
 					 uint64_t *h_nal_start, uint64_t *h_nal_end,
 					 uint64_t *h_nal_rbsp, uint64_t *n_nal,
 					 uint64_t *rbsp_bytes, uint64_t *final_off);
+
+/*
+ * Reader session: the device-resident path h264_reader_parse drives.  The buffer is copied to
+ * the GPU ONCE (pooled device memory, the context's own stream; H264GPU_REGISTER_INPUT=1
+ * page-locks the caller's buffer for the copy), the scan-only kernel builds the NAL table
+ * (replaces the h264_find_nalu loop, src/h264_reader.c:133-140) and the slice kernels then
+ * parse out of the same resident copy (include/h264gpu_slice.h: h264gpu_reader_parse_cavlc).
+ * *h_start / *h_end point into pooled pinned memory of the context and stay valid until the
+ * next h264gpu_reader_* or *_parse_host call.  *final_off: what h264_reader_parse leaves in
+ * *off (src/h264_reader.c:139).  One operation per context at a time: the pools and the
+ * workspaces are shared by every entry point of a context.
+ */
+H264GPU_API int h264gpu_reader_scan(h264gpu_ctx *ctx, const uint8_t *h_buf, uint64_t len,
+				    const uint64_t **h_start, const uint64_t **h_end,
+				    uint64_t *n_nal, uint64_t *final_off);
+H264GPU_API int h264gpu_reader_upload(h264gpu_ctx *ctx, const uint8_t *h_buf, uint64_t len);
+/* the copy left on the device by h264gpu_reader_scan / _upload */
+H264GPU_API int h264gpu_reader_resident(h264gpu_ctx *ctx, const uint8_t **d_stream, uint64_t *len);
 
 /*
  * Writer side: escape n payloads d_rbsp[d_off[k], d_off[k+1]) and put a start

@@ -170,6 +170,21 @@ H264GPU_API int h264gpu_cabac_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stre
 					 uint64_t n_records,
 					 struct h264gpu_slice_result *h_results);
 
+/*
+ * The same parses out of the buffer h264gpu_reader_scan / h264gpu_reader_upload left on the
+ * device (include/h264gpu.h): no second upload, pooled device and pinned memory, the context's
+ * own stream.  *h_records / *h_results point into the context's pinned pool and stay valid until
+ * the next reader / parse call on the context.
+ */
+H264GPU_API int h264gpu_reader_parse_cavlc(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,
+					   uint32_t n_slices, uint64_t n_records,
+					   const struct h264gpu_mb_record **h_records,
+					   const struct h264gpu_slice_result **h_results);
+H264GPU_API int h264gpu_reader_parse_cabac(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,
+					   uint32_t n_slices, uint64_t n_records,
+					   const struct h264gpu_mb_record **h_records,
+					   const struct h264gpu_slice_result **h_results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,7 +71,8 @@ SLICE_PARAMS = np.dtype([("nal_off", "<u8"), ("nal_len", "<u4"), ("data_bit_off"
 assert SLICE_PARAMS.itemsize == C.sizeof(SliceParams) == 56
 
 SLICE_SYMBOLS = ["h264gpu_cavlc_parse_dev", "h264gpu_cavlc_parse_host",
-                 "h264gpu_cabac_parse_dev", "h264gpu_cabac_parse_host"]
+                 "h264gpu_cabac_parse_dev", "h264gpu_cabac_parse_host",
+                 "h264gpu_reader_parse_cavlc", "h264gpu_reader_parse_cabac"]
 
 # every symbol include/h264gpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = [
@@ -82,6 +83,7 @@ GPU_SYMBOLS = [
     "h264gpu_merge_finish", "h264gpu_split_strip_host", "h264gpu_frame_dev",
     "h264gpu_frame_host", "h264gpu_timer_create", "h264gpu_timer_destroy",
     "h264gpu_timer_start", "h264gpu_timer_stop", "h264gpu_timer_elapsed_ms",
+    "h264gpu_reader_scan", "h264gpu_reader_upload", "h264gpu_reader_resident",
 ]
 
 _libs = {}

@@ -97,6 +97,18 @@ int h264gpu_destroy(h264gpu_ctx *ctx)
 	free_pipeline(ctx);
 	cudaFree(ctx->ws);
 	cudaFree(ctx->ws7);
+	cudaFree(ctx->rd_stream.p);
+	cudaFree(ctx->rd_tab.p);
+	cudaFree(ctx->rd_res.p);
+	cudaFree(ctx->rd_params.p);
+	cudaFree(ctx->rd_records.p);
+	cudaFree(ctx->rd_results.p);
+	cudaFreeHost(ctx->rh_tab.p);
+	cudaFreeHost(ctx->rh_res.p);
+	cudaFreeHost(ctx->rh_records.p);
+	cudaFreeHost(ctx->rh_results.p);
+	if (ctx->s_rd)
+		cudaStreamDestroy(ctx->s_rd);
 	free(ctx);
 	return 0;
 }
@@ -822,6 +834,151 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 		free(h);
 		cudaFree(d_trace);
 	}
+	return 0;
+}
+
+/* ---- reader session: what h264_reader_parse drives -------------------------------- */
+
+int h264gpu_pool_dev(h264gpu_ctx *ctx, struct h264gpu_ctx::h264gpu_pool *pl, size_t bytes)
+{
+	if (bytes <= pl->cap)
+		return 0;
+	if (ctx->s_rd)
+		CU_TRY(cudaStreamSynchronize(ctx->s_rd));
+	if (pl->p)
+		CU_TRY(cudaFree(pl->p));
+	pl->p = NULL;
+	pl->cap = 0;
+	const size_t want = ((bytes + (bytes >> 2)) + 4095) & ~(size_t)4095;
+	CU_TRY(cudaMalloc(&pl->p, want));
+	pl->cap = want;
+	return 0;
+}
+
+int h264gpu_pool_host(h264gpu_ctx *ctx, struct h264gpu_ctx::h264gpu_pool *pl, size_t bytes)
+{
+	if (bytes <= pl->cap)
+		return 0;
+	if (ctx->s_rd)
+		CU_TRY(cudaStreamSynchronize(ctx->s_rd));
+	if (pl->p)
+		CU_TRY(cudaFreeHost(pl->p));
+	pl->p = NULL;
+	pl->cap = 0;
+	const size_t want = ((bytes + (bytes >> 2)) + 4095) & ~(size_t)4095;
+	CU_TRY(cudaMallocHost(&pl->p, want));
+	pl->cap = want;
+	return 0;
+}
+
+int h264gpu_reader_stream(h264gpu_ctx *ctx, cudaStream_t *st)
+{
+	if (ctx->s_rd == NULL)
+		CU_TRY(cudaStreamCreateWithFlags(&ctx->s_rd, cudaStreamNonBlocking));
+	*st = ctx->s_rd;
+	return 0;
+}
+
+extern "C" int h264gpu_reader_upload(h264gpu_ctx *ctx, const uint8_t *h_buf, uint64_t len)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (h_buf == NULL && len)
+		return -EINVAL;
+	cudaStream_t st;
+	if ((r = h264gpu_reader_stream(ctx, &st)) < 0)
+		return r;
+	if ((r = h264gpu_pool_dev(ctx, &ctx->rd_stream, len + 64)) < 0)
+		return r;
+	ctx->rd_stream_len = 0;
+	/* H264GPU_REGISTER_INPUT=1: page-lock the caller's buffer for the copy (pays off for large
+	 * buffers that are parsed more than once; a pageable copy is staged by the driver) */
+	static int reg = -1;
+	if (reg < 0) {
+		const char *e = getenv("H264GPU_REGISTER_INPUT");
+		reg = e != NULL && atoi(e) > 0;
+	}
+	bool registered = false;
+	if (reg && len >= (1u << 20))
+		registered = cudaHostRegister((void *)h_buf, len, cudaHostRegisterReadOnly) == cudaSuccess ||
+			     cudaHostRegister((void *)h_buf, len, cudaHostRegisterDefault) == cudaSuccess;
+	if (!registered)
+		(void)cudaGetLastError();
+	cudaError_t ce = len ? cudaMemcpyAsync(ctx->rd_stream.p, h_buf, len, cudaMemcpyHostToDevice, st) : cudaSuccess;
+	/* the kernels may read a few bytes past the end of a NAL: keep them defined */
+	if (ce == cudaSuccess)
+		ce = cudaMemsetAsync((uint8_t *)ctx->rd_stream.p + len, 0xff, 64, st);
+	if (registered) {
+		cudaStreamSynchronize(st);
+		cudaHostUnregister((void *)h_buf);
+	}
+	CU_TRY(ce);
+	ctx->rd_stream_len = len;
+	return 0;
+}
+
+extern "C" int h264gpu_reader_scan(h264gpu_ctx *ctx, const uint8_t *h_buf, uint64_t len,
+				   const uint64_t **h_start, const uint64_t **h_end, uint64_t *n_nal,
+				   uint64_t *final_off)
+{
+	if (h_start == NULL || h_end == NULL || n_nal == NULL)
+		return -EINVAL;
+	*h_start = *h_end = NULL;
+	*n_nal = 0;
+	if (final_off)
+		*final_off = 0;
+	int r = h264gpu_reader_upload(ctx, h_buf, len);
+	if (r < 0 || len == 0)
+		return r;
+	cudaStream_t st = ctx->s_rd;
+	/* table capacity: a NAL per 256 bytes is generous for video; the scan reports how many it
+	 * found, and a second launch with the exact size follows if that was not enough */
+	uint64_t cap = len / 256 + 1024;
+	for (int pass = 0; pass < 2; pass++) {
+		if ((r = h264gpu_pool_dev(ctx, &ctx->rd_tab, cap * 16)) < 0 ||
+		    (r = h264gpu_pool_dev(ctx, &ctx->rd_res, sizeof(struct h264gpu_scan_result))) < 0 ||
+		    (r = h264gpu_pool_host(ctx, &ctx->rh_res, sizeof(struct h264gpu_scan_result))) < 0)
+			return r;
+		uint64_t *d_st = (uint64_t *)ctx->rd_tab.p, *d_en = d_st + cap;
+		struct h264gpu_scan_result *d_res = (struct h264gpu_scan_result *)ctx->rd_res.p;
+		struct h264gpu_scan_result *h_res = (struct h264gpu_scan_result *)ctx->rh_res.p;
+		r = h264gpu_split_strip_inplace_dev(ctx, (const uint8_t *)ctx->rd_stream.p, len, 0, NULL, NULL, d_st,
+						    d_en, NULL, NULL, cap, d_res, st);
+		if (r < 0)
+			return r;
+		CU_TRY(cudaMemcpyAsync(h_res, d_res, sizeof(*h_res), cudaMemcpyDeviceToHost, st));
+		CU_TRY(cudaStreamSynchronize(st));
+		if (h_res->n_nal <= cap && !h_res->reserved) {
+			const uint64_t n = h_res->n_nal;
+			if ((r = h264gpu_pool_host(ctx, &ctx->rh_tab, (n + 1) * 16)) < 0)
+				return r;
+			uint64_t *hs = (uint64_t *)ctx->rh_tab.p, *he = hs + n + 1;
+			if (n) {
+				CU_TRY(cudaMemcpyAsync(hs, d_st, n * 8, cudaMemcpyDeviceToHost, st));
+				CU_TRY(cudaMemcpyAsync(he, d_en, n * 8, cudaMemcpyDeviceToHost, st));
+				CU_TRY(cudaStreamSynchronize(st));
+			}
+			*h_start = hs;
+			*h_end = he;
+			*n_nal = n;
+			/* what h264_reader_parse leaves in *off (src/h264_reader.c:139): the end of the last
+			 * NAL, which is `len` when it ran to the end of the buffer */
+			if (final_off)
+				*final_off = n ? he[n - 1] : 0;
+			return 0;
+		}
+		cap = h_res->reserved ? len / 3 + 2 : h_res->n_nal + 16;
+	}
+	return -E2BIG;
+}
+
+extern "C" int h264gpu_reader_resident(h264gpu_ctx *ctx, const uint8_t **d_stream, uint64_t *len)
+{
+	if (ctx == NULL || d_stream == NULL || len == NULL)
+		return -EINVAL;
+	*d_stream = (const uint8_t *)ctx->rd_stream.p;
+	*len = ctx->rd_stream_len;
 	return 0;
 }
 

@@ -36,7 +36,21 @@ struct h264gpu_ctx {
 	size_t tab_cap;
 	cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
 	int scan_items; /* 16-byte vectors per thread (1, 2 or 4) */
+	/* reader session (h264gpu_reader_*, h264gpu_*_parse_host): grow-only device and pinned
+	 * buffers on a private stream, so that a call costs no cudaMalloc */
+	cudaStream_t s_rd;
+	struct h264gpu_pool {
+		void *p;
+		size_t cap;
+	} rd_stream, rd_tab, rd_res, rd_params, rd_records, rd_results; /* device */
+	struct h264gpu_pool rh_tab, rh_res, rh_records, rh_results;         /* pinned host */
+	uint64_t rd_stream_len; /* bytes of the buffer resident in rd_stream */
+	size_t cabac_smem_set;  /* dynamic shared memory the CABAC kernel is configured for on this device */
 };
+
+int h264gpu_pool_dev(h264gpu_ctx *ctx, struct h264gpu_ctx::h264gpu_pool *pl, size_t bytes);
+int h264gpu_pool_host(h264gpu_ctx *ctx, struct h264gpu_ctx::h264gpu_pool *pl, size_t bytes);
+int h264gpu_reader_stream(h264gpu_ctx *ctx, cudaStream_t *st);
 
 #define CU_TRY(expr)                                                                       \
 	do {                                                                               \

@@ -66,53 +66,87 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 typedef int (*parse_dev_fn)(h264gpu_ctx *, const uint8_t *, uint64_t, const struct h264gpu_slice_params *,
 			    uint32_t, struct h264gpu_mb_record *, struct h264gpu_slice_result *, void *);
 
+/* upload (unless the stream is the one resident from h264gpu_reader_scan), launch, download into
+ * pooled pinned memory; *out_records / *out_results stay valid until the next reader / parse call */
+static int parse_pooled(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_stream, uint64_t stream_len,
+			const struct h264gpu_slice_params *h_params, uint32_t n_slices, uint64_t n_records,
+			const struct h264gpu_mb_record **out_records,
+			const struct h264gpu_slice_result **out_results)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	cudaStream_t st;
+	if ((r = h264gpu_reader_stream(ctx, &st)) < 0)
+		return r;
+	if (h_stream != NULL) {
+		if ((r = h264gpu_reader_upload(ctx, h_stream, stream_len)) < 0)
+			return r;
+	} else if (ctx->rd_stream_len == 0) {
+		return -EINVAL;
+	}
+	if ((r = h264gpu_pool_dev(ctx, &ctx->rd_params, (size_t)n_slices * sizeof(*h_params))) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_records, (n_records + 1) * sizeof(struct h264gpu_mb_record))) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_results, (size_t)n_slices * sizeof(struct h264gpu_slice_result))) < 0 ||
+	    (r = h264gpu_pool_host(ctx, &ctx->rh_records, (n_records + 1) * sizeof(struct h264gpu_mb_record))) < 0 ||
+	    (r = h264gpu_pool_host(ctx, &ctx->rh_results, (size_t)n_slices * sizeof(struct h264gpu_slice_result))) < 0)
+		return r;
+	CU_TRY(cudaMemcpyAsync(ctx->rd_params.p, h_params, (size_t)n_slices * sizeof(*h_params),
+			       cudaMemcpyHostToDevice, st));
+	r = dev(ctx, (const uint8_t *)ctx->rd_stream.p, ctx->rd_stream_len,
+		(const struct h264gpu_slice_params *)ctx->rd_params.p, n_slices,
+		(struct h264gpu_mb_record *)ctx->rd_records.p, (struct h264gpu_slice_result *)ctx->rd_results.p, st);
+	if (r < 0)
+		return r;
+	if (n_records)
+		CU_TRY(cudaMemcpyAsync(ctx->rh_records.p, ctx->rd_records.p, n_records * sizeof(struct h264gpu_mb_record),
+				       cudaMemcpyDeviceToHost, st));
+	CU_TRY(cudaMemcpyAsync(ctx->rh_results.p, ctx->rd_results.p, (size_t)n_slices * sizeof(struct h264gpu_slice_result),
+			       cudaMemcpyDeviceToHost, st));
+	CU_TRY(cudaStreamSynchronize(st));
+	*out_records = (const struct h264gpu_mb_record *)ctx->rh_records.p;
+	*out_results = (const struct h264gpu_slice_result *)ctx->rh_results.p;
+	return 0;
+}
+
 static int parse_host(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_stream, uint64_t stream_len,
 		      const struct h264gpu_slice_params *h_params, uint32_t n_slices,
 		      struct h264gpu_mb_record *h_records, uint64_t n_records,
 		      struct h264gpu_slice_result *h_results)
 {
-	int r = h264gpu_use(ctx);
-	if (r < 0)
-		return r;
 	if (n_slices == 0)
 		return 0;
 	if (h_stream == NULL || h_params == NULL || h_records == NULL || h_results == NULL)
 		return -EINVAL;
-	uint8_t *d_stream = NULL;
-	struct h264gpu_slice_params *d_params = NULL;
-	struct h264gpu_mb_record *d_records = NULL;
-	struct h264gpu_slice_result *d_results = NULL;
-	int rc = 0;
-	cudaStream_t st = 0;
-#define SL_TRY(expr)                                                                       \
-	do {                                                                               \
-		if ((expr) != cudaSuccess) {                                               \
-			rc = -EIO;                                                         \
-			goto out;                                                          \
-		}                                                                          \
-	} while (0)
-	SL_TRY(cudaMalloc(&d_stream, stream_len + 16));
-	SL_TRY(cudaMalloc(&d_params, (size_t)n_slices * sizeof(*d_params)));
-	SL_TRY(cudaMalloc(&d_records, (n_records + 1) * sizeof(*d_records)));
-	SL_TRY(cudaMalloc(&d_results, (size_t)n_slices * sizeof(*d_results)));
-	SL_TRY(cudaMemcpyAsync(d_stream, h_stream, stream_len, cudaMemcpyHostToDevice, st));
-	SL_TRY(cudaMemcpyAsync(d_params, h_params, (size_t)n_slices * sizeof(*d_params),
-			       cudaMemcpyHostToDevice, st));
-	rc = dev(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, st);
-	if (rc < 0)
-		goto out;
-	SL_TRY(cudaMemcpyAsync(h_records, d_records, n_records * sizeof(*d_records),
-			       cudaMemcpyDeviceToHost, st));
-	SL_TRY(cudaMemcpyAsync(h_results, d_results, (size_t)n_slices * sizeof(*d_results),
-			       cudaMemcpyDeviceToHost, st));
-	SL_TRY(cudaStreamSynchronize(st));
-out:
-#undef SL_TRY
-	cudaFree(d_stream);
-	cudaFree(d_params);
-	cudaFree(d_records);
-	cudaFree(d_results);
-	return rc;
+	const struct h264gpu_mb_record *rec = NULL;
+	const struct h264gpu_slice_result *res = NULL;
+	const int r = parse_pooled(dev, ctx, h_stream, stream_len, h_params, n_slices, n_records, &rec, &res);
+	if (r < 0)
+		return r;
+	memcpy(h_records, rec, n_records * sizeof(*rec));
+	memcpy(h_results, res, (size_t)n_slices * sizeof(*res));
+	return 0;
+}
+
+/* the slices of the buffer h264gpu_reader_scan left on the device (no second upload) */
+extern "C" int h264gpu_reader_parse_cavlc(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,
+					  uint32_t n_slices, uint64_t n_records,
+					  const struct h264gpu_mb_record **h_records,
+					  const struct h264gpu_slice_result **h_results)
+{
+	if (h_params == NULL || h_records == NULL || h_results == NULL || n_slices == 0)
+		return -EINVAL;
+	return parse_pooled(h264gpu_cavlc_parse_dev, ctx, NULL, 0, h_params, n_slices, n_records, h_records, h_results);
+}
+
+extern "C" int h264gpu_reader_parse_cabac(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,
+					  uint32_t n_slices, uint64_t n_records,
+					  const struct h264gpu_mb_record **h_records,
+					  const struct h264gpu_slice_result **h_results)
+{
+	if (h_params == NULL || h_records == NULL || h_results == NULL || n_slices == 0)
+		return -EINVAL;
+	return parse_pooled(h264gpu_cabac_parse_dev, ctx, NULL, 0, h_params, n_slices, n_records, h_records, h_results);
 }
 
 extern "C" int h264gpu_cavlc_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stream,
@@ -185,11 +219,10 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	const uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
 	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
 	const size_t smem = cabac::smem_bytes((threads / 32) << lanes_log2);
-	static size_t smem_set = 0;
-	if (smem > smem_set) {
+	if (smem > ctx->cabac_smem_set) { /* function attributes are per device: cached per context */
 		CU_TRY(cudaFuncSetAttribute(cabac::cabac_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 					    (int)smem));
-		smem_set = smem;
+		ctx->cabac_smem_set = smem;
 	}
 	cabac::cabac_parse_kernel<<<blocks, threads, smem, st>>>(a);
 	CU_TRY(cudaGetLastError());

@@ -68,7 +68,8 @@ struct h264_reader {
 	struct h264_ctx *ctx;
 	int stop;
 	uint32_t flags;
-	h264gpu_ctx *gpu; /* created on first bulk / slice-data use */
+	h264gpu_ctx *gpu; /* created on first bulk use */
+	h264gpu_ctx *gpu_single; /* one-slice launches (h264_reader_parse_nalu, fall-backs) */
 	/* bulk parse: macroblock records of every slice of the buffer, filled by the GPU */
 	const struct h264gpu_mb_record *records;
 	const struct h264gpu_slice_result *results;

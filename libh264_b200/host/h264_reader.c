@@ -5,13 +5,16 @@
  * src/h264_syntax.h:1446-1604), re-ordered for bulk work:
  *
  *   h264_reader_parse(buf)
- *     1. ONE Annex-B scan of the whole buffer on the GPU (h264gpu_split_strip_host)
- *        instead of the h264_find_nalu loop (src/h264_reader.c:133-140);
+ *     1. the buffer goes to the GPU ONCE (pooled device memory) and ONE scan-only launch
+ *        builds the NAL table (h264gpu_reader_scan) instead of the h264_find_nalu loop
+ *        (src/h264_reader.c:133-140);
  *     2. with H264_READER_FLAGS_SLICE_DATA: a silent header pass over the NAL units (a
  *        shadow context, no callbacks) collects one parameter block per CAVLC slice,
- *        and ONE launch parses the macroblock layer of all of them
- *        (h264gpu_cavlc_parse_host) instead of _h264_read_slice_data_internal per slice
- *        (src/h264_syntax_slice_data.h:701-787);
+ *        and ONE launch parses the macroblock layer of all of them out of the resident
+ *        copy (h264gpu_reader_parse_cavlc) instead of _h264_read_slice_data_internal per
+ *        slice (src/h264_syntax_slice_data.h:701-787); the records arrive in pooled
+ *        pinned memory.  A slice's record budget ends where the next slice of its picture
+ *        begins, so the records of a buffer add up to its macroblocks;
  *     3. the replay pass parses the headers again on the caller's context and fires the
  *        callbacks in the reference's order, slice_data_mb from the GPU records.
  *
@@ -48,6 +51,8 @@ int h264_reader_destroy(struct h264_reader *reader)
 	h264_ctx_destroy(reader->ctx);
 	if (reader->gpu != NULL)
 		h264gpu_destroy(reader->gpu);
+	if (reader->gpu_single != NULL)
+		h264gpu_destroy(reader->gpu_single);
 	free(reader);
 	return 0;
 }
@@ -128,6 +133,7 @@ int h264_reader_slice_data(struct h264_reader *reader, struct h264_ctx *ctx, con
 	if (cbs->slice_data_begin != NULL)
 		cbs->slice_data_begin(ctx, &ctx->sh, reader->userdata);
 
+	int bulk = 0;
 	if (reader->records != NULL && reader->next_slice < reader->n_slices &&
 	    reader->bulk_base + reader->params[reader->next_slice].nal_off == nal) {
 		/* bulk mode: this slice was parsed with all the others */
@@ -135,13 +141,23 @@ int h264_reader_slice_data(struct h264_reader *reader, struct h264_ctx *ctx, con
 		rec = reader->records + p->mb_out_off;
 		result = reader->results[reader->next_slice];
 		reader->next_slice++;
-	} else {
-		/* single NAL unit: one-slice launch */
+		/* a slice that runs past the start of the next one (only a broken stream does) ran out
+		 * of its record budget: parse it again on its own with the whole picture as budget */
+		bulk = result.status != -ENOBUFS;
+	}
+	if (!bulk) {
+		/* single NAL unit: one-slice launch (own context: the bulk records stay untouched) */
 		struct h264gpu_slice_params p;
-		int res = reader_gpu(reader);
-		if (res < 0)
-			return res;
-		res = h264_fill_slice_params(ctx, &p);
+		if (reader->gpu_single == NULL) {
+			int dev = 0;
+			const char *e = getenv("H264_GPU_DEVICE");
+			if (e != NULL)
+				dev = atoi(e);
+			int res = h264gpu_create(dev, &reader->gpu_single);
+			if (res < 0)
+				return res;
+		}
+		int res = h264_fill_slice_params(ctx, &p);
 		if (res < 0)
 			return res;
 		p.nal_off = 0;
@@ -150,7 +166,7 @@ int h264_reader_slice_data(struct h264_reader *reader, struct h264_ctx *ctx, con
 		own = malloc(((size_t)p.mb_out_cap + 1) * sizeof(*own));
 		if (own == NULL)
 			return -ENOMEM;
-		res = h264gpu_cavlc_parse_host(reader->gpu, nal, nal_len, &p, 1, own, p.mb_out_cap,
+		res = h264gpu_cavlc_parse_host(reader->gpu_single, nal, nal_len, &p, 1, own, p.mb_out_cap,
 					       &result);
 		if (res < 0) {
 			free(own);
@@ -244,6 +260,18 @@ static int collect_slices(struct h264_reader *reader, const uint8_t *buf, const 
 			continue;
 		p->nal_off = st[k];
 		p->nal_len = (uint32_t)len;
+		/* the slice before this one, if it belongs to the same picture and starts earlier,
+		 * ends where this one begins: give its unused record budget back */
+		if (out->n > 0 && !shadow->first_vcl && !shadow->MbaffFrameFlag) {
+			struct h264gpu_slice_params *q = &out->params[out->n - 1];
+			if (q->first_mb_in_slice < p->first_mb_in_slice && q->mb_out_off + (uint64_t)q->mb_out_cap == out->records) {
+				const uint32_t cap = p->first_mb_in_slice - q->first_mb_in_slice;
+				if (cap < q->mb_out_cap) {
+					out->records -= q->mb_out_cap - cap;
+					q->mb_out_cap = cap;
+				}
+			}
+		}
 		if (out->records + p->mb_out_cap > UINT32_MAX)
 			break; /* record index space exhausted: the rest parses one by one */
 		p->mb_out_off = (uint32_t)out->records;
@@ -267,52 +295,32 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 	if (res < 0)
 		return res;
 
-	/* 1. NAL table of the whole buffer */
-	uint64_t cap = len / 256 + 1024, n_nal = 0, final_off = 0;
-	uint64_t *st = NULL, *en = NULL;
-	for (;;) {
-		free(st);
-		free(en);
-		st = malloc(cap * sizeof(*st));
-		en = malloc(cap * sizeof(*en));
-		if (st == NULL || en == NULL) {
-			res = -ENOMEM;
-			goto out;
-		}
-		n_nal = cap;
-		res = h264gpu_split_strip_host(reader->gpu, buf, len, NULL, st, en, NULL, &n_nal, NULL,
-					       &final_off);
-		if (res != -ENOBUFS)
-			break;
-		cap = len / 3 + 2; /* worst case: one start code every three bytes */
-	}
+	/* 1. one upload, NAL table of the whole buffer (pooled pinned memory of the GPU context) */
+	uint64_t n_nal = 0, final_off = 0;
+	const uint64_t *st = NULL, *en = NULL;
+	res = h264gpu_reader_scan(reader->gpu, buf, len, &st, &en, &n_nal, &final_off);
 	if (res < 0)
-		goto out;
+		return res;
 
-	/* 2. macroblock layer of every CAVLC slice, one launch */
+	/* 2. macroblock layer of every CAVLC slice, one launch on the resident copy */
 	struct slice_list sl;
 	memset(&sl, 0, sizeof(sl));
-	struct h264gpu_mb_record *records = NULL;
-	struct h264gpu_slice_result *results = NULL;
 	if (flags & H264_READER_FLAGS_SLICE_DATA) {
+		const struct h264gpu_mb_record *records = NULL;
+		const struct h264gpu_slice_result *results = NULL;
 		res = collect_slices(reader, buf, st, en, n_nal, &sl);
-		if (res >= 0 && sl.n > 0) {
-			records = malloc((sl.records + 1) * sizeof(*records));
-			results = malloc((size_t)sl.n * sizeof(*results));
-			if (records == NULL || results == NULL)
-				res = -ENOMEM;
-			else
-				res = h264gpu_cavlc_parse_host(reader->gpu, buf, len, sl.params, sl.n,
-							       records, sl.records, results);
-		}
+		if (res >= 0 && sl.n > 0)
+			res = h264gpu_reader_parse_cavlc(reader->gpu, sl.params, sl.n, sl.records, &records, &results);
 		if (res < 0)
 			goto out_slices;
-		reader->records = records;
-		reader->results = results;
-		reader->params = sl.params;
-		reader->n_slices = sl.n;
-		reader->next_slice = 0;
-		reader->bulk_base = buf;
+		if (sl.n > 0) {
+			reader->records = records;
+			reader->results = results;
+			reader->params = sl.params;
+			reader->n_slices = sl.n;
+			reader->next_slice = 0;
+			reader->bulk_base = buf;
+		}
 	}
 
 	/* 3. callbacks, in stream order (per-NAL errors are ignored like the reference
@@ -336,11 +344,6 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 	reader->n_slices = 0;
 out_slices:
 	free(sl.params);
-	free(records);
-	free(results);
-out:
-	free(st);
-	free(en);
 	return res;
 }
 

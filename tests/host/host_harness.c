@@ -297,6 +297,83 @@ int hh_trace(const char *libpath, const uint8_t *buf, size_t len, uint32_t flags
 	return t.overflow ? -ENOBUFS : 0;
 }
 
+/* ---- timing: h264_reader_parse with counting callbacks ------------------------------------
+ * counts: [0] nalu_begin  [1] slices  [2] slice_data_mb  [3] sps + pps  [4] sum of mb_addr ^ mb_type
+ * (so that the macroblock callbacks cannot be optimised into nothing and both libraries can be
+ * checked to have delivered the same thing).  Returns the best wall time of `reps` calls after
+ * one warm-up call, or a negative errno. */
+#include <time.h>
+struct counts {
+	uint64_t c[5];
+};
+static void ct_nalu_begin(struct h264_ctx *c, enum h264_nalu_type type, const uint8_t *buf, size_t len,
+			  const struct h264_nalu_header *nh, void *u)
+{
+	((struct counts *)u)->c[0]++;
+}
+static void ct_slice(struct h264_ctx *c, const uint8_t *buf, size_t len, const struct h264_slice_header *sh,
+		     void *u)
+{
+	((struct counts *)u)->c[1]++;
+}
+static void ct_sd_mb(struct h264_ctx *c, const struct h264_slice_header *sh, uint32_t addr, enum h264_mb_type ty,
+		     void *u)
+{
+	struct counts *k = u;
+	k->c[2]++;
+	k->c[4] += addr ^ ((uint32_t)ty << 20);
+}
+static void ct_sps(struct h264_ctx *c, const uint8_t *buf, size_t len, const struct h264_sps *s, void *u)
+{
+	((struct counts *)u)->c[3]++;
+}
+static void ct_pps(struct h264_ctx *c, const uint8_t *buf, size_t len, const struct h264_pps *p, void *u)
+{
+	((struct counts *)u)->c[3]++;
+}
+
+double hh_time_parse(const char *libpath, const uint8_t *buf, size_t len, uint32_t flags, int reps,
+		     uint64_t *counts_out)
+{
+	struct api a;
+	int r = api_open(&a, libpath);
+	if (r < 0)
+		return (double)r;
+	struct h264_ctx_cbs cbs;
+	memset(&cbs, 0, sizeof(cbs));
+	cbs.nalu_begin = ct_nalu_begin;
+	cbs.slice = ct_slice;
+	cbs.slice_data_mb = ct_sd_mb;
+	cbs.sps = ct_sps;
+	cbs.pps = ct_pps;
+	struct counts k;
+	struct h264_reader *rd = NULL;
+	r = a.reader_new(&cbs, &k, &rd);
+	if (r < 0)
+		return (double)r;
+	double best = -1;
+	for (int i = 0; i <= reps; i++) {
+		struct timespec t0, t1;
+		size_t off = 0;
+		memset(&k, 0, sizeof(k));
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		r = a.reader_parse(rd, flags, buf, len, &off);
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		if (r < 0) {
+			a.reader_destroy(rd);
+			return (double)r;
+		}
+		const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+		if (i > 0 && (best < 0 || dt < best))
+			best = dt;
+	}
+	if (counts_out)
+		memcpy(counts_out, k.c, sizeof(k.c));
+	a.reader_destroy(rd);
+	dlclose(a.h);
+	return best;
+}
+
 /* ---- generator ----------------------------------------------------------------------------- */
 
 static uint64_t rng_state;

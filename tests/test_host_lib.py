@@ -32,7 +32,19 @@ def harness():
     lib.hh_trace.restype = C.c_int
     lib.hh_trace.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p,
                              C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.hh_time_parse.restype = C.c_double
+    lib.hh_time_parse.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
     return lib
+
+
+def time_parse(lib, path, stream, flags=1, reps=3):
+    """Best wall time of h264_reader_parse(stream) through `path`'s public API with counting
+    callbacks, and the counts [nalu, slices, macroblocks, sps + pps, macroblock checksum]."""
+    stream = np.ascontiguousarray(stream)
+    counts = np.zeros(5, np.uint64)
+    dt = lib.hh_time_parse(path.encode(), stream.ctypes.data, len(stream), flags, reps, counts.ctypes.data)
+    assert dt > 0, (path, dt)
+    return dt, counts
 
 
 def gen(lib, path, seed, rounds=6, conceal=0):
