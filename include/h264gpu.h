@@ -95,6 +95,9 @@ H264GPU_API int h264gpu_memcpy_h2d(h264gpu_ctx *ctx, void *d_dst, const void *h_
 H264GPU_API int h264gpu_memcpy_d2h(h264gpu_ctx *ctx, void *h_dst, const void *d_src,
 				   size_t bytes, void *stream);
 H264GPU_API int h264gpu_sync(h264gpu_ctx *ctx, void *stream);
+/* A non-blocking stream of the context's device, as the opaque `stream` argument of the calls above. */
+H264GPU_API int h264gpu_stream_create(h264gpu_ctx *ctx, void **stream);
+H264GPU_API int h264gpu_stream_destroy(h264gpu_ctx *ctx, void *stream);
 
 /*
  * Annex-B scan (+ EPB strip when d_rbsp != NULL) of d_in[0,len).

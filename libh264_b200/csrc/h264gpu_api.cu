@@ -188,6 +188,26 @@ int h264gpu_sync(h264gpu_ctx *ctx, void *stream)
 	return 0;
 }
 
+int h264gpu_stream_create(h264gpu_ctx *ctx, void **stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0 || stream == NULL)
+		return r < 0 ? r : -EINVAL;
+	cudaStream_t st;
+	CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	*stream = (void *)st;
+	return 0;
+}
+
+int h264gpu_stream_destroy(h264gpu_ctx *ctx, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaStreamDestroy((cudaStream_t)stream));
+	return 0;
+}
+
 /* ---- timers ------------------------------------------------------------ */
 
 struct gpu_timer {
@@ -507,16 +527,16 @@ static int scan7_launch_t(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, u
 		/* tickets go round robin over K regions: a span's predecessor was taken K tickets
 		 * (K x ~2 ns) before it.  K = a quarter of the resident warps gives ~3 us of lead, the
 		 * time a span needs from its ticket to its chain word; every region start defers ~17
-		 * spans (up to the first start code) to the second pass, so K is also kept below 1/128
-		 * of the spans.  Measured at 4 GiB: K = 1 1719, 370 2068, 740 2108, 1480 2136, 5920 2116 GB/s */
+		 * spans (up to the first start code) to the second pass, so K is also kept below 1/512
+		 * of the spans (at most ~3 % of them deferred).  Measured at 4 GiB: K = 1 1719, 370 2068, 740 2108, 1480 2136, 5920 2116 GB/s */
 		uint32_t K = grid * annexb7::kW / 4;
 		{
 			const char *e = getenv("H264GPU_SCAN7_REGIONS");
 			if (e != NULL && atoi(e) > 0)
 				K = (uint32_t)atoi(e);
 		}
-		if (K > nspans / 128)
-			K = (uint32_t)(nspans / 128);
+		if (K > nspans / 512)
+			K = (uint32_t)(nspans / 512);
 		if (K < 1)
 			K = 1;
 		a.regions = K;
