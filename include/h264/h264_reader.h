@@ -14,6 +14,11 @@ struct h264_reader;
 /* also parse slice data and deliver slice_data_* callbacks (CAVLC slices only,
  * like the reference: CABAC slice data is skipped, src/h264_syntax_slice_data.h:715-717) */
 #define H264_READER_FLAGS_SLICE_DATA 0x01
+/* Extension of this library (not in the reference): with H264_READER_FLAGS_SLICE_DATA, also parse
+ * the slice data of CABAC slices on the GPU and deliver slice_data_begin / slice_data_mb /
+ * slice_data_end for them.  Without this bit CABAC slices get no slice-data callbacks, exactly
+ * like the reference (src/h264_syntax_slice_data.h:715-717). */
+#define H264_READER_FLAGS_SLICE_DATA_CABAC 0x02
 
 H264_API int h264_reader_new(const struct h264_ctx_cbs *cbs, void *userdata,
 			     struct h264_reader **ret_obj);

@@ -180,6 +180,11 @@ H264GPU_API int h264gpu_reader_parse_cavlc(h264gpu_ctx *ctx, const struct h264gp
 					   uint32_t n_slices, uint64_t n_records,
 					   const struct h264gpu_mb_record **h_records,
 					   const struct h264gpu_slice_result **h_results);
+/* a list that mixes CAVLC and CABAC slices: one launch of each kernel over the same records */
+H264GPU_API int h264gpu_reader_parse_slices(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,
+					    uint32_t n_slices, uint64_t n_records,
+					    const struct h264gpu_mb_record **h_records,
+					    const struct h264gpu_slice_result **h_results);
 H264GPU_API int h264gpu_reader_parse_cabac(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,
 					   uint32_t n_slices, uint64_t n_records,
 					   const struct h264gpu_mb_record **h_records,

@@ -71,7 +71,7 @@ typedef int (*parse_dev_fn)(h264gpu_ctx *, const uint8_t *, uint64_t, const stru
 static int parse_pooled(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_stream, uint64_t stream_len,
 			const struct h264gpu_slice_params *h_params, uint32_t n_slices, uint64_t n_records,
 			const struct h264gpu_mb_record **out_records,
-			const struct h264gpu_slice_result **out_results)
+			const struct h264gpu_slice_result **out_results, parse_dev_fn dev2 = NULL)
 {
 	int r = h264gpu_use(ctx);
 	if (r < 0)
@@ -87,9 +87,9 @@ static int parse_pooled(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_str
 	}
 	if ((r = h264gpu_pool_dev(ctx, &ctx->rd_params, (size_t)n_slices * sizeof(*h_params))) < 0 ||
 	    (r = h264gpu_pool_dev(ctx, &ctx->rd_records, (n_records + 1) * sizeof(struct h264gpu_mb_record))) < 0 ||
-	    (r = h264gpu_pool_dev(ctx, &ctx->rd_results, (size_t)n_slices * sizeof(struct h264gpu_slice_result))) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_results, 2 * (size_t)n_slices * sizeof(struct h264gpu_slice_result))) < 0 ||
 	    (r = h264gpu_pool_host(ctx, &ctx->rh_records, (n_records + 1) * sizeof(struct h264gpu_mb_record))) < 0 ||
-	    (r = h264gpu_pool_host(ctx, &ctx->rh_results, (size_t)n_slices * sizeof(struct h264gpu_slice_result))) < 0)
+	    (r = h264gpu_pool_host(ctx, &ctx->rh_results, 2 * (size_t)n_slices * sizeof(struct h264gpu_slice_result))) < 0)
 		return r;
 	CU_TRY(cudaMemcpyAsync(ctx->rd_params.p, h_params, (size_t)n_slices * sizeof(*h_params),
 			       cudaMemcpyHostToDevice, st));
@@ -98,14 +98,30 @@ static int parse_pooled(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_str
 		(struct h264gpu_mb_record *)ctx->rd_records.p, (struct h264gpu_slice_result *)ctx->rd_results.p, st);
 	if (r < 0)
 		return r;
+	if (dev2 != NULL) {
+		/* the other entropy coder's slices: same records array (every kernel writes only the
+		 * records of the slices it parses), second half of the results */
+		r = dev2(ctx, (const uint8_t *)ctx->rd_stream.p, ctx->rd_stream_len,
+			 (const struct h264gpu_slice_params *)ctx->rd_params.p, n_slices,
+			 (struct h264gpu_mb_record *)ctx->rd_records.p,
+			 (struct h264gpu_slice_result *)ctx->rd_results.p + n_slices, st);
+		if (r < 0)
+			return r;
+	}
 	if (n_records)
 		CU_TRY(cudaMemcpyAsync(ctx->rh_records.p, ctx->rd_records.p, n_records * sizeof(struct h264gpu_mb_record),
 				       cudaMemcpyDeviceToHost, st));
-	CU_TRY(cudaMemcpyAsync(ctx->rh_results.p, ctx->rd_results.p, (size_t)n_slices * sizeof(struct h264gpu_slice_result),
+	CU_TRY(cudaMemcpyAsync(ctx->rh_results.p, ctx->rd_results.p,
+			       (dev2 ? 2 : 1) * (size_t)n_slices * sizeof(struct h264gpu_slice_result),
 			       cudaMemcpyDeviceToHost, st));
 	CU_TRY(cudaStreamSynchronize(st));
+	struct h264gpu_slice_result *res = (struct h264gpu_slice_result *)ctx->rh_results.p;
+	if (dev2 != NULL)
+		for (uint32_t i = 0; i < n_slices; i++)
+			if (res[i].status == H264GPU_SLICE_SKIPPED)
+				res[i] = res[n_slices + i];
 	*out_records = (const struct h264gpu_mb_record *)ctx->rh_records.p;
-	*out_results = (const struct h264gpu_slice_result *)ctx->rh_results.p;
+	*out_results = res;
 	return 0;
 }
 
@@ -137,6 +153,18 @@ extern "C" int h264gpu_reader_parse_cavlc(h264gpu_ctx *ctx, const struct h264gpu
 	if (h_params == NULL || h_records == NULL || h_results == NULL || n_slices == 0)
 		return -EINVAL;
 	return parse_pooled(h264gpu_cavlc_parse_dev, ctx, NULL, 0, h_params, n_slices, n_records, h_records, h_results);
+}
+
+/* CAVLC and CABAC slices of one parameter list (two launches on the same records array) */
+extern "C" int h264gpu_reader_parse_slices(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,
+					   uint32_t n_slices, uint64_t n_records,
+					   const struct h264gpu_mb_record **h_records,
+					   const struct h264gpu_slice_result **h_results)
+{
+	if (h_params == NULL || h_records == NULL || h_results == NULL || n_slices == 0)
+		return -EINVAL;
+	return parse_pooled(h264gpu_cavlc_parse_dev, ctx, NULL, 0, h_params, n_slices, n_records, h_records, h_results,
+			    h264gpu_cabac_parse_dev);
 }
 
 extern "C" int h264gpu_reader_parse_cabac(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,

@@ -121,8 +121,10 @@ int h264_reader_slice_data(struct h264_reader *reader, struct h264_ctx *ctx, con
 			   size_t nal_len)
 {
 	/* CABAC slice data is not parsed, and nothing is delivered for it: exactly the
-	 * reference's behaviour (src/h264_syntax_slice_data.h:715-717) */
-	if (ctx->pps->entropy_coding_mode_flag)
+	 * reference's behaviour (src/h264_syntax_slice_data.h:715-717), unless the caller opted in
+	 * to this library's extension (H264_READER_FLAGS_SLICE_DATA_CABAC) */
+	const int cabac = ctx->pps->entropy_coding_mode_flag != 0;
+	if (cabac && !(reader->flags & H264_READER_FLAGS_SLICE_DATA_CABAC))
 		return 0;
 	const struct h264_ctx_cbs *cbs = &reader->cbs;
 	const struct h264gpu_mb_record *rec = NULL;
@@ -166,8 +168,10 @@ int h264_reader_slice_data(struct h264_reader *reader, struct h264_ctx *ctx, con
 		own = malloc(((size_t)p.mb_out_cap + 1) * sizeof(*own));
 		if (own == NULL)
 			return -ENOMEM;
-		res = h264gpu_cavlc_parse_host(reader->gpu_single, nal, nal_len, &p, 1, own, p.mb_out_cap,
-					       &result);
+		res = cabac ? h264gpu_cabac_parse_host(reader->gpu_single, nal, nal_len, &p, 1, own, p.mb_out_cap,
+						       &result)
+			    : h264gpu_cavlc_parse_host(reader->gpu_single, nal, nal_len, &p, 1, own, p.mb_out_cap,
+						       &result);
 		if (res < 0) {
 			free(own);
 			return res;
@@ -213,6 +217,7 @@ struct slice_list {
 	struct h264gpu_slice_params *params;
 	uint32_t n, cap;
 	uint64_t records;
+	int any_cabac;
 };
 
 /* header-only pass on a private context: which NAL units are CAVLC slices, and with
@@ -243,8 +248,10 @@ static int collect_slices(struct h264_reader *reader, const uint8_t *buf, const 
 		if (parse_one(reader, shadow, NULL, nal, len) < 0)
 			continue; /* the replay pass reports it */
 		if (type == H264_NALU_TYPE_SPS || type == H264_NALU_TYPE_PPS ||
-		    shadow->pps->entropy_coding_mode_flag)
+		    (shadow->pps->entropy_coding_mode_flag && !(reader->flags & H264_READER_FLAGS_SLICE_DATA_CABAC)))
 			continue;
+		if (shadow->pps->entropy_coding_mode_flag)
+			out->any_cabac = 1;
 		if (out->n == out->cap) {
 			const uint32_t cap = out->cap ? out->cap * 2 : 256;
 			void *p = realloc(out->params, (size_t)cap * sizeof(*out->params));
@@ -305,12 +312,15 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 	/* 2. macroblock layer of every CAVLC slice, one launch on the resident copy */
 	struct slice_list sl;
 	memset(&sl, 0, sizeof(sl));
+	reader->flags = flags;
 	if (flags & H264_READER_FLAGS_SLICE_DATA) {
 		const struct h264gpu_mb_record *records = NULL;
 		const struct h264gpu_slice_result *results = NULL;
 		res = collect_slices(reader, buf, st, en, n_nal, &sl);
 		if (res >= 0 && sl.n > 0)
-			res = h264gpu_reader_parse_cavlc(reader->gpu, sl.params, sl.n, sl.records, &records, &results);
+			res = sl.any_cabac
+				? h264gpu_reader_parse_slices(reader->gpu, sl.params, sl.n, sl.records, &records, &results)
+				: h264gpu_reader_parse_cavlc(reader->gpu, sl.params, sl.n, sl.records, &records, &results);
 		if (res < 0)
 			goto out_slices;
 		if (sl.n > 0) {

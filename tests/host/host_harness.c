@@ -43,6 +43,7 @@ struct api {
 	int (*bs_write_bits)(struct h264_bitstream *, uint64_t, uint32_t);
 	int (*bs_acquire_buf)(struct h264_bitstream *, uint8_t **, size_t *);
 	int (*get_info)(const uint8_t *, size_t, const uint8_t *, size_t, struct h264_info *);
+	int (*rewrite_slice_header)(struct h264_bitstream *, struct h264_ctx *, const struct h264_slice_header *);
 };
 
 #define SYM(field, name)                                                                       \
@@ -84,6 +85,7 @@ static int api_open(struct api *a, const char *path)
 	SYM(bs_write_bits, "h264_bs_write_bits");
 	SYM(bs_acquire_buf, "h264_bs_acquire_buf");
 	SYM(get_info, "h264_get_info");
+	SYM(rewrite_slice_header, "h264_rewrite_slice_header");
 	return 0;
 }
 
@@ -372,6 +374,67 @@ double hh_time_parse(const char *libpath, const uint8_t *buf, size_t len, uint32
 	a.reader_destroy(rd);
 	dlclose(a.h);
 	return best;
+}
+
+/* ---- h264_rewrite_slice_header: patch every slice of a stream in place ---------------------
+ * mode 0: frame_num ^ 1 (a fixed-width field: same bit length, must succeed and change bytes)
+ * mode 1: slice_qp_delta + 17 (an se(v) that grows: must fail with -EPROTO and leave the NAL and
+ *         the context's slice header untouched)
+ * `out` receives a copy of the stream with the patched NALs; rcs[k] = return code for slice k. */
+struct rw_state {
+	struct api *a;
+	const uint8_t *base;
+	uint8_t *out;
+	int mode;
+	int32_t *rcs;
+	uint32_t n, cap;
+};
+
+static void rw_slice(struct h264_ctx *c, const uint8_t *buf, size_t len, const struct h264_slice_header *sh,
+		     void *u)
+{
+	struct rw_state *st = u;
+	struct h264_slice_header nsh = *sh;
+	struct h264_bitstream bs;
+	if (st->mode == 0)
+		nsh.frame_num ^= 1;
+	else
+		nsh.slice_qp_delta += 17;
+	h264_bs_init(&bs, st->out + (buf - st->base), len, 1);
+	const int r = st->a->rewrite_slice_header(&bs, c, &nsh);
+	if (st->n < st->cap)
+		st->rcs[st->n] = r;
+	st->n++;
+}
+
+long hh_rewrite(const char *libpath, const uint8_t *buf, size_t len, int mode, uint8_t *out, int32_t *rcs,
+		uint32_t cap)
+{
+	struct api a;
+	int r = api_open(&a, libpath);
+	if (r < 0)
+		return r;
+	memcpy(out, buf, len);
+	struct rw_state st = {&a, buf, out, mode, rcs, 0, cap};
+	struct h264_ctx_cbs cbs;
+	memset(&cbs, 0, sizeof(cbs));
+	cbs.slice = rw_slice;
+	struct h264_reader *rd = NULL;
+	r = a.reader_new(&cbs, &st, &rd);
+	if (r < 0)
+		return r;
+	/* NAL by NAL (headers only: no GPU stage is involved) */
+	size_t off = 0, start = 0, end = 0;
+	while (off < len) {
+		int fr = a.find_nalu(buf + off, len - off, &start, &end);
+		if (fr < 0 && fr != -EAGAIN)
+			break;
+		a.reader_parse_nalu(rd, 0, buf + off + start, end - start);
+		off += end;
+	}
+	a.reader_destroy(rd);
+	dlclose(a.h);
+	return (long)st.n;
 }
 
 /* ---- generator ----------------------------------------------------------------------------- */

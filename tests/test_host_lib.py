@@ -32,6 +32,8 @@ def harness():
     lib.hh_trace.restype = C.c_int
     lib.hh_trace.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p,
                              C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.hh_rewrite.restype = C.c_long
+    lib.hh_rewrite.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.hh_time_parse.restype = C.c_double
     lib.hh_time_parse.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
     return lib
@@ -197,3 +199,41 @@ def test_small_utilities_match_reference():
     assert np.array_equal(a, b) and not np.array_equal(a, base)
     assert ours.h264_avcc_to_byte_stream(a.ctypes.data, len(a)) == ref.h264_avcc_to_byte_stream(b.ctypes.data, len(b))
     assert np.array_equal(a, b) and np.array_equal(a, base)
+
+
+def test_rewrite_slice_header_behaviour():
+    """h264_rewrite_slice_header (src/h264_writer.c:311-370) on every slice of generated streams:
+    an edit that keeps the bit length patches the NAL in place exactly like the reference does
+    (whole header bytes + the bits of the byte shared with the slice data), one that changes the
+    length fails with -EPROTO and leaves the bytes alone."""
+    lib = harness()
+    import libh264_b200 as L
+    streams = [gen(lib, REF, 400 + k, rounds=6) for k in range(3)]
+    streams.append(L.synth_video(frames=4, width_mbs=20, height_mbs=12, slices_per_frame=3, profile_idc=100,
+                                 transform_8x8=1, b_frames=1, num_ref_frames=2, idr_period=3, pct_skip=30,
+                                 coef_density=50, seed=21)[0])
+    patched = 0
+    for s in streams:
+        s = np.ascontiguousarray(s)
+        for mode in (0, 1):
+            outs, rcs = [], []
+            for path in (OURS, REF):
+                out = np.zeros(len(s), np.uint8)
+                rc = np.full(4096, 99, np.int32)
+                n = lib.hh_rewrite(path.encode(), s.ctypes.data, len(s), mode, out.ctypes.data, rc.ctypes.data, len(rc))
+                assert n >= 0
+                outs.append(out)
+                rcs.append(rc[:n].copy())
+            assert np.array_equal(rcs[0], rcs[1]), (mode, rcs)
+            assert np.array_equal(outs[0], outs[1]), mode
+            if mode == 0:
+                ok = rcs[0] == 0
+                patched += int(ok.sum())
+                if ok.any():
+                    assert not np.array_equal(outs[0], s)  # frame_num really changed in the bytes
+            else:
+                changed = rcs[0] == 0  # slice_qp_delta + 17 may keep its length for some values
+                if not changed.any():
+                    assert np.array_equal(outs[0], s)
+                assert ((rcs[0] == 0) | (rcs[0] == -71)).all(), rcs[0]  # -EPROTO
+    assert patched > 10

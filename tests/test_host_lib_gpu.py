@@ -81,3 +81,39 @@ def assert_same_trace_outside_ub(a, b, what):
             j += 1
     assert (i == len(ea)) == (j == len(eb)), what
     return excused
+
+
+def test_cabac_slice_data_through_the_api_is_opt_in():
+    """CABAC slices: with H264_READER_FLAGS_SLICE_DATA alone the callbacks are the reference's
+    (it returns before CABAC slice data, src/h264_syntax_slice_data.h:715-717); with this library's
+    extra bit H264_READER_FLAGS_SLICE_DATA_CABAC (0x02) every macroblock is delivered, the same
+    (mb_addr, mb_type) the CABAC kernel returns through the C-ABI, in stream order; a stream that
+    mixes CAVLC and CABAC pictures gets both in one pass."""
+    lib = T.harness()
+    cfg = dict(frames=4, width_mbs=20, height_mbs=12, slices_per_frame=3, profile_idc=77, transform_8x8=0,
+               b_frames=1, num_ref_frames=2, idr_period=3, pct_skip=30, coef_density=50, seed=31)
+    cab, nmb, nsl, params = L.synth_video(entropy_cabac=1, want_params=True, **cfg)
+    T.assert_same_trace(T.trace(lib, T.OURS, cab, 1, 0), T.trace(lib, T.REF, cab, 1, 0), "cabac, flags=1")
+    g = L.Gpu(0)
+    try:
+        recs, res = g.cabac_parse_host(cab, params, nmb)
+    finally:
+        g.close()
+    assert (res["status"] == 0).all()
+    for mode in (0, 1):  # bulk and NAL by NAL
+        mbs = [np.frombuffer(p, "<u4") for t, p in T.split_log(T.trace(lib, T.OURS, cab, 3, mode)) if t == T_SD_MB]
+        assert len(mbs) == nmb
+        P = np.frombuffer(params, L.SLICE_PARAMS)
+        want = np.concatenate([np.stack([recs["mb_addr"][int(p["mb_out_off"]):int(p["mb_out_off"]) + int(r["mb_count"])],
+                                         recs["mb_type"][int(p["mb_out_off"]):int(p["mb_out_off"]) + int(r["mb_count"])]], 1)
+                               for p, r in zip(P, res)])
+        assert np.array_equal(np.stack(mbs), want), mode
+    # CAVLC pictures followed by CABAC pictures (new SPS/PPS in between): CAVLC part identical to the
+    # reference, CABAC part delivered on top
+    cav, nmb2, _ = L.synth_video(**dict(cfg, profile_idc=100, transform_8x8=1, seed=32))
+    both = np.concatenate([cav, cab])
+    ours = T.split_log(T.trace(lib, T.OURS, both, 3, 0))
+    ref = T.split_log(T.trace(lib, T.REF, both, 1, 0))
+    assert sum(1 for t, _ in ours if t == T_SD_MB) == nmb + nmb2
+    assert sum(1 for t, _ in ref if t == T_SD_MB) == nmb2
+    assert [e for e in ours if e[0] != T_SD_MB][:50] == [e for e in ref if e[0] != T_SD_MB][:50]
