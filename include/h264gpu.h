@@ -223,6 +223,26 @@ H264GPU_API int h264gpu_reader_upload(h264gpu_ctx *ctx, const uint8_t *h_buf, ui
 H264GPU_API int h264gpu_reader_resident(h264gpu_ctx *ctx, const uint8_t **d_stream, uint64_t *len);
 
 /*
+ * h264_byte_stream_to_avcc (src/h264.c:210-246) on the GPU: every 4-byte start code
+ * 00 00 00 01 of d_data[0,len) is replaced, in place, by the big-endian length of the NAL
+ * behind it (up to the next 4-byte code or the end of the buffer; a code within the last 4
+ * bytes stays, as in the reference's `while (len > 4)`).  3-byte codes are not start codes here,
+ * exactly like the reference's find_start_code (src/h264.c:184-207).
+ *   max_nal   capacity of d_pos and of the scan's code table (0 = worst case len / 4)
+ *   d_pos     optional: offsets of the codes found, in order;  d_count: how many were found
+ *             (if *d_count > max_nal the table overflowed and the conversion is incomplete)
+ * The host form uploads the buffer, fetches the code offsets and patches the 4-byte length
+ * fields in h_data itself (nothing else changes, so the buffer is not copied back).
+ * h264_avcc_to_byte_stream is a pointer chase (each length gives the next position, one
+ * dependent load per NAL) and stays on the host (libh264.so).
+ */
+H264GPU_API int h264gpu_byte_stream_to_avcc_dev(h264gpu_ctx *ctx, uint8_t *d_data, uint64_t len,
+						uint64_t max_nal, uint64_t *d_pos, uint64_t *d_count,
+						void *stream);
+H264GPU_API int h264gpu_byte_stream_to_avcc_host(h264gpu_ctx *ctx, uint8_t *h_data, uint64_t len,
+						 uint64_t *n_nal);
+
+/*
  * Writer side: escape n payloads d_rbsp[d_off[k], d_off[k+1]) and put a start
  * code of sc_len (3 or 4; 0 = none) bytes in front of each.
  *   d_out       capacity out_cap bytes (worst case 3/2 * payload + n*sc_len)

@@ -86,6 +86,7 @@ GPU_SYMBOLS = [
     "h264gpu_timer_start", "h264gpu_timer_stop", "h264gpu_timer_elapsed_ms",
     "h264gpu_reader_scan", "h264gpu_reader_upload", "h264gpu_reader_resident",
     "h264gpu_stream_create", "h264gpu_stream_destroy",
+    "h264gpu_byte_stream_to_avcc_dev", "h264gpu_byte_stream_to_avcc_host",
 ]
 
 _libs = {}

@@ -61,6 +61,7 @@ namespace annexb7 {
 
 constexpr int kT = 256;
 constexpr int kW = kT / 32;
+constexpr size_t kCtrlBytes = 256; /* control words at the head of the workspace */
 constexpr uint64_t kValMask = (1ull << 40) - 1;
 constexpr uint64_t kPfxBit = 1ull << 41;
 
@@ -161,6 +162,15 @@ __device__ __forceinline__ TMasks t_masks(uint32_t pw, uint32_t w0, uint32_t w1,
 	m.ev16 = (ev >> 4) & 0xffffu;
 	m.sc16 = (sc >> 4) & 0xffffu;
 	return m;
+}
+
+/* bit j: byte j of the chunk is the 01 of a 4-byte start code 00 00 00 01 (window [-4, 16)) */
+__device__ __forceinline__ uint32_t code4_mask(uint32_t pw, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
+{
+	const uint32_t k1 = 0x01010101u;
+	const uint32_t Z = zmask4(pw) | zmask4(w0) << 4 | zmask4(w1) << 8 | zmask4(w2) << 12 | zmask4(w3) << 16;
+	const uint32_t O = zmask4(w0 ^ k1) << 4 | zmask4(w1 ^ k1) << 8 | zmask4(w2 ^ k1) << 12 | zmask4(w3 ^ k1) << 16;
+	return ((O & (Z << 1) & (Z << 2) & (Z << 3)) >> 4) & 0xffffu;
 }
 
 /* bit j: byte j of the chunk is a reset point (the three bytes before it are 00 00 01) */
@@ -875,7 +885,7 @@ __global__ void __launch_bounds__(kT, MINB) scan7_kernel(const Scan7Args a)
  * them there; 1.0 B of traffic per input byte.  Events are rare: only rows with a candidate
  * (00 00 followed by a byte <= 1) evaluate the exact masks.
  */
-template <int ROWS, int MINB>
+template <int ROWS, int MINB, bool AVCC = false>
 __global__ void __launch_bounds__(kT, MINB) scan7_only_kernel(const Scan7Args a)
 {
 	using C = Cfg<ROWS>;
@@ -924,11 +934,20 @@ __global__ void __launch_bounds__(kT, MINB) scan7_only_kernel(const Scan7Args a)
 			masks[i] = 0;
 			if (acc & 0x80808080u) {
 				const uint32_t p0 = (uint32_t)(i * 32 + lane) * 16;
-				const TMasks m = t_masks(pw, w0, w1, w2, w3);
-				const uint32_t evm = event_valid16(p0, nvalid, t == 0);
-				masks[i] = (m.ev16 & evm) | (m.sc16 & evm) << 16;
-				nev += (uint32_t)__popc(m.ev16 & evm);
-				nsc += (uint32_t)__popc(m.sc16 & evm);
+				if (AVCC) {
+					/* 4-byte start codes 00 00 00 01 only (src/h264.c:184-207), owned by the
+					 * position of their 01 byte; the record carries the code's first byte */
+					const uint32_t m4 = code4_mask(pw, w0, w1, w2, w3) & valid16(p0, nvalid);
+					masks[i] = m4 | m4 << 16;
+					nev += (uint32_t)__popc(m4);
+					nsc += (uint32_t)__popc(m4);
+				} else {
+					const TMasks m = t_masks(pw, w0, w1, w2, w3);
+					const uint32_t evm = event_valid16(p0, nvalid, t == 0);
+					masks[i] = (m.ev16 & evm) | (m.sc16 & evm) << 16;
+					nev += (uint32_t)__popc(m.ev16 & evm);
+					nsc += (uint32_t)__popc(m.sc16 & evm);
+				}
 			}
 		}
 		nev = warp_add(nev);
@@ -958,7 +977,7 @@ __global__ void __launch_bounds__(kT, MINB) scan7_only_kernel(const Scan7Args a)
 					const uint32_t j = (uint32_t)__ffs((int)x) - 1;
 					x &= x - 1;
 					if ((uint64_t)idx < a.ev_cap) {
-						a.evbuf[2 * (uint64_t)idx] = (span_off + p0 + j - 2) | (uint64_t)((sc >> j) & 1) << 62;
+						a.evbuf[2 * (uint64_t)idx] = (span_off + p0 + j - (AVCC ? 3 : 2)) | (uint64_t)((sc >> j) & 1) << 62;
 						a.evbuf[2 * (uint64_t)idx + 1] = 0;
 					}
 				}
@@ -1197,6 +1216,43 @@ __global__ void __launch_bounds__(256) fin7_table(const Fin7Args f)
 	f.ctrl[4] = 0;
 	f.ctrl[5] = 0;
 	f.ctrl[6] = 0;
+}
+
+/*
+ * h264_byte_stream_to_avcc (src/h264.c:210-246), the part after the scan: every 4-byte start
+ * code becomes the big-endian length of the NAL behind it (up to the next code or the end).
+ * ordered: fin7_order's output for a scan7_only_kernel<.., AVCC = true> launch.  The reference
+ * stops when 4 bytes or fewer are left (`while (len > 4)`): a code in the last 4 bytes stays.
+ */
+__global__ void __launch_bounds__(256) avcc_write_kernel(const uint64_t *ordered, const uint64_t *totals,
+							  uint64_t ev_cap, uint8_t *data, uint64_t len,
+							  uint64_t *pos_out, uint64_t *count_out)
+{
+	const uint64_t n = totals[0] < ev_cap ? totals[0] : ev_cap;
+	const uint64_t posmask = (1ull << 40) - 1;
+	for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t p = ordered[3 * e] & posmask;
+		const uint64_t nxt = e + 1 < n ? (ordered[3 * (e + 1)] & posmask) : len;
+		if (pos_out)
+			pos_out[e] = p;
+		if (len - p <= 4)
+			continue;
+		const uint32_t nal = (uint32_t)(nxt - p - 4);
+		if (data) {
+			data[p] = (uint8_t)(nal >> 24);
+			data[p + 1] = (uint8_t)(nal >> 16);
+			data[p + 2] = (uint8_t)(nal >> 8);
+			data[p + 3] = (uint8_t)nal;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0 && count_out)
+		*count_out = totals[0];
+}
+
+/* re-arm the control words after an AVCC scan (fin7_table, which does it for the NAL scan, is not run) */
+__global__ void avcc_rearm_kernel(uint32_t *ctrl)
+{
+	ctrl[0] = ctrl[1] = ctrl[2] = ctrl[3] = ctrl[4] = ctrl[5] = ctrl[6] = 0;
 }
 
 } /* namespace annexb7 */

@@ -646,6 +646,133 @@ static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uin
 				    d_nal_rbsp_len, nal_cap, d_result, st);
 }
 
+/* ---- Annex-B (4-byte start codes) -> AVCC lengths, in place on the device ---------------- */
+
+extern "C" int h264gpu_byte_stream_to_avcc_dev(h264gpu_ctx *ctx, uint8_t *d_data, uint64_t len, uint64_t max_nal,
+						uint64_t *d_pos, uint64_t *d_count, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (d_data == NULL || len == 0 || ((uintptr_t)d_data & 15))
+		return -EINVAL;
+	if (len >= (1ull << 40))
+		return -E2BIG;
+	constexpr int ROWS = 8;
+	cudaStream_t st = (cudaStream_t)stream;
+	const uint64_t span = (uint64_t)annexb7::Cfg<ROWS>::SPAN;
+	const uint64_t nspans = (len + span - 1) / span;
+	uint64_t ev_cap = max_nal ? max_nal : len / 4 + 2;
+	if (ev_cap > len / 4 + 2)
+		ev_cap = len / 4 + 2;
+	if (ev_cap >= 0xffffffffull)
+		ev_cap = 0xfffffffeull;
+	const uint64_t nblk = (nspans + annexb7::kFinT - 1) / annexb7::kFinT;
+	const size_t fin_off = (size_t)annexb7::kCtrlBytes;
+	const size_t pre_off = fin_off + (size_t)nspans * 8;
+	const size_t blk_off = pre_off + (size_t)nspans * 8;
+	const size_t tot_off = blk_off + (size_t)nblk * 16;
+	const size_t ev_off = tot_off + 64;
+	const size_t ord_off = ev_off + (size_t)ev_cap * 16;
+	const size_t need = ord_off + (size_t)ev_cap * 24;
+	const size_t had = ctx->ws7_bytes;
+	if ((r = ws7_reserve(ctx, need)) < 0)
+		return r;
+	if (ctx->ws7_bytes != had)
+		ctx->epoch7 = 0;
+	uint8_t *ws = (uint8_t *)ctx->ws7;
+	annexb7::Scan7Args a;
+	memset(&a, 0, sizeof(a));
+	a.in = d_data;
+	a.len = len;
+	a.fin = (uint64_t *)(ws + fin_off);
+	a.ctrl = (uint32_t *)ws;
+	a.evbuf = (uint64_t *)(ws + ev_off);
+	a.ev_cap = ev_cap;
+	a.num_spans = (uint32_t)nspans;
+	a.halo_left = 0xffffffffu;
+	a.right[0] = a.right[1] = 0xff;
+	const int sms = device_sms(ctx);
+	const uint64_t ctas = (nspans + annexb7::kW - 1) / annexb7::kW;
+	const uint32_t grid = (uint32_t)(ctas < (uint64_t)sms * 4 ? ctas : (uint64_t)sms * 4);
+	annexb7::scan7_only_kernel<ROWS, 4, true><<<grid, annexb7::kT, 0, st>>>(a);
+	annexb7::Fin7Args f;
+	memset(&f, 0, sizeof(f));
+	f.fin = a.fin;
+	f.num_spans = (uint32_t)nspans;
+	f.nblk = (uint32_t)nblk;
+	f.evbuf = a.evbuf;
+	f.ev_cap = ev_cap;
+	f.ordered = (uint64_t *)(ws + ord_off);
+	f.span_pre = (uint64_t *)(ws + pre_off);
+	f.blk = (uint64_t *)(ws + blk_off);
+	f.totals = (uint64_t *)(ws + tot_off);
+	f.ctrl = a.ctrl;
+	annexb7::fin7_spans<<<(uint32_t)nblk, annexb7::kFinT, 0, st>>>(f);
+	annexb7::fin7_order<<<(uint32_t)((nspans + 255) / 256), 256, 0, st>>>(f);
+	uint64_t tb = (ev_cap + 255) / 256;
+	if (tb > (uint64_t)sms * 8)
+		tb = (uint64_t)sms * 8;
+	annexb7::avcc_write_kernel<<<(uint32_t)(tb ? tb : 1), 256, 0, st>>>(f.ordered, f.totals, ev_cap, d_data, len, d_pos,
+									   d_count);
+	annexb7::avcc_rearm_kernel<<<1, 1, 0, st>>>(a.ctrl);
+	CU_TRY(cudaGetLastError());
+	ctx->launches += 5;
+	return 0;
+}
+
+extern "C" int h264gpu_byte_stream_to_avcc_host(h264gpu_ctx *ctx, uint8_t *h_data, uint64_t len, uint64_t *n_nal)
+{
+	if (n_nal)
+		*n_nal = 0;
+	if (h_data == NULL || len == 0)
+		return -EINVAL;
+	int r = h264gpu_reader_upload(ctx, h_data, len);
+	if (r < 0)
+		return r;
+	cudaStream_t st = ctx->s_rd;
+	/* only the 4-byte length fields change: the positions come back and the host patches them */
+	uint64_t cap = len / 64 + 4096;
+	for (int pass = 0; pass < 2; pass++) {
+		if ((r = h264gpu_pool_dev(ctx, &ctx->rd_tab, (cap + 1) * 8)) < 0 ||
+		    (r = h264gpu_pool_host(ctx, &ctx->rh_tab, (cap + 1) * 8)) < 0)
+			return r;
+		uint64_t *d_pos = (uint64_t *)ctx->rd_tab.p, *h_pos = (uint64_t *)ctx->rh_tab.p;
+		r = h264gpu_byte_stream_to_avcc_dev(ctx, (uint8_t *)ctx->rd_stream.p, len, cap, d_pos + 1, d_pos, st);
+		if (r < 0)
+			return r;
+		CU_TRY(cudaMemcpyAsync(h_pos, d_pos, 8, cudaMemcpyDeviceToHost, st));
+		CU_TRY(cudaStreamSynchronize(st));
+		const uint64_t n = h_pos[0];
+		if (n > cap) {
+			cap = len / 4 + 2;
+			/* the device copy was patched with an incomplete table: start over */
+			if ((r = h264gpu_reader_upload(ctx, h_data, len)) < 0)
+				return r;
+			continue;
+		}
+		if (n) {
+			CU_TRY(cudaMemcpyAsync(h_pos + 1, d_pos + 1, n * 8, cudaMemcpyDeviceToHost, st));
+			CU_TRY(cudaStreamSynchronize(st));
+		}
+		for (uint64_t e = 0; e < n; e++) {
+			const uint64_t p = h_pos[1 + e];
+			const uint64_t nxt = e + 1 < n ? h_pos[2 + e] : len;
+			if (len - p <= 4)
+				continue;
+			const uint32_t nal = (uint32_t)(nxt - p - 4);
+			h_data[p] = (uint8_t)(nal >> 24);
+			h_data[p + 1] = (uint8_t)(nal >> 16);
+			h_data[p + 2] = (uint8_t)(nal >> 8);
+			h_data[p + 3] = (uint8_t)nal;
+		}
+		if (n_nal)
+			*n_nal = n;
+		return 0;
+	}
+	return -E2BIG;
+}
+
 /* ---- scan + strip, RBSP in place (gen 5) ----------------------------------- */
 
 extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len,

@@ -200,6 +200,61 @@ static int emu_scan7(const uint8_t *buf, uint64_t len, uint64_t base, const stru
 	return 0;
 }
 
+/* h264_byte_stream_to_avcc on the emulator: AVCC-mode scan + ordering + length write, in place */
+extern "C" int emu_avcc(uint8_t *data, uint64_t len, uint64_t ev_cap, uint64_t *pos, uint64_t *count, int rows)
+{
+	using namespace annexb7;
+	if (len == 0)
+		return -1;
+	const uint64_t span = (uint64_t)rows * 512;
+	const uint32_t nspans = (uint32_t)((len + span - 1) / span);
+	const uint32_t nblk = (nspans + kFinT - 1) / kFinT;
+	std::vector<uint64_t> fin(nspans, ~0ull), pre(nspans, ~0ull), blk(2 * (size_t)nblk, ~0ull);
+	std::vector<uint64_t> evbuf(2 * (ev_cap ? ev_cap : 1), 0), ordered(3 * (ev_cap ? ev_cap : 1), 0);
+	uint64_t totals[8] = {0};
+	static uint32_t ctrl[64] = {0};
+	uint8_t *buf = (uint8_t *)aligned_alloc(16, (len + 15) & ~15ull);
+	memcpy(buf, data, len);
+	Scan7Args a;
+	memset(&a, 0, sizeof(a));
+	a.in = buf;
+	a.len = len;
+	a.fin = fin.data();
+	a.ctrl = ctrl;
+	a.evbuf = evbuf.data();
+	a.ev_cap = ev_cap;
+	a.num_spans = nspans;
+	a.halo_left = 0xffffffffu;
+	a.right[0] = a.right[1] = 0xff;
+	Fin7Args f;
+	memset(&f, 0, sizeof(f));
+	f.fin = fin.data();
+	f.num_spans = nspans;
+	f.nblk = nblk;
+	f.evbuf = evbuf.data();
+	f.ev_cap = ev_cap;
+	f.ordered = ordered.data();
+	f.span_pre = pre.data();
+	f.blk = blk.data();
+	f.totals = totals;
+	f.ctrl = ctrl;
+	const uint32_t nctas = (nspans + kW - 1) / kW;
+	dim3 grid(nctas < 3 ? nctas : 3), block(kT), gs(nblk), bs(kFinT), b256(256), go((nspans + 255) / 256), g2(2), one(1);
+	if (rows == 1) EMU_LAUNCH((scan7_only_kernel<1, 1, true>), grid, block, a);
+	else if (rows == 2) EMU_LAUNCH((scan7_only_kernel<2, 1, true>), grid, block, a);
+	else EMU_LAUNCH((scan7_only_kernel<8, 1, true>), grid, block, a);
+	EMU_LAUNCH((fin7_spans), gs, bs, f);
+	EMU_LAUNCH((fin7_order), go, b256, f);
+	EMU_LAUNCH((avcc_write_kernel), g2, b256, f.ordered, f.totals, ev_cap, buf, len, pos, count);
+	EMU_LAUNCH((avcc_rearm_kernel), one, one, ctrl);
+	memcpy(data, buf, len);
+	free(buf);
+	for (int i = 0; i < 7; i++)
+		if (ctrl[i] != 0)
+			return -2;
+	return 0;
+}
+
 /* gen 5: in-place RBSP (annexb_scan5.cuh).  cpt = 16-byte chunks per thread (1, 2 or 8). */
 extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t base,
 				       const struct h264gpu_shard_edge *edge, uint8_t *rbsp,
