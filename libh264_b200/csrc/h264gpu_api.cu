@@ -8,8 +8,6 @@
 
 #include "annexb_scan.cuh"
 #include "annexb_scan2.cuh"
-#include "annexb_scan5.cuh"
-#include "annexb_scan6.cuh"
 #include "annexb_scan7.cuh"
 
 extern "C" {
@@ -42,13 +40,13 @@ int h264gpu_create(int device, h264gpu_ctx **out)
 	if (ctx == NULL)
 		return -ENOMEM;
 	ctx->device = device;
-	/* 16-byte chunks per thread: 1/2/4 = first-generation kernel, 104/108 =
-	 * second generation (annexb_scan2.cuh) with 4/8 chunks per thread */
-	ctx->scan_items = 108;
+	/* tile shape of the packed-RBSP kernel and of the writer kernel: 16-byte chunks per thread
+	 * (8 = 32 KiB tiles; 1, 2, 4 = small tiles, used by the tests to get many seams on small inputs) */
+	ctx->scan_items = 8;
 	const char *e = getenv("H264GPU_SCAN_ITEMS");
 	if (e != NULL) {
 		int v = atoi(e);
-		if (v == 1 || v == 2 || v == 4 || v == 104 || v == 108 || v == 114 || v == 118)
+		if (v == 1 || v == 2 || v == 4 || v == 8)
 			ctx->scan_items = v;
 	}
 	size_t chunk_mb = 128;
@@ -290,27 +288,12 @@ int h264gpu_ws_reserve(h264gpu_ctx *ctx, size_t bytes)
 
 /* ---- scan (+strip) ------------------------------------------------------- */
 
-template <int ITEMS>
-static cudaError_t launch_scan(const annexb::ScanArgs &a, bool strip, cudaStream_t st)
-{
-	if (strip)
-		annexb::scan_kernel<ITEMS, true><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
-	else
-		annexb::scan_kernel<ITEMS, false><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
-	return cudaGetLastError();
-}
-
 template <int CPT, int MINB>
 static cudaError_t launch_scan2(const annexb::ScanArgs &a, bool strip, cudaStream_t st)
 {
-	static bool carved = false;
-	if (!carved) {
-		cudaFuncSetAttribute(annexb2::scan2_kernel<CPT, true, MINB>,
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-		cudaFuncSetAttribute(annexb2::scan2_kernel<CPT, false, MINB>,
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-		carved = true;
-	}
+	/* function attributes are per device: set on every launch path (a cheap driver call) */
+	cudaFuncSetAttribute(annexb2::scan2_kernel<CPT, true, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+	cudaFuncSetAttribute(annexb2::scan2_kernel<CPT, false, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 	if (strip)
 		annexb2::scan2_kernel<CPT, true, MINB><<<a.num_tiles, annexb2::kT, 0, st>>>(a);
 	else
@@ -318,12 +301,9 @@ static cudaError_t launch_scan2(const annexb::ScanArgs &a, bool strip, cudaStrea
 	return cudaGetLastError();
 }
 
-/* scan kernel configurations selectable by H264GPU_SCAN_ITEMS (A/B testing) */
 static uint64_t scan_tile_bytes(int items)
 {
-	if (items >= 100)
-		return (uint64_t)annexb2::kT * (items % 10) * 16;
-	return (uint64_t)annexb::kBlock * items * 16;
+	return (uint64_t)annexb2::kT * items * 16;
 }
 
 extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len,
@@ -388,25 +368,19 @@ extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, ui
 	/* diagnostics: per-tile phase timestamps dumped to the file named by H264GPU_SCAN_TRACE */
 	const char *trace_path = getenv("H264GPU_SCAN_TRACE");
 	uint64_t *d_trace = NULL;
-	if (trace_path != NULL && items >= 100) {
+	if (trace_path != NULL) {
 		CU_TRY(cudaMalloc(&d_trace, ntiles * 64));
 		CU_TRY(cudaMemsetAsync(d_trace, 0, ntiles * 64, st));
 		a.trace = d_trace;
 	}
-	if (items == 108)
+	if (items == 8)
 		ce = launch_scan2<8, 4>(a, strip, st);
-	else if (items == 118)
-		ce = launch_scan2<8, 5>(a, strip, st);
-	else if (items == 104)
+	else if (items == 4)
 		ce = launch_scan2<4, 6>(a, strip, st);
-	else if (items == 114)
-		ce = launch_scan2<4, 8>(a, strip, st);
-	else if (items == 1)
-		ce = launch_scan<1>(a, strip, st);
 	else if (items == 2)
-		ce = launch_scan<2>(a, strip, st);
+		ce = launch_scan2<2, 6>(a, strip, st);
 	else
-		ce = launch_scan<4>(a, strip, st);
+		ce = launch_scan2<1, 6>(a, strip, st);
 	CU_TRY(ce);
 	ctx->launches++;
 	if (d_trace != NULL) {
@@ -637,11 +611,7 @@ static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uin
 			uint64_t *d_nal_end, uint64_t *d_nal_rbsp, uint64_t *d_nal_rbsp_len, uint64_t nal_cap,
 			struct h264gpu_scan_result *d_result, cudaStream_t st)
 {
-	/* span shape: 8 rows (4 KiB, 5 CTAs per SM) or 6 rows (3 KiB, 6 CTAs per SM) */
-	const char *e = getenv("H264GPU_SCAN7_ROWS");
-	if (e != NULL && atoi(e) == 6)
-		return scan7_launch_t<6, 6>(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp,
-					    d_nal_rbsp_len, nal_cap, d_result, st);
+	/* 8 rows = 4 KiB spans, 5 CTAs per SM (3 KiB spans at 6 CTAs per SM measured 11 % slower) */
 	return scan7_launch_t<8, 5>(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp,
 				    d_nal_rbsp_len, nal_cap, d_result, st);
 }
@@ -773,7 +743,7 @@ extern "C" int h264gpu_byte_stream_to_avcc_host(h264gpu_ctx *ctx, uint8_t *h_dat
 	return -E2BIG;
 }
 
-/* ---- scan + strip, RBSP in place (gen 5) ----------------------------------- */
+/* ---- scan + strip, RBSP in place: C-ABI entry -------------------------------------- */
 
 extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len,
 					       uint64_t base, const struct h264gpu_shard_edge *edge,
@@ -796,192 +766,8 @@ extern "C" int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t *
 	}
 	if (len >= (1ull << 40))
 		return -E2BIG;
-	{
-		/* kernel generation: 7 = warp-autonomous spans (annexb_scan7.cuh, default); 6 / 5 = the
-		 * block-wide tile kernels kept for A/B runs (H264GPU_INPLACE_GEN) */
-		const char *e = getenv("H264GPU_INPLACE_GEN");
-		if (e == NULL || atoi(e) == 7 || atoi(e) == 0)
-			return scan7_launch(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp,
-					    d_nal_rbsp_len, nal_cap, d_result, st);
-	}
-	/* tile shape: 85 = 8 chunks/thread, 5 CTAs/SM (default); 84: 4 CTAs; 45 / 46 = 4 chunks, 5 / 6 CTAs */
-	int shape = 85;
-	{
-		const char *e = getenv("H264GPU_SCAN5_SHAPE");
-		if (e != NULL && (atoi(e) == 45 || atoi(e) == 46 || atoi(e) == 84))
-			shape = atoi(e);
-	}
-	/* kernel generation: 6 = warp-autonomous tiles (annexb_scan6.cuh, default), 5 = block-wide
-	 * unit binning (annexb_scan5.cuh, kept as the A/B baseline) */
-	int gen = 6;
-	{
-		const char *e = getenv("H264GPU_INPLACE_GEN");
-		if (e != NULL && (atoi(e) == 5 || atoi(e) == 7))
-			gen = atoi(e);
-	}
-	const bool piped = gen == 7; /* gen 6 stages, two 16 KiB tiles per CTA in flight */
-	if (piped)
-		gen = 6;
-	const int CPT = shape / 10;
-	const uint64_t tile = piped ? (uint64_t)annexb6::Cfg<4>::TILE
-			    : (gen == 6 ? (uint64_t)annexb6::Cfg<8>::TILE : (uint64_t)annexb5::kT * CPT * 16);
-	/* gen 6 owns a boundary event by its third byte: the launch covers the two edge bytes too */
-	const uint64_t ntiles = ((gen == 6 ? len + 2 : len) + tile - 1) / tile;
-	/* events: a start code and at most a few terminators per NAL in real streams */
-	uint64_t ev_cap = 4 * nal_cap + 4096;
-	if (ev_cap > len / 3 + 2)
-		ev_cap = len / 3 + 2;
-	if (ev_cap >= 0xffffffffull)
-		ev_cap = 0xfffffffeull;
-	/* workspace: [256 control][32 B per tile][2 words per tile][events][ordered events] */
-	const size_t desc_end = 256 + (size_t)ntiles * 32;
-	const size_t pre_off = (desc_end + 255) & ~(size_t)255;
-	const size_t ev_off = pre_off + (size_t)ntiles * 16;
-	const size_t ord_off = ev_off + (size_t)ev_cap * 8;
-	const size_t tot_off = ord_off + (size_t)ev_cap * 24;
-	const size_t blk_off = tot_off + 64;
-	const size_t need = blk_off + ((size_t)ntiles / annexb5::kFinT + 1) * 24;
-	r = h264gpu_ws_reserve(ctx, need);
-	if (r < 0)
-		return r;
-	CU_TRY(cudaMemsetAsync(ctx->ws, 0xff, desc_end, st));
-
-	annexb::ScanArgs a;
-	memset(&a, 0, sizeof(a));
-	a.in = d_in;
-	a.len = len;
-	a.base = base;
-	a.rbsp = d_rbsp;
-	a.ticket = (uint32_t *)ctx->ws;
-	a.ev_cursor = (uint32_t *)((uint8_t *)ctx->ws + 8);
-	a.desc = (uint64_t *)((uint8_t *)ctx->ws + 256);
-	a.evbuf = (uint64_t *)((uint8_t *)ctx->ws + ev_off);
-	a.ev_cap = ev_cap;
-	a.result = d_result;
-	a.num_tiles = (uint32_t)ntiles;
-	a.halo_left = 0xffffffffu;
-	a.right[0] = a.right[1] = 0xff;
-	int assume_in = 0;
-	if (edge != NULL) {
-		if (edge->has_left)
-			a.halo_left = 0xffffu | (uint32_t)edge->left[0] << 16 | (uint32_t)edge->left[1] << 24;
-		a.has_right = edge->has_right ? 1 : 0;
-		a.right[0] = edge->right[0];
-		a.right[1] = edge->right[1];
-		assume_in = edge->assume_in ? 1 : 0;
-	}
-	const char *trace_path = getenv("H264GPU_SCAN_TRACE");
-	uint64_t *d_trace = NULL;
-	if (trace_path != NULL) {
-		CU_TRY(cudaMalloc(&d_trace, ntiles * 64));
-		CU_TRY(cudaMemsetAsync(d_trace, 0, ntiles * 64, st));
-		a.trace = d_trace;
-	}
-#define SCAN5_LAUNCH(C, S, B)                                                                 \
-	do {                                                                                  \
-		cudaFuncSetAttribute(annexb5::scan5_kernel<C, S, B>,                          \
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
-		annexb5::scan5_kernel<C, S, B><<<(uint32_t)ntiles, annexb5::kT, 0, st>>>(a);  \
-	} while (0)
-	const bool strip5 = d_rbsp != NULL;
-	if (gen == 6) {
-		/* persistent CTAs: one wave, every CTA takes tiles by ticket */
-		int sms = 148;
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-		auto grid6 = [](uint64_t nt, int cap) { return (uint32_t)(nt < (uint64_t)cap ? nt : (uint64_t)cap); };
-		{
-			const char *e = getenv("H264GPU_SCAN6_FLAGS");
-			a.flags = e != NULL ? (uint32_t)atoi(e) : 0u;
-			if (a.flags & 1u)
-				sms = 1 << 24; /* one tile per CTA */
-		}
-		int minb = 5;
-		{
-			const char *e = getenv("H264GPU_SCAN6_CTAS");
-			if (e != NULL && (atoi(e) == 4 || atoi(e) == 3))
-				minb = atoi(e);
-		}
-#define SCAN6_LAUNCH(S, B)                                                                    \
-	do {                                                                                  \
-		cudaFuncSetAttribute(annexb6::scan6_kernel<8, S, B>,                          \
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
-		annexb6::scan6_kernel<8, S, B><<<grid6(ntiles, sms * B), annexb6::kT, 0, st>>>(a); \
-	} while (0)
-		if (piped) {
-#define SCAN6P_LAUNCH(S, T)                                                                   \
-	do {                                                                                  \
-		cudaFuncSetAttribute(annexb6::scan6p_kernel<4, S, 5, T>,                      \
-				     cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
-		annexb6::scan6p_kernel<4, S, 5, T><<<grid6(ntiles, sms * 5), annexb6::kT, 0, st>>>(a); \
-	} while (0)
-			if (a.trace != NULL && strip5) SCAN6P_LAUNCH(true, true);
-			else if (strip5) SCAN6P_LAUNCH(true, false);
-			else SCAN6P_LAUNCH(false, false);
-#undef SCAN6P_LAUNCH
-		} else if (a.trace != NULL && strip5) {
-			/* diagnostics build of the same kernel: per-tile phase timestamps */
-			cudaFuncSetAttribute(annexb6::scan6_kernel<8, true, 5, true>,
-					     cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-			annexb6::scan6_kernel<8, true, 5, true><<<grid6(ntiles, sms * 5), annexb6::kT, 0, st>>>(a);
-		} else if (minb == 5) {
-			if (strip5) SCAN6_LAUNCH(true, 5); else SCAN6_LAUNCH(false, 5);
-		} else if (minb == 4) {
-			if (strip5) SCAN6_LAUNCH(true, 4); else SCAN6_LAUNCH(false, 4);
-		} else {
-			if (strip5) SCAN6_LAUNCH(true, 3); else SCAN6_LAUNCH(false, 3);
-		}
-#undef SCAN6_LAUNCH
-	} else if (shape == 45) {
-		if (strip5) SCAN5_LAUNCH(4, true, 5); else SCAN5_LAUNCH(4, false, 5);
-	} else if (shape == 46) {
-		if (strip5) SCAN5_LAUNCH(4, true, 6); else SCAN5_LAUNCH(4, false, 6);
-	} else if (shape == 84) {
-		if (strip5) SCAN5_LAUNCH(8, true, 4); else SCAN5_LAUNCH(8, false, 4);
-	} else {
-		if (strip5) SCAN5_LAUNCH(8, true, 5); else SCAN5_LAUNCH(8, false, 5);
-	}
-#undef SCAN5_LAUNCH
-	CU_TRY(cudaGetLastError());
-
-	annexb5::FinArgs f;
-	memset(&f, 0, sizeof(f));
-	f.desc = a.desc;
-	f.num_tiles = (uint32_t)ntiles;
-	f.tile_bytes = (uint32_t)tile;
-	f.evbuf = a.evbuf;
-	f.ev_cap = ev_cap;
-	f.ordered = (uint64_t *)((uint8_t *)ctx->ws + ord_off);
-	f.tile_pre = (uint64_t *)((uint8_t *)ctx->ws + pre_off);
-	f.totals = (uint64_t *)((uint8_t *)ctx->ws + tot_off);
-	f.blk_tot = (uint64_t *)((uint8_t *)ctx->ws + blk_off);
-	f.len = len;
-	f.base = base;
-	f.nal_start = d_nal_start;
-	f.nal_end = d_nal_end;
-	f.nal_rbsp = d_nal_rbsp;
-	f.nal_rbsp_len = d_nal_rbsp_len;
-	f.nal_cap = nal_cap;
-	f.result = d_result;
-	f.has_right = a.has_right;
-	f.strip = d_rbsp != NULL ? 1 : 0;
-	f.assume_in = (uint32_t)assume_in;
-	/* the table kernel is sized for the events the workspace can hold; in the common case
-	 * (few events per NAL) most of its threads exit at once */
-	CU_TRY(annexb5::launch_finalize(f, nal_cap * 2 + 4096 < ev_cap ? nal_cap * 2 + 4096 : ev_cap, st));
-	ctx->launches += 5;
-	if (d_trace != NULL) {
-		uint64_t *h = (uint64_t *)malloc(ntiles * 64);
-		CU_TRY(cudaStreamSynchronize(st));
-		CU_TRY(cudaMemcpy(h, d_trace, ntiles * 64, cudaMemcpyDeviceToHost));
-		FILE *fp = fopen(trace_path, "wb");
-		if (fp != NULL) {
-			fwrite(h, 64, ntiles, fp);
-			fclose(fp);
-		}
-		free(h);
-		cudaFree(d_trace);
-	}
-	return 0;
+	return scan7_launch(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp, d_nal_rbsp_len,
+			    nal_cap, d_result, st);
 }
 
 /* ---- reader session: what h264_reader_parse drives -------------------------------- */
@@ -1358,32 +1144,17 @@ extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, u
 #include "annexb_frame.cuh"
 #include "annexb_frame6.cuh"
 
-/* K3 generation: 6 = frame6_kernel (persistent CTAs, units straight from the staged source tile,
- * the default), 1 = frame_kernel (A/B baseline); H264GPU_FRAME_GEN */
-static int frame_gen(void)
-{
-	static int gen = 0;
-	if (gen == 0) {
-		const char *e = getenv("H264GPU_FRAME_GEN");
-		gen = (e != NULL && atoi(e) == 1) ? 1 : 6;
-	}
-	return gen;
-}
-
 template <int ROWS>
 static cudaError_t launch_frame6(const frame::FrameArgs &a, cudaStream_t st)
 {
 	const uint32_t pthreads = 128;
 	const uint32_t pblocks = (a.num_tiles + 1 + pthreads - 1) / pthreads;
 	frame::frame_prepass<ROWS><<<pblocks, pthreads, 0, st>>>(a);
-	static int sms = 0;
-	if (sms == 0) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		if (sms <= 0)
-			sms = 148;
-	}
+	int sms = 0, dev = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (sms <= 0)
+		sms = 148;
 	/* resident CTAs per SM the 32 KiB-tile kernel is compiled for: 5 (48 registers, the default) or
 	 * 4 (64 registers); H264GPU_FRAME_CTAS */
 	static int minb = 0;
@@ -1402,27 +1173,6 @@ static cudaError_t launch_frame6(const frame::FrameArgs &a, cudaStream_t st)
 		const uint32_t cap = (uint32_t)sms * 4;
 		frame6::frame6_kernel<ROWS, 4><<<a.num_tiles < cap ? a.num_tiles : cap, frame6::kT, 0, st>>>(a);
 	}
-	return cudaGetLastError();
-}
-
-template <int ITEMS>
-static cudaError_t launch_frame(const frame::FrameArgs &a, cudaStream_t st)
-{
-	const uint32_t pthreads = 128;
-	const uint32_t pblocks = (a.num_tiles + 1 + pthreads - 1) / pthreads;
-	frame::frame_prepass<ITEMS><<<pblocks, pthreads, 0, st>>>(a);
-	/* resident CTAs per SM the kernel is compiled for (register budget): 4 (64 registers), 5 or 6 */
-	static int minb = 0;
-	if (minb == 0) {
-		const char *e = getenv("H264GPU_FRAME_CTAS");
-		minb = (e != NULL && (atoi(e) == 4 || atoi(e) == 6)) ? atoi(e) : 5;
-	}
-	if (minb == 4)
-		frame::frame_kernel<ITEMS, 4><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
-	else if (minb == 6)
-		frame::frame_kernel<ITEMS, 6><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
-	else
-		frame::frame_kernel<ITEMS, 5><<<a.num_tiles, annexb::kBlock, 0, st>>>(a);
 	return cudaGetLastError();
 }
 
@@ -1446,8 +1196,7 @@ extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const 
 	CU_TRY(cudaStreamSynchronize(st));
 	if (len && d_rbsp == NULL)
 		return -EINVAL;
-	const int gen = frame_gen();
-	const int items = ctx->scan_items >= 100 ? (gen == 6 ? 8 : 4) : ctx->scan_items;
+	const int items = ctx->scan_items;
 	const uint64_t tile = (uint64_t)annexb::kBlock * items * 16;
 	uint64_t ntiles = (len + tile - 1) / tile;
 	if (ntiles == 0)
@@ -1481,17 +1230,10 @@ extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const 
 	a.tail = (uint32_t *)((uint8_t *)ctx->ws + tail_off);
 	a.num_tiles = (uint32_t)ntiles;
 	cudaError_t ce;
-	if (gen == 6)
-		ce = items == 1 ? launch_frame6<1>(a, st)
-		   : items == 2 ? launch_frame6<2>(a, st)
-		   : items == 4 ? launch_frame6<4>(a, st)
-				: launch_frame6<8>(a, st);
-	else if (items == 1)
-		ce = launch_frame<1>(a, st);
-	else if (items == 2)
-		ce = launch_frame<2>(a, st);
-	else
-		ce = launch_frame<4>(a, st);
+	ce = items == 1 ? launch_frame6<1>(a, st)
+	   : items == 2 ? launch_frame6<2>(a, st)
+	   : items == 4 ? launch_frame6<4>(a, st)
+			: launch_frame6<8>(a, st);
 	CU_TRY(ce);
 	ctx->launches += 2;
 	return 0;

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A/B of the in-place scan kernels on one GPU: same buffer, device resident, CUDA events.
-   python scripts/scan_ab.py [--size-mb 4096] [--gens 6,7] [--steps 10]"""
+"""The in-place scan + strip kernel and the scan-only kernel on one GPU: same buffer, device
+resident, CUDA events (tuning knobs: H264GPU_SCAN7_REGIONS / _PF / _NAP).
+   python scripts/scan_ab.py [--size-mb 4096] [--steps 10]"""
 import argparse, ctypes as C, json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +11,6 @@ from bench import make_workload, SEED
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size-mb", type=int, default=4096)
-ap.add_argument("--gens", default="6,7")
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 args = ap.parse_args()
@@ -30,8 +30,7 @@ d_in.upload(stream)
 g.sync()
 out = {}
 for strip in (True, False):
-    for gen in [int(x) for x in args.gens.split(",")]:
-        os.environ["H264GPU_INPLACE_GEN"] = str(gen)
+    for gen in (7,):
         def step():
             g.split_strip_inplace_dev(d_in.ptr, n_in, d_rbsp.ptr if strip else 0, d_tab.ptr, d_tab.ptr + cap * 8,
                                       d_tab.ptr + cap * 16, d_tab.ptr + cap * 24, cap, d_res.ptr)

@@ -5,8 +5,6 @@
  */
 #include "annexb_scan.cuh"
 #include "annexb_scan2.cuh"
-#include "annexb_scan5.cuh"
-#include "annexb_scan6.cuh"
 #include "annexb_scan7.cuh"
 #include "annexb_frame.cuh"
 #include "annexb_frame6.cuh"
@@ -23,10 +21,9 @@ extern "C" int emu_split_strip(const uint8_t *in, uint64_t len, uint64_t base,
 	using namespace annexb;
 	if (len == 0)
 		return -1;
-	/* items 1xx selects the second-generation kernel with CPT = items - 100 */
-	const bool gen2 = items >= 100;
+	/* items = 16-byte chunks per thread of the packed-RBSP kernel (1, 2 or 8; 1xx accepted too) */
 	const int cpt = items % 100;
-	const uint64_t tile = gen2 ? (uint64_t)annexb2::kT * cpt * 16 : (uint64_t)kBlock * items * 16;
+	const uint64_t tile = (uint64_t)annexb2::kT * (cpt == 1 || cpt == 2 ? cpt : 8) * 16;
 	const uint32_t ntiles = (uint32_t)((len + tile - 1) / tile);
 	std::vector<uint64_t> desc((size_t)ntiles * 4, ~0ull);
 	uint32_t ticket = 0xffffffffu;
@@ -58,26 +55,15 @@ extern "C" int emu_split_strip(const uint8_t *in, uint64_t len, uint64_t base,
 		a.right[1] = edge->right[1];
 		a.init_in = edge->assume_in;
 	}
-	dim3 grid(ntiles), block(kBlock);
-	if (gen2) {
-		dim3 b2(annexb2::kT);
-		if (rbsp) {
-			if (cpt == 1) EMU_LAUNCH((annexb2::scan2_kernel<1, true>), grid, b2, a);
-			else if (cpt == 2) EMU_LAUNCH((annexb2::scan2_kernel<2, true>), grid, b2, a);
-			else EMU_LAUNCH((annexb2::scan2_kernel<8, true>), grid, b2, a);
-		} else {
-			if (cpt == 1) EMU_LAUNCH((annexb2::scan2_kernel<1, false>), grid, b2, a);
-			else if (cpt == 2) EMU_LAUNCH((annexb2::scan2_kernel<2, false>), grid, b2, a);
-			else EMU_LAUNCH((annexb2::scan2_kernel<8, false>), grid, b2, a);
-		}
-	} else if (rbsp) {
-		if (items == 1) EMU_LAUNCH((scan_kernel<1, true>), grid, block, a);
-		else if (items == 2) EMU_LAUNCH((scan_kernel<2, true>), grid, block, a);
-		else EMU_LAUNCH((scan_kernel<4, true>), grid, block, a);
+	dim3 grid(ntiles), b2(annexb2::kT);
+	if (rbsp) {
+		if (cpt == 1) EMU_LAUNCH((annexb2::scan2_kernel<1, true>), grid, b2, a);
+		else if (cpt == 2) EMU_LAUNCH((annexb2::scan2_kernel<2, true>), grid, b2, a);
+		else EMU_LAUNCH((annexb2::scan2_kernel<8, true>), grid, b2, a);
 	} else {
-		if (items == 1) EMU_LAUNCH((scan_kernel<1, false>), grid, block, a);
-		else if (items == 2) EMU_LAUNCH((scan_kernel<2, false>), grid, block, a);
-		else EMU_LAUNCH((scan_kernel<4, false>), grid, block, a);
+		if (cpt == 1) EMU_LAUNCH((annexb2::scan2_kernel<1, false>), grid, b2, a);
+		else if (cpt == 2) EMU_LAUNCH((annexb2::scan2_kernel<2, false>), grid, b2, a);
+		else EMU_LAUNCH((annexb2::scan2_kernel<8, false>), grid, b2, a);
 	}
 	free(buf);
 	return 0;
@@ -255,126 +241,22 @@ extern "C" int emu_avcc(uint8_t *data, uint64_t len, uint64_t ev_cap, uint64_t *
 	return 0;
 }
 
-/* gen 5: in-place RBSP (annexb_scan5.cuh).  cpt = 16-byte chunks per thread (1, 2 or 8). */
+/* in-place RBSP (annexb_scan7.cuh): cpt % 10 = 512-byte rows per span (1, 2, 6 or 8) */
 extern "C" int emu_split_strip_inplace(const uint8_t *in, uint64_t len, uint64_t base,
 				       const struct h264gpu_shard_edge *edge, uint8_t *rbsp,
 				       uint64_t *nal_start, uint64_t *nal_end, uint64_t *nal_rbsp,
 				       uint64_t *nal_rbsp_len, uint64_t nal_cap,
 				       struct h264gpu_scan_result *result, int cpt, uint64_t ev_cap)
 {
-	using namespace annexb;
 	if (len == 0)
 		return -1;
-	/* cpt 6x selects the sixth-generation kernel with x 512-byte rows per warp, 7x its pipelined
-	 * form (two tiles per CTA in flight) */
-	const bool gen6 = cpt >= 60;
-	const bool piped = cpt >= 70;
-	const int rows = cpt % 10;
-	const uint64_t tile = gen6 ? (uint64_t)annexb6::kT * rows * 16 : (uint64_t)annexb5::kT * cpt * 16;
-	const uint32_t ntiles = (uint32_t)(((gen6 ? len + 2 : len) + tile - 1) / tile);
-	std::vector<uint64_t> desc((size_t)ntiles * 4, ~0ull), pre((size_t)ntiles * 2, 0);
-	std::vector<uint64_t> evbuf(ev_cap ? ev_cap : 1, 0), ordered(3 * (ev_cap ? ev_cap : 1), 0);
-	uint64_t totals[4] = {0, 0, 0, 0};
-	std::vector<uint64_t> blk_tot(3 * ((size_t)ntiles / annexb5::kFinT + 1), 0);
-	uint32_t ctrl[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
 	memset(result, 0xff, sizeof(*result));
 	uint8_t *buf = (uint8_t *)aligned_alloc(16, (len + 15) & ~15ull);
 	memcpy(buf, in, len);
-	if (cpt >= 80) {
-		const int rc = emu_scan7(buf, len, base, edge, rbsp, nal_start, nal_end, nal_rbsp, nal_rbsp_len,
-					 nal_cap, result, cpt % 10, ev_cap);
-		free(buf);
-		return rc;
-	}
-	ScanArgs a;
-	memset(&a, 0, sizeof(a));
-	a.in = buf;
-	a.len = len;
-	a.base = base;
-	a.rbsp = rbsp;
-	a.desc = desc.data();
-	a.ticket = &ctrl[0];
-	a.ev_cursor = &ctrl[2];
-	a.evbuf = evbuf.data();
-	a.ev_cap = ev_cap;
-	a.result = result;
-	a.num_tiles = ntiles;
-	a.halo_left = 0xffffffffu;
-	a.right[0] = a.right[1] = 0xff;
-	int assume_in = 0;
-	if (edge) {
-		if (edge->has_left)
-			a.halo_left = 0xffffu | (uint32_t)edge->left[0] << 16 | (uint32_t)edge->left[1] << 24;
-		a.has_right = edge->has_right;
-		a.right[0] = edge->right[0];
-		a.right[1] = edge->right[1];
-		assume_in = edge->assume_in;
-	}
-	dim3 grid(ntiles), block(annexb5::kT);
-	if (gen6) {
-		/* persistent CTAs: a few of them share the tiles (the emulator runs them one after
-		 * the other, so the first takes every ticket and the others find none) */
-		grid = dim3(ntiles < 3 ? ntiles : 3);
-		if (piped) {
-			if (rbsp) {
-				if (rows == 1) EMU_LAUNCH((annexb6::scan6p_kernel<1, true, 1>), grid, block, a);
-				else if (rows == 2) EMU_LAUNCH((annexb6::scan6p_kernel<2, true, 1>), grid, block, a);
-				else EMU_LAUNCH((annexb6::scan6p_kernel<4, true, 1>), grid, block, a);
-			} else {
-				if (rows == 1) EMU_LAUNCH((annexb6::scan6p_kernel<1, false, 1>), grid, block, a);
-				else if (rows == 2) EMU_LAUNCH((annexb6::scan6p_kernel<2, false, 1>), grid, block, a);
-				else EMU_LAUNCH((annexb6::scan6p_kernel<4, false, 1>), grid, block, a);
-			}
-		} else if (rbsp) {
-			if (rows == 1) EMU_LAUNCH((annexb6::scan6_kernel<1, true, 1>), grid, block, a);
-			else if (rows == 2) EMU_LAUNCH((annexb6::scan6_kernel<2, true, 1>), grid, block, a);
-			else EMU_LAUNCH((annexb6::scan6_kernel<8, true, 1>), grid, block, a);
-		} else {
-			if (rows == 1) EMU_LAUNCH((annexb6::scan6_kernel<1, false, 1>), grid, block, a);
-			else if (rows == 2) EMU_LAUNCH((annexb6::scan6_kernel<2, false, 1>), grid, block, a);
-			else EMU_LAUNCH((annexb6::scan6_kernel<8, false, 1>), grid, block, a);
-		}
-	} else if (rbsp) {
-		if (cpt == 1) EMU_LAUNCH((annexb5::scan5_kernel<1, true, 1>), grid, block, a);
-		else if (cpt == 2) EMU_LAUNCH((annexb5::scan5_kernel<2, true, 1>), grid, block, a);
-		else EMU_LAUNCH((annexb5::scan5_kernel<8, true, 1>), grid, block, a);
-	} else {
-		if (cpt == 1) EMU_LAUNCH((annexb5::scan5_kernel<1, false, 1>), grid, block, a);
-		else if (cpt == 2) EMU_LAUNCH((annexb5::scan5_kernel<2, false, 1>), grid, block, a);
-		else EMU_LAUNCH((annexb5::scan5_kernel<8, false, 1>), grid, block, a);
-	}
-	annexb5::FinArgs f;
-	memset(&f, 0, sizeof(f));
-	f.desc = desc.data();
-	f.num_tiles = ntiles;
-	f.tile_bytes = (uint32_t)tile;
-	f.evbuf = evbuf.data();
-	f.ev_cap = ev_cap;
-	f.ordered = ordered.data();
-	f.tile_pre = pre.data();
-	f.totals = totals;
-	f.blk_tot = blk_tot.data();
-	f.len = len;
-	f.base = base;
-	f.nal_start = nal_start;
-	f.nal_end = nal_end;
-	f.nal_rbsp = nal_rbsp;
-	f.nal_rbsp_len = nal_rbsp_len;
-	f.nal_cap = nal_cap;
-	f.result = result;
-	f.has_right = a.has_right;
-	f.strip = rbsp ? 1 : 0;
-	f.assume_in = (uint32_t)assume_in;
-	dim3 g1(1), b1(annexb5::kFinT), b256(256), one(1);
-	dim3 gft((ntiles + annexb5::kFinT - 1) / annexb5::kFinT);
-	EMU_LAUNCH((annexb5::fin_tiles), gft, b1, f);
-	dim3 gt((ntiles + 255) / 256);
-	EMU_LAUNCH((annexb5::fin_order), gt, b256, f);
-	EMU_LAUNCH((annexb5::fin_head), g1, one, f);
-	dim3 ge((uint32_t)((ev_cap + 255) / 256 ? (ev_cap + 255) / 256 : 1));
-	EMU_LAUNCH((annexb5::fin_table), ge, b256, f);
+	const int rc = emu_scan7(buf, len, base, edge, rbsp, nal_start, nal_end, nal_rbsp, nal_rbsp_len, nal_cap,
+				 result, cpt % 10, ev_cap);
 	free(buf);
-	return 0;
+	return rc;
 }
 
 extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off, uint64_t n,
@@ -382,9 +264,8 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 			 uint64_t *total, int items)
 {
 	using namespace frame;
-	/* items 1/2/4: frame_kernel; 61/62/64/68: frame6_kernel with 1/2/4/8 rows per warp */
-	const bool gen6 = items > 60;
-	if (gen6)
+	/* items (or 60 + items): frame6_kernel with 1/2/4/8 rows per warp */
+	if (items > 60)
 		items -= 60;
 	const uint64_t tile = (uint64_t)kBlock * items * 16;
 	uint32_t ntiles = (uint32_t)((len + tile - 1) / tile);
@@ -411,32 +292,21 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 	a.first = first.data();
 	a.tail = tail.data();
 	a.num_tiles = ntiles;
-	dim3 pgrid((ntiles + 1 + 127) / 128), pblock(128), grid(ntiles), block(kBlock);
-	if (gen6) {
-		/* persistent CTAs: a few of them share the tiles */
-		dim3 g6(ntiles < 3 ? ntiles : 3);
-		if (items == 1) {
-			EMU_LAUNCH((frame_prepass<1>), pgrid, pblock, a);
-			EMU_LAUNCH((frame6::frame6_kernel<1, 1>), g6, block, a);
-		} else if (items == 2) {
-			EMU_LAUNCH((frame_prepass<2>), pgrid, pblock, a);
-			EMU_LAUNCH((frame6::frame6_kernel<2, 1>), g6, block, a);
-		} else if (items == 4) {
-			EMU_LAUNCH((frame_prepass<4>), pgrid, pblock, a);
-			EMU_LAUNCH((frame6::frame6_kernel<4, 1>), g6, block, a);
-		} else {
-			EMU_LAUNCH((frame_prepass<8>), pgrid, pblock, a);
-			EMU_LAUNCH((frame6::frame6_kernel<8, 1>), g6, block, a);
-		}
-	} else if (items == 1) {
+	dim3 pgrid((ntiles + 1 + 127) / 128), pblock(128), block(kBlock);
+	/* persistent CTAs: a few of them share the tiles */
+	dim3 g6(ntiles < 3 ? ntiles : 3);
+	if (items == 1) {
 		EMU_LAUNCH((frame_prepass<1>), pgrid, pblock, a);
-		EMU_LAUNCH((frame_kernel<1>), grid, block, a);
+		EMU_LAUNCH((frame6::frame6_kernel<1, 1>), g6, block, a);
 	} else if (items == 2) {
 		EMU_LAUNCH((frame_prepass<2>), pgrid, pblock, a);
-		EMU_LAUNCH((frame_kernel<2>), grid, block, a);
-	} else {
+		EMU_LAUNCH((frame6::frame6_kernel<2, 1>), g6, block, a);
+	} else if (items == 4) {
 		EMU_LAUNCH((frame_prepass<4>), pgrid, pblock, a);
-		EMU_LAUNCH((frame_kernel<4>), grid, block, a);
+		EMU_LAUNCH((frame6::frame6_kernel<4, 1>), g6, block, a);
+	} else {
+		EMU_LAUNCH((frame_prepass<8>), pgrid, pblock, a);
+		EMU_LAUNCH((frame6::frame6_kernel<8, 1>), g6, block, a);
 	}
 	free(buf);
 	return 0;
