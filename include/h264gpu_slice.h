@@ -135,6 +135,22 @@ H264GPU_API int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_strea
 					struct h264gpu_slice_result *d_results,
 					void *stream);
 
+/*
+ * The same parse with FULL per-macroblock records: d_syntax[i] (struct h264_mb_syntax,
+ * include/h264gpu_mb_syntax.h, 3108 bytes) receives every syntax element of the macroblock of
+ * d_records[i] -- what the reference keeps in its private ctx->mb (src/h264_macroblock.h:105-167)
+ * and walks in its dump (src/h264_dump.c:295-316): raw types, prediction modes, ref_idx, mvd,
+ * cbp, qp delta, DC / AC / 4x4 levels, I_PCM samples.  d_syntax = NULL: records only.
+ */
+struct h264_mb_syntax;
+H264GPU_API int h264gpu_cavlc_parse_full_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
+					     uint64_t stream_len,
+					     const struct h264gpu_slice_params *d_params,
+					     uint32_t n_slices,
+					     struct h264gpu_mb_record *d_records,
+					     struct h264gpu_slice_result *d_results,
+					     struct h264_mb_syntax *d_syntax, void *stream);
+
 /* Host-buffer form: uploads the stream and parameter blocks, runs the kernel,
  * downloads records and results.  Synchronous. */
 H264GPU_API int h264gpu_cavlc_parse_host(h264gpu_ctx *ctx, const uint8_t *h_stream,

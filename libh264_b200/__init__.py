@@ -73,7 +73,7 @@ assert SLICE_PARAMS.itemsize == C.sizeof(SliceParams) == 56
 SLICE_SYMBOLS = ["h264gpu_cavlc_parse_dev", "h264gpu_cavlc_parse_host",
                  "h264gpu_cabac_parse_dev", "h264gpu_cabac_parse_host",
                  "h264gpu_reader_parse_cavlc", "h264gpu_reader_parse_cabac",
-                 "h264gpu_reader_parse_slices"]
+                 "h264gpu_reader_parse_slices", "h264gpu_cavlc_parse_full_dev"]
 
 # every symbol include/h264gpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = [

@@ -32,6 +32,7 @@
 
 #include "gpu_compat.h"
 #include "h264gpu_slice.h"
+#include "h264gpu_mb_syntax.h"
 
 #ifdef H264_EMU
 #define CAVLC_TAB static const
@@ -284,10 +285,41 @@ struct SliceCtx {
 	uint8_t nz[48];    /* current macroblock */
 	bool availA, availB;
 	uint64_t hash;
+	h264_mb_syntax *syn; /* full record of the current macroblock, or NULL */
 };
+
+/* the element's place in the full record (same indexing as the checksum fields) */
+__device__ __noinline__ void syn_store(h264_mb_syntax *o, uint32_t field, uint32_t idx, int64_t v)
+{
+	switch (field) {
+	case H264GPU_F_RAW_MB_TYPE: o->raw_mb_type = (uint32_t)v; break;
+	case H264GPU_F_TRANSFORM_8X8: o->transform_size_8x8_flag = (uint8_t)v; break;
+	case H264GPU_F_MB_QP_DELTA: o->mb_qp_delta = (int32_t)v; break;
+	case H264GPU_F_CBP_LUMA: o->cbp_luma = (uint8_t)v; break;
+	case H264GPU_F_CBP_CHROMA: o->cbp_chroma = (uint8_t)v; break;
+	case H264GPU_F_INTRA_CHROMA_PRED_MODE: o->intra_chroma_pred_mode = (uint8_t)v; break;
+	case H264GPU_F_INTRA4X4_PRED_MODE: o->intra4x4_pred_mode[idx & 15] = (int8_t)v; break;
+	case H264GPU_F_INTRA8X8_PRED_MODE: o->intra8x8_pred_mode[idx & 3] = (int8_t)v; break;
+	case H264GPU_F_REF_IDX_L0: o->ref_idx[0][idx & 3] = (uint8_t)v; break;
+	case H264GPU_F_REF_IDX_L1: o->ref_idx[1][idx & 3] = (uint8_t)v; break;
+	case H264GPU_F_MVD_L0: o->mvd[0][(idx >> 1) & 15][idx & 1] = (int16_t)v; break;
+	case H264GPU_F_MVD_L1: o->mvd[1][(idx >> 1) & 15][idx & 1] = (int16_t)v; break;
+	case H264GPU_F_RAW_SUB_MB_TYPE: o->raw_sub_mb_type[idx & 3] = (uint32_t)v; break;
+	case H264GPU_F_I16_DC: o->dc16[idx & 15] = (int16_t)v; break;
+	case H264GPU_F_I16_AC: o->ac16[(idx >> 4) & 15][idx & 15] = (int16_t)v; break;
+	case H264GPU_F_LEVEL4X4: o->l4[(idx >> 4) & 15][idx & 15] = (int16_t)v; break;
+	case H264GPU_F_CHROMA_DC: o->cdc[(idx >> 4) & 1][idx & 15] = (int16_t)v; break;
+	case H264GPU_F_CHROMA_AC: o->cac[(idx >> 8) & 1][(idx >> 4) & 15][idx & 15] = (int16_t)v; break;
+	case H264GPU_F_PCM_LUMA: o->pcm[idx & 255] = (uint8_t)v; break;
+	case H264GPU_F_PCM_CHROMA: o->pcm[256 + (idx & 511)] = (uint8_t)v; break;
+	default: break; /* CBP (derived), I16 pred mode (in raw_mb_type), Cb / Cr of 4:4:4: not in the record */
+	}
+}
 
 __device__ __forceinline__ void hash_add(SliceCtx &s, uint32_t field, uint32_t idx, int64_t v)
 {
+	if (s.syn != nullptr && v != 0)
+		syn_store(s.syn, field, idx, v);
 	/* device-side twin of h264gpu_mb_hash_term (include/h264gpu_slice.h) */
 	if (v != 0) {
 		const uint64_t key = ((uint64_t)field << 16) | idx;
@@ -788,18 +820,31 @@ __device__ __forceinline__ bool macroblock_layer(SliceCtx &s, uint32_t &mb_type_
 struct SliceRun {
 	SliceCtx s;
 	h264gpu_mb_record *rec;
+	h264_mb_syntax *syn_base; /* full records, same indexing as rec, or NULL */
 	uint32_t pic_size, first, cur, count, mb_type;
 	int status;
 	bool inter, done, i16;
 };
 
+__device__ __forceinline__ void syn_open(h264_mb_syntax *o, uint32_t mb_addr, uint32_t mb_type)
+{
+	uint32_t *w = (uint32_t *)o;
+	for (uint32_t i = 0; i < (uint32_t)sizeof(*o) / 4; i++)
+		w[i] = 0;
+	o->mb_addr = mb_addr;
+	o->mb_type = mb_type;
+}
+
 __device__ __forceinline__ void slice_begin(SliceRun &r, const uint8_t *stream, uint64_t stream_len,
-					     const h264gpu_slice_params &sp, uint8_t *ring, h264gpu_mb_record *rec)
+					     const h264gpu_slice_params &sp, uint8_t *ring, h264gpu_mb_record *rec,
+					     h264_mb_syntax *syn = nullptr)
 {
 	r.status = 0;
 	r.count = 0;
 	r.done = true;
 	r.rec = rec;
+	r.syn_base = syn;
+	r.s.syn = nullptr;
 	r.s.sp = &sp;
 	r.s.br.p = stream;
 	r.s.br.len = r.s.br.pos = 0;
@@ -857,6 +902,8 @@ __device__ __forceinline__ uint64_t mb_begin(SliceRun &r)
 			r.rec[r.count].mb_addr = r.cur;
 			r.rec[r.count].mb_type = sp.slice_type == ST_B ? MB_B_SKIP : MB_P_SKIP;
 			r.rec[r.count].hash = 0;
+			if (r.syn_base)
+				syn_open(r.syn_base + r.count, r.cur, sp.slice_type == ST_B ? MB_B_SKIP : MB_P_SKIP);
 			r.count++;
 			r.cur++;
 		}
@@ -876,6 +923,9 @@ __device__ __forceinline__ uint64_t mb_begin(SliceRun &r)
 	for (int k = 0; k < 48; k++)
 		s.nz[k] = 0;
 	s.hash = 0;
+	s.syn = r.syn_base ? r.syn_base + r.count : nullptr;
+	if (s.syn)
+		syn_open(s.syn, r.cur, 0);
 	r.mb_type = MB_UNKNOWN;
 	uint64_t slots = 0;
 	if (!macroblock_layer(s, r.mb_type, slots, r.i16)) {
@@ -901,6 +951,8 @@ __device__ __forceinline__ void mb_end(SliceRun &r)
 	r.rec[r.count].mb_addr = r.cur;
 	r.rec[r.count].mb_type = r.mb_type;
 	r.rec[r.count].hash = s.hash;
+	if (s.syn)
+		s.syn->mb_type = r.mb_type;
 	r.count++;
 	r.cur++;
 	if (!br_more_rbsp_data(s.br))
@@ -917,10 +969,10 @@ __device__ __forceinline__ void slice_end(const SliceRun &r, h264gpu_slice_resul
 /* the serial form (emulator harness, one slice per call) */
 __device__ __forceinline__ void parse_slice(const uint8_t *stream, uint64_t stream_len,
 					     const h264gpu_slice_params &sp, uint8_t *ring, h264gpu_mb_record *rec,
-					     h264gpu_slice_result &res)
+					     h264gpu_slice_result &res, h264_mb_syntax *syn = nullptr)
 {
 	SliceRun r;
-	slice_begin(r, stream, stream_len, sp, ring, rec);
+	slice_begin(r, stream, stream_len, sp, ring, rec, syn);
 	while (!r.done) {
 		uint64_t slots = mb_begin(r);
 		if (r.done)
@@ -946,6 +998,7 @@ struct CavlcArgs {
 	uint64_t ring_stride;
 	uint32_t ring_w; /* widest picture (in MBs) a ring slot row can hold */
 	uint32_t lanes_log2; /* log2 of the slices carried by one warp (0..5) */
+	h264_mb_syntax *syntax; /* full records (index = record index), or NULL */
 };
 
 /*
@@ -976,7 +1029,7 @@ __global__ void __launch_bounds__(128) cavlc_parse_kernel(const CavlcArgs a)
 			r.status = -7; /* -E2BIG */
 		else
 			slice_begin(r, a.stream, a.stream_len, sp, a.ring + (uint64_t)i * a.ring_stride,
-				    a.records + sp.mb_out_off);
+				    a.records + sp.mb_out_off, a.syntax ? a.syntax + sp.mb_out_off : nullptr);
 	}
 	while (__any_sync(FULL_MASK, !r.done)) {
 		uint64_t slots = 0;

@@ -13,6 +13,15 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 				       uint32_t n_slices, struct h264gpu_mb_record *d_records,
 				       struct h264gpu_slice_result *d_results, void *stream)
 {
+	return h264gpu_cavlc_parse_full_dev(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, NULL,
+					    stream);
+}
+
+extern "C" int h264gpu_cavlc_parse_full_dev(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_t stream_len,
+					    const struct h264gpu_slice_params *d_params, uint32_t n_slices,
+					    struct h264gpu_mb_record *d_records, struct h264gpu_slice_result *d_results,
+					    struct h264_mb_syntax *d_syntax, void *stream)
+{
 	int r = h264gpu_use(ctx);
 	if (r < 0)
 		return r;
@@ -39,6 +48,7 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	a.ring = (uint8_t *)ctx->ws;
 	a.ring_stride = ring_stride;
 	a.ring_w = ring_w;
+	a.syntax = d_syntax;
 	/* Slices per warp.  Slices diverge completely, so a warp runs its lanes one after the
 	 * other: one slice per warp is best while the warps fit the machine, and lanes are packed
 	 * only beyond ~32 warps per SM (measured, profiles/r01_slice_lane_packing.txt: 4000 slices

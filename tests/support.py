@@ -345,6 +345,21 @@ def emu_split_strip_inplace(buf, strip=True, cpt=8, edge=None, base=0, ev_cap=No
                 nal_rbsp=per_nal, body=body, res=res)
 
 
+def emu_cavlc_parse_full(stream, params, n_records):
+    """The CAVLC parse with full per-macroblock records (struct h264_mb_syntax blobs)."""
+    lib = emu()
+    lib.emu_cavlc_parse_full.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
+    sz = ref().ref_sizeof_mb_syntax()
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    n = len(params) // PARAMS_SIZE
+    recs = np.zeros(max(n_records, 1), MB_RECORD)
+    res = np.zeros(max(n, 1), SLICE_RESULT)
+    syn = np.full((max(n_records, 1), sz), 0xEE, np.uint8)
+    lib.emu_cavlc_parse_full(ptr(stream), len(stream), ptr(params), n, ptr(recs), ptr(res), ptr(syn))
+    return recs[:n_records], res[:n], syn[:n_records]
+
+
 def emu_cavlc_parse(stream, params, n_records):
     lib = emu()
     lib.emu_cavlc_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]

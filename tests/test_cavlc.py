@@ -110,3 +110,51 @@ def test_gpu_parse_many_slices_vs_reference(gpu):
     recs, res = gpu.cavlc_parse_host(stream, S.slice_params_from_trace(ev), nmb)
     assert (res["status"] == 0).all() and int(res["mb_count"].sum()) == nmb
     assert np.array_equal(recs, mbs)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_emu_full_records_match_the_reference_ctx_mb(name):
+    """N2: the full per-macroblock record (struct h264_mb_syntax) the kernel writes is, byte for
+    byte, what the reference holds in its private ctx->mb for the same macroblock
+    (src/h264_macroblock.h:105-167; dumped by oracle/ref_harness.c mb_syntax_from_ref)."""
+    stream, nmb, nsl = L.synth_video(**CASES[name])
+    ev, mbs, syn = S.ref_trace_syntax(stream)
+    recs, res, got = S.emu_cavlc_parse_full(stream, S.slice_params_from_trace(ev), nmb)
+    assert (res["status"] == 0).all() and len(syn) == nmb
+    assert np.array_equal(recs["hash"], mbs["hash"])
+    if CASES[name].get("chroma_format_idc", 1) == 3:
+        return  # the record has no room for the Cb / Cr planes of 4:4:4 (checksum only)
+    bad = np.nonzero((got != syn).any(axis=1))[0]
+    assert len(bad) == 0, (name, bad[:5], np.nonzero(got[bad[0]] != syn[bad[0]])[0][:10])
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_gpu_full_records_match_the_reference_ctx_mb(gpu):
+    import ctypes as C
+    cfg = dict(frames=6, width_mbs=40, height_mbs=30, slices_per_frame=5, profile_idc=100, transform_8x8=1,
+               b_frames=1, num_ref_frames=2, idr_period=4, pct_skip=20, coef_density=60, seed=12)
+    stream, nmb, nsl = L.synth_video(**cfg)
+    ev, mbs, syn = S.ref_trace_syntax(stream)
+    params = S.slice_params_from_trace(ev)
+    sz = syn.shape[1]
+    d_s = gpu.alloc(len(stream) + 64)
+    d_s.upload(stream)
+    d_p = gpu.alloc(len(params))
+    d_p.upload(params)
+    d_r, d_q, d_y = gpu.alloc(nmb * 16 + 16), gpu.alloc(nsl * 16), gpu.alloc(nmb * sz + 16)
+    d_y.upload(np.full(nmb * sz, 0xEE, np.uint8))
+    try:
+        L._check(gpu.lib.h264gpu_cavlc_parse_full_dev(gpu.h, C.c_void_p(d_s.ptr), C.c_uint64(len(stream)), C.c_void_p(d_p.ptr),
+                                                      C.c_uint32(nsl), C.c_void_p(d_r.ptr), C.c_void_p(d_q.ptr),
+                                                      C.c_void_p(d_y.ptr), None), "h264gpu_cavlc_parse_full_dev")
+        gpu.sync()
+        got = d_y.download(nmb * sz).reshape(nmb, sz)
+        res = d_q.download(dtype=np.uint8).view(L.SLICE_RESULT)
+    finally:
+        for d in (d_s, d_p, d_r, d_q, d_y):
+            d.free()
+    assert (res["status"] == 0).all()
+    bad = np.nonzero((got != syn).any(axis=1))[0]
+    assert len(bad) == 0, (bad[:5],)
