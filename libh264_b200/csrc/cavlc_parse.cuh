@@ -27,8 +27,14 @@
  * the order-independent checksum of every decoded syntax element
  * (include/h264gpu_slice.h).
  */
-#ifndef CAVLC_PARSE_CUH
-#define CAVLC_PARSE_CUH
+/*
+ * The body below is compiled once per namespace: CAVLC_NS = cavlc with CAVLC_FULL 0 (the
+ * default kernel: no trace of the full-record path in its code) and, when the includer asks
+ * for it by including this file again with CAVLC_NS = cavlc_full and CAVLC_FULL 1, the
+ * variant that also fills struct h264_mb_syntax records.
+ */
+#ifndef CAVLC_PARSE_PRELUDE
+#define CAVLC_PARSE_PRELUDE
 
 #include "gpu_compat.h"
 #include "h264gpu_slice.h"
@@ -51,7 +57,14 @@
 #define ENOBUFS 105
 #endif
 
-namespace cavlc {
+#endif /* CAVLC_PARSE_PRELUDE */
+
+#ifndef CAVLC_NS
+#define CAVLC_NS cavlc
+#define CAVLC_FULL 0
+#endif
+
+namespace CAVLC_NS {
 
 /* enum h264_mb_type values (include/h264/h264_types.h:70-90) */
 enum {
@@ -288,6 +301,7 @@ struct SliceCtx {
 	h264_mb_syntax *syn; /* full record of the current macroblock, or NULL */
 };
 
+#if CAVLC_FULL
 /* the element's place in the full record (same indexing as the checksum fields) */
 __device__ __noinline__ void syn_store(h264_mb_syntax *o, uint32_t field, uint32_t idx, int64_t v)
 {
@@ -315,11 +329,14 @@ __device__ __noinline__ void syn_store(h264_mb_syntax *o, uint32_t field, uint32
 	default: break; /* CBP (derived), I16 pred mode (in raw_mb_type), Cb / Cr of 4:4:4: not in the record */
 	}
 }
+#endif
 
 __device__ __forceinline__ void hash_add(SliceCtx &s, uint32_t field, uint32_t idx, int64_t v)
 {
+#if CAVLC_FULL
 	if (s.syn != nullptr && v != 0)
 		syn_store(s.syn, field, idx, v);
+#endif
 	/* device-side twin of h264gpu_mb_hash_term (include/h264gpu_slice.h) */
 	if (v != 0) {
 		const uint64_t key = ((uint64_t)field << 16) | idx;
@@ -902,7 +919,7 @@ __device__ __forceinline__ uint64_t mb_begin(SliceRun &r)
 			r.rec[r.count].mb_addr = r.cur;
 			r.rec[r.count].mb_type = sp.slice_type == ST_B ? MB_B_SKIP : MB_P_SKIP;
 			r.rec[r.count].hash = 0;
-			if (r.syn_base)
+			if (CAVLC_FULL && r.syn_base)
 				syn_open(r.syn_base + r.count, r.cur, sp.slice_type == ST_B ? MB_B_SKIP : MB_P_SKIP);
 			r.count++;
 			r.cur++;
@@ -923,8 +940,8 @@ __device__ __forceinline__ uint64_t mb_begin(SliceRun &r)
 	for (int k = 0; k < 48; k++)
 		s.nz[k] = 0;
 	s.hash = 0;
-	s.syn = r.syn_base ? r.syn_base + r.count : nullptr;
-	if (s.syn)
+	s.syn = CAVLC_FULL && r.syn_base ? r.syn_base + r.count : nullptr;
+	if (CAVLC_FULL && s.syn)
 		syn_open(s.syn, r.cur, 0);
 	r.mb_type = MB_UNKNOWN;
 	uint64_t slots = 0;
@@ -951,7 +968,7 @@ __device__ __forceinline__ void mb_end(SliceRun &r)
 	r.rec[r.count].mb_addr = r.cur;
 	r.rec[r.count].mb_type = r.mb_type;
 	r.rec[r.count].hash = s.hash;
-	if (s.syn)
+	if (CAVLC_FULL && s.syn)
 		s.syn->mb_type = r.mb_type;
 	r.count++;
 	r.cur++;
@@ -1050,6 +1067,7 @@ __global__ void __launch_bounds__(128) cavlc_parse_kernel(const CavlcArgs a)
 	}
 }
 
-} /* namespace cavlc */
+} /* namespace CAVLC_NS */
 
-#endif /* CAVLC_PARSE_CUH */
+#undef CAVLC_NS
+#undef CAVLC_FULL

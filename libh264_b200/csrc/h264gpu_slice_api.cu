@@ -5,6 +5,9 @@
 #include "h264gpu_internal.h"
 
 #include "cavlc_parse.cuh"
+#define CAVLC_NS cavlc_full
+#define CAVLC_FULL 1
+#include "cavlc_parse.cuh" /* the same parse with struct h264_mb_syntax records (opt-in entry point) */
 #include "cabac_parse.cuh"
 
 extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
@@ -67,7 +70,14 @@ extern "C" int h264gpu_cavlc_parse_full_dev(h264gpu_ctx *ctx, const uint8_t *d_s
 	const uint32_t threads = 128; /* 4 warps per block */
 	const uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
 	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
-	cavlc::cavlc_parse_kernel<<<blocks, threads, 0, st>>>(a);
+	if (d_syntax == NULL) {
+		cavlc::cavlc_parse_kernel<<<blocks, threads, 0, st>>>(a);
+	} else {
+		cavlc_full::CavlcArgs f;
+		static_assert(sizeof(f) == sizeof(a), "same argument block in both instantiations");
+		memcpy(&f, &a, sizeof(f));
+		cavlc_full::cavlc_parse_kernel<<<blocks, threads, 0, st>>>(f);
+	}
 	CU_TRY(cudaGetLastError());
 	ctx->launches++;
 	return 0;

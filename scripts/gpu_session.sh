@@ -39,3 +39,6 @@ out = {"kernel": "annexb7::scan7_kernel<8> (main pass + second pass of one step)
 json.dump(out, open("gpurun_out/${TAG}_traffic.json", "w"), indent=1)
 print(out)
 PY
+echo "== CAVLC / CABAC parse at 16000 slices vs slices per warp"
+timeout 600 python scripts/bench_parse.py --cabac 0 --frames 1000 --lanes auto,2,3,5 2>&1 | tee gpurun_out/${TAG}_parse_cavlc.log
+timeout 600 python scripts/bench_parse.py --cabac 1 --frames 250 --lanes auto,0,2 2>&1 | tee gpurun_out/${TAG}_parse_cabac.log

@@ -314,6 +314,9 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 
 /* K4: the per-slice parse is plain serial code, so the emulation is a host loop */
 #include "cavlc_parse.cuh"
+#define CAVLC_NS cavlc_full
+#define CAVLC_FULL 1
+#include "cavlc_parse.cuh"
 
 extern "C" int emu_cavlc_parse_full(const uint8_t *stream, uint64_t stream_len,
 				    const struct h264gpu_slice_params *params, uint32_t n_slices,
@@ -323,8 +326,8 @@ extern "C" int emu_cavlc_parse_full(const uint8_t *stream, uint64_t stream_len,
 	for (uint32_t i = 0; i < n_slices; i++) {
 		const h264gpu_slice_params &sp = params[i];
 		std::vector<uint8_t> ring(((size_t)sp.pic_width_in_mbs + 1) * 48 + 64, 0xEE);
-		cavlc::parse_slice(stream, stream_len, sp, ring.data(), records + sp.mb_out_off, results[i],
-				   syn ? syn + sp.mb_out_off : nullptr);
+		cavlc_full::parse_slice(stream, stream_len, sp, ring.data(), records + sp.mb_out_off, results[i],
+					syn ? syn + sp.mb_out_off : nullptr);
 	}
 	return 0;
 }
