@@ -69,6 +69,10 @@ H264_API int h264_ctx_is_nalu_unknown(struct h264_ctx *ctx);
 H264_API int h264_ctx_set_aud(struct h264_ctx *ctx, const struct h264_aud *aud);
 H264_API int h264_ctx_set_sps(struct h264_ctx *ctx, const struct h264_sps *sps);
 H264_API int h264_ctx_set_pps(struct h264_ctx *ctx, const struct h264_pps *pps);
+/* Extension of this library (not in the reference, which keeps the map private in ctx->slice):
+ * the macroblock -> slice group map (8.2.2) of the slice whose header is current, one byte per
+ * macroblock.  Returns PicSizeInMbs, or a negative errno. */
+H264_API int h264_ctx_get_slice_group_map(const struct h264_ctx *ctx, uint8_t *map, size_t cap);
 H264_API int h264_ctx_set_filler(struct h264_ctx *ctx, size_t len);
 H264_API const struct h264_sps *h264_ctx_get_sps(struct h264_ctx *ctx);
 H264_API const struct h264_pps *h264_ctx_get_pps(struct h264_ctx *ctx);

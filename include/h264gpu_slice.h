@@ -42,7 +42,8 @@ struct h264gpu_slice_params {
 	uint32_t first_mb_in_slice;
 	uint32_t mb_out_off;   /* first record index of this slice in the record array */
 	uint32_t mb_out_cap;   /* records this slice may write */
-	uint32_t row_state_off; /* scratch offset (units of PicWidthInMbs entries) */
+	uint32_t row_state_off; /* num_slice_groups_minus1 != 0: byte offset of the slice's macroblock ->
+				   slice group map in the group map buffer (else unused) */
 	uint16_t pic_width_in_mbs;
 	uint16_t pic_height_in_mbs; /* PicHeightInMbs of the slice's picture */
 	uint8_t slice_type;         /* 0 P, 1 B, 2 I, 3 SP, 4 SI (slice_type % 5) */
@@ -124,8 +125,8 @@ static inline uint64_t h264gpu_mb_hash_term(uint32_t field, uint32_t index, int6
  *   d_params   n_slices parameter blocks
  *   d_records  record array (capacity = sum of mb_out_cap)
  *   d_results  n_slices results
- * Unsupported stream features (MBAFF, more than one slice group) give
- * status -ENOSYS for that slice; there is no CPU fallback.
+ * MBAFF slices, and slices of pictures with several slice groups parsed without their map
+ * (h264gpu_cavlc_parse_fmo_dev), give status -ENOSYS for that slice; there is no CPU fallback.
  */
 H264GPU_API int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
 					uint64_t stream_len,
@@ -150,6 +151,46 @@ H264GPU_API int h264gpu_cavlc_parse_full_dev(h264gpu_ctx *ctx, const uint8_t *d_
 					     struct h264gpu_mb_record *d_records,
 					     struct h264gpu_slice_result *d_results,
 					     struct h264_mb_syntax *d_syntax, void *stream);
+
+/*
+ * Flexible macroblock ordering (several slice groups, 8.2.2).  The reference builds the map
+ * unit -> slice group map of the picture (h264_gen_slice_group_map, src/h264_fmo.c:244-291),
+ * walks the slice with h264_next_mb_addr (:308-319) and finds neighbours through its per-slice
+ * macroblock table; the kernel needs the finished macroblock -> slice group map, one byte per
+ * macroblock, of every slice with num_slice_groups_minus1 != 0:
+ *   h264gpu_fmo_mb_map        host-side: 8.2.2.1 - 8.2.2.8 from the PPS / slice header fields
+ *   d_group_maps              the maps back to back; slice i's map starts at byte
+ *                             d_params[i].row_state_off (slices of one picture may share a map)
+ */
+struct h264gpu_fmo_desc {
+	uint32_t num_slice_groups_minus1;   /* 1..7 */
+	uint32_t slice_group_map_type;      /* 0..6 */
+	const uint32_t *run_length_minus1;  /* type 0: [num_slice_groups_minus1 + 1] */
+	const uint32_t *top_left;           /* type 2: [num_slice_groups_minus1] */
+	const uint32_t *bottom_right;
+	int slice_group_change_direction_flag; /* types 3..5 */
+	uint32_t map_units_in_slice_group0; /* types 3..5: Min(slice_group_change_cycle *
+					       SliceGroupChangeRate, PicSizeInMapUnits) */
+	const uint32_t *slice_group_id;     /* type 6: [n_slice_group_id] */
+	uint32_t n_slice_group_id;
+	uint32_t pic_width_in_mbs, pic_height_in_map_units;
+	int frame_mbs_only_flag, field_pic_flag, mbaff_frame_flag;
+	uint32_t pic_size_in_mbs;           /* bytes written to mb_map */
+};
+H264GPU_API int h264gpu_fmo_mb_map(const struct h264gpu_fmo_desc *desc, uint8_t *mb_map);
+
+H264GPU_API int h264gpu_cavlc_parse_fmo_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
+					    uint64_t stream_len,
+					    const struct h264gpu_slice_params *d_params,
+					    uint32_t n_slices,
+					    struct h264gpu_mb_record *d_records,
+					    struct h264gpu_slice_result *d_results,
+					    struct h264_mb_syntax *d_syntax, /* or NULL */
+					    const uint8_t *d_group_maps, void *stream);
+
+/* Host-buffer forms: the group maps the NEXT h264gpu_cavlc_parse_host / h264gpu_reader_parse_cavlc /
+ * h264gpu_reader_parse_slices call on this context uses (copied; forgotten after that call). */
+H264GPU_API int h264gpu_reader_set_group_maps(h264gpu_ctx *ctx, const uint8_t *h_maps, uint64_t bytes);
 
 /* Host-buffer form: uploads the stream and parameter blocks, runs the kernel,
  * downloads records and results.  Synchronous. */

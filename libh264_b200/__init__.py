@@ -73,7 +73,8 @@ assert SLICE_PARAMS.itemsize == C.sizeof(SliceParams) == 56
 SLICE_SYMBOLS = ["h264gpu_cavlc_parse_dev", "h264gpu_cavlc_parse_host",
                  "h264gpu_cabac_parse_dev", "h264gpu_cabac_parse_host",
                  "h264gpu_reader_parse_cavlc", "h264gpu_reader_parse_cabac",
-                 "h264gpu_reader_parse_slices", "h264gpu_cavlc_parse_full_dev"]
+                 "h264gpu_reader_parse_slices", "h264gpu_cavlc_parse_full_dev",
+                 "h264gpu_cavlc_parse_fmo_dev", "h264gpu_fmo_mb_map", "h264gpu_reader_set_group_maps"]
 
 # every symbol include/h264gpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = [
@@ -433,25 +434,27 @@ class VideoCfg(C.Structure):
                 ("entropy_cabac", C.c_uint32), ("pct_skip", C.c_uint32),
                 ("pct_intra_in_inter", C.c_uint32), ("pct_pcm", C.c_uint32),
                 ("coef_density", C.c_uint32), ("seed", C.c_uint64),
-                ("cabac_twin", C.c_uint32), ("reserved", C.c_uint32)]
+                ("cabac_twin", C.c_uint32), ("fmo", C.c_uint32)]
 
 
 def synth_video(width_mbs, height_mbs, frames, slices_per_frame=1, profile_idc=66, chroma_format_idc=1,
                 transform_8x8=0, idr_period=30, b_frames=0, num_ref_frames=1, pct_skip=30,
                 pct_intra_in_inter=10, pct_pcm=5, coef_density=60, seed=0x264, out=None,
-                want_params=False, entropy_cabac=0, cabac_twin=0):
+                want_params=False, entropy_cabac=0, cabac_twin=0, fmo=0):
     """Synthetic elementary stream (Annex-B), CAVLC or (entropy_cabac=1) CABAC slice data.
     Returns (stream, total_mbs, total_slices) and, with want_params, the packed
-    h264gpu_slice_params block of every slice."""
+    h264gpu_slice_params block of every slice.  fmo = slice groups | slice_group_map_type << 4
+    (CAVLC only; every group of a frame is cut into slices_per_frame slices; the parameter blocks
+    carry num_slice_groups_minus1 but no map: build it with h264gpu_fmo / the host library)."""
     lib = load_synth_lib()
     cfg = VideoCfg(width_mbs, height_mbs, frames, slices_per_frame, profile_idc, chroma_format_idc,
                    transform_8x8, idr_period, b_frames, num_ref_frames, entropy_cabac, pct_skip,
-                   pct_intra_in_inter, pct_pcm, coef_density, seed, cabac_twin, 0)
+                   pct_intra_in_inter, pct_pcm, coef_density, seed, cabac_twin, fmo)
     mbs, sl = C.c_uint64(0), C.c_uint64(0)
     if out is None:
         need = lib.synth_video(C.byref(cfg), None, 0, C.byref(mbs), C.byref(sl), None, 0)
         out = np.empty(need, np.uint8)
-    nsl = frames * max(1, slices_per_frame)
+    nsl = frames * max(1, slices_per_frame) * max(1, fmo & 15)
     params = np.zeros(nsl, SLICE_PARAMS) if want_params else None
     n = lib.synth_video(C.byref(cfg), _ptr(out), len(out), C.byref(mbs), C.byref(sl),
                         _ptr(params.view(np.uint8)) if want_params else None, nsl)

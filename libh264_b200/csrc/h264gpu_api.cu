@@ -101,6 +101,7 @@ int h264gpu_destroy(h264gpu_ctx *ctx)
 	cudaFree(ctx->rd_params.p);
 	cudaFree(ctx->rd_records.p);
 	cudaFree(ctx->rd_results.p);
+	cudaFree(ctx->rd_maps.p);
 	cudaFreeHost(ctx->rh_tab.p);
 	cudaFreeHost(ctx->rh_res.p);
 	cudaFreeHost(ctx->rh_records.p);

@@ -8,7 +8,71 @@
 #define CAVLC_NS cavlc_full
 #define CAVLC_FULL 1
 #include "cavlc_parse.cuh" /* the same parse with struct h264_mb_syntax records (opt-in entry point) */
+#include "cavlc_steps.cuh"
 #include "cabac_parse.cuh"
+
+
+/*
+ * K4, second generation (cavlc_steps.cuh): lanes pull slices from a counter; one ring of
+ * bottom-row counts per LANE ((PicWidthInMbs + 1) x 16 bytes, pictures up to 8192 luma samples
+ * wide; wider slices get -E2BIG).
+ *   H264GPU_CAVLC_LANES_LOG2  log2 of the working lanes per warp (default: by slice count)
+ *   H264GPU_CAVLC_PER_LANE    slices per lane the grid is sized for (default 1)
+ */
+static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_t stream_len,
+			      const struct h264gpu_slice_params *d_params, uint32_t n_slices,
+			      struct h264gpu_mb_record *d_records, struct h264gpu_slice_result *d_results,
+			      struct h264_mb_syntax *d_syntax, const uint8_t *d_group_maps, cudaStream_t st, int sms)
+{
+	uint32_t lanes_log2 = 0;
+	const char *env = getenv("H264GPU_CAVLC_LANES_LOG2");
+	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
+		lanes_log2 = (uint32_t)atoi(env);
+	} else {
+		/* one slice per warp while that fills the machine with warps to switch between, then
+		 * more lanes per warp: the steps of a warp's lanes share their instructions */
+		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > (uint64_t)sms * 8)
+			lanes_log2++;
+	}
+	uint32_t per_lane = 1;
+	env = getenv("H264GPU_CAVLC_PER_LANE");
+	if (env != NULL && atoi(env) >= 1 && atoi(env) <= 64)
+		per_lane = (uint32_t)atoi(env);
+	const uint64_t lanes = ((uint64_t)n_slices + per_lane - 1) / per_lane;
+	const uint32_t threads = CAVLC2_STRIDE;
+	const uint64_t warps = (lanes + (1u << lanes_log2) - 1) >> lanes_log2;
+	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
+	const uint64_t grid_lanes = ((uint64_t)blocks * threads / 32) << lanes_log2;
+	const uint32_t ring_w = 512;
+	const uint64_t ring_stride = (uint64_t)(ring_w + 1) * 16;
+	const size_t counter_off = (size_t)(grid_lanes * ring_stride);
+	int r = h264gpu_ws_reserve(ctx, counter_off + 16);
+	if (r < 0)
+		return r;
+	cavlc2::CavlcArgs a;
+	a.stream = d_stream;
+	a.stream_len = stream_len;
+	a.params = d_params;
+	a.n_slices = n_slices;
+	a.records = d_records;
+	a.results = d_results;
+	a.ring = (uint8_t *)ctx->ws;
+	a.ring_stride = ring_stride;
+	a.ring_w = ring_w;
+	a.lanes_log2 = lanes_log2;
+	a.syntax = d_syntax;
+	a.group_maps = d_group_maps;
+	a.next_slice = (uint32_t *)((uint8_t *)ctx->ws + counter_off);
+	CU_TRY(cudaMemsetAsync(a.next_slice, 0, 16, st));
+	const size_t smem = (size_t)CAVLC2_SM_WORDS * threads * 4;
+	if (d_syntax == NULL)
+		cavlc2::cavlc_steps_kernel<false><<<blocks, threads, smem, st>>>(a);
+	else
+		cavlc2::cavlc_steps_kernel<true><<<blocks, threads, smem, st>>>(a);
+	CU_TRY(cudaGetLastError());
+	ctx->launches++;
+	return 0;
+}
 
 extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
 				       uint64_t stream_len,
@@ -16,14 +80,80 @@ extern "C" int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 				       uint32_t n_slices, struct h264gpu_mb_record *d_records,
 				       struct h264gpu_slice_result *d_results, void *stream)
 {
-	return h264gpu_cavlc_parse_full_dev(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, NULL,
-					    stream);
+	return h264gpu_cavlc_parse_fmo_dev(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, NULL,
+					   NULL, stream);
 }
 
 extern "C" int h264gpu_cavlc_parse_full_dev(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_t stream_len,
 					    const struct h264gpu_slice_params *d_params, uint32_t n_slices,
 					    struct h264gpu_mb_record *d_records, struct h264gpu_slice_result *d_results,
 					    struct h264_mb_syntax *d_syntax, void *stream)
+{
+	return h264gpu_cavlc_parse_fmo_dev(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results,
+					   d_syntax, NULL, stream);
+}
+
+/* A12: 8.2.2 on the host (fmo_map.h), for callers that build the parameter blocks themselves */
+#include "fmo_map.h"
+extern "C" int h264gpu_fmo_mb_map(const struct h264gpu_fmo_desc *desc, uint8_t *mb_map)
+{
+	if (desc == NULL || mb_map == NULL || desc->pic_width_in_mbs == 0 || desc->pic_height_in_map_units == 0)
+		return -EINVAL;
+	struct fmo_desc d;
+	memset(&d, 0, sizeof(d));
+	d.num_slice_groups_minus1 = desc->num_slice_groups_minus1;
+	d.map_type = desc->slice_group_map_type;
+	d.run_length_minus1 = desc->run_length_minus1;
+	d.top_left = desc->top_left;
+	d.bottom_right = desc->bottom_right;
+	d.change_direction_flag = desc->slice_group_change_direction_flag;
+	d.map_units_in_slice_group0 = desc->map_units_in_slice_group0;
+	d.slice_group_id = desc->slice_group_id;
+	d.n_slice_group_id = desc->n_slice_group_id;
+	d.pic_width_in_mbs = desc->pic_width_in_mbs;
+	d.pic_height_in_map_units = desc->pic_height_in_map_units;
+	d.frame_mbs_only_flag = desc->frame_mbs_only_flag;
+	d.field_pic_flag = desc->field_pic_flag;
+	d.mbaff_frame_flag = desc->mbaff_frame_flag;
+	d.pic_size_in_mbs = desc->pic_size_in_mbs;
+	if ((d.map_type == 0 && d.run_length_minus1 == NULL) ||
+	    (d.map_type == 2 && (d.top_left == NULL || d.bottom_right == NULL)) ||
+	    (d.map_type == 6 && d.slice_group_id == NULL))
+		return -EINVAL;
+	const size_t units = (size_t)d.pic_width_in_mbs * d.pic_height_in_map_units;
+	uint8_t *u = (uint8_t *)malloc(units);
+	if (u == NULL)
+		return -ENOMEM;
+	const int r = fmo_map_units(&d, u);
+	if (r == 0)
+		fmo_mb_map(&d, u, mb_map);
+	free(u);
+	return r < 0 ? -EINVAL : 0;
+}
+
+extern "C" int h264gpu_reader_set_group_maps(h264gpu_ctx *ctx, const uint8_t *h_maps, uint64_t bytes)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	ctx->rd_maps_len = 0;
+	if (bytes == 0)
+		return 0;
+	if (h_maps == NULL)
+		return -EINVAL;
+	cudaStream_t st;
+	if ((r = h264gpu_reader_stream(ctx, &st)) < 0 || (r = h264gpu_pool_dev(ctx, &ctx->rd_maps, bytes)) < 0)
+		return r;
+	CU_TRY(cudaMemcpyAsync(ctx->rd_maps.p, h_maps, bytes, cudaMemcpyHostToDevice, st));
+	CU_TRY(cudaStreamSynchronize(st)); /* h_maps is the caller's again */
+	ctx->rd_maps_len = bytes;
+	return 0;
+}
+
+extern "C" int h264gpu_cavlc_parse_fmo_dev(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_t stream_len,
+					   const struct h264gpu_slice_params *d_params, uint32_t n_slices,
+					   struct h264gpu_mb_record *d_records, struct h264gpu_slice_result *d_results,
+					   struct h264_mb_syntax *d_syntax, const uint8_t *d_group_maps, void *stream)
 {
 	int r = h264gpu_use(ctx);
 	if (r < 0)
@@ -33,7 +163,13 @@ extern "C" int h264gpu_cavlc_parse_full_dev(h264gpu_ctx *ctx, const uint8_t *d_s
 	if (d_stream == NULL || d_params == NULL || d_records == NULL || d_results == NULL)
 		return -EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
-	/* nC context ring per slice: (PicWidthInMbs + 1) macroblocks x 48 counts, sized
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	const char *gen = getenv("H264GPU_CAVLC_GEN");
+	if (gen == NULL || atoi(gen) != 1)
+		return cavlc_steps_launch(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, d_syntax,
+					  d_group_maps, st, sms);
+	/* first generation (A/B): nC context ring per slice: (PicWidthInMbs + 1) macroblocks x 48 counts, sized
 	 * for pictures up to 8192 luma samples wide (512 MBs); wider slices get -E2BIG. */
 	const uint32_t ring_w = 512;
 	const uint64_t ring_stride = (uint64_t)(ring_w + 1) * 48;
@@ -52,12 +188,6 @@ extern "C" int h264gpu_cavlc_parse_full_dev(h264gpu_ctx *ctx, const uint8_t *d_s
 	a.ring_stride = ring_stride;
 	a.ring_w = ring_w;
 	a.syntax = d_syntax;
-	/* Slices per warp.  Slices diverge completely, so a warp runs its lanes one after the
-	 * other: one slice per warp is best while the warps fit the machine, and lanes are packed
-	 * only beyond ~32 warps per SM (measured, profiles/r01_slice_lane_packing.txt: 4000 slices
-	 * -> 1 per warp, 16000 slices -> 4 per warp). */
-	int sms = 148;
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
 	uint32_t lanes_log2 = 0;
 	const char *env = getenv("H264GPU_CAVLC_LANES_LOG2");
 	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
@@ -164,6 +294,17 @@ static int parse_host(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_strea
 	return 0;
 }
 
+/* the CAVLC parse of the pooled paths: with the group maps h264gpu_reader_set_group_maps left */
+static int cavlc_parse_pooled_dev(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_t stream_len,
+				  const struct h264gpu_slice_params *d_params, uint32_t n_slices,
+				  struct h264gpu_mb_record *d_records, struct h264gpu_slice_result *d_results, void *stream)
+{
+	const uint8_t *maps = ctx->rd_maps_len ? (const uint8_t *)ctx->rd_maps.p : NULL;
+	ctx->rd_maps_len = 0;
+	return h264gpu_cavlc_parse_fmo_dev(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, NULL,
+					   maps, stream);
+}
+
 /* the slices of the buffer h264gpu_reader_scan left on the device (no second upload) */
 extern "C" int h264gpu_reader_parse_cavlc(h264gpu_ctx *ctx, const struct h264gpu_slice_params *h_params,
 					  uint32_t n_slices, uint64_t n_records,
@@ -172,7 +313,7 @@ extern "C" int h264gpu_reader_parse_cavlc(h264gpu_ctx *ctx, const struct h264gpu
 {
 	if (h_params == NULL || h_records == NULL || h_results == NULL || n_slices == 0)
 		return -EINVAL;
-	return parse_pooled(h264gpu_cavlc_parse_dev, ctx, NULL, 0, h_params, n_slices, n_records, h_records, h_results);
+	return parse_pooled(cavlc_parse_pooled_dev, ctx, NULL, 0, h_params, n_slices, n_records, h_records, h_results);
 }
 
 /* CAVLC and CABAC slices of one parameter list (two launches on the same records array) */
@@ -183,7 +324,7 @@ extern "C" int h264gpu_reader_parse_slices(h264gpu_ctx *ctx, const struct h264gp
 {
 	if (h_params == NULL || h_records == NULL || h_results == NULL || n_slices == 0)
 		return -EINVAL;
-	return parse_pooled(h264gpu_cavlc_parse_dev, ctx, NULL, 0, h_params, n_slices, n_records, h_records, h_results,
+	return parse_pooled(cavlc_parse_pooled_dev, ctx, NULL, 0, h_params, n_slices, n_records, h_records, h_results,
 			    h264gpu_cabac_parse_dev);
 }
 
@@ -203,7 +344,7 @@ extern "C" int h264gpu_cavlc_parse_host(h264gpu_ctx *ctx, const uint8_t *h_strea
 					uint32_t n_slices, struct h264gpu_mb_record *h_records,
 					uint64_t n_records, struct h264gpu_slice_result *h_results)
 {
-	return parse_host(h264gpu_cavlc_parse_dev, ctx, h_stream, stream_len, h_params, n_slices, h_records,
+	return parse_host(cavlc_parse_pooled_dev, ctx, h_stream, stream_len, h_params, n_slices, h_records,
 			  n_records, h_results);
 }
 

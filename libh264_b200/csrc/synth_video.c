@@ -20,6 +20,7 @@
 
 #define CAVLC_TAB static const
 #include "cavlc_luts.h"
+#include "fmo_map.h"
 
 struct synth_video_cfg {
 	uint32_t width_mbs, height_mbs;
@@ -40,7 +41,9 @@ struct synth_video_cfg {
 	uint32_t cabac_twin;        /* CAVLC only: restrict to syntax CABAC can carry too (no
 				       P_8x8ref0, 8x8-transform blocks with a set cbp bit are
 				       never empty), for the CAVLC <-> CABAC twin test */
-	uint32_t reserved;
+	uint32_t fmo;               /* CAVLC only: slice groups (8.2.2): number of groups (2..8, 0/1 =
+				       none) | slice_group_map_type << 4 (0..6; 6 needs W * H <= 256);
+				       every group of a frame is cut into slices_per_frame slices */
 };
 
 /* CABAC slice data (synth_cabac.cpp): RBSP bytes of slice_data() incl. the stop bit */
@@ -243,7 +246,41 @@ struct gen {
 	/* optional: the parameter block of every slice (include/h264gpu_slice.h layout) */
 	struct slice_params_out *params;
 	uint64_t params_cap, params_n;
+	/* slice groups */
+	uint32_t fmo_groups, fmo_type, fmo_rate, fmo_cycle_bits, fmo_cycle;
+	int fmo_dir;
+	uint8_t *fmo_units, *fmo_map; /* map unit / macroblock -> slice group of the current picture */
+	uint32_t fmo_run[8], fmo_tl[8], fmo_br[8], fmo_ids[256];
 };
+
+/* the macroblock -> slice group map of the current picture (types 3..5 move with fmo_cycle) */
+static void fmo_picture_map(struct gen *g)
+{
+	struct fmo_desc d;
+	const uint32_t W = g->cfg.width_mbs, H = g->cfg.height_mbs, N = W * H;
+	memset(&d, 0, sizeof(d));
+	d.num_slice_groups_minus1 = g->fmo_groups - 1;
+	d.map_type = g->fmo_type;
+	d.run_length_minus1 = g->fmo_run;
+	d.top_left = g->fmo_tl;
+	d.bottom_right = g->fmo_br;
+	d.change_direction_flag = g->fmo_dir;
+	const uint64_t units = (uint64_t)g->fmo_cycle * g->fmo_rate;
+	d.map_units_in_slice_group0 = units < N ? (uint32_t)units : N;
+	d.slice_group_id = g->fmo_ids;
+	d.n_slice_group_id = N <= 256 ? N : 256;
+	d.pic_width_in_mbs = W;
+	d.pic_height_in_map_units = H;
+	d.frame_mbs_only_flag = 1;
+	d.pic_size_in_mbs = N;
+	fmo_map_units(&d, g->fmo_units);
+	fmo_mb_map(&d, g->fmo_units, g->fmo_map);
+}
+
+static uint32_t gen_next_mb(const struct gen *g, uint32_t a)
+{
+	return g->fmo_groups >= 2 ? fmo_next_mb_addr(g->fmo_map, g->cfg.width_mbs * g->cfg.height_mbs, a) : a + 1;
+}
 
 /* mirror of struct h264gpu_slice_params (include/h264gpu_slice.h), kept local so the
  * generator has no dependency on the GPU library */
@@ -785,6 +822,8 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 	bw_ue(w, 0);        /* disable_deblocking_filter_idc */
 	bw_se(w, 0);
 	bw_se(w, 0);
+	if (g->fmo_groups >= 2 && g->fmo_type >= 3 && g->fmo_type <= 5 && g->fmo_cycle_bits)
+		bw_bits(w, g->fmo_cycle, (int)g->fmo_cycle_bits); /* slice_group_change_cycle */
 	/* raw bit offset of slice_data() in the NAL (what the reference keeps in
 	 * ctx->slice.hdr_len); fixed up by bw_byte if an EPB lands before this byte */
 	uint32_t data_bit_off = (uint32_t)((w->len - nal_off) * 8 + (size_t)w->nacc);
@@ -830,7 +869,7 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 		g->n_mbs += count;
 		count = 0; /* the CAVLC loop below does nothing */
 	}
-	for (uint32_t a = first; a < first + count; a++) {
+	for (uint32_t a = first, i = 0; i < count; i++, a = gen_next_mb(g, a)) {
 		g->cur_mb = a;
 		g->cur_t8 = 0;
 		g->mbs[a].avail = 1;
@@ -879,6 +918,7 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 		p->entropy_coding_mode_flag = (uint8_t)(g->cfg.entropy_cabac ? 1 : 0);
 		p->cabac_init_idc = (uint8_t)cabac_init_idc;
 		p->slice_qp = (int8_t)(26 + qp_delta);
+		p->num_slice_groups_minus1 = (uint8_t)(g->fmo_groups >= 2 ? g->fmo_groups - 1 : 0);
 	}
 	g->params_n++;
 }
@@ -952,7 +992,55 @@ uint64_t synth_video(const struct synth_video_cfg *cfg, uint8_t *out, uint64_t c
 	bw_ue(w, 0);
 	bw_bits(w, cfg->entropy_cabac ? 1 : 0, 1);
 	bw_bits(w, 0, 1);
-	bw_ue(w, 0); /* num_slice_groups_minus1 */
+	g.fmo_groups = cfg->entropy_cabac ? 0 : (cfg->fmo & 15);
+	g.fmo_type = (cfg->fmo >> 4) & 15;
+	if (g.fmo_groups > 8 || g.fmo_type > 6 || (g.fmo_type == 6 && W * H > 256))
+		g.fmo_groups = 0;
+	if (g.fmo_groups >= 2 && g.fmo_type >= 3 && g.fmo_type <= 5)
+		g.fmo_groups = 2; /* the evolving map types have two groups */
+	if (g.fmo_groups < 2) {
+		g.fmo_groups = 0;
+		bw_ue(w, 0); /* num_slice_groups_minus1 */
+	} else {
+		const uint32_t N = W * H;
+		g.fmo_units = malloc(N);
+		g.fmo_map = malloc(N);
+		bw_ue(w, g.fmo_groups - 1);
+		bw_ue(w, g.fmo_type);
+		if (g.fmo_type == 0) {
+			for (uint32_t i = 0; i < g.fmo_groups; i++) {
+				g.fmo_run[i] = W / 2 + 3 * i;
+				bw_ue(w, g.fmo_run[i]);
+			}
+		} else if (g.fmo_type == 2) {
+			for (uint32_t i = 0; i + 1 < g.fmo_groups; i++) {
+				const uint32_t x0 = i % W, y0 = i % H;
+				const uint32_t x1 = W / 2 + i < W ? W / 2 + i : W - 1, y1 = H / 2 + i < H ? H / 2 + i : H - 1;
+				g.fmo_tl[i] = y0 * W + x0;
+				g.fmo_br[i] = y1 * W + x1;
+				bw_ue(w, g.fmo_tl[i]);
+				bw_ue(w, g.fmo_br[i]);
+			}
+		} else if (g.fmo_type >= 3 && g.fmo_type <= 5) {
+			g.fmo_dir = (int)(cfg->seed & 1);
+			g.fmo_rate = W / 2 + 1;
+			bw_bits(w, (uint32_t)g.fmo_dir, 1);
+			bw_ue(w, g.fmo_rate - 1);
+			uint32_t v = N / g.fmo_rate + 1, b = 0;
+			while (b < 32 && (1ull << b) < v)
+				b++;
+			g.fmo_cycle_bits = b;
+		} else if (g.fmo_type == 6) {
+			uint32_t b = 0;
+			while ((1u << b) < g.fmo_groups)
+				b++;
+			bw_ue(w, N - 1);
+			for (uint32_t i = 0; i < N; i++) {
+				g.fmo_ids[i] = (uint32_t)((((i + 1) * 2654435761u) >> 16) % g.fmo_groups);
+				bw_bits(w, g.fmo_ids[i], (int)b);
+			}
+		}
+	}
 	bw_ue(w, g.cfg.num_ref_frames - 1);
 	bw_ue(w, g.cfg.num_ref_frames - 1);
 	bw_bits(w, 0, 1);
@@ -977,6 +1065,32 @@ uint64_t synth_video(const struct synth_video_cfg *cfg, uint8_t *out, uint64_t c
 	for (uint32_t f = 0; f < cfg->frames; f++) {
 		int idr = (f % g.cfg.idr_period) == 0;
 		int type = idr ? 2 : ((cfg->b_frames && (f & 1)) ? 1 : 0);
+		if (g.fmo_groups >= 2) {
+			/* every slice group of the picture in turn, each cut into S slices of consecutive
+			 * macroblocks of the group */
+			if (g.fmo_cycle_bits)
+				g.fmo_cycle = f % ((N + g.fmo_rate - 1) / g.fmo_rate + 1);
+			fmo_picture_map(&g);
+			for (uint32_t grp = 0; grp < g.fmo_groups; grp++) {
+				uint32_t n_grp = 0, a0 = N;
+				for (uint32_t a = 0; a < N; a++)
+					if (g.fmo_map[a] == grp) {
+						if (n_grp++ == 0)
+							a0 = a;
+					}
+				uint32_t a = a0, done = 0;
+				for (uint32_t s = 0; s < S && n_grp > 0; s++) {
+					const uint32_t upto = (uint32_t)((uint64_t)n_grp * (s + 1) / S);
+					if (upto == done)
+						continue;
+					put_slice(&g, f, idr, type, a, upto - done);
+					nslices++;
+					for (; done < upto; done++)
+						a = gen_next_mb(&g, a);
+				}
+			}
+			continue;
+		}
 		for (uint32_t s = 0; s < S; s++) {
 			uint32_t first = (uint32_t)((uint64_t)N * s / S);
 			uint32_t next = (uint32_t)((uint64_t)N * (s + 1) / S);
@@ -985,6 +1099,8 @@ uint64_t synth_video(const struct synth_video_cfg *cfg, uint8_t *out, uint64_t c
 		}
 	}
 	free(g.mbs);
+	free(g.fmo_units);
+	free(g.fmo_map);
 	free(g.cabac_buf);
 	if (total_mbs)
 		*total_mbs = g.n_mbs;

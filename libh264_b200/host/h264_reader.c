@@ -168,6 +168,19 @@ int h264_reader_slice_data(struct h264_reader *reader, struct h264_ctx *ctx, con
 		own = malloc(((size_t)p.mb_out_cap + 1) * sizeof(*own));
 		if (own == NULL)
 			return -ENOMEM;
+		if (p.num_slice_groups_minus1 != 0 && !cabac) {
+			/* several slice groups: the slice's macroblock -> slice group map goes with it */
+			uint8_t *map = malloc(ctx->PicSizeInMbs ? ctx->PicSizeInMbs : 1);
+			res = map == NULL ? -ENOMEM : h264_ctx_get_slice_group_map(ctx, map, ctx->PicSizeInMbs);
+			if (res >= 0)
+				res = h264gpu_reader_set_group_maps(reader->gpu_single, map, ctx->PicSizeInMbs);
+			free(map);
+			if (res < 0) {
+				free(own);
+				return res;
+			}
+			p.row_state_off = 0;
+		}
 		res = cabac ? h264gpu_cabac_parse_host(reader->gpu_single, nal, nal_len, &p, 1, own, p.mb_out_cap,
 						       &result)
 			    : h264gpu_cavlc_parse_host(reader->gpu_single, nal, nal_len, &p, 1, own, p.mb_out_cap,
@@ -218,7 +231,38 @@ struct slice_list {
 	uint32_t n, cap;
 	uint64_t records;
 	int any_cabac;
+	/* pictures with several slice groups: macroblock -> slice group maps, back to back */
+	uint8_t *maps;
+	size_t maps_len, maps_cap;
 };
+
+/* the map of the slice whose header the context holds: appended to the list (or the previous
+ * slice's map again if nothing changed) */
+static int add_group_map(struct slice_list *out, const struct h264_ctx *ctx, struct h264gpu_slice_params *p)
+{
+	const size_t n = ctx->PicSizeInMbs;
+	if (out->maps_len + n > out->maps_cap) {
+		const size_t cap = (out->maps_cap ? out->maps_cap * 2 : 65536) + n;
+		void *m = realloc(out->maps, cap);
+		if (m == NULL)
+			return -ENOMEM;
+		out->maps = m;
+		out->maps_cap = cap;
+	}
+	uint8_t *map = out->maps + out->maps_len;
+	const int r = h264_ctx_get_slice_group_map(ctx, map, n);
+	if (r < 0)
+		return r;
+	if (out->maps_len >= n && memcmp(map - n, map, n) == 0) {
+		p->row_state_off = (uint32_t)(out->maps_len - n);
+		return 0;
+	}
+	if (out->maps_len + n > UINT32_MAX)
+		return -E2BIG;
+	p->row_state_off = (uint32_t)out->maps_len;
+	out->maps_len += n;
+	return 0;
+}
 
 /* header-only pass on a private context: which NAL units are CAVLC slices, and with
  * which parameters */
@@ -267,9 +311,13 @@ static int collect_slices(struct h264_reader *reader, const uint8_t *buf, const 
 			continue;
 		p->nal_off = st[k];
 		p->nal_len = (uint32_t)len;
+		if (p->num_slice_groups_minus1 != 0 && add_group_map(out, shadow, p) < 0)
+			continue; /* parsed on its own by the replay pass */
 		/* the slice before this one, if it belongs to the same picture and starts earlier,
-		 * ends where this one begins: give its unused record budget back */
-		if (out->n > 0 && !shadow->first_vcl && !shadow->MbaffFrameFlag) {
+		 * ends where this one begins: give its unused record budget back (one slice group only:
+		 * slices of different groups interleave) */
+		if (out->n > 0 && !shadow->first_vcl && !shadow->MbaffFrameFlag && p->num_slice_groups_minus1 == 0 &&
+		    out->params[out->n - 1].num_slice_groups_minus1 == 0) {
 			struct h264gpu_slice_params *q = &out->params[out->n - 1];
 			if (q->first_mb_in_slice < p->first_mb_in_slice && q->mb_out_off + (uint64_t)q->mb_out_cap == out->records) {
 				const uint32_t cap = p->first_mb_in_slice - q->first_mb_in_slice;
@@ -317,6 +365,8 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 		const struct h264gpu_mb_record *records = NULL;
 		const struct h264gpu_slice_result *results = NULL;
 		res = collect_slices(reader, buf, st, en, n_nal, &sl);
+		if (res >= 0 && sl.n > 0 && sl.maps_len > 0)
+			res = h264gpu_reader_set_group_maps(reader->gpu, sl.maps, sl.maps_len);
 		if (res >= 0 && sl.n > 0)
 			res = sl.any_cabac
 				? h264gpu_reader_parse_slices(reader->gpu, sl.params, sl.n, sl.records, &records, &results)
@@ -354,6 +404,7 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 	reader->n_slices = 0;
 out_slices:
 	free(sl.params);
+	free(sl.maps);
 	return res;
 }
 

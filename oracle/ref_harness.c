@@ -231,6 +231,8 @@ enum {
 	TR_AUD = 9,        /* u32 primary_pic_type */
 	TR_SEI = 10,       /* u32 type, raw payload bytes */
 	TR_SLICE_PARAMS = 11, /* struct h264gpu_slice_params (off/out fields filled) */
+	TR_GROUP_MAP = 12, /* slices of pictures with several slice groups: the reference's macroblock ->
+			      slice group map (ctx->slice.group_map through 8.2.2.8), one byte per macroblock */
 };
 
 struct ref_tracer {
@@ -466,6 +468,19 @@ static void cb_slice(struct h264_ctx *ctx, const uint8_t *buf, size_t len,
 	/* emitted after the slice's macroblocks: mb_out_off/mb_out_cap delimit its records */
 	fill_params(t, ctx, &p);
 	tr_put(t, TR_SLICE_PARAMS, &p, sizeof(p));
+	if (ctx->pps->num_slice_groups_minus1 > 0 && ctx->slice.group_map != NULL) {
+		/* h264_mb_to_slice_group (static in src/h264_fmo.c:217-235) over the whole picture */
+		const uint32_t n = ctx->derived.PicSizeInMbs, W = ctx->sps_derived.PicWidthInMbs;
+		uint8_t *m = malloc(n ? n : 1);
+		for (uint32_t i = 0; i < n; i++) {
+			uint32_t u = i;
+			if (!(ctx->sps->frame_mbs_only_flag || sh->field_pic_flag))
+				u = ctx->derived.MbaffFrameFlag ? i / 2 : (i / (2 * W)) * W + (i % W);
+			m[i] = (uint8_t)ctx->slice.group_map[u];
+		}
+		tr_put(t, TR_GROUP_MAP, m, n);
+		free(m);
+	}
 }
 
 static void cb_sd_begin(struct h264_ctx *ctx, const struct h264_slice_header *sh, void *ud)

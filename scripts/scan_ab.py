@@ -13,6 +13,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size-mb", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--cap-extra", type=int, default=1024)
+ap.add_argument("--alloc-extra", type=int, default=16)
+ap.add_argument("--stage", type=int, default=0, help="1: copy through a second pinned buffer like bench.py")
+ap.add_argument("--sampler", type=int, default=0, help="1: nvidia-smi clock sampler running like bench.py")
+ap.add_argument("--order", default="strip,only")
 args = ap.parse_args()
 g = L.Gpu(0)
 size = args.size_mb << 20
@@ -23,13 +28,35 @@ tz = 0
 while stream[n_in - 1 - tz] == 0:
     tz += 1
 n_rbsp = len(rbsp_ref) + tz
-cap = n_nal + 1024
-d_in, d_rbsp = g.alloc(n_in + 16), g.alloc(n_in + 16)
+cap = n_nal + args.cap_extra
+d_in, d_rbsp = g.alloc(n_in + args.alloc_extra), g.alloc(n_in + args.alloc_extra)
 d_tab, d_res = g.alloc(cap * 32), g.alloc(C.sizeof(L.ScanResult))
-d_in.upload(stream)
+def one_call():
+    g.split_strip_inplace_dev(d_in.ptr, n_in, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8,
+                              d_tab.ptr + cap * 16, d_tab.ptr + cap * 24, cap, d_res.ptr)
+    g.sync()
+if args.stage == 3:  # the scan workspace exists before the second pinned buffer does
+    one_call()
+if args.stage:
+    stage = g.pinned(n_in + 64)
+    if args.stage != 4:
+        stage.array[:n_in] = stream
+        L._check(g.lib.h264gpu_memcpy_h2d(g.h, C.c_void_p(d_in.ptr), stage.array.ctypes.data_as(C.c_void_p), n_in, None), "h2d")
+    else:  # 4: the buffer exists but is never touched or copied from
+        d_in.upload(stream)
+    g.sync()
+    if args.stage == 2:
+        stage.free()
+        stage = None
+else:
+    d_in.upload(stream)
 g.sync()
+if args.sampler:
+    from bench import ClockSampler
+    smp = ClockSampler(0)
+    smp.start()
 out = {}
-for strip in (True, False):
+for strip in [x == "strip" for x in args.order.split(",")]:
     for gen in (7,):
         def step():
             g.split_strip_inplace_dev(d_in.ptr, n_in, d_rbsp.ptr if strip else 0, d_tab.ptr, d_tab.ptr + cap * 8,

@@ -343,3 +343,26 @@ extern "C" int emu_cavlc_parse(const uint8_t *stream, uint64_t stream_len,
 	}
 	return 0;
 }
+
+/* K4, second generation: the same step function the kernel's lanes run, one slice at a time */
+#include "cavlc_steps.cuh"
+
+extern "C" int emu_cavlc_steps(const uint8_t *stream, uint64_t stream_len,
+			       const struct h264gpu_slice_params *params, uint32_t n_slices,
+			       struct h264gpu_mb_record *records, struct h264gpu_slice_result *results,
+			       struct h264_mb_syntax *syn, const uint8_t *group_maps)
+{
+	for (uint32_t i = 0; i < n_slices; i++) {
+		const h264gpu_slice_params &sp = params[i];
+		std::vector<uint8_t> ring(((size_t)sp.pic_width_in_mbs + 1) * 16 + 64, 0xEE);
+		uint32_t sm[CAVLC2_SM_WORDS];
+		memset(sm, 0xEE, sizeof(sm));
+		if (syn)
+			cavlc2::parse_slice<true>(stream, stream_len, sp, ring.data(), records + sp.mb_out_off, results[i],
+						  syn + sp.mb_out_off, group_maps, sm);
+		else
+			cavlc2::parse_slice<false>(stream, stream_len, sp, ring.data(), records + sp.mb_out_off, results[i],
+						   nullptr, group_maps, sm);
+	}
+	return 0;
+}

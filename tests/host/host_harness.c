@@ -299,6 +299,58 @@ int hh_trace(const char *libpath, const uint8_t *buf, size_t len, uint32_t flags
 	return t.overflow ? -ENOBUFS : 0;
 }
 
+/* ---- A12: the macroblock -> slice group map of every slice (this library's extension
+ * h264_ctx_get_slice_group_map), NAL by NAL without slice data: no GPU involved ------------- */
+struct gm_out {
+	int (*get)(const struct h264_ctx *, uint8_t *, size_t);
+	uint8_t *out;
+	size_t cap, used;
+	int err;
+};
+static void gm_slice(struct h264_ctx *c, const uint8_t *buf, size_t len, const struct h264_slice_header *sh,
+		     void *u)
+{
+	struct gm_out *g = u;
+	(void)buf;
+	(void)len;
+	(void)sh;
+	int n = g->get(c, g->out + g->used, g->cap - g->used);
+	if (n < 0)
+		g->err = n;
+	else
+		g->used += (size_t)n;
+}
+int hh_group_maps(const char *libpath, const uint8_t *buf, size_t len, uint8_t *out, size_t cap, size_t *used)
+{
+	struct api a;
+	int r = api_open(&a, libpath);
+	if (r < 0)
+		return r;
+	struct gm_out g = {NULL, out, cap, 0, 0};
+	*(void **)&g.get = dlsym(a.h, "h264_ctx_get_slice_group_map");
+	if (g.get == NULL)
+		return -ENOSYS;
+	struct h264_ctx_cbs cbs;
+	memset(&cbs, 0, sizeof(cbs));
+	cbs.slice = gm_slice;
+	struct h264_reader *rd = NULL;
+	r = a.reader_new(&cbs, &g, &rd);
+	if (r < 0)
+		return r;
+	size_t off = 0, start = 0, end = 0;
+	while (off < len) {
+		int fr = a.find_nalu(buf + off, len - off, &start, &end);
+		if (fr < 0 && fr != -EAGAIN)
+			break;
+		a.reader_parse_nalu(rd, 0, buf + off + start, end - start);
+		off += end;
+	}
+	a.reader_destroy(rd);
+	*used = g.used;
+	dlclose(a.h);
+	return g.err;
+}
+
 /* ---- timing: h264_reader_parse with counting callbacks ------------------------------------
  * counts: [0] nalu_begin  [1] slices  [2] slice_data_mb  [3] sps + pps  [4] sum of mb_addr ^ mb_type
  * (so that the macroblock callbacks cannot be optimised into nothing and both libraries can be

@@ -235,7 +235,7 @@ def emu_split_strip(buf, strip=True, items=4, edge=None, base=0, gen=None):
 # full-reader trace through the compiled reference (oracle/ref_harness.c)
 
 TR_NALU_BEGIN, TR_NALU_END, TR_AU_END, TR_SPS, TR_PPS, TR_SLICE = 1, 2, 3, 4, 5, 6
-TR_SLICE_DATA_BEGIN, TR_SLICE_DATA_END, TR_AUD, TR_SEI, TR_SLICE_PARAMS = 7, 8, 9, 10, 11
+TR_SLICE_DATA_BEGIN, TR_SLICE_DATA_END, TR_AUD, TR_SEI, TR_SLICE_PARAMS, TR_GROUP_MAP = 7, 8, 9, 10, 11, 12
 MB_RECORD = np.dtype([("mb_addr", "<u4"), ("mb_type", "<u4"), ("hash", "<u8")])
 SLICE_RESULT = np.dtype([("status", "<i4"), ("mb_count", "<u4"), ("end_bit", "<u8")])
 PARAMS_SIZE = 56
@@ -301,6 +301,22 @@ def ref_trace_syntax(stream, flags=1):
     return ev, mbs[:mn.value].copy(), syn[:mn.value].copy()
 
 
+def group_maps_from_trace(ev):
+    """For streams with several slice groups: (params, maps) where maps is the concatenation of
+    the reference's macroblock -> slice group map of every slice and params[i].row_state_off is
+    slice i's offset into it (the group_maps argument of the CAVLC kernel)."""
+    params = slice_params_from_trace(ev).view(SLICE_PARAMS).copy()
+    maps, offs, k = [], 0, 0
+    for t, p in ev:
+        if t == TR_SLICE_PARAMS:
+            k += 1
+        elif t == TR_GROUP_MAP:
+            params["row_state_off"][k - 1] = offs
+            maps.append(np.frombuffer(bytes(p), np.uint8))
+            offs += len(p)
+    return params.view(np.uint8), (np.concatenate(maps) if maps else np.zeros(0, np.uint8))
+
+
 def slice_params_from_trace(ev):
     """The packed h264gpu_slice_params blocks the reference's ctx held for every slice."""
     parts = [bytes(p[:PARAMS_SIZE]) for t, p in ev if t == TR_SLICE_PARAMS]
@@ -345,8 +361,28 @@ def emu_split_strip_inplace(buf, strip=True, cpt=8, edge=None, base=0, ev_cap=No
                 nal_rbsp=per_nal, body=body, res=res)
 
 
-def emu_cavlc_parse_full(stream, params, n_records):
+def _emu_cavlc_steps(stream, params, n_records, full, group_maps):
+    """K4 second generation (cavlc_steps.cuh): the lane step function run serially per slice."""
+    lib = emu()
+    lib.emu_cavlc_steps.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    n = len(params) // PARAMS_SIZE
+    recs = np.zeros(max(n_records, 1), MB_RECORD)
+    res = np.zeros(max(n, 1), SLICE_RESULT)
+    syn = np.full((max(n_records, 1), ref().ref_sizeof_mb_syntax()), 0xEE, np.uint8) if full else None
+    gm = np.ascontiguousarray(group_maps, dtype=np.uint8) if group_maps is not None else None
+    lib.emu_cavlc_steps(ptr(stream), len(stream), ptr(params), n, ptr(recs), ptr(res),
+                        ptr(syn) if full else None, ptr(gm) if gm is not None else None)
+    if full:
+        return recs[:n_records], res[:n], syn[:n_records]
+    return recs[:n_records], res[:n]
+
+
+def emu_cavlc_parse_full(stream, params, n_records, gen=2):
     """The CAVLC parse with full per-macroblock records (struct h264_mb_syntax blobs)."""
+    if gen == 2:
+        return _emu_cavlc_steps(stream, params, n_records, True, None)
     lib = emu()
     lib.emu_cavlc_parse_full.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                          C.c_void_p]
@@ -360,7 +396,9 @@ def emu_cavlc_parse_full(stream, params, n_records):
     return recs[:n_records], res[:n], syn[:n_records]
 
 
-def emu_cavlc_parse(stream, params, n_records):
+def emu_cavlc_parse(stream, params, n_records, gen=2, group_maps=None):
+    if gen == 2:
+        return _emu_cavlc_steps(stream, params, n_records, False, group_maps)
     lib = emu()
     lib.emu_cavlc_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     stream = np.ascontiguousarray(stream, dtype=np.uint8)

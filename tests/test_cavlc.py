@@ -158,3 +158,82 @@ def test_gpu_full_records_match_the_reference_ctx_mb(gpu):
     assert (res["status"] == 0).all()
     bad = np.nonzero((got != syn).any(axis=1))[0]
     assert len(bad) == 0, (bad[:5],)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_emu_step_machine_agrees_with_first_generation(name):
+    """Both generations of K4 (cavlc_steps.cuh: one syntax element per lane per step;
+    cavlc_parse.cuh: call tree per slice) give the same records, counts, status and end position."""
+    g = load_golden(name)
+    stream, nmb, nsl = L.synth_video(**CASES[name])
+    r2, q2 = S.emu_cavlc_parse(stream, g["params"], nmb, gen=2)
+    r1, q1 = S.emu_cavlc_parse(stream, g["params"], nmb, gen=1)
+    assert np.array_equal(r1, r2) and np.array_equal(q1, q2)
+    nal_len = g["params"].view(L.SLICE_PARAMS)["nal_len"].astype(np.uint64)
+    assert ((q2["end_bit"] > (nal_len - 2) * 8) & (q2["end_bit"] < nal_len * 8)).all()
+    # truncated slices: same verdict from both
+    p = g["params"].copy().view(L.SLICE_PARAMS)
+    p["nal_len"] = p["nal_len"] * 2 // 3
+    r2, q2 = S.emu_cavlc_parse(stream, p.view(np.uint8), nmb, gen=2)
+    r1, q1 = S.emu_cavlc_parse(stream, p.view(np.uint8), nmb, gen=1)
+    assert np.array_equal(q1["status"], q2["status"]) and np.array_equal(q1["mb_count"], q2["mb_count"])
+
+
+@needs_ref
+@pytest.mark.parametrize("map_type", range(7))
+def test_emu_slice_groups_match_the_reference(map_type):
+    """N3 / A12 (FMO): streams with 2-3 slice groups of every slice_group_map_type; the kernel walks
+    each slice with the macroblock -> slice group map (next macroblock of the group, neighbours only
+    from the slice's own group) and delivers what the reference delivers."""
+    for groups in (2, 3):
+        kw = dict(width_mbs=11, height_mbs=9, frames=6, slices_per_frame=2, b_frames=1, num_ref_frames=2,
+                  profile_idc=100, transform_8x8=1, pct_skip=25, seed=5 + map_type, idr_period=4,
+                  fmo=groups | map_type << 4)
+        stream, nmb, nsl = L.synth_video(**kw)
+        ev, mbs, off = S.ref_trace(stream)
+        assert len(mbs) == nmb and off == len(stream)
+        params, maps = S.group_maps_from_trace(ev)
+        assert len(maps) == nsl * 99
+        recs, res = S.emu_cavlc_parse(stream, params, nmb, group_maps=maps)
+        assert (res["status"] == 0).all(), res["status"]
+        assert np.array_equal(recs, mbs), (map_type, groups)
+        # without the maps the slices are refused, not misparsed
+        recs, res = S.emu_cavlc_parse(stream, params, nmb)
+        assert (res["status"] == -38).all()
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_gpu_slice_groups_match_the_reference(gpu):
+    import ctypes as C
+    for map_type in range(7):
+        kw = dict(width_mbs=16, height_mbs=15, frames=6, slices_per_frame=3, b_frames=1, num_ref_frames=2,
+                  profile_idc=100, transform_8x8=1, pct_skip=25, seed=15 + map_type, idr_period=4,
+                  fmo=3 | map_type << 4)
+        stream, nmb, nsl = L.synth_video(**kw)
+        ev, mbs, off = S.ref_trace(stream)
+        params, maps = S.group_maps_from_trace(ev)
+        L._check(gpu.lib.h264gpu_reader_set_group_maps(gpu.h, C.c_void_p(maps.ctypes.data), C.c_uint64(len(maps))),
+                 "h264gpu_reader_set_group_maps")
+        recs, res = gpu.cavlc_parse_host(stream, params, nmb)
+        assert (res["status"] == 0).all() and np.array_equal(recs, mbs), map_type
+        recs, res = gpu.cavlc_parse_host(stream, params, nmb)  # the maps were for one call
+        assert (res["status"] == -38).all()
+
+
+@pytest.mark.gpu
+def test_gpu_step_machine_agrees_with_first_generation(gpu, monkeypatch):
+    """Same records / results from both kernel generations, at every packing of slices into warps."""
+    stream, nmb, nsl, params = L.synth_video(width_mbs=40, height_mbs=30, frames=24, slices_per_frame=10,
+                                             profile_idc=100, transform_8x8=1, b_frames=1, num_ref_frames=3,
+                                             idr_period=8, pct_skip=35, pct_pcm=20, seed=77, want_params=True)
+    monkeypatch.setenv("H264GPU_CAVLC_GEN", "1")
+    r1, q1 = gpu.cavlc_parse_host(stream, params, nmb)
+    monkeypatch.delenv("H264GPU_CAVLC_GEN")
+    assert (q1["status"] == 0).all() and int(q1["mb_count"].sum()) == nmb
+    for lanes in ("0", "2", "5"):
+        for per_lane in ("1", "3"):
+            monkeypatch.setenv("H264GPU_CAVLC_LANES_LOG2", lanes)
+            monkeypatch.setenv("H264GPU_CAVLC_PER_LANE", per_lane)
+            r2, q2 = gpu.cavlc_parse_host(stream, params, nmb)
+            assert np.array_equal(r1, r2) and np.array_equal(q1, q2), (lanes, per_lane)

@@ -237,3 +237,27 @@ def test_rewrite_slice_header_behaviour():
                     assert np.array_equal(outs[0], s)
                 assert ((rcs[0] == 0) | (rcs[0] == -71)).all(), rcs[0]  # -EPROTO
     assert patched > 10
+
+
+@pytest.mark.parametrize("map_type", range(7))
+def test_slice_group_map_matches_the_reference(map_type):
+    """Row A12: the macroblock -> slice group map the host library builds for every slice
+    (h264_ctx_get_slice_group_map, libh264_b200/host/h264_fmo.c) is the one the reference holds in
+    ctx->slice.group_map (h264_gen_slice_group_map, src/h264_fmo.c:244-291) for the same slice: all
+    seven slice_group_map_type values, maps that move with slice_group_change_cycle (types 3-5)."""
+    import libh264_b200 as L
+    lib = harness()
+    lib.hh_group_maps.restype = C.c_int
+    lib.hh_group_maps.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    for groups, seed in ((2, 3), (3, 4), (5, 9)):
+        stream, nmb, nsl = L.synth_video(width_mbs=13, height_mbs=7, frames=9, slices_per_frame=1, idr_period=5,
+                                         seed=seed, fmo=groups | map_type << 4)
+        ev, mbs, off = S.ref_trace(stream)
+        want = np.concatenate([np.frombuffer(bytes(p), np.uint8) for t, p in ev if t == S.TR_GROUP_MAP])
+        assert len(want) == nsl * 91 and len(np.unique(want)) == (2 if 3 <= map_type <= 5 else groups)
+        got = np.zeros(len(want) + 91, np.uint8)
+        used = C.c_size_t(0)
+        stream = np.ascontiguousarray(stream)
+        rc = lib.hh_group_maps(OURS.encode(), stream.ctypes.data, len(stream), got.ctypes.data, len(got), C.byref(used))
+        assert rc == 0 and used.value == len(want)
+        assert np.array_equal(got[:used.value], want), (map_type, groups)

@@ -117,3 +117,19 @@ def test_cabac_slice_data_through_the_api_is_opt_in():
     assert sum(1 for t, _ in ours if t == T_SD_MB) == nmb + nmb2
     assert sum(1 for t, _ in ref if t == T_SD_MB) == nmb2
     assert [e for e in ours if e[0] != T_SD_MB][:50] == [e for e in ref if e[0] != T_SD_MB][:50]
+
+
+@pytest.mark.parametrize("map_type", range(7))
+def test_slice_groups_through_the_api(map_type):
+    """N3 (FMO): h264_reader_parse(SLICE_DATA) of streams with several slice groups, bulk and NAL
+    by NAL, callback for callback what the reference delivers (macroblock addresses follow the
+    slice group map; the round-1 library answered -ENOSYS here)."""
+    lib = T.harness()
+    for groups in (2, 4):
+        stream, nmb, nsl = L.synth_video(width_mbs=16, height_mbs=14, frames=5, slices_per_frame=2, b_frames=1,
+                                         num_ref_frames=2, profile_idc=66, pct_skip=25, seed=40 + map_type,
+                                         idr_period=3, fmo=groups | map_type << 4)
+        for mode in (0, 1):
+            ours = T.trace(lib, T.OURS, stream, 1, mode)
+            T.assert_same_trace(ours, T.trace(lib, T.REF, stream, 1, mode), "fmo type %d mode %d" % (map_type, mode))
+            assert sum(1 for t, _ in T.split_log(ours) if t == T_SD_MB) == nmb
