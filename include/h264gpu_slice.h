@@ -247,6 +247,43 @@ H264GPU_API int h264gpu_reader_parse_cabac(h264gpu_ctx *ctx, const struct h264gp
 					   const struct h264gpu_mb_record **h_records,
 					   const struct h264gpu_slice_result **h_results);
 
+
+/*
+ * N4: bulk synthesis of concealment slices, one slice per GPU lane.  What the reference writes
+ * one NAL at a time with h264_write_grey_i_slice / h264_write_skipped_p_slice
+ * (src/h264_writer.c:49-219; CABAC: src/h264_cabac.c, src/h264_bac.c:232-345): the NAL + slice
+ * header bits come from the host syntax walk (h264_write_nalu without slice data), the slice data
+ * of mb_count grey Intra16x16 / skipped macroblocks, CAVLC or CABAC, is generated here.
+ *   h_hdr / d_hdr   the slices' unescaped header bytes; slice k: hdr_bits bits from byte hdr_off
+ *   _dev            d_payload gets the unescaped NAL payloads back to back, d_off[0..n] their
+ *                   offsets (d_off[n] = total; if it exceeds payload_cap nothing is written):
+ *                   the input of h264gpu_frame_dev
+ *   _host           the finished byte stream: start codes of sc_len bytes, emulation prevention
+ *                   bytes inserted (h264gpu_frame_dev); h_out_off[0..n] = NAL offsets
+ */
+#define H264GPU_CONCEAL_GREY_I 0
+#define H264GPU_CONCEAL_SKIPPED_P 1
+struct h264gpu_conceal_params {
+	uint64_t hdr_off;
+	uint32_t hdr_bits;
+	uint32_t mb_count;
+	uint32_t first_mb_in_slice;
+	uint16_t pic_width_in_mbs;
+	uint8_t kind;                     /* H264GPU_CONCEAL_* */
+	uint8_t entropy_coding_mode_flag;
+	uint8_t slice_type;               /* 0 P, 1 B, 2 I, 3 SP, 4 SI */
+	uint8_t cabac_init_idc;
+	int8_t slice_qp;                  /* SliceQPY */
+	uint8_t reserved[5];
+};
+H264GPU_API int h264gpu_conceal_slices_dev(h264gpu_ctx *ctx, const struct h264gpu_conceal_params *d_params,
+					   uint32_t n, const uint8_t *d_hdr, uint8_t *d_payload,
+					   uint64_t payload_cap, uint64_t *d_off, void *stream);
+H264GPU_API int h264gpu_conceal_slices_host(h264gpu_ctx *ctx, const struct h264gpu_conceal_params *h_params,
+					    uint32_t n, const uint8_t *h_hdr, uint64_t hdr_bytes, int sc_len,
+					    uint8_t *h_out, uint64_t out_cap, uint64_t *h_out_off,
+					    uint64_t *total);
+
 #ifdef __cplusplus
 }
 #endif

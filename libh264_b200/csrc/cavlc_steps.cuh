@@ -1224,8 +1224,62 @@ struct CavlcArgs {
 	uint32_t lanes_log2; /* log2 of the lanes of a warp that carry slices (0..5) */
 	h264_mb_syntax *syntax; /* full records (index = record index), or NULL */
 	const uint8_t *group_maps; /* macroblock -> slice group maps (slice i: + params[i].row_state_off), or NULL */
-	uint32_t *next_slice; /* work counter, zero at launch */
+	uint32_t *next_slice; /* work counter: tickets into order[]; set by order_kernel */
+	uint32_t *order;      /* slice indices, longest NAL first */
 };
+
+/*
+ * Slices in descending order of NAL length (counting sort on the top 8 bits, one block).  The
+ * lanes of a warp take consecutive tickets: slices of similar length share a warp, so its lanes
+ * finish together (with the list order, a warp waited for its one I slice with 3 of 16 lanes
+ * busy), and the longest slices start first.
+ */
+#define CAVLC2_ORDER_T 1024
+__global__ void __launch_bounds__(CAVLC2_ORDER_T) order_kernel(const h264gpu_slice_params *params, uint32_t n,
+								 uint32_t *order, uint32_t *counter, uint32_t counter_init, uint32_t sort)
+{
+#ifndef H264_EMU
+	if (!sort) { /* A/B: list order */
+		for (uint32_t i = threadIdx.x; i < n; i += CAVLC2_ORDER_T)
+			order[i] = i;
+		if (threadIdx.x == 0)
+			*counter = counter_init;
+		return;
+	}
+	__shared__ uint32_t hist[256];
+	__shared__ uint32_t smax;
+	const uint32_t t = threadIdx.x;
+	if (t < 256)
+		hist[t] = 0;
+	if (t == 0)
+		smax = 0;
+	__syncthreads();
+	uint32_t m = 0;
+	for (uint32_t i = t; i < n; i += CAVLC2_ORDER_T)
+		m = max(m, params[i].nal_len);
+	m = __reduce_max_sync(FULL_MASK, m);
+	if ((t & 31) == 0)
+		atomicMax(&smax, m);
+	__syncthreads();
+	const uint32_t bits = 32 - (uint32_t)__clz((int)(smax | 1u));
+	const uint32_t shift = bits > 8 ? bits - 8 : 0;
+	for (uint32_t i = t; i < n; i += CAVLC2_ORDER_T)
+		atomicAdd(&hist[255 - (params[i].nal_len >> shift)], 1u);
+	__syncthreads();
+	if (t == 0) {
+		uint32_t acc = 0;
+		for (uint32_t b = 0; b < 256; b++) {
+			const uint32_t c = hist[b];
+			hist[b] = acc;
+			acc += c;
+		}
+		*counter = counter_init;
+	}
+	__syncthreads();
+	for (uint32_t i = t; i < n; i += CAVLC2_ORDER_T)
+		order[atomicAdd(&hist[255 - (params[i].nal_len >> shift)], 1u)] = i;
+#endif
+}
 
 /*
  * Every working lane pulls slices from a counter until none is left (slices differ a lot in
@@ -1246,7 +1300,7 @@ __global__ void __launch_bounds__(CAVLC2_STRIDE) cavlc_steps_kernel(const CavlcA
 	l.sm = smem + threadIdx.x;
 	l.state = S_DONE;
 	uint32_t slice = 0xffffffffu;
-	bool out = !worker;
+	bool out = !worker, first_done = false;
 	for (;;) {
 		if (!out && l.state == S_DONE) {
 			if (slice != 0xffffffffu) {
@@ -1254,10 +1308,13 @@ __global__ void __launch_bounds__(CAVLC2_STRIDE) cavlc_steps_kernel(const CavlcA
 				slice_end(l, res);
 				a.results[slice] = res;
 			}
-			slice = atomicAdd(a.next_slice, 1u);
-			if (slice >= a.n_slices) {
+			/* first ticket = the lane's own number (consecutive within the warp), then the counter */
+			const uint32_t ticket = slice == 0xffffffffu && !first_done ? glane : atomicAdd(a.next_slice, 1u);
+			first_done = true;
+			if (ticket >= a.n_slices) {
 				out = true;
 			} else {
+				slice = a.order[ticket];
 				const h264gpu_slice_params &sp = a.params[slice];
 				slice_begin(l, a.stream, a.stream_len, sp, a.ring + (uint64_t)glane * a.ring_stride,
 					    a.records + sp.mb_out_off, FULL && a.syntax ? a.syntax + sp.mb_out_off : nullptr,

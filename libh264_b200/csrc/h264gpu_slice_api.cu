@@ -10,6 +10,7 @@
 #include "cavlc_parse.cuh" /* the same parse with struct h264_mb_syntax records (opt-in entry point) */
 #include "cavlc_steps.cuh"
 #include "cabac_parse.cuh"
+#include "conceal.cuh"
 
 
 /*
@@ -46,7 +47,8 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 	const uint32_t ring_w = 512;
 	const uint64_t ring_stride = (uint64_t)(ring_w + 1) * 16;
 	const size_t counter_off = (size_t)(grid_lanes * ring_stride);
-	int r = h264gpu_ws_reserve(ctx, counter_off + 16);
+	const size_t order_off = counter_off + 16;
+	int r = h264gpu_ws_reserve(ctx, order_off + (size_t)n_slices * 4);
 	if (r < 0)
 		return r;
 	cavlc2::CavlcArgs a;
@@ -63,7 +65,12 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 	a.syntax = d_syntax;
 	a.group_maps = d_group_maps;
 	a.next_slice = (uint32_t *)((uint8_t *)ctx->ws + counter_off);
-	CU_TRY(cudaMemsetAsync(a.next_slice, 0, 16, st));
+	a.order = (uint32_t *)((uint8_t *)ctx->ws + order_off);
+	/* longest slices first; the first grid_lanes tickets are the lanes' own numbers */
+	env = getenv("H264GPU_CAVLC_SORT");
+	cavlc2::order_kernel<<<1, CAVLC2_ORDER_T, 0, st>>>(d_params, n_slices, a.order, a.next_slice, (uint32_t)grid_lanes,
+						    env != NULL && atoi(env) == 0 ? 0u : 1u);
+	ctx->launches++;
 	const size_t smem = (size_t)CAVLC2_SM_WORDS * threads * 4;
 	if (d_syntax == NULL)
 		cavlc2::cavlc_steps_kernel<false><<<blocks, threads, smem, st>>>(a);
@@ -417,4 +424,90 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	CU_TRY(cudaGetLastError());
 	ctx->launches++;
 	return 0;
+}
+
+/* ---- N4: concealment slices ------------------------------------------------------------- */
+
+extern "C" int h264gpu_conceal_slices_dev(h264gpu_ctx *ctx, const struct h264gpu_conceal_params *d_params,
+					  uint32_t n, const uint8_t *d_hdr, uint8_t *d_payload,
+					  uint64_t payload_cap, uint64_t *d_off, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (d_off == NULL)
+		return -EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (n == 0) {
+		CU_TRY(cudaMemsetAsync(d_off, 0, 8, st));
+		return 0;
+	}
+	if (d_params == NULL || d_hdr == NULL || d_payload == NULL)
+		return -EINVAL;
+	conceal::ConcealArgs a;
+	a.params = d_params;
+	a.n = n;
+	a.hdr = d_hdr;
+	a.off = d_off;
+	a.out = d_payload;
+	a.cap = payload_cap;
+	const uint32_t blocks = (n + 127) / 128;
+	conceal::conceal_kernel<false><<<blocks, 128, 0, st>>>(a); /* lengths */
+	conceal::conceal_scan<<<1, 1024, 0, st>>>(d_off, n);
+	conceal::conceal_kernel<true><<<blocks, 128, 0, st>>>(a);  /* bytes */
+	CU_TRY(cudaGetLastError());
+	ctx->launches += 3;
+	return 0;
+}
+
+extern "C" int h264gpu_conceal_slices_host(h264gpu_ctx *ctx, const struct h264gpu_conceal_params *h_params,
+					   uint32_t n, const uint8_t *h_hdr, uint64_t hdr_bytes, int sc_len,
+					   uint8_t *h_out, uint64_t out_cap, uint64_t *h_out_off, uint64_t *total)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (total == NULL || (n && (h_params == NULL || h_hdr == NULL || h_out == NULL)))
+		return -EINVAL;
+	*total = 0;
+	if (n == 0)
+		return 0;
+	/* an upper bound of the payload bytes: header + 2 bytes per macroblock + slack (a CABAC
+	 * macroblock of these slices is at most 10 bins; a CAVLC one exactly one byte) */
+	uint64_t bound = 0;
+	for (uint32_t k = 0; k < n; k++)
+		bound += (h_params[k].hdr_bits >> 3) + 2ull * h_params[k].mb_count + 16;
+	cudaStream_t st;
+	if ((r = h264gpu_reader_stream(ctx, &st)) < 0)
+		return r;
+	/* pooled buffers of the reader session, reused: params | header bytes | offsets (in) | payload |
+	 * offsets (out) + total | stream */
+	const size_t p_bytes = (size_t)n * sizeof(*h_params), o_bytes = ((size_t)n + 2) * 8;
+	if ((r = h264gpu_pool_dev(ctx, &ctx->rd_params, p_bytes + hdr_bytes + 16)) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_tab, 2 * o_bytes)) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_records, bound + 16)) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_stream, out_cap + 64)) < 0)
+		return r;
+	ctx->rd_stream_len = 0; /* the resident reader buffer is gone */
+	uint8_t *d_params = (uint8_t *)ctx->rd_params.p, *d_hdr = d_params + p_bytes;
+	uint64_t *d_off = (uint64_t *)ctx->rd_tab.p, *d_out_off = d_off + n + 2, *d_total = d_out_off + n + 1;
+	uint8_t *d_payload = (uint8_t *)ctx->rd_records.p, *d_out = (uint8_t *)ctx->rd_stream.p;
+	CU_TRY(cudaMemcpyAsync(d_params, h_params, p_bytes, cudaMemcpyHostToDevice, st));
+	CU_TRY(cudaMemcpyAsync(d_hdr, h_hdr, hdr_bytes, cudaMemcpyHostToDevice, st));
+	r = h264gpu_conceal_slices_dev(ctx, (const struct h264gpu_conceal_params *)d_params, n, d_hdr, d_payload, bound,
+				       d_off, st);
+	if (r < 0)
+		return r;
+	r = h264gpu_frame_dev(ctx, d_payload, d_off, n, sc_len, d_out, out_cap, d_out_off, d_total, st);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaMemcpyAsync(total, d_total, 8, cudaMemcpyDeviceToHost, st));
+	CU_TRY(cudaStreamSynchronize(st));
+	if (h_out_off)
+		CU_TRY(cudaMemcpyAsync(h_out_off, d_out_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+	const uint64_t ncopy = *total < out_cap ? *total : out_cap;
+	if (ncopy)
+		CU_TRY(cudaMemcpyAsync(h_out, d_out, ncopy, cudaMemcpyDeviceToHost, st));
+	CU_TRY(cudaStreamSynchronize(st));
+	return *total > out_cap ? -ENOBUFS : 0;
 }

@@ -37,8 +37,14 @@ def one_call():
     g.sync()
 if args.stage == 3:  # the scan workspace exists before the second pinned buffer does
     one_call()
+if args.stage == 5:  # a first small launch (kernel loaded, small workspace) before the second pinned buffer
+    g.split_strip_inplace_dev(d_in.ptr, 1 << 20, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8,
+                              d_tab.ptr + cap * 16, d_tab.ptr + cap * 24, cap, d_res.ptr)
+    g.sync()
+print("d_in %x d_rbsp %x d_tab %x" % (d_in.ptr, d_rbsp.ptr, d_tab.ptr), file=sys.stderr)
 if args.stage:
     stage = g.pinned(n_in + 64)
+    print("stage %x" % stage.array.ctypes.data, file=sys.stderr)
     if args.stage != 4:
         stage.array[:n_in] = stream
         L._check(g.lib.h264gpu_memcpy_h2d(g.h, C.c_void_p(d_in.ptr), stage.array.ctypes.data_as(C.c_void_p), n_in, None), "h2d")

@@ -366,3 +366,25 @@ extern "C" int emu_cavlc_steps(const uint8_t *stream, uint64_t stream_len,
 	}
 	return 0;
 }
+
+/* N4: concealment slice synthesis, both passes of the kernel; the scan in between on the host */
+#include "conceal.cuh"
+
+extern "C" int emu_conceal(const struct h264gpu_conceal_params *params, uint32_t n, const uint8_t *hdr,
+			   uint8_t *out, uint64_t cap, uint64_t *off)
+{
+	conceal::ConcealArgs a;
+	a.params = params;
+	a.n = n;
+	a.hdr = hdr;
+	a.off = off;
+	a.out = out;
+	a.cap = cap;
+	dim3 grid((n + 127) / 128), block(128);
+	off[0] = 0;
+	EMU_LAUNCH((conceal::conceal_kernel<false>), grid, block, a);
+	for (uint32_t k = 0; k < n; k++)
+		off[k + 1] += off[k];
+	EMU_LAUNCH((conceal::conceal_kernel<true>), grid, block, a);
+	return 0;
+}

@@ -958,6 +958,41 @@ static void gen_slice_header(struct h264_slice_header *sh, const struct h264_sps
  * (random header followed by opaque bytes, or a concealment slice), all written by the
  * library under test.  Returns the stream length or a negative errno.
  */
+/* N4 test input: for every concealment slice hh_gen writes, what a bulk synthesiser needs (the
+ * unescaped NAL + slice header bits from h264_write_nalu, the slice's parameters) and where the
+ * library's own h264_write_grey_i_slice / h264_write_skipped_p_slice output sits in the stream */
+struct conceal_rec {
+	uint64_t hdr_off;
+	uint32_t hdr_bits, mb_count, first_mb_in_slice;
+	uint16_t pic_width_in_mbs;
+	uint8_t kind, entropy_coding_mode_flag, slice_type, cabac_init_idc;
+	int8_t slice_qp;
+	uint8_t reserved[5];
+	uint64_t ref_off, ref_len; /* start code included */
+};
+static struct {
+	struct conceal_rec *recs;
+	size_t cap, n;
+	uint8_t *hdr;
+	size_t hdr_cap, hdr_used;
+} clog;
+
+long hh_gen(const char *libpath, uint64_t seed, int rounds, int conceal, uint8_t *outbuf, size_t cap);
+long hh_gen_conceal(const char *libpath, uint64_t seed, int rounds, uint8_t *outbuf, size_t cap,
+		    struct conceal_rec *recs, size_t recs_cap, size_t *nrecs, uint8_t *hdr, size_t hdr_cap)
+{
+	clog.recs = recs;
+	clog.cap = recs_cap;
+	clog.n = 0;
+	clog.hdr = hdr;
+	clog.hdr_cap = hdr_cap;
+	clog.hdr_used = 0;
+	long r = hh_gen(libpath, seed, rounds, 1, outbuf, cap);
+	*nrecs = clog.n;
+	clog.recs = NULL;
+	return r;
+}
+
 long hh_gen(const char *libpath, uint64_t seed, int rounds, int conceal, uint8_t *outbuf, size_t cap)
 {
 	struct api a;
@@ -1055,7 +1090,33 @@ long hh_gen(const char *libpath, uint64_t seed, int rounds, int conceal, uint8_t
 				struct h264_bitstream bs;
 				h264_bs_init(&bs, NULL, 0, 1);
 				const uint32_t n = 1 + rn(pic - sh->first_mb_in_slice);
+				if (clog.recs != NULL && clog.n < clog.cap) {
+					/* header only, no emulation prevention: the synthesiser's input */
+					struct h264_bitstream hb;
+					h264_bs_init(&hb, NULL, 0, 0);
+					if (a.write_nalu(&hb, ctx) >= 0 && clog.hdr_used + hb.off + 1 <= clog.hdr_cap) {
+						struct conceal_rec *c = &clog.recs[clog.n];
+						memset(c, 0, sizeof(*c));
+						c->hdr_off = clog.hdr_used;
+						c->hdr_bits = (uint32_t)(hb.off * 8 + hb.cachebits);
+						memcpy(clog.hdr + clog.hdr_used, hb.data, hb.off);
+						clog.hdr[clog.hdr_used + hb.off] = (uint8_t)hb.cache;
+						clog.hdr_used += hb.off + 1;
+						c->mb_count = n;
+						c->first_mb_in_slice = sh->first_mb_in_slice;
+						c->pic_width_in_mbs = (uint16_t)w;
+						c->kind = grey ? 0 : 1;
+						c->entropy_coding_mode_flag = (uint8_t)pps->entropy_coding_mode_flag;
+						c->slice_type = (uint8_t)(sh->slice_type % 5);
+						c->cabac_init_idc = (uint8_t)sh->cabac_init_idc;
+						c->slice_qp = (int8_t)(26 + pps->pic_init_qp_minus26 + sh->slice_qp_delta);
+						c->ref_off = o.len;
+					}
+					h264_bs_clear(&hb);
+				}
 				r = grey ? a.write_grey_i_slice(&bs, ctx, n) : a.write_skipped_p_slice(&bs, ctx, n);
+				if (r >= 0 && clog.recs != NULL && clog.n < clog.cap && clog.recs[clog.n].hdr_bits)
+					clog.recs[clog.n++].ref_len = 4 + bs.off;
 				if (r >= 0 && o.len + 4 + bs.off <= o.cap) {
 					static const uint8_t sc[4] = {0, 0, 0, 1};
 					memcpy(o.buf + o.len, sc, 4);
