@@ -125,8 +125,13 @@ static inline uint64_t h264gpu_mb_hash_term(uint32_t field, uint32_t index, int6
  *   d_params   n_slices parameter blocks
  *   d_records  record array (capacity = sum of mb_out_cap)
  *   d_results  n_slices results
- * MBAFF slices, and slices of pictures with several slice groups parsed without their map
- * (h264gpu_cavlc_parse_fmo_dev), give status -ENOSYS for that slice; there is no CPU fallback.
+ * Frame pictures, field pictures (field_pic_flag) and MBAFF frames (macroblock pairs,
+ * mb_field_decoding_flag read / inherited / inferred like the reference's h264_new_macroblock,
+ * src/h264_slice_data.c:1144-1205; neighbours of 6.4.12.2, src/h264_macroblock.c:110-231; in
+ * MBAFF slices first_mb_in_slice counts pairs and the records carry macroblock addresses).
+ * Slices of pictures with several slice groups need their map (h264gpu_cavlc_parse_fmo_dev);
+ * without it, or with MBAFF and slice groups together, the slice gets status -ENOSYS.  There is no
+ * CPU fallback.
  */
 H264GPU_API int h264gpu_cavlc_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream,
 					uint64_t stream_len,

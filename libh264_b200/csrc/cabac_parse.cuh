@@ -40,6 +40,7 @@ namespace cabac {
 
 struct CabacArgs {
 	const uint8_t *stream;
+	uint64_t stream_len;
 	const h264gpu_slice_params *params;
 	uint32_t n_slices;
 	h264gpu_mb_record *records;
@@ -61,7 +62,7 @@ __host__ __device__ inline uint32_t smem_bytes(uint32_t slices_per_block)
 	return ((kTabBytes + kNumCtx * slices_per_block + 15) & ~15u) + slices_per_block * kSlotBytes;
 }
 
-__device__ __forceinline__ void parse_slice(const uint8_t *stream, const h264gpu_slice_params &sp, Nb *ring,
+__device__ __forceinline__ void parse_slice(const uint8_t *stream, uint64_t stream_len, const h264gpu_slice_params &sp, Nb *ring,
 					     h264gpu_mb_record *rec, h264gpu_slice_result &res, uint8_t *ctx_states,
 					     uint32_t ctx_stride, const uint8_t *tabs, uint8_t *slot)
 {
@@ -75,6 +76,11 @@ __device__ __forceinline__ void parse_slice(const uint8_t *stream, const h264gpu
 	if (sp.mbaff_frame_flag || sp.num_slice_groups_minus1 != 0 || sp.pic_width_in_mbs == 0 ||
 	    sp.chroma_array_type == 3 || sp.slice_type == ST_SI || sp.slice_type > ST_SI) {
 		res.status = -ENOSYS;
+		return;
+	}
+	/* a parameter block that points outside the stream must not be followed */
+	if ((uint64_t)sp.nal_off + sp.nal_len > stream_len || sp.data_bit_off >= 8ull * sp.nal_len) {
+		res.status = -22; /* -EINVAL */
 		return;
 	}
 	Walk<Dec> &w = *reinterpret_cast<Walk<Dec> *>(slot);
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(128) cabac_parse_kernel(const CabacArgs a)
 		return;
 	}
 	uint8_t *slots = smem + ((kTabBytes + kNumCtx * per_block + 15) & ~15u);
-	parse_slice(a.stream, sp, a.ring + (uint64_t)i * a.ring_stride, a.records + sp.mb_out_off, res,
+	parse_slice(a.stream, a.stream_len, sp, a.ring + (uint64_t)i * a.ring_stride, a.records + sp.mb_out_off, res,
 		    smem + kTabBytes + slot, per_block, smem, slots + (size_t)slot * kSlotBytes);
 	a.results[i] = res;
 }

@@ -14,8 +14,8 @@
  * the block being decoded sit in shared memory (dynamic index), the row of counts above in a
  * 16-byte-per-macroblock ring in global memory.
  *
- * Reference behaviour reproduced (Parrot-Developers/libh264), frame / field pictures without
- * MBAFF, any number of slice groups:
+ * Reference behaviour reproduced (Parrot-Developers/libh264): frame and field pictures, MBAFF
+ * frames (macroblock pairs, 6.4.12.2 neighbours: mbaff_nb.h), any number of slice groups:
  *   slice_data loop, skip runs, end test   src/h264_syntax_slice_data.h:701-787
  *   macroblock_layer                       src/h264_syntax_slice_data.h:604-696
  *   mb_pred / sub_mb_pred                  src/h264_syntax_slice_data.h:422-601
@@ -36,6 +36,7 @@
 #include "gpu_compat.h"
 #include "h264gpu_slice.h"
 #include "h264gpu_mb_syntax.h"
+#include "mbaff_nb.h"
 
 #ifdef H264_EMU
 #define CAVLC_TAB static const
@@ -83,6 +84,8 @@ enum {
 	S_MB_END,       /* counts row, record, end-of-slice test         -  */
 	S_PCM_ALIGN,    /* pcm_alignment_zero_bits                       */
 	S_PCM,          /* one pcm sample                                */
+	S_MB_FIELD,     /* MBAFF: mb_field_decoding_flag (top macroblock of a pair, or the bottom one
+			   after a skipped top)                          1 bit */
 	S_DONE,
 };
 #define CAVLC2_UE_STATES                                                                               \
@@ -106,6 +109,13 @@ enum {
 	F_DIRECT16 = 1u << 12,
 	F_WHICH = 1u << 13,    /* which shared count buffer is the current macroblock's */
 	F_PRED8 = 1u << 14,    /* S_PRED reads intra 8x8 modes */
+	F_MBAFF = 1u << 15,    /* MbaffFrameFlag: macroblock pairs */
+	F_CUR_FIELD = 1u << 16,   /* mb_field_decoding_flag of the current pair */
+	F_TOP_SKIPPED = 1u << 17, /* the top macroblock of the current pair was skipped */
+	F_A_FIELD = 1u << 18,     /* field flag of the pair before (the pair to the left when F_AVAIL_A) */
+	F_B_FIELD = 1u << 19,     /* field flag of the pair above */
+	F_PREV_SKIPPED = 1u << 20, /* the mb_skip_run read last was not 0 (prevMbSkipped, 7.3.4) */
+	F_FIELD_PIC = 1u << 21,    /* field_pic_flag: every macroblock is a field macroblock */
 };
 
 #ifdef H264_EMU
@@ -113,7 +123,8 @@ enum {
 #else
 #define CAVLC2_STRIDE 128u /* threads per block: shared words of a lane are interleaved by thread */
 #endif
-#define CAVLC2_SM_WORDS 32u /* per lane: 2 x 12 words of counts, 8 words of levels */
+#define CAVLC2_SM_WORDS 56u /* per lane: 4 x 12 words of counts (this and the previous macroblock or pair), 8 words of levels */
+#define CAVLC2_RING_SLOT 32u /* bytes per macroblock (or pair) in the ring of bottom-row counts */
 
 struct Lane {
 	/* bit reader over the escaped NAL */
@@ -138,7 +149,8 @@ struct Lane {
 	/* macroblock */
 	uint64_t hash, slots, mvd_mask;
 	uint32_t ref_mask, k, kend, mb_type, cbp;
-	uint32_t top0, top1, top2; /* bottom-row counts of the macroblock above, per colour component */
+	uint32_t top0, top1, top2; /* bottom-row counts of the macroblock above (MBAFF: top macroblock of the pair above) */
+	uint32_t tb0, tb1, tb2;    /* MBAFF: bottom-row counts of the bottom macroblock of the pair above */
 	/* residual block */
 	uint32_t tc, ci, suffix_len, zeros_left, field, idx_base, out, maxc;
 	int32_t cpos;
@@ -151,9 +163,15 @@ __device__ __forceinline__ uint8_t *nz_ptr(const Lane &l, uint32_t buf, uint32_t
 }
 __device__ __forceinline__ int16_t *lev_ptr(const Lane &l, uint32_t i)
 {
-	return (int16_t *)(l.sm + (24u + (i >> 1)) * CAVLC2_STRIDE) + (i & 1u);
+	return (int16_t *)(l.sm + (48u + (i >> 1)) * CAVLC2_STRIDE) + (i & 1u);
 }
-__device__ __forceinline__ uint32_t cur_buf(const Lane &l) { return (l.flags & F_WHICH) ? 1u : 0u; }
+/* count buffers: 2 * which + (bottom macroblock of an MBAFF pair); the other two hold the
+ * macroblock (pair) before */
+__device__ __forceinline__ uint32_t cur_buf(const Lane &l)
+{
+	return ((l.flags & F_WHICH) ? 2u : 0u) | ((l.flags & F_MBAFF) ? (l.cur & 1u) : 0u);
+}
+__device__ __forceinline__ uint32_t prev_buf(const Lane &l) { return (l.flags & F_WHICH) ? 0u : 2u; }
 
 /* ---- bit reader ---------------------------------------------------------------------------- */
 /* 4 raw bytes at p (any alignment) as a big-endian word; reads the two aligned words around them */
@@ -322,34 +340,57 @@ __device__ __forceinline__ uint32_t blk_idx(uint32_t x, uint32_t y)
 /* 6.4.11.4 / 6.4.11.5 + 9.2.1: nC of a block from the counts left of and above it */
 __device__ __forceinline__ uint32_t calc_nc(const Lane &l, uint32_t comp, uint32_t blk, bool chroma_ac)
 {
-	const uint32_t cb = cur_buf(l), pb = cb ^ 1u;
+	const uint32_t cb = cur_buf(l), pb = prev_buf(l);
 	uint32_t nA = 0, nB = 0;
 	bool aA, aB;
-	uint32_t x, y, left_in, left_out, up_in;
+	uint32_t x, y, left_in, up_in;
 	if (!chroma_ac) {
 		x = blk_x(blk);
 		y = blk_y(blk);
 		left_in = blk_idx(x - 1, y);
-		left_out = blk_idx(3, y);
 		up_in = blk_idx(x, y - 1);
 	} else {
 		x = blk & 1;
 		y = blk >> 1;
 		left_in = blk - 1;
-		left_out = 2 * y + 1;
 		up_in = blk - 2;
 	}
+	const bool mbaff = (l.flags & F_MBAFF) != 0;
 	if (x > 0) {
 		aA = true;
 		nA = *nz_ptr(l, cb, comp * 16 + left_in);
-	} else if ((aA = (l.flags & F_AVAIL_A) != 0)) {
-		nA = (l.flags & F_PREV_ZERO) ? 0u : *nz_ptr(l, pb, comp * 16 + left_out);
+	} else if (!mbaff) {
+		if ((aA = (l.flags & F_AVAIL_A) != 0))
+			nA = (l.flags & F_PREV_ZERO) ? 0u : *nz_ptr(l, pb, comp * 16 + (chroma_ac ? 2 * y + 1 : blk_idx(3, y)));
+	} else {
+		/* 6.4.12.2: which macroblock of the pair to the left, and which of its rows */
+		const int maxH = chroma_ac ? (l.cat == 1 ? 8 : 16) : 16;
+		int yM = 0;
+		const int w = mbaff_left((l.flags & F_CUR_FIELD) != 0, (int)(l.cur & 1), (l.flags & F_AVAIL_A) != 0,
+					 (l.flags & F_A_FIELD) != 0, (int)(4 * y), maxH, &yM);
+		if ((aA = w != MBAFF_NB_NONE)) {
+			const uint32_t row = (uint32_t)yM >> 2;
+			nA = *nz_ptr(l, pb | (w == MBAFF_NB_A_BOT ? 1u : 0u), comp * 16 + (chroma_ac ? 2 * row + 1 : blk_idx(3, row)));
+		}
 	}
 	if (y > 0) {
 		aB = true;
 		nB = *nz_ptr(l, cb, comp * 16 + up_in);
-	} else if ((aB = (l.flags & F_AVAIL_B) != 0)) {
-		nB = ((comp == 0 ? l.top0 : comp == 1 ? l.top1 : l.top2) >> (8 * x)) & 0xffu;
+	} else if (!mbaff) {
+		if ((aB = (l.flags & F_AVAIL_B) != 0))
+			nB = ((comp == 0 ? l.top0 : comp == 1 ? l.top1 : l.top2) >> (8 * x)) & 0xffu;
+	} else {
+		const int w = mbaff_up((l.flags & F_CUR_FIELD) != 0, (int)(l.cur & 1), (l.flags & F_AVAIL_B) != 0,
+				       (l.flags & F_B_FIELD) != 0);
+		aB = w != MBAFF_NB_NONE;
+		if (w == MBAFF_NB_CUR_TOP) {
+			const uint32_t bot = chroma_ac ? (l.cat == 1 ? 2u : 6u) + x : blk_idx(x, 3);
+			nB = *nz_ptr(l, cb & 2u, comp * 16 + bot);
+		} else if (w == MBAFF_NB_B_TOP) {
+			nB = ((comp == 0 ? l.top0 : comp == 1 ? l.top1 : l.top2) >> (8 * x)) & 0xffu;
+		} else if (w == MBAFF_NB_B_BOT) {
+			nB = ((comp == 0 ? l.tb0 : comp == 1 ? l.tb1 : l.tb2) >> (8 * x)) & 0xffu;
+		}
 	}
 	if (aA && aB)
 		return (nA + nB + 1) >> 1;
@@ -412,7 +453,46 @@ __device__ __forceinline__ void bottom_rows(const Lane &l, uint32_t w[3])
 
 __device__ __forceinline__ uint32_t *ring_slot(const Lane &l, uint32_t mb)
 {
-	return (uint32_t *)(l.ring + (size_t)(mb % (l.W + 1)) * 16);
+	return (uint32_t *)(l.ring + (size_t)(mb % (l.W + 1)) * CAVLC2_RING_SLOT);
+}
+
+/* ---- MBAFF: macroblock pairs ----------------------------------------------------------------- */
+/* the top macroblock of a pair begins (coded or skipped): neighbouring pairs inside the slice
+ * (6.4.10; the reference: h264_compute_neighbouring_macroblocks, src/h264_macroblock.c:327-336) */
+__device__ __forceinline__ void pair_begin(Lane &l)
+{
+	const uint32_t half = l.cur >> 1;
+	const bool aA = half >= l.first + 1 && half % l.W != 0;
+	const bool aB = half >= l.first + l.W;
+	l.flags &= ~(F_AVAIL_A | F_AVAIL_B | F_B_FIELD | F_CUR_FIELD | F_TOP_SKIPPED);
+	l.flags |= (aA ? F_AVAIL_A : 0u) | (aB ? F_AVAIL_B : 0u);
+	if (aB) {
+		const uint32_t *up = ring_slot(l, half - l.W);
+		l.top0 = up[0];
+		l.top1 = up[1];
+		l.top2 = up[2];
+		if (up[3])
+			l.flags |= F_B_FIELD;
+		l.tb0 = up[4];
+		l.tb1 = up[5];
+		l.tb2 = up[6];
+	}
+}
+
+/* the bottom macroblock of a pair is done: the pair becomes the pair before */
+__device__ __forceinline__ void pair_end(Lane &l)
+{
+	const bool field = (l.flags & F_CUR_FIELD) != 0;
+	ring_slot(l, l.cur >> 1)[3] = field ? 1u : 0u;
+	l.flags = ((l.flags & ~F_A_FIELD) | (field ? F_A_FIELD : 0u)) ^ F_WHICH;
+}
+
+/* where a lane goes for its next coded macroblock */
+__device__ __forceinline__ uint32_t mb_start_state(const Lane &l)
+{
+	if ((l.flags & F_MBAFF) && (!(l.cur & 1u) || (l.flags & F_PREV_SKIPPED)))
+		return S_MB_FIELD;
+	return S_MB_TYPE;
 }
 
 /* ---- slice begin / end ------------------------------------------------------------------- */
@@ -437,7 +517,7 @@ __device__ __forceinline__ void slice_begin(Lane &l, const uint8_t *stream, uint
 		l.status = H264GPU_SLICE_SKIPPED;
 		return;
 	}
-	if (sp.mbaff_frame_flag || sp.pic_width_in_mbs == 0 || (sp.num_slice_groups_minus1 != 0 && group_maps == nullptr)) {
+	if (sp.pic_width_in_mbs == 0 || (sp.num_slice_groups_minus1 != 0 && (group_maps == nullptr || sp.mbaff_frame_flag))) {
 		l.status = -ENOSYS;
 		return;
 	}
@@ -461,8 +541,9 @@ __device__ __forceinline__ void slice_begin(Lane &l, const uint8_t *stream, uint
 	l.max1 = sp.num_ref_idx_l1_active_minus1;
 	const bool inter = sp.slice_type != ST_I && sp.slice_type != ST_SI;
 	l.flags = (inter ? F_INTER : 0u) | (sp.slice_type == ST_B ? F_B : 0u) |
-		  (sp.transform_8x8_mode_flag ? F_T8MODE : 0u) | (sp.direct_8x8_inference_flag ? F_D8INF : 0u);
-	l.cur = l.first;
+		  (sp.transform_8x8_mode_flag ? F_T8MODE : 0u) | (sp.direct_8x8_inference_flag ? F_D8INF : 0u) |
+		  (sp.mbaff_frame_flag ? F_MBAFF : 0u) | (sp.field_pic_flag ? F_FIELD_PIC : 0u);
+	l.cur = sp.mbaff_frame_flag ? 2 * l.first : l.first;
 	l.prev_addr = 0xffffffffu;
 	/* position the reader at raw bit offset data_bit_off of the NAL: if the offset is byte
 	 * aligned the reference has not fetched that byte yet */
@@ -479,7 +560,7 @@ __device__ __forceinline__ void slice_begin(Lane &l, const uint8_t *stream, uint
 		l.cache <<= drop;
 		l.nbits -= (int)drop;
 	}
-	l.state = inter ? S_SKIP_RUN : S_MB_TYPE;
+	l.state = inter ? (uint32_t)S_SKIP_RUN : mb_start_state(l);
 }
 
 __device__ __forceinline__ void slice_end(const Lane &l, h264gpu_slice_result &res)
@@ -760,6 +841,8 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 	if (state == S_REF) {
 		rbit = (uint32_t)__ffs((int)l.ref_mask) - 1;
 		rmax = (rbit & 4) ? l.max1 : l.max0;
+		if ((l.flags & F_MBAFF) && (l.flags & F_CUR_FIELD))
+			rmax = 2 * rmax + 1;
 		want_ue = rmax > 1;
 	}
 	if (want_ue) {
@@ -788,9 +871,11 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 	case S_SKIP_RUN:
 		if (val > 0) {
 			l.k = val;
+			l.flags |= F_PREV_SKIPPED;
 			l.state = S_SKIP_EMIT;
 		} else {
-			l.state = S_MB_TYPE;
+			l.flags &= ~F_PREV_SKIPPED;
+			l.state = mb_start_state(l);
 		}
 		break;
 
@@ -799,24 +884,55 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 			fail(l, -ENOBUFS);
 			return;
 		}
-		uint32_t *slot = ring_slot(l, l.cur);
-		slot[0] = slot[1] = slot[2] = 0;
 		const uint32_t t = (l.flags & F_B) ? MB_B_SKIP : MB_P_SKIP;
+		/* what the reference holds in mb_field_decoding_flag when it delivers the macroblock
+		 * (h264_new_macroblock, src/h264_slice_data.c:1144-1175) */
+		uint32_t field = (l.flags & F_FIELD_PIC) ? 1u : 0u;
+		if (l.flags & F_MBAFF) {
+			const uint32_t bottom = l.cur & 1u;
+			if (!bottom) {
+				pair_begin(l);
+				l.flags |= F_TOP_SKIPPED; /* the flag waits for the bottom macroblock: 0 for now */
+			} else if (l.flags & F_TOP_SKIPPED) {
+				/* both skipped: inferred from the pair to the left, else the pair above, else frame */
+				const bool f = (l.flags & F_AVAIL_A) ? (l.flags & F_A_FIELD) != 0
+							       : (l.flags & F_AVAIL_B) ? (l.flags & F_B_FIELD) != 0 : false;
+				l.flags = (l.flags & ~F_CUR_FIELD) | (f ? F_CUR_FIELD : 0u);
+				field = f;
+			} else {
+				field = (l.flags & F_CUR_FIELD) ? 1u : 0u; /* the top macroblock's */
+			}
+			uint32_t *slot = ring_slot(l, l.cur >> 1) + (bottom ? 4 : 0);
+			slot[0] = slot[1] = slot[2] = 0;
+			const uint32_t cb = cur_buf(l);
+#pragma unroll
+			for (uint32_t w = 0; w < 12; w++)
+				l.sm[(cb * 12u + w) * CAVLC2_STRIDE] = 0;
+		} else {
+			uint32_t *slot = ring_slot(l, l.cur);
+			slot[0] = slot[1] = slot[2] = 0;
+		}
 		l.rec[l.count].mb_addr = l.cur;
 		l.rec[l.count].mb_type = t;
-		l.rec[l.count].hash = 0;
+		l.rec[l.count].hash = field ? hash_term(H264GPU_F_MB_FIELD_DECODING_FLAG, 0, 1) : 0;
 		if (FULL && l.syn)
 			syn_open(l.syn + l.count, l.cur, t);
 		l.count++;
-		l.prev_addr = l.cur;
-		l.flags |= F_PREV_ZERO;
-		l.cur = next_mb_addr(l, l.cur);
+		if (l.flags & F_MBAFF) {
+			if (l.cur & 1u)
+				pair_end(l);
+			l.cur++;
+		} else {
+			l.prev_addr = l.cur;
+			l.flags |= F_PREV_ZERO;
+			l.cur = next_mb_addr(l, l.cur);
+		}
 		if (--l.k == 0) {
 			if (!more_rbsp_data(l)) {
 				l.state = S_DONE;
 				return;
 			}
-			l.state = S_MB_TYPE;
+			l.state = mb_start_state(l);
 		}
 		break;
 	}
@@ -829,21 +945,25 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		/* new macroblock: neighbours (6.4.9; with several slice groups a neighbour also has to
 		 * be of this slice's group), counts cleared */
 		const uint32_t cur = l.cur;
-		bool aA = cur >= l.first + 1 && cur % l.W != 0;
-		bool aB = cur >= l.first + l.W;
-		if (l.gmap != nullptr) {
-			aA = aA && l.gmap[cur - 1] == l.gmap[cur];
-			aB = aB && l.gmap[cur - l.W] == l.gmap[cur];
-		}
-		if (aA && l.prev_addr != cur - 1)
-			aA = false; /* cannot happen: the macroblock before cur in the slice is cur - 1 then */
-		l.flags &= ~(F_AVAIL_A | F_AVAIL_B | F_I16 | F_T8 | F_NO_SUB_LT8 | F_NXN | F_INTRA_CBP | F_DIRECT16 | F_PRED8);
-		l.flags |= (aA ? F_AVAIL_A : 0u) | (aB ? F_AVAIL_B : 0u) | F_NO_SUB_LT8;
-		if (aB) {
-			const uint32_t *up = ring_slot(l, cur - l.W);
-			l.top0 = up[0];
-			l.top1 = up[1];
-			l.top2 = up[2];
+		l.flags &= ~(F_I16 | F_T8 | F_NO_SUB_LT8 | F_NXN | F_INTRA_CBP | F_DIRECT16 | F_PRED8);
+		l.flags |= F_NO_SUB_LT8;
+		if (!(l.flags & F_MBAFF)) { /* MBAFF: pair_begin did this for the pair */
+			bool aA = cur >= l.first + 1 && cur % l.W != 0;
+			bool aB = cur >= l.first + l.W;
+			if (l.gmap != nullptr) {
+				aA = aA && l.gmap[cur - 1] == l.gmap[cur];
+				aB = aB && l.gmap[cur - l.W] == l.gmap[cur];
+			}
+			if (aA && l.prev_addr != cur - 1)
+				aA = false; /* cannot happen: the macroblock before cur in the slice is cur - 1 then */
+			l.flags &= ~(F_AVAIL_A | F_AVAIL_B);
+			l.flags |= (aA ? F_AVAIL_A : 0u) | (aB ? F_AVAIL_B : 0u);
+			if (aB) {
+				const uint32_t *up = ring_slot(l, cur - l.W);
+				l.top0 = up[0];
+				l.top1 = up[1];
+				l.top2 = up[2];
+			}
 		}
 		{
 			const uint32_t cb = cur_buf(l);
@@ -859,6 +979,12 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		l.mb_type = MB_UNKNOWN;
 		if (FULL && l.syn)
 			syn_open(l.syn + l.count, cur, 0);
+		/* field macroblock: field picture, or the pair's flag in an MBAFF frame; ref_idx then
+		 * ranges over fields (src/h264_slice_data.c:1199-1205) and is sent even for one frame */
+		const bool mb_field = (l.flags & F_MBAFF) ? (l.flags & F_CUR_FIELD) != 0 : (l.flags & F_FIELD_PIC) != 0;
+		const bool mf = (l.flags & F_MBAFF) && mb_field;
+		const bool r0 = l.max0 > 0 || mf, r1 = l.max1 > 0 || mf;
+		hash_add<FULL>(l, H264GPU_F_MB_FIELD_DECODING_FLAG, 0, mb_field ? 1 : 0);
 
 		/* h264_read_mb_type: src/h264_slice_data.c:839-969 */
 		uint32_t type = val;
@@ -961,12 +1087,12 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 			for (uint32_t i = 0; i < num_part; i++) {
 				const uint32_t m = i ? m1 : m0;
 				if (m != 1) { /* uses list 0 */
-					if (l.max0 > 0)
+					if (r0)
 						l.ref_mask |= 1u << i;
 					l.mvd_mask |= 3ull << (8 * i);
 				}
 				if (m != 0) { /* uses list 1 */
-					if (l.max1 > 0)
+					if (r1)
 						l.ref_mask |= 16u << i;
 					l.mvd_mask |= 3ull << (32 + 8 * i);
 				}
@@ -1002,13 +1128,14 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		}
 		if (!direct) {
 			const uint64_t bits = (1ull << (2 * nsub)) - 1;
+			const bool mf = (l.flags & F_MBAFF) && (l.flags & F_CUR_FIELD);
 			if (m != 1) {
-				if (l.max0 > 0 && l.mb_type != MB_P_8x8ref0)
+				if ((l.max0 > 0 || mf) && l.mb_type != MB_P_8x8ref0)
 					l.ref_mask |= 1u << i;
 				l.mvd_mask |= bits << (8 * i);
 			}
 			if (m != 0) {
-				if (l.max1 > 0)
+				if (l.max1 > 0 || mf)
 					l.ref_mask |= 16u << i;
 				l.mvd_mask |= bits << (32 + 8 * i);
 			}
@@ -1112,7 +1239,8 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 	case S_MB_END: {
 		uint32_t w[3];
 		bottom_rows(l, w);
-		uint32_t *slot = ring_slot(l, l.cur);
+		const bool mbaff = (l.flags & F_MBAFF) != 0;
+		uint32_t *slot = mbaff ? ring_slot(l, l.cur >> 1) + ((l.cur & 1u) ? 4 : 0) : ring_slot(l, l.cur);
 		slot[0] = w[0];
 		slot[1] = w[1];
 		slot[2] = w[2];
@@ -1122,14 +1250,20 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		if (FULL && l.syn)
 			l.syn[l.count].mb_type = l.mb_type;
 		l.count++;
-		l.prev_addr = l.cur;
-		l.flags = (l.flags & ~F_PREV_ZERO) ^ F_WHICH;
-		l.cur = next_mb_addr(l, l.cur);
+		if (mbaff) {
+			if (l.cur & 1u)
+				pair_end(l);
+			l.cur++;
+		} else {
+			l.prev_addr = l.cur;
+			l.flags = (l.flags & ~F_PREV_ZERO) ^ F_WHICH;
+			l.cur = next_mb_addr(l, l.cur);
+		}
 		if (!more_rbsp_data(l)) {
 			l.state = S_DONE;
 			return;
 		}
-		l.state = (l.flags & F_INTER) ? S_SKIP_RUN : S_MB_TYPE;
+		l.state = (l.flags & F_INTER) ? (uint32_t)S_SKIP_RUN : mb_start_state(l);
 		break;
 	}
 
@@ -1167,6 +1301,16 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		}
 		break;
 	}
+
+	case S_MB_FIELD:
+		/* 7.3.4: read with the top macroblock of a pair, or with the bottom one when the top was
+		 * skipped (then it also becomes the skipped top's flag) */
+		if (!(l.cur & 1u))
+			pair_begin(l);
+		n = 1;
+		l.flags = (l.flags & ~F_CUR_FIELD) | ((top >> 31) ? F_CUR_FIELD : 0u);
+		l.state = S_MB_TYPE;
+		break;
 
 	default:
 		break;

@@ -45,7 +45,7 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
 	const uint64_t grid_lanes = ((uint64_t)blocks * threads / 32) << lanes_log2;
 	const uint32_t ring_w = 512;
-	const uint64_t ring_stride = (uint64_t)(ring_w + 1) * 16;
+	const uint64_t ring_stride = (uint64_t)(ring_w + 1) * CAVLC2_RING_SLOT;
 	const size_t counter_off = (size_t)(grid_lanes * ring_stride);
 	const size_t order_off = counter_off + 16;
 	int r = h264gpu_ws_reserve(ctx, order_off + (size_t)n_slices * 4);
@@ -380,7 +380,6 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 		return 0;
 	if (d_stream == NULL || d_params == NULL || d_records == NULL || d_results == NULL)
 		return -EINVAL;
-	(void)stream_len;
 	cudaStream_t st = (cudaStream_t)stream;
 	/* neighbour ring per slice: (PicWidthInMbs + 1) records of 64 B, sized for pictures up
 	 * to 8192 luma samples wide (512 MBs); wider slices get -E2BIG. */
@@ -391,6 +390,7 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 		return r;
 	cabac::CabacArgs a;
 	a.stream = d_stream;
+	a.stream_len = stream_len;
 	a.params = d_params;
 	a.n_slices = n_slices;
 	a.records = d_records;

@@ -21,6 +21,7 @@
 #define CAVLC_TAB static const
 #include "cavlc_luts.h"
 #include "fmo_map.h"
+#include "mbaff_nb.h"
 
 struct synth_video_cfg {
 	uint32_t width_mbs, height_mbs;
@@ -43,7 +44,12 @@ struct synth_video_cfg {
 				       never empty), for the CAVLC <-> CABAC twin test */
 	uint32_t fmo;               /* CAVLC only: slice groups (8.2.2): number of groups (2..8, 0/1 =
 				       none) | slice_group_map_type << 4 (0..6; 6 needs W * H <= 256);
-				       every group of a frame is cut into slices_per_frame slices */
+				       every group of a frame is cut into slices_per_frame slices
+				       | 0x100: MBAFF frames (frame_mbs_only_flag = 0,
+				       mb_adaptive_frame_field_flag = 1, even height, no slice groups):
+				       macroblock pairs, a random mb_field_decoding_flag per pair
+				       | 0x200: field pictures (frame_mbs_only_flag = 0, every picture a
+				       field of height_mbs / 2 macroblock rows, field_pic_flag = 1) */
 };
 
 /* CABAC slice data (synth_cabac.cpp): RBSP bytes of slice_data() incl. the stop bit */
@@ -246,6 +252,12 @@ struct gen {
 	/* optional: the parameter block of every slice (include/h264gpu_slice.h layout) */
 	struct slice_params_out *params;
 	uint64_t params_cap, params_n;
+	/* MBAFF / field pictures */
+	int mbaff, cur_field, paff;
+	uint32_t pic_h; /* PicHeightInMbs */
+	uint8_t *pair_field;  /* mb_field_decoding_flag of every macroblock pair, reset per slice */
+	int ref_present;      /* ref_idx is sent for this macroblock */
+	uint32_t ref_range;   /* number of values te() of ref_idx covers */
 	/* slice groups */
 	uint32_t fmo_groups, fmo_type, fmo_rate, fmo_cycle_bits, fmo_cycle;
 	int fmo_dir;
@@ -313,8 +325,61 @@ static int mb_avail_b(struct gen *g)
 	return g->cur_mb >= g->first_mb + W && g->mbs[g->cur_mb - W].avail;
 }
 
+/* MBAFF frames: 6.4.10 (pairs to the left / above inside the slice) + 6.4.12.2 (mbaff_nb.h) */
+static uint32_t calc_nc_mbaff(struct gen *g, int comp, int blk, int chroma_ac)
+{
+	const uint32_t W = g->cfg.width_mbs, cur = g->cur_mb, half = cur / 2;
+	const int bottom = (int)(cur & 1);
+	const int a_avail = half >= g->first_mb + 1 && half % W != 0 && g->mbs[2 * (half - 1)].avail;
+	const int b_avail = half >= g->first_mb + W && g->mbs[2 * (half - W)].avail;
+	const int a_field = a_avail ? g->pair_field[half - 1] : 0, b_field = b_avail ? g->pair_field[half - W] : 0;
+	int x, y, maxH, wb, hb;
+	if (!chroma_ac) {
+		x = luma_xy[blk][0] / 4;
+		y = luma_xy[blk][1] / 4;
+		maxH = 16;
+		wb = hb = 4;
+	} else {
+		x = blk & 1;
+		y = blk >> 1;
+		maxH = (int)g->mbh_c;
+		wb = (int)g->mbw_c / 4;
+		hb = (int)g->mbh_c / 4;
+	}
+#define BLK(xx, yy) (chroma_ac ? 2 * (yy) + (xx) : luma_idx[(xx)][(yy)])
+	int availA = 1, availB = 1;
+	uint32_t nA = 0, nB = 0;
+	if (x > 0) {
+		nA = g->mbs[cur].nz[comp * 16 + BLK(x - 1, y)];
+	} else {
+		int yM = 0;
+		const int w = mbaff_left(g->cur_field, bottom, a_avail, a_field, 4 * y, maxH, &yM);
+		if (w == MBAFF_NB_NONE)
+			availA = 0;
+		else
+			nA = g->mbs[2 * (half - 1) + (w == MBAFF_NB_A_BOT)].nz[comp * 16 + BLK(wb - 1, yM / 4)];
+	}
+	if (y > 0) {
+		nB = g->mbs[cur].nz[comp * 16 + BLK(x, y - 1)];
+	} else {
+		const int w = mbaff_up(g->cur_field, bottom, b_avail, b_field);
+		if (w == MBAFF_NB_NONE)
+			availB = 0;
+		else if (w == MBAFF_NB_CUR_TOP)
+			nB = g->mbs[cur - 1].nz[comp * 16 + BLK(x, hb - 1)];
+		else
+			nB = g->mbs[2 * (half - W) + (w == MBAFF_NB_B_BOT)].nz[comp * 16 + BLK(x, hb - 1)];
+	}
+#undef BLK
+	if (availA && availB)
+		return (nA + nB + 1) >> 1;
+	return availA ? nA : availB ? nB : 0;
+}
+
 static uint32_t calc_nc(struct gen *g, int comp, int blk, int chroma_ac)
 {
+	if (g->mbaff)
+		return calc_nc_mbaff(g, comp, blk, chroma_ac);
 	uint32_t W = g->cfg.width_mbs;
 	int availA, availB;
 	uint32_t nA = 0, nB = 0;
@@ -654,20 +719,19 @@ static void put_inter_tail(struct gen *g, int allow_t8)
 static void put_p_mb(struct gen *g)
 {
 	struct bw *w = &g->w;
-	uint32_t nref = g->cfg.num_ref_frames;
 	uint32_t sel = rnd_n(&g->r, 100);
 	if (sel < 45) {
 		bw_ue(w, 0); /* P_L0_16x16 */
-		if (nref > 1)
-			bw_te(w, rnd_n(&g->r, nref), nref - 1);
+		if (g->ref_present)
+			bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
 		bw_se(w, rand_mvd(g));
 		bw_se(w, rand_mvd(g));
 		put_inter_tail(g, 1);
 	} else if (sel < 70) {
 		bw_ue(w, 1 + (rnd(&g->r) & 1)); /* 16x8 / 8x16 */
-		if (nref > 1) {
-			bw_te(w, rnd_n(&g->r, nref), nref - 1);
-			bw_te(w, rnd_n(&g->r, nref), nref - 1);
+		if (g->ref_present) {
+			bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
+			bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
 		}
 		for (int i = 0; i < 4; i++)
 			bw_se(w, rand_mvd(g));
@@ -683,9 +747,9 @@ static void put_p_mb(struct gen *g)
 			if (sub[i] != 0)
 				no_small = 0;
 		}
-		if (nref > 1 && !ref0)
+		if (g->ref_present && !ref0)
 			for (int i = 0; i < 4; i++)
-				bw_te(w, rnd_n(&g->r, nref), nref - 1);
+				bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
 		static const int nsub[4] = {1, 2, 2, 4};
 		for (int i = 0; i < 4; i++)
 			for (int s = 0; s < nsub[sub[i]]; s++) {
@@ -706,7 +770,6 @@ static const uint8_t b_part[18][2] = {{0, 0}, {0, 0}, {1, 1}, {1, 1}, {0, 1}, {0
 static void put_b_mb(struct gen *g)
 {
 	struct bw *w = &g->w;
-	uint32_t nref = g->cfg.num_ref_frames;
 	uint32_t sel = rnd_n(&g->r, 100);
 	if (sel < 15) {
 		bw_ue(w, 0); /* B_Direct_16x16 */
@@ -715,10 +778,10 @@ static void put_b_mb(struct gen *g)
 		uint32_t ty = 1 + rnd_n(&g->r, 3); /* L0, L1, Bi 16x16 */
 		bw_ue(w, ty);
 		int use0 = ty != 2, use1 = ty != 1;
-		if (nref > 1 && use0)
-			bw_te(w, rnd_n(&g->r, nref), nref - 1);
-		if (nref > 1 && use1)
-			bw_te(w, rnd_n(&g->r, nref), nref - 1);
+		if (g->ref_present && use0)
+			bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
+		if (g->ref_present && use1)
+			bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
 		if (use0) {
 			bw_se(w, rand_mvd(g));
 			bw_se(w, rand_mvd(g));
@@ -732,14 +795,14 @@ static void put_b_mb(struct gen *g)
 		uint32_t ty = 4 + rnd_n(&g->r, 18);
 		bw_ue(w, ty);
 		const uint8_t *pp = b_part[ty - 4];
-		if (nref > 1)
+		if (g->ref_present)
 			for (int i = 0; i < 2; i++)
 				if (pp[i] != 1)
-					bw_te(w, rnd_n(&g->r, nref), nref - 1);
-		if (nref > 1)
+					bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
+		if (g->ref_present)
 			for (int i = 0; i < 2; i++)
 				if (pp[i] != 0)
-					bw_te(w, rnd_n(&g->r, nref), nref - 1);
+					bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
 		for (int i = 0; i < 2; i++)
 			if (pp[i] != 1) {
 				bw_se(w, rand_mvd(g));
@@ -761,14 +824,14 @@ static void put_b_mb(struct gen *g)
 			if (sub[i] != 0 && b_sub[sub[i]][0] > 1)
 				no_small = 0;
 		}
-		if (nref > 1)
+		if (g->ref_present)
 			for (int i = 0; i < 4; i++)
 				if (b_sub[sub[i]][1] != 3 && b_sub[sub[i]][1] != 1)
-					bw_te(w, rnd_n(&g->r, nref), nref - 1);
-		if (nref > 1)
+					bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
+		if (g->ref_present)
 			for (int i = 0; i < 4; i++)
 				if (b_sub[sub[i]][1] != 3 && b_sub[sub[i]][1] != 0)
-					bw_te(w, rnd_n(&g->r, nref), nref - 1);
+					bw_te(w, rnd_n(&g->r, g->ref_range), g->ref_range - 1);
 		for (int i = 0; i < 4; i++)
 			if (b_sub[sub[i]][1] != 3 && b_sub[sub[i]][1] != 1)
 				for (int s = 0; s < b_sub[sub[i]][0]; s++) {
@@ -798,6 +861,12 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 	bw_ue(w, (uint32_t)type + ((frame & 1) ? 5 : 0)); /* both slice_type codings */
 	bw_ue(w, 0);
 	bw_bits(w, frame & 0xff, 8); /* frame_num, log2_max_frame_num = 8 */
+	if (g->mbaff)
+		bw_bits(w, 0, 1); /* field_pic_flag: a frame, so MbaffFrameFlag = 1 */
+	if (g->paff) {
+		bw_bits(w, 1, 1);         /* field_pic_flag */
+		bw_bits(w, frame & 1, 1); /* bottom_field_flag */
+	}
 	if (idr)
 		bw_ue(w, frame & 0xffff);
 	bw_bits(w, (2 * frame) & 0xff, 8); /* pic_order_cnt_lsb */
@@ -869,6 +938,53 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 		g->n_mbs += count;
 		count = 0; /* the CAVLC loop below does nothing */
 	}
+	g->ref_present = g->cfg.num_ref_frames > 1;
+	g->ref_range = g->cfg.num_ref_frames;
+	g->cur_field = 0;
+	if (g->mbaff) {
+		/* macroblock pairs first .. first + count - 1: addresses 2 * first .. 2 * (first + count) - 1 */
+		memset(g->pair_field, 0, (size_t)W * H / 2);
+		int top_skipped = 0;
+		for (uint32_t a = 2 * first; a < 2 * (first + count); a++) {
+			const int bottom = (int)(a & 1);
+			g->cur_mb = a;
+			g->cur_t8 = 0;
+			g->mbs[a].avail = 1;
+			g->n_mbs++;
+			if (!bottom) {
+				g->pair_field[a / 2] = (uint8_t)(rnd(&g->r) & 1);
+				top_skipped = 0;
+			}
+			if (type != 2 && rnd_pct(&g->r, g->cfg.pct_skip)) {
+				pending_skip++;
+				if (!bottom)
+					top_skipped = 1;
+				else if (top_skipped)
+					g->pair_field[a / 2] = 0; /* inferred by the reader; its counts are all 0 */
+				continue;
+			}
+			if (type != 2) {
+				bw_ue(w, pending_skip);
+				pending_skip = 0;
+			}
+			/* mb_field_decoding_flag: with the top macroblock, or with the bottom one when the
+			 * top was skipped (7.3.4) */
+			g->cur_field = g->pair_field[a / 2];
+			if (!bottom || top_skipped)
+				bw_bits(w, (uint32_t)g->cur_field, 1);
+			g->ref_present = g->cfg.num_ref_frames > 1 || g->cur_field;
+			g->ref_range = g->cur_field ? 2 * g->cfg.num_ref_frames : g->cfg.num_ref_frames;
+			if (type == 2)
+				put_intra_mb(g, 0);
+			else if (rnd_pct(&g->r, g->cfg.pct_intra_in_inter))
+				put_intra_mb(g, type == 0 ? 5 : 23);
+			else if (type == 0)
+				put_p_mb(g);
+			else
+				put_b_mb(g);
+		}
+		count = 0;
+	}
 	for (uint32_t a = first, i = 0; i < count; i++, a = gen_next_mb(g, a)) {
 		g->cur_mb = a;
 		g->cur_t8 = 0;
@@ -906,7 +1022,8 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 		p->mb_out_off = (uint32_t)mb0;
 		p->mb_out_cap = (uint32_t)(g->n_mbs - mb0);
 		p->pic_width_in_mbs = (uint16_t)W;
-		p->pic_height_in_mbs = (uint16_t)H;
+		p->pic_height_in_mbs = (uint16_t)g->pic_h;
+		p->field_pic_flag = (uint8_t)g->paff;
 		p->slice_type = (uint8_t)type;
 		p->chroma_array_type = (uint8_t)g->cat;
 		p->bit_depth_luma = 8;
@@ -919,6 +1036,7 @@ static void put_slice(struct gen *g, uint32_t frame, int idr, int type, uint32_t
 		p->cabac_init_idc = (uint8_t)cabac_init_idc;
 		p->slice_qp = (int8_t)(26 + qp_delta);
 		p->num_slice_groups_minus1 = (uint8_t)(g->fmo_groups >= 2 ? g->fmo_groups - 1 : 0);
+		p->mbaff_frame_flag = (uint8_t)g->mbaff;
 	}
 	g->params_n++;
 }
@@ -978,9 +1096,19 @@ uint64_t synth_video(const struct synth_video_cfg *cfg, uint8_t *out, uint64_t c
 	bw_ue(w, 4); /* log2_max_pic_order_cnt_lsb_minus4 */
 	bw_ue(w, 4); /* max_num_ref_frames */
 	bw_bits(w, 0, 1);
+	g.mbaff = !cfg->entropy_cabac && (cfg->fmo & 0x100) && (H % 2) == 0;
 	bw_ue(w, W - 1);
-	bw_ue(w, H - 1);
-	bw_bits(w, 1, 1); /* frame_mbs_only_flag */
+	g.paff = !g.mbaff && (cfg->fmo & 0x200) && (H % 2) == 0;
+	g.pic_h = g.paff ? H / 2 : H;
+	if (g.mbaff || g.paff) {
+		g.pair_field = calloc((size_t)W * H / 2 + 1, 1);
+		bw_ue(w, H / 2 - 1); /* pic_height_in_map_units_minus1: pairs / field rows */
+		bw_bits(w, 0, 1);    /* frame_mbs_only_flag */
+		bw_bits(w, g.mbaff ? 1 : 0, 1); /* mb_adaptive_frame_field_flag */
+	} else {
+		bw_ue(w, H - 1);
+		bw_bits(w, 1, 1); /* frame_mbs_only_flag */
+	}
 	bw_bits(w, 1, 1); /* direct_8x8_inference_flag */
 	bw_bits(w, 0, 1); /* frame_cropping_flag */
 	bw_bits(w, 0, 1); /* vui_parameters_present_flag */
@@ -992,7 +1120,7 @@ uint64_t synth_video(const struct synth_video_cfg *cfg, uint8_t *out, uint64_t c
 	bw_ue(w, 0);
 	bw_bits(w, cfg->entropy_cabac ? 1 : 0, 1);
 	bw_bits(w, 0, 1);
-	g.fmo_groups = cfg->entropy_cabac ? 0 : (cfg->fmo & 15);
+	g.fmo_groups = cfg->entropy_cabac || g.mbaff ? 0 : (cfg->fmo & 15);
 	g.fmo_type = (cfg->fmo >> 4) & 15;
 	if (g.fmo_groups > 8 || g.fmo_type > 6 || (g.fmo_type == 6 && W * H > 256))
 		g.fmo_groups = 0;
@@ -1059,7 +1187,7 @@ uint64_t synth_video(const struct synth_video_cfg *cfg, uint8_t *out, uint64_t c
 	bw_trailing(w);
 
 	uint64_t nslices = 0;
-	uint32_t S = g.cfg.slices_per_frame, N = W * H;
+	uint32_t S = g.cfg.slices_per_frame, N = W * g.pic_h;
 	if (S > N)
 		S = N;
 	for (uint32_t f = 0; f < cfg->frames; f++) {
@@ -1092,13 +1220,17 @@ uint64_t synth_video(const struct synth_video_cfg *cfg, uint8_t *out, uint64_t c
 			continue;
 		}
 		for (uint32_t s = 0; s < S; s++) {
-			uint32_t first = (uint32_t)((uint64_t)N * s / S);
-			uint32_t next = (uint32_t)((uint64_t)N * (s + 1) / S);
+			const uint32_t units = g.mbaff ? N / 2 : N; /* first_mb_in_slice counts pairs in MBAFF frames */
+			uint32_t first = (uint32_t)((uint64_t)units * s / S);
+			uint32_t next = (uint32_t)((uint64_t)units * (s + 1) / S);
+			if (next == first)
+				continue;
 			put_slice(&g, f, idr, type, first, next - first);
 			nslices++;
 		}
 	}
 	free(g.mbs);
+	free(g.pair_field);
 	free(g.fmo_units);
 	free(g.fmo_map);
 	free(g.cabac_buf);

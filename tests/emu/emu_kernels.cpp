@@ -354,7 +354,7 @@ extern "C" int emu_cavlc_steps(const uint8_t *stream, uint64_t stream_len,
 {
 	for (uint32_t i = 0; i < n_slices; i++) {
 		const h264gpu_slice_params &sp = params[i];
-		std::vector<uint8_t> ring(((size_t)sp.pic_width_in_mbs + 1) * 16 + 64, 0xEE);
+		std::vector<uint8_t> ring(((size_t)sp.pic_width_in_mbs + 1) * CAVLC2_RING_SLOT + 64, 0xEE);
 		uint32_t sm[CAVLC2_SM_WORDS];
 		memset(sm, 0xEE, sizeof(sm));
 		if (syn)

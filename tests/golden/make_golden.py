@@ -30,6 +30,15 @@ CASES = {
     "high_444": dict(width_mbs=6, height_mbs=5, frames=4, profile_idc=100, chroma_format_idc=3,
                      transform_8x8=1),
     "high_mono": dict(width_mbs=6, height_mbs=5, frames=4, profile_idc=100, chroma_format_idc=0),
+    # round 2 (N3): MBAFF frames, field pictures, slice groups (fmo = groups | map type << 4)
+    "mbaff_b": dict(width_mbs=9, height_mbs=6, frames=6, slices_per_frame=2, b_frames=1, num_ref_frames=2,
+                    profile_idc=100, transform_8x8=1, pct_skip=35, idr_period=3, seed=91, fmo=0x100),
+    "field_pictures": dict(width_mbs=8, height_mbs=6, frames=8, slices_per_frame=2, b_frames=1, num_ref_frames=2,
+                           profile_idc=77, pct_skip=30, idr_period=4, seed=92, fmo=0x200),
+    "fmo_dispersed": dict(width_mbs=9, height_mbs=7, frames=5, slices_per_frame=2, num_ref_frames=2,
+                          profile_idc=66, pct_skip=25, idr_period=3, seed=93, fmo=3 | 1 << 4),
+    "fmo_box_out": dict(width_mbs=9, height_mbs=7, frames=7, slices_per_frame=1, num_ref_frames=1,
+                        profile_idc=66, pct_skip=25, idr_period=4, seed=94, fmo=2 | 3 << 4),
 }
 
 
@@ -37,12 +46,12 @@ def main():
     for name, kw in CASES.items():
         stream, nmb, nsl = L.synth_video(**kw)
         ev, mbs, off = S.ref_trace(stream)
-        params = S.slice_params_from_trace(ev)
+        params, maps = S.group_maps_from_trace(ev)  # maps: the reference's, empty without slice groups
         counts = np.array([int(p.view(np.uint32)[0]) for t, p in ev if t == S.TR_SLICE_DATA_END], np.uint32)
         order = np.array([t for t, _ in ev], np.uint8)
         np.savez_compressed(os.path.join(HERE, "cavlc_%s.npz" % name), crc=np.uint32(zlib.crc32(stream.tobytes())),
                             mbs=mbs, params=params, mb_counts=counts, callback_order=order,
-                            final_off=np.uint64(off))
+                            final_off=np.uint64(off), group_maps=maps)
         print(name, len(stream), "bytes", nmb, "mbs", nsl, "slices")
 
 

@@ -379,10 +379,10 @@ def _emu_cavlc_steps(stream, params, n_records, full, group_maps):
     return recs[:n_records], res[:n]
 
 
-def emu_cavlc_parse_full(stream, params, n_records, gen=2):
+def emu_cavlc_parse_full(stream, params, n_records, gen=2, group_maps=None):
     """The CAVLC parse with full per-macroblock records (struct h264_mb_syntax blobs)."""
     if gen == 2:
-        return _emu_cavlc_steps(stream, params, n_records, True, None)
+        return _emu_cavlc_steps(stream, params, n_records, True, group_maps)
     lib = emu()
     lib.emu_cavlc_parse_full.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                          C.c_void_p]

@@ -18,12 +18,17 @@ def load_golden(name):
     return np.load(os.path.join(GOLD, "cavlc_%s.npz" % name))
 
 
+def group_maps(g):
+    """The reference's macroblock -> slice group maps of a fixture (None without slice groups)."""
+    return g["group_maps"] if "group_maps" in g.files and len(g["group_maps"]) else None
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_emu_parse_matches_golden(name):
     g = load_golden(name)
     stream, nmb, nsl = L.synth_video(**CASES[name])
     assert zlib.crc32(stream.tobytes()) == int(g["crc"]), "generator output changed"
-    recs, res = S.emu_cavlc_parse(stream, g["params"], len(g["mbs"]))
+    recs, res = S.emu_cavlc_parse(stream, g["params"], len(g["mbs"]), group_maps=group_maps(g))
     assert (res["status"] == 0).all()
     assert np.array_equal(res["mb_count"], g["mb_counts"])
     assert np.array_equal(recs["mb_addr"], g["mbs"]["mb_addr"])
@@ -38,7 +43,7 @@ def test_golden_is_what_the_reference_says(name):
     stream, nmb, nsl = L.synth_video(**CASES[name])
     ev, mbs, off = S.ref_trace(stream)
     assert len(mbs) == nmb and np.array_equal(mbs, g["mbs"])
-    assert np.array_equal(S.slice_params_from_trace(ev), g["params"])
+    assert np.array_equal(S.group_maps_from_trace(ev)[0], g["params"])
     assert off == int(g["final_off"]) == len(stream)
 
 
@@ -91,8 +96,14 @@ def test_truncated_slice_reports_eio_not_garbage():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_gpu_parse_matches_golden(gpu, name):
+    import ctypes as C
     g = load_golden(name)
     stream, nmb, nsl = L.synth_video(**CASES[name])
+    maps = group_maps(g)
+    if maps is not None:
+        maps = np.ascontiguousarray(maps)
+        L._check(gpu.lib.h264gpu_reader_set_group_maps(gpu.h, C.c_void_p(maps.ctypes.data), C.c_uint64(len(maps))),
+                 "h264gpu_reader_set_group_maps")
     recs, res = gpu.cavlc_parse_host(stream, g["params"], len(g["mbs"]))
     assert (res["status"] == 0).all() and np.array_equal(res["mb_count"], g["mb_counts"])
     assert np.array_equal(recs, g["mbs"])
@@ -120,7 +131,8 @@ def test_emu_full_records_match_the_reference_ctx_mb(name):
     (src/h264_macroblock.h:105-167; dumped by oracle/ref_harness.c mb_syntax_from_ref)."""
     stream, nmb, nsl = L.synth_video(**CASES[name])
     ev, mbs, syn = S.ref_trace_syntax(stream)
-    recs, res, got = S.emu_cavlc_parse_full(stream, S.slice_params_from_trace(ev), nmb)
+    params, maps = S.group_maps_from_trace(ev)
+    recs, res, got = S.emu_cavlc_parse_full(stream, params, nmb, group_maps=maps if len(maps) else None)
     assert (res["status"] == 0).all() and len(syn) == nmb
     assert np.array_equal(recs["hash"], mbs["hash"])
     if CASES[name].get("chroma_format_idc", 1) == 3:
@@ -164,6 +176,8 @@ def test_gpu_full_records_match_the_reference_ctx_mb(gpu):
 def test_emu_step_machine_agrees_with_first_generation(name):
     """Both generations of K4 (cavlc_steps.cuh: one syntax element per lane per step;
     cavlc_parse.cuh: call tree per slice) give the same records, counts, status and end position."""
+    if CASES[name].get("fmo"):
+        pytest.skip("MBAFF / field pictures / slice groups exist in the second generation only")
     g = load_golden(name)
     stream, nmb, nsl = L.synth_video(**CASES[name])
     r2, q2 = S.emu_cavlc_parse(stream, g["params"], nmb, gen=2)
@@ -237,3 +251,40 @@ def test_gpu_step_machine_agrees_with_first_generation(gpu, monkeypatch):
             monkeypatch.setenv("H264GPU_CAVLC_PER_LANE", per_lane)
             r2, q2 = gpu.cavlc_parse_host(stream, params, nmb)
             assert np.array_equal(r1, r2) and np.array_equal(q1, q2), (lanes, per_lane)
+
+
+MBAFF_CASES = [dict(width_mbs=11, height_mbs=8, frames=6, slices_per_frame=1 + s % 3, b_frames=s & 1,
+                    num_ref_frames=1 + s % 3, profile_idc=[77, 100, 100][s % 3], transform_8x8=int(s % 3 == 1),
+                    pct_skip=[0, 25, 50, 70][s % 4], pct_pcm=10 * (s % 2), seed=50 + s, fmo=0x100, idr_period=4,
+                    chroma_format_idc=[1, 1, 2, 3, 0][s % 5]) for s in range(10)]
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", MBAFF_CASES, ids=lambda k: "seed%d" % k["seed"])
+def test_emu_mbaff_matches_the_reference(kw):
+    """N3 (MBAFF): frames coded as macroblock pairs with a field / frame decision per pair
+    (mb_field_decoding_flag read, inherited or inferred; 6.4.12.2 neighbours for nC; ref_idx over
+    fields): records -- addresses, types and the checksum that includes mb_field_decoding_flag as
+    the reference holds it at callback time -- identical to the reference's."""
+    stream, nmb, nsl = L.synth_video(**kw)
+    ev, mbs, off = S.ref_trace(stream)
+    assert len(mbs) == nmb and off == len(stream)
+    params = S.slice_params_from_trace(ev)
+    assert (params.view(L.SLICE_PARAMS)["mbaff_frame_flag"] == 1).all()
+    recs, res = S.emu_cavlc_parse(stream, params, nmb)
+    assert (res["status"] == 0).all(), res["status"]
+    bad = np.nonzero(recs != mbs)[0]
+    assert len(bad) == 0, (bad[:5], recs[bad[:3]], mbs[bad[:3]])
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_gpu_mbaff_and_field_pictures_match_the_reference(gpu):
+    for fmo in (0x100, 0x200):
+        for seed in (71, 72, 73):
+            stream, nmb, nsl = L.synth_video(width_mbs=30, height_mbs=16, frames=8, slices_per_frame=4, b_frames=seed & 1,
+                                             num_ref_frames=1 + seed % 3, profile_idc=100, transform_8x8=1,
+                                             pct_skip=20 * (seed % 4), pct_pcm=10, seed=seed, idr_period=4, fmo=fmo)
+            ev, mbs, off = S.ref_trace(stream)
+            recs, res = gpu.cavlc_parse_host(stream, S.slice_params_from_trace(ev), nmb)
+            assert (res["status"] == 0).all() and np.array_equal(recs, mbs), (fmo, seed)

@@ -133,3 +133,18 @@ def test_slice_groups_through_the_api(map_type):
             ours = T.trace(lib, T.OURS, stream, 1, mode)
             T.assert_same_trace(ours, T.trace(lib, T.REF, stream, 1, mode), "fmo type %d mode %d" % (map_type, mode))
             assert sum(1 for t, _ in T.split_log(ours) if t == T_SD_MB) == nmb
+
+
+@pytest.mark.parametrize("fmo", [0x100, 0x200], ids=["mbaff", "field_pictures"])
+def test_mbaff_and_field_pictures_through_the_api(fmo):
+    """N3 (MBAFF) and field pictures: h264_reader_parse(SLICE_DATA), bulk and NAL by NAL, callback
+    for callback what the reference delivers (MBAFF slices answered -ENOSYS in round 1)."""
+    lib = T.harness()
+    for seed in (61, 62):
+        stream, nmb, nsl = L.synth_video(width_mbs=20, height_mbs=12, frames=6, slices_per_frame=3, b_frames=1,
+                                         num_ref_frames=2, profile_idc=100, transform_8x8=1, pct_skip=30,
+                                         seed=seed, idr_period=3, fmo=fmo)
+        for mode in (0, 1):
+            ours = T.trace(lib, T.OURS, stream, 1, mode)
+            T.assert_same_trace(ours, T.trace(lib, T.REF, stream, 1, mode), "fmo %x mode %d" % (fmo, mode))
+            assert sum(1 for t, _ in T.split_log(ours) if t == T_SD_MB) == nmb
