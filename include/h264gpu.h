@@ -144,6 +144,16 @@ H264GPU_API int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t 
 						void *stream);
 
 /*
+ * Reserve the workspace of h264gpu_split_strip_inplace_dev for streams of up to len bytes and
+ * nal_cap NAL units now, instead of at the first call.  WHEN it is allocated matters on B200:
+ * the kernel's look-back polls chain words in this buffer, and the same launch over the same 4 GiB
+ * took 2.0 ms when the workspace had been allocated right after the stream buffers and 2.8 - 2.9 ms
+ * when it had been allocated before them, or after a large page-locked host buffer
+ * (profiles/r02_scan_workspace_placement.txt).  Call it right after allocating d_in / d_rbsp.
+ */
+H264GPU_API int h264gpu_scan_reserve(h264gpu_ctx *ctx, uint64_t len, uint64_t nal_cap);
+
+/*
  * Host-side merge of per-shard results (byte-range shards of one stream, in
  * stream order: chunks of the host pipeline, or one shard per GPU).  No device
  * work and no collective: each shard contributes its small result struct and

@@ -82,7 +82,7 @@ GPU_SYMBOLS = [
     "h264gpu_device_count", "h264gpu_create", "h264gpu_destroy", "h264gpu_device",
     "h264gpu_version", "h264gpu_launch_count", "h264gpu_malloc", "h264gpu_free",
     "h264gpu_host_alloc", "h264gpu_host_free", "h264gpu_memcpy_h2d", "h264gpu_memcpy_d2h",
-    "h264gpu_sync", "h264gpu_split_strip_dev", "h264gpu_split_strip_inplace_dev", "h264gpu_merge_init", "h264gpu_merge_shard", "h264gpu_merge_shard_inplace",
+    "h264gpu_sync", "h264gpu_split_strip_dev", "h264gpu_split_strip_inplace_dev", "h264gpu_scan_reserve", "h264gpu_merge_init", "h264gpu_merge_shard", "h264gpu_merge_shard_inplace",
     "h264gpu_merge_finish", "h264gpu_split_strip_host", "h264gpu_frame_dev",
     "h264gpu_frame_host", "h264gpu_timer_create", "h264gpu_timer_destroy",
     "h264gpu_timer_start", "h264gpu_timer_stop", "h264gpu_timer_elapsed_ms",
@@ -118,6 +118,7 @@ def load_gpu_lib():
         lib.h264gpu_split_strip_dev.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, u64, vp, vp]
         lib.h264gpu_split_strip_host.argtypes = [vp, vp, u64, vp, vp, vp, vp, u64p, u64p, u64p]
         lib.h264gpu_split_strip_inplace_dev.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, u64, vp, vp]
+        lib.h264gpu_scan_reserve.argtypes = [vp, u64, u64]
         lib.h264gpu_merge_init.restype = None
         lib.h264gpu_merge_init.argtypes = [vp]
         lib.h264gpu_merge_shard.argtypes = [vp, vp, vp, vp, vp, u64, u64, u64p, u64p]

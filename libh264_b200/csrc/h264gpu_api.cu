@@ -25,6 +25,8 @@ int h264gpu_device_count(void)
 	return n;
 }
 
+static int ws7_reserve(h264gpu_ctx *ctx, size_t bytes);
+
 int h264gpu_create(int device, h264gpu_ctx **out)
 {
 	if (out == NULL)
@@ -469,8 +471,15 @@ static int scan7_launch_t(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, u
 	int r = ws7_reserve(ctx, need);
 	if (r < 0)
 		return r;
-	if (ctx->ws7_bytes != had)
+	if (ctx->ws7_bytes != had) {
 		ctx->epoch7 = 0; /* fresh zeroed buffer */
+	} else if (ctx->ws7_spans != nspans) {
+		/* another stream length: the arrays behind the chain words move, and what a shorter
+		 * launch left where chain words of this one will be (span words whose top 16 bits are a
+		 * start-code count) could pass for a word of this launch's epoch */
+		CU_TRY(cudaMemsetAsync((uint8_t *)ctx->ws7 + chain_off, 0, (size_t)nspans * 8, st));
+	}
+	ctx->ws7_spans = nspans;
 	if (++ctx->epoch7 > 0xffffu) {
 		/* epoch wrap: stale chain words of 65535 launches ago could look valid */
 		CU_TRY(cudaMemsetAsync((uint8_t *)ctx->ws7 + chain_off, 0, (size_t)nspans * 8, st));
@@ -612,6 +621,31 @@ static int scan7_launch_t(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, u
 	CU_TRY(cudaGetLastError());
 	ctx->launches += 4;
 	return 0;
+}
+
+/* bytes of workspace a launch over len bytes with room for nal_cap NAL units needs (the layout
+ * of scan7_launch_t) */
+static size_t scan7_workspace_bytes(uint64_t len, uint64_t nal_cap)
+{
+	const uint64_t span = annexb7::Cfg<8>::SPAN;
+	const uint64_t nspans = (len + 2 + span - 1) / span;
+	uint64_t ev_cap = 4 * nal_cap + 4096;
+	if (ev_cap > len / 3 + 2)
+		ev_cap = len / 3 + 2;
+	const uint64_t nblk = (nspans + annexb7::kFinT - 1) / annexb7::kFinT;
+	return 256 + (size_t)nspans * 28 + (size_t)nblk * 16 + 64 + (size_t)ev_cap * 40;
+}
+
+extern "C" int h264gpu_scan_reserve(h264gpu_ctx *ctx, uint64_t len, uint64_t nal_cap)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	const size_t had = ctx->ws7_bytes;
+	r = ws7_reserve(ctx, scan7_workspace_bytes(len, nal_cap));
+	if (r >= 0 && ctx->ws7_bytes != had)
+		ctx->epoch7 = 0;
+	return r;
 }
 
 static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uint64_t base,

@@ -23,6 +23,7 @@ struct h264gpu_ctx {
 	void *ws7;
 	size_t ws7_bytes;
 	uint32_t epoch7;
+	uint64_t ws7_spans; /* spans of the last launch: another length moves the arrays behind the chain words */
 	uint32_t attr_set; /* per-context (= per-device) cudaFuncSetAttribute done: bit 0 scan7 */
 	int sms;
 	/* host-buffer pipeline */

@@ -4,10 +4,6 @@
  */
 #include "h264gpu_internal.h"
 
-#include "cavlc_parse.cuh"
-#define CAVLC_NS cavlc_full
-#define CAVLC_FULL 1
-#include "cavlc_parse.cuh" /* the same parse with struct h264_mb_syntax records (opt-in entry point) */
 #include "cavlc_steps.cuh"
 #include "cabac_parse.cuh"
 #include "conceal.cuh"
@@ -30,9 +26,11 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
 		lanes_log2 = (uint32_t)atoi(env);
 	} else {
-		/* one slice per warp while that fills the machine with warps to switch between, then
-		 * more lanes per warp: the steps of a warp's lanes share their instructions */
-		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > (uint64_t)sms * 8)
+		/* one slice per warp while the warps fit the machine (~32 per SM), then more lanes per
+		 * warp (measured at 16000 slices on 148 SMs: 4 lanes 95 M, 8 lanes 93 M, 16 lanes 71 M,
+		 * 32 lanes 57 M macroblocks/s: the warps to switch between are worth more than the shared
+		 * instruction issue) */
+		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > (uint64_t)sms * 32)
 			lanes_log2++;
 	}
 	uint32_t per_lane = 1;
@@ -172,52 +170,8 @@ extern "C" int h264gpu_cavlc_parse_fmo_dev(h264gpu_ctx *ctx, const uint8_t *d_st
 	cudaStream_t st = (cudaStream_t)stream;
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-	const char *gen = getenv("H264GPU_CAVLC_GEN");
-	if (gen == NULL || atoi(gen) != 1)
-		return cavlc_steps_launch(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, d_syntax,
-					  d_group_maps, st, sms);
-	/* first generation (A/B): nC context ring per slice: (PicWidthInMbs + 1) macroblocks x 48 counts, sized
-	 * for pictures up to 8192 luma samples wide (512 MBs); wider slices get -E2BIG. */
-	const uint32_t ring_w = 512;
-	const uint64_t ring_stride = (uint64_t)(ring_w + 1) * 48;
-	const size_t need = (size_t)n_slices * ring_stride;
-	r = h264gpu_ws_reserve(ctx, need);
-	if (r < 0)
-		return r;
-	cavlc::CavlcArgs a;
-	a.stream = d_stream;
-	a.stream_len = stream_len;
-	a.params = d_params;
-	a.n_slices = n_slices;
-	a.records = d_records;
-	a.results = d_results;
-	a.ring = (uint8_t *)ctx->ws;
-	a.ring_stride = ring_stride;
-	a.ring_w = ring_w;
-	a.syntax = d_syntax;
-	uint32_t lanes_log2 = 0;
-	const char *env = getenv("H264GPU_CAVLC_LANES_LOG2");
-	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
-		lanes_log2 = (uint32_t)atoi(env);
-	} else {
-		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > (uint64_t)sms * 32)
-			lanes_log2++;
-	}
-	a.lanes_log2 = lanes_log2;
-	const uint32_t threads = 128; /* 4 warps per block */
-	const uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
-	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
-	if (d_syntax == NULL) {
-		cavlc::cavlc_parse_kernel<<<blocks, threads, 0, st>>>(a);
-	} else {
-		cavlc_full::CavlcArgs f;
-		static_assert(sizeof(f) == sizeof(a), "same argument block in both instantiations");
-		memcpy(&f, &a, sizeof(f));
-		cavlc_full::cavlc_parse_kernel<<<blocks, threads, 0, st>>>(f);
-	}
-	CU_TRY(cudaGetLastError());
-	ctx->launches++;
-	return 0;
+	return cavlc_steps_launch(ctx, d_stream, stream_len, d_params, n_slices, d_records, d_results, d_syntax,
+				  d_group_maps, st, sms);
 }
 
 typedef int (*parse_dev_fn)(h264gpu_ctx *, const uint8_t *, uint64_t, const struct h264gpu_slice_params *,

@@ -37,6 +37,8 @@ def one_call():
     g.sync()
 if args.stage == 3:  # the scan workspace exists before the second pinned buffer does
     one_call()
+if args.stage == 6:  # the library's own answer: reserve the workspace right after the stream buffers
+    L._check(g.lib.h264gpu_scan_reserve(g.h, C.c_uint64(n_in), C.c_uint64(cap)), "reserve")
 if args.stage == 5:  # a first small launch (kernel loaded, small workspace) before the second pinned buffer
     g.split_strip_inplace_dev(d_in.ptr, 1 << 20, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8,
                               d_tab.ptr + cap * 16, d_tab.ptr + cap * 24, cap, d_res.ptr)

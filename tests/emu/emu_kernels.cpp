@@ -312,39 +312,7 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 	return 0;
 }
 
-/* K4: the per-slice parse is plain serial code, so the emulation is a host loop */
-#include "cavlc_parse.cuh"
-#define CAVLC_NS cavlc_full
-#define CAVLC_FULL 1
-#include "cavlc_parse.cuh"
-
-extern "C" int emu_cavlc_parse_full(const uint8_t *stream, uint64_t stream_len,
-				    const struct h264gpu_slice_params *params, uint32_t n_slices,
-				    struct h264gpu_mb_record *records, struct h264gpu_slice_result *results,
-				    struct h264_mb_syntax *syn)
-{
-	for (uint32_t i = 0; i < n_slices; i++) {
-		const h264gpu_slice_params &sp = params[i];
-		std::vector<uint8_t> ring(((size_t)sp.pic_width_in_mbs + 1) * 48 + 64, 0xEE);
-		cavlc_full::parse_slice(stream, stream_len, sp, ring.data(), records + sp.mb_out_off, results[i],
-					syn ? syn + sp.mb_out_off : nullptr);
-	}
-	return 0;
-}
-
-extern "C" int emu_cavlc_parse(const uint8_t *stream, uint64_t stream_len,
-			       const struct h264gpu_slice_params *params, uint32_t n_slices,
-			       struct h264gpu_mb_record *records, struct h264gpu_slice_result *results)
-{
-	for (uint32_t i = 0; i < n_slices; i++) {
-		const h264gpu_slice_params &sp = params[i];
-		std::vector<uint8_t> ring(((size_t)sp.pic_width_in_mbs + 1) * 48 + 64, 0xEE);
-		cavlc::parse_slice(stream, stream_len, sp, ring.data(), records + sp.mb_out_off, results[i]);
-	}
-	return 0;
-}
-
-/* K4, second generation: the same step function the kernel's lanes run, one slice at a time */
+/* K4: the same step function the kernel's lanes run, one slice at a time */
 #include "cavlc_steps.cuh"
 
 extern "C" int emu_cavlc_steps(const uint8_t *stream, uint64_t stream_len,

@@ -362,7 +362,7 @@ def emu_split_strip_inplace(buf, strip=True, cpt=8, edge=None, base=0, ev_cap=No
 
 
 def _emu_cavlc_steps(stream, params, n_records, full, group_maps):
-    """K4 second generation (cavlc_steps.cuh): the lane step function run serially per slice."""
+    """K4 (cavlc_steps.cuh): the lane step function run serially per slice."""
     lib = emu()
     lib.emu_cavlc_steps.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
@@ -379,34 +379,13 @@ def _emu_cavlc_steps(stream, params, n_records, full, group_maps):
     return recs[:n_records], res[:n]
 
 
-def emu_cavlc_parse_full(stream, params, n_records, gen=2, group_maps=None):
+def emu_cavlc_parse_full(stream, params, n_records, group_maps=None):
     """The CAVLC parse with full per-macroblock records (struct h264_mb_syntax blobs)."""
-    if gen == 2:
-        return _emu_cavlc_steps(stream, params, n_records, True, group_maps)
-    lib = emu()
-    lib.emu_cavlc_parse_full.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
-                                         C.c_void_p]
-    sz = ref().ref_sizeof_mb_syntax()
-    stream = np.ascontiguousarray(stream, dtype=np.uint8)
-    n = len(params) // PARAMS_SIZE
-    recs = np.zeros(max(n_records, 1), MB_RECORD)
-    res = np.zeros(max(n, 1), SLICE_RESULT)
-    syn = np.full((max(n_records, 1), sz), 0xEE, np.uint8)
-    lib.emu_cavlc_parse_full(ptr(stream), len(stream), ptr(params), n, ptr(recs), ptr(res), ptr(syn))
-    return recs[:n_records], res[:n], syn[:n_records]
+    return _emu_cavlc_steps(stream, params, n_records, True, group_maps)
 
 
-def emu_cavlc_parse(stream, params, n_records, gen=2, group_maps=None):
-    if gen == 2:
-        return _emu_cavlc_steps(stream, params, n_records, False, group_maps)
-    lib = emu()
-    lib.emu_cavlc_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
-    stream = np.ascontiguousarray(stream, dtype=np.uint8)
-    n = len(params) // PARAMS_SIZE
-    recs = np.zeros(max(n_records, 1), MB_RECORD)
-    res = np.zeros(max(n, 1), SLICE_RESULT)
-    lib.emu_cavlc_parse(ptr(stream), len(stream), ptr(params), n, ptr(recs), ptr(res))
-    return recs[:n_records], res[:n]
+def emu_cavlc_parse(stream, params, n_records, group_maps=None):
+    return _emu_cavlc_steps(stream, params, n_records, False, group_maps)
 
 
 # ----------------------------------------------------------------------------

@@ -173,24 +173,19 @@ def test_gpu_full_records_match_the_reference_ctx_mb(gpu):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_emu_step_machine_agrees_with_first_generation(name):
-    """Both generations of K4 (cavlc_steps.cuh: one syntax element per lane per step;
-    cavlc_parse.cuh: call tree per slice) give the same records, counts, status and end position."""
-    if CASES[name].get("fmo"):
-        pytest.skip("MBAFF / field pictures / slice groups exist in the second generation only")
+def test_emu_end_position_and_truncated_slices(name):
+    """end_bit sits in the slice's last byte (right before the stop bit); a truncated slice gives
+    -EIO or a shorter clean parse, never more macroblocks than the slice has."""
     g = load_golden(name)
     stream, nmb, nsl = L.synth_video(**CASES[name])
-    r2, q2 = S.emu_cavlc_parse(stream, g["params"], nmb, gen=2)
-    r1, q1 = S.emu_cavlc_parse(stream, g["params"], nmb, gen=1)
-    assert np.array_equal(r1, r2) and np.array_equal(q1, q2)
+    r, q = S.emu_cavlc_parse(stream, g["params"], nmb, group_maps=group_maps(g))
     nal_len = g["params"].view(L.SLICE_PARAMS)["nal_len"].astype(np.uint64)
-    assert ((q2["end_bit"] > (nal_len - 2) * 8) & (q2["end_bit"] < nal_len * 8)).all()
-    # truncated slices: same verdict from both
+    assert ((q["end_bit"] > (nal_len - 2) * 8) & (q["end_bit"] < nal_len * 8)).all()
     p = g["params"].copy().view(L.SLICE_PARAMS)
     p["nal_len"] = p["nal_len"] * 2 // 3
-    r2, q2 = S.emu_cavlc_parse(stream, p.view(np.uint8), nmb, gen=2)
-    r1, q1 = S.emu_cavlc_parse(stream, p.view(np.uint8), nmb, gen=1)
-    assert np.array_equal(q1["status"], q2["status"]) and np.array_equal(q1["mb_count"], q2["mb_count"])
+    r, q = S.emu_cavlc_parse(stream, p.view(np.uint8), nmb, group_maps=group_maps(g))
+    assert ((q["status"] == -5) | (q["status"] == 0)).all() and (q["status"] == -5).any()
+    assert (q["mb_count"] <= g["mb_counts"]).all()
 
 
 @needs_ref
@@ -235,22 +230,21 @@ def test_gpu_slice_groups_match_the_reference(gpu):
         assert (res["status"] == -38).all()
 
 
+@needs_ref
 @pytest.mark.gpu
-def test_gpu_step_machine_agrees_with_first_generation(gpu, monkeypatch):
-    """Same records / results from both kernel generations, at every packing of slices into warps."""
-    stream, nmb, nsl, params = L.synth_video(width_mbs=40, height_mbs=30, frames=24, slices_per_frame=10,
-                                             profile_idc=100, transform_8x8=1, b_frames=1, num_ref_frames=3,
-                                             idr_period=8, pct_skip=35, pct_pcm=20, seed=77, want_params=True)
-    monkeypatch.setenv("H264GPU_CAVLC_GEN", "1")
-    r1, q1 = gpu.cavlc_parse_host(stream, params, nmb)
-    monkeypatch.delenv("H264GPU_CAVLC_GEN")
-    assert (q1["status"] == 0).all() and int(q1["mb_count"].sum()) == nmb
+def test_gpu_every_lane_packing_gives_the_reference_records(gpu, monkeypatch):
+    """Same records / results at every packing of slices into warps and with several slices per lane."""
+    stream, nmb, nsl = L.synth_video(width_mbs=40, height_mbs=30, frames=24, slices_per_frame=10,
+                                     profile_idc=100, transform_8x8=1, b_frames=1, num_ref_frames=3,
+                                     idr_period=8, pct_skip=35, pct_pcm=20, seed=77)
+    ev, mbs, off = S.ref_trace(stream)
+    params = S.slice_params_from_trace(ev)
     for lanes in ("0", "2", "5"):
         for per_lane in ("1", "3"):
             monkeypatch.setenv("H264GPU_CAVLC_LANES_LOG2", lanes)
             monkeypatch.setenv("H264GPU_CAVLC_PER_LANE", per_lane)
-            r2, q2 = gpu.cavlc_parse_host(stream, params, nmb)
-            assert np.array_equal(r1, r2) and np.array_equal(q1, q2), (lanes, per_lane)
+            recs, res = gpu.cavlc_parse_host(stream, params, nmb)
+            assert (res["status"] == 0).all() and np.array_equal(recs, mbs), (lanes, per_lane)
 
 
 MBAFF_CASES = [dict(width_mbs=11, height_mbs=8, frames=6, slices_per_frame=1 + s % 3, b_frames=s & 1,

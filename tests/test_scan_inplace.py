@@ -296,3 +296,15 @@ def test_gpu_sharded_merge(gpu):
         n = len(b)
         cuts = sorted(set(int(c) // 16 * 16 for c in rng.integers(16, n, 3)) - {0})
         check_merged(_merge_shards(run, b, cuts), S.oracle_split_strip(b), (it, cuts))
+
+
+@pytest.mark.gpu
+def test_gpu_one_context_streams_of_changing_length(gpu):
+    """The workspace is one buffer whose arrays move with the stream length: a long stream, then
+    shorter and again longer ones on the SAME context (a dense start-code pattern, so that the
+    span words a shorter launch leaves behind have small non-zero top bits, like launch epochs)."""
+    rng = np.random.default_rng(5)
+    L._check(gpu.lib.h264gpu_scan_reserve(gpu.h, 48 << 20, 1 << 20), "h264gpu_scan_reserve")
+    for it, mb in enumerate([24, 1, 9, 2, 17, 3, 12, 5]):
+        buf = S.gen_annexb(rng, 1100 * mb, lo=1, hi=2000, p_zero=3 / 16)[:mb << 20]
+        check_per_nal(gpu.split_strip_inplace(buf), S.oracle_split_strip(buf), ("changing length", it, mb))
