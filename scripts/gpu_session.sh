@@ -20,7 +20,7 @@ echo "== ncu full: scan, scan-only, frame, cavlc, cabac"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan7_kernel -s 6 -c 2 -f -o gpurun_out/${TAG}_prof_scan python bench.py $SHORT > gpurun_out/${TAG}_ncu_scan.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan7_only -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_scanonly python bench.py $SHORT > gpurun_out/${TAG}_ncu_scanonly.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:frame6_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_frame python bench.py $SHORT > gpurun_out/${TAG}_ncu_frame.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:cavlc_parse -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_cavlc python bench.py $SHORT > gpurun_out/${TAG}_ncu_cavlc.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:cavlc_steps -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_cavlc python bench.py $SHORT > gpurun_out/${TAG}_ncu_cavlc.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:cabac_parse -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_cabac python bench.py $SHORT > gpurun_out/${TAG}_ncu_cabac.log 2>&1
 ls -la gpurun_out/${TAG}_*
 echo "== dram traffic of the scan kernels at the bench size"

@@ -335,3 +335,75 @@ def test_gpu_many_slices_all_lane_packings(gpu, lanes, monkeypatch):
     assert (res2["status"][ok] == 0).all()
     lo, hi = int(P["mb_out_off"][5]), int(P["mb_out_off"][5] + P["mb_out_cap"][5])
     assert np.array_equal(recs2[:lo], want[:lo]) and np.array_equal(recs2[hi:], want[hi:])
+
+
+# ---- 5. the independent decoder (oracle/oracle_cabac_spec.c) -----------------------------------
+# Written from H.264 9.3 without the shared walker / engine of cabac_syntax.h + cabac_engine.h.
+# It must agree with (a) the REFERENCE's records of every twin stream, (b) the reference writer's
+# concealment slices, (c) the generator's intended records on every generator stream: any ctxIdx /
+# binarisation drift that generator and kernel share would show up as a disagreement here.
+
+def spec_decode(stream, params, n_records):
+    lib = S.oracle()
+    lib.oracle_cabac_spec_decode.restype = C.c_int
+    lib.oracle_cabac_spec_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                             C.c_void_p]
+    stream = np.ascontiguousarray(stream, np.uint8)
+    params = np.ascontiguousarray(params, np.uint8)
+    n = len(params) // S.PARAMS_SIZE
+    recs = np.zeros(max(n_records, 1), S.MB_RECORD)
+    res = np.zeros(max(n, 1), S.SLICE_RESULT)
+    assert lib.oracle_cabac_spec_decode(S.ptr(stream), len(stream), S.ptr(params), n, S.ptr(recs), n_records,
+                                        S.ptr(res)) == 0
+    return recs[:n_records], res[:n]
+
+
+@pytest.mark.parametrize("cfg", TWIN_CFGS, ids=lambda c: "seed%d" % c["seed"])
+def test_independent_decoder_on_twin_streams(cfg):
+    blob, params, ref_mbs = make_twin(cfg)
+    recs, res = spec_decode(blob, params.view(np.uint8), len(ref_mbs))
+    assert (res["status"] == 0).all(), res
+    assert np.array_equal(res["mb_count"], params["mb_out_cap"])
+    bad = np.nonzero(recs != ref_mbs)[0]
+    assert len(bad) == 0, (bad[:5], recs[bad[:3]], ref_mbs[bad[:3]])
+    k_recs, k_res = cpu_decode(blob, params.view(np.uint8), len(ref_mbs))
+    assert np.array_equal(k_res["end_bit"], res["end_bit"])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_independent_decoder_on_golden_twins(name):
+    blob, params, ref_mbs = load_golden_twin(name)
+    recs, res = spec_decode(blob, params, len(ref_mbs))
+    assert (res["status"] == 0).all() and np.array_equal(recs, ref_mbs)
+
+
+@pytest.mark.parametrize("seed", CONCEAL_SEEDS)
+def test_independent_decoder_on_reference_concealment_slices(seed):
+    stream, params, cap = conceal_slices(seed)
+    if len(params) == 0:
+        pytest.skip("no CABAC concealment slice for this seed")
+    recs, res = spec_decode(stream, params.view(np.uint8), cap)
+    check_concealment(stream, params, recs, res)
+
+
+@pytest.mark.parametrize("cfg", CFGS, ids=lambda c: "seed%d" % c["seed"])
+def test_independent_decoder_on_generator_streams(cfg):
+    stream, params, want = gen_cabac(**cfg)
+    recs, res = spec_decode(stream, params, len(want))
+    P = np.frombuffer(params, S.SLICE_PARAMS)
+    assert (res["status"] == 0).all(), res["status"]
+    assert np.array_equal(res["mb_count"], P["mb_out_cap"])
+    bad = np.nonzero(recs != want)[0]
+    assert len(bad) == 0, (bad[:5], recs[bad[:3]], want[bad[:3]])
+    k_recs, k_res = cpu_decode(stream, params, len(want))
+    assert np.array_equal(k_res["end_bit"], res["end_bit"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", CFGS[:3], ids=lambda c: "seed%d" % c["seed"])
+def test_gpu_kernel_agrees_with_the_independent_decoder(gpu, cfg):
+    stream, params, want = gen_cabac(**cfg)
+    recs, res = gpu.cabac_parse_host(stream, params, len(want))
+    s_recs, s_res = spec_decode(stream, params, len(want))
+    assert (res["status"] == 0).all() and np.array_equal(recs, s_recs)
+    assert np.array_equal(res["mb_count"], s_res["mb_count"]) and np.array_equal(res["end_bit"], s_res["end_bit"])
