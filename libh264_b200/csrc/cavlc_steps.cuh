@@ -118,6 +118,9 @@ enum {
 	F_FIELD_PIC = 1u << 21,    /* field_pic_flag: every macroblock is a field macroblock */
 };
 
+/* MBAFF slice in an instantiation that carries the macroblock-pair code */
+#define CAVLC2_MBAFF(l) ((l).can_mbaff && ((l).flags & F_MBAFF) != 0)
+
 #ifdef H264_EMU
 #define CAVLC2_STRIDE 1u
 #else
@@ -145,6 +148,7 @@ struct Lane {
 	uint32_t *sm;        /* this lane's shared words (stride CAVLC2_STRIDE) */
 	uint32_t W, pic_size, first, cap, cat, max0, max1;
 	uint32_t flags, state, cur, count, prev_addr;
+	bool can_mbaff;      /* constant of the kernel instantiation: false removes the macroblock-pair code */
 	int status;
 	/* macroblock */
 	uint64_t hash, slots, mvd_mask;
@@ -169,7 +173,7 @@ __device__ __forceinline__ int16_t *lev_ptr(const Lane &l, uint32_t i)
  * macroblock (pair) before */
 __device__ __forceinline__ uint32_t cur_buf(const Lane &l)
 {
-	return ((l.flags & F_WHICH) ? 2u : 0u) | ((l.flags & F_MBAFF) ? (l.cur & 1u) : 0u);
+	return ((l.flags & F_WHICH) ? 2u : 0u) | (CAVLC2_MBAFF(l) ? (l.cur & 1u) : 0u);
 }
 __device__ __forceinline__ uint32_t prev_buf(const Lane &l) { return (l.flags & F_WHICH) ? 0u : 2u; }
 
@@ -355,7 +359,7 @@ __device__ __forceinline__ uint32_t calc_nc(const Lane &l, uint32_t comp, uint32
 		left_in = blk - 1;
 		up_in = blk - 2;
 	}
-	const bool mbaff = (l.flags & F_MBAFF) != 0;
+	const bool mbaff = CAVLC2_MBAFF(l);
 	if (x > 0) {
 		aA = true;
 		nA = *nz_ptr(l, cb, comp * 16 + left_in);
@@ -490,7 +494,7 @@ __device__ __forceinline__ void pair_end(Lane &l)
 /* where a lane goes for its next coded macroblock */
 __device__ __forceinline__ uint32_t mb_start_state(const Lane &l)
 {
-	if ((l.flags & F_MBAFF) && (!(l.cur & 1u) || (l.flags & F_PREV_SKIPPED)))
+	if (CAVLC2_MBAFF(l) && (!(l.cur & 1u) || (l.flags & F_PREV_SKIPPED)))
 		return S_MB_FIELD;
 	return S_MB_TYPE;
 }
@@ -841,7 +845,7 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 	if (state == S_REF) {
 		rbit = (uint32_t)__ffs((int)l.ref_mask) - 1;
 		rmax = (rbit & 4) ? l.max1 : l.max0;
-		if ((l.flags & F_MBAFF) && (l.flags & F_CUR_FIELD))
+		if (CAVLC2_MBAFF(l) && (l.flags & F_CUR_FIELD))
 			rmax = 2 * rmax + 1;
 		want_ue = rmax > 1;
 	}
@@ -888,7 +892,7 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		/* what the reference holds in mb_field_decoding_flag when it delivers the macroblock
 		 * (h264_new_macroblock, src/h264_slice_data.c:1144-1175) */
 		uint32_t field = (l.flags & F_FIELD_PIC) ? 1u : 0u;
-		if (l.flags & F_MBAFF) {
+		if (CAVLC2_MBAFF(l)) {
 			const uint32_t bottom = l.cur & 1u;
 			if (!bottom) {
 				pair_begin(l);
@@ -918,7 +922,7 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		if (FULL && l.syn)
 			syn_open(l.syn + l.count, l.cur, t);
 		l.count++;
-		if (l.flags & F_MBAFF) {
+		if (CAVLC2_MBAFF(l)) {
 			if (l.cur & 1u)
 				pair_end(l);
 			l.cur++;
@@ -947,7 +951,7 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		const uint32_t cur = l.cur;
 		l.flags &= ~(F_I16 | F_T8 | F_NO_SUB_LT8 | F_NXN | F_INTRA_CBP | F_DIRECT16 | F_PRED8);
 		l.flags |= F_NO_SUB_LT8;
-		if (!(l.flags & F_MBAFF)) { /* MBAFF: pair_begin did this for the pair */
+		if (!CAVLC2_MBAFF(l)) { /* MBAFF: pair_begin did this for the pair */
 			bool aA = cur >= l.first + 1 && cur % l.W != 0;
 			bool aB = cur >= l.first + l.W;
 			if (l.gmap != nullptr) {
@@ -981,8 +985,8 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 			syn_open(l.syn + l.count, cur, 0);
 		/* field macroblock: field picture, or the pair's flag in an MBAFF frame; ref_idx then
 		 * ranges over fields (src/h264_slice_data.c:1199-1205) and is sent even for one frame */
-		const bool mb_field = (l.flags & F_MBAFF) ? (l.flags & F_CUR_FIELD) != 0 : (l.flags & F_FIELD_PIC) != 0;
-		const bool mf = (l.flags & F_MBAFF) && mb_field;
+		const bool mb_field = CAVLC2_MBAFF(l) ? (l.flags & F_CUR_FIELD) != 0 : (l.flags & F_FIELD_PIC) != 0;
+		const bool mf = CAVLC2_MBAFF(l) && mb_field;
 		const bool r0 = l.max0 > 0 || mf, r1 = l.max1 > 0 || mf;
 		hash_add<FULL>(l, H264GPU_F_MB_FIELD_DECODING_FLAG, 0, mb_field ? 1 : 0);
 
@@ -1128,7 +1132,7 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 		}
 		if (!direct) {
 			const uint64_t bits = (1ull << (2 * nsub)) - 1;
-			const bool mf = (l.flags & F_MBAFF) && (l.flags & F_CUR_FIELD);
+			const bool mf = CAVLC2_MBAFF(l) && (l.flags & F_CUR_FIELD);
 			if (m != 1) {
 				if ((l.max0 > 0 || mf) && l.mb_type != MB_P_8x8ref0)
 					l.ref_mask |= 1u << i;
@@ -1239,7 +1243,7 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 	case S_MB_END: {
 		uint32_t w[3];
 		bottom_rows(l, w);
-		const bool mbaff = (l.flags & F_MBAFF) != 0;
+		const bool mbaff = CAVLC2_MBAFF(l);
 		uint32_t *slot = mbaff ? ring_slot(l, l.cur >> 1) + ((l.cur & 1u) ? 4 : 0) : ring_slot(l, l.cur);
 		slot[0] = w[0];
 		slot[1] = w[1];
@@ -1349,6 +1353,7 @@ __device__ __forceinline__ void parse_slice(const uint8_t *stream, uint64_t stre
 {
 	Lane l;
 	l.sm = sm;
+	l.can_mbaff = true;
 	slice_begin(l, stream, stream_len, sp, ring, rec, syn, group_maps, 0xffffu);
 	while (l.state != S_DONE)
 		step<FULL>(l);
@@ -1368,7 +1373,8 @@ struct CavlcArgs {
 	uint32_t lanes_log2; /* log2 of the lanes of a warp that carry slices (0..5) */
 	h264_mb_syntax *syntax; /* full records (index = record index), or NULL */
 	const uint8_t *group_maps; /* macroblock -> slice group maps (slice i: + params[i].row_state_off), or NULL */
-	uint32_t *next_slice; /* work counter: tickets into order[]; set by order_kernel */
+	uint32_t *next_slice; /* [0] ticket counter of the frame / field kernel, [1] of the MBAFF kernel,
+				 [2] number of MBAFF slices; set by order_kernel */
 	uint32_t *order;      /* slice indices, longest NAL first */
 };
 
@@ -1386,8 +1392,10 @@ __global__ void __launch_bounds__(CAVLC2_ORDER_T) order_kernel(const h264gpu_sli
 	if (!sort) { /* A/B: list order */
 		for (uint32_t i = threadIdx.x; i < n; i += CAVLC2_ORDER_T)
 			order[i] = i;
-		if (threadIdx.x == 0)
-			*counter = counter_init;
+		if (threadIdx.x == 0) {
+			counter[0] = counter[1] = counter_init;
+			counter[2] = 1; /* unknown: let the MBAFF kernel look */
+		}
 		return;
 	}
 	__shared__ uint32_t hist[256];
@@ -1398,9 +1406,16 @@ __global__ void __launch_bounds__(CAVLC2_ORDER_T) order_kernel(const h264gpu_sli
 	if (t == 0)
 		smax = 0;
 	__syncthreads();
-	uint32_t m = 0;
-	for (uint32_t i = t; i < n; i += CAVLC2_ORDER_T)
+	uint32_t m = 0, n_mbaff = 0;
+	for (uint32_t i = t; i < n; i += CAVLC2_ORDER_T) {
 		m = max(m, params[i].nal_len);
+		n_mbaff += params[i].mbaff_frame_flag && !params[i].entropy_coding_mode_flag;
+	}
+	if (t == 0)
+		counter[2] = 0;
+	__syncthreads();
+	if (n_mbaff)
+		atomicAdd(&counter[2], n_mbaff);
 	m = __reduce_max_sync(FULL_MASK, m);
 	if ((t & 31) == 0)
 		atomicMax(&smax, m);
@@ -1417,7 +1432,7 @@ __global__ void __launch_bounds__(CAVLC2_ORDER_T) order_kernel(const h264gpu_sli
 			hist[b] = acc;
 			acc += c;
 		}
-		*counter = counter_init;
+		counter[0] = counter[1] = counter_init;
 	}
 	__syncthreads();
 	for (uint32_t i = t; i < n; i += CAVLC2_ORDER_T)
@@ -1430,11 +1445,16 @@ __global__ void __launch_bounds__(CAVLC2_ORDER_T) order_kernel(const h264gpu_sli
  * length: I / P / B, skip runs) and the warp steps its lanes together.  Few slices are spread
  * over more warps (lanes_log2 < 5) so that the SMs have warps to switch between.
  */
-template <bool FULL>
+template <bool FULL, bool MBAFF>
 __global__ void __launch_bounds__(CAVLC2_STRIDE) cavlc_steps_kernel(const CavlcArgs a)
 {
 #ifndef H264_EMU
 	extern __shared__ uint32_t smem[];
+	/* two instantiations share a launch's slices: frame / field slices here, MBAFF slices in the
+	 * one that carries the macroblock-pair code (launched behind it, gone at once when the list
+	 * has no MBAFF slice) */
+	if (MBAFF && a.next_slice[2] == 0)
+		return;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t step_l = 32u >> a.lanes_log2; /* working lanes are multiples of this */
 	const bool worker = !(lane & (step_l - 1));
@@ -1442,6 +1462,7 @@ __global__ void __launch_bounds__(CAVLC2_STRIDE) cavlc_steps_kernel(const CavlcA
 	const uint32_t glane = (gwarp << a.lanes_log2) + lane / step_l;
 	Lane l;
 	l.sm = smem + threadIdx.x;
+	l.can_mbaff = MBAFF;
 	l.state = S_DONE;
 	uint32_t slice = 0xffffffffu;
 	bool out = !worker, first_done = false;
@@ -1453,13 +1474,17 @@ __global__ void __launch_bounds__(CAVLC2_STRIDE) cavlc_steps_kernel(const CavlcA
 				a.results[slice] = res;
 			}
 			/* first ticket = the lane's own number (consecutive within the warp), then the counter */
-			const uint32_t ticket = slice == 0xffffffffu && !first_done ? glane : atomicAdd(a.next_slice, 1u);
+			const uint32_t ticket = slice == 0xffffffffu && !first_done ? glane : atomicAdd(a.next_slice + (MBAFF ? 1 : 0), 1u);
 			first_done = true;
 			if (ticket >= a.n_slices) {
 				out = true;
 			} else {
 				slice = a.order[ticket];
 				const h264gpu_slice_params &sp = a.params[slice];
+				if ((sp.mbaff_frame_flag != 0 && !sp.entropy_coding_mode_flag) != MBAFF) {
+					slice = 0xffffffffu; /* the other instantiation's */
+					continue;
+				}
 				slice_begin(l, a.stream, a.stream_len, sp, a.ring + (uint64_t)glane * a.ring_stride,
 					    a.records + sp.mb_out_off, FULL && a.syntax ? a.syntax + sp.mb_out_off : nullptr,
 					    a.group_maps, a.ring_w);

@@ -1293,46 +1293,30 @@ extern "C" int h264gpu_frame_host(h264gpu_ctx *ctx, const uint8_t *h_rbsp, const
 	const uint64_t len = h_off[n];
 	if (len && h_rbsp == NULL)
 		return -EINVAL;
-	uint8_t *d_rbsp = NULL, *d_out = NULL;
-	uint64_t *d_off = NULL, *d_out_off = NULL, *d_total = NULL;
-	const uint64_t dcap = out_cap;
-	int rc = 0;
-	cudaStream_t st = 0;
-#define FR_TRY(expr)                                                                       \
-	do {                                                                               \
-		if ((expr) != cudaSuccess) {                                               \
-			rc = -EIO;                                                         \
-			goto out;                                                          \
-		}                                                                          \
-	} while (0)
-	FR_TRY(cudaMalloc(&d_rbsp, len + 16));
-	FR_TRY(cudaMalloc(&d_out, dcap + 16));
-	FR_TRY(cudaMalloc(&d_off, (n + 1) * 8));
-	FR_TRY(cudaMalloc(&d_out_off, (n + 2) * 8));
-	d_total = d_out_off + n + 1;
+	/* pooled device buffers of the reader session on its private stream: a call costs no
+	 * cudaMalloc / cudaFree (round 1 allocated four buffers per call on the default stream) */
+	cudaStream_t st;
+	if ((r = h264gpu_reader_stream(ctx, &st)) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_stream, len + 64)) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_records, out_cap + 64)) < 0 ||
+	    (r = h264gpu_pool_dev(ctx, &ctx->rd_tab, (2 * n + 4) * 8)) < 0)
+		return r;
+	ctx->rd_stream_len = 0; /* the reader's resident buffer is gone */
+	uint8_t *d_rbsp = (uint8_t *)ctx->rd_stream.p, *d_out = (uint8_t *)ctx->rd_records.p;
+	uint64_t *d_off = (uint64_t *)ctx->rd_tab.p, *d_out_off = d_off + n + 1, *d_total = d_out_off + n + 1;
 	if (len)
-		FR_TRY(cudaMemcpyAsync(d_rbsp, h_rbsp, len, cudaMemcpyHostToDevice, st));
-	FR_TRY(cudaMemcpyAsync(d_off, h_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-	rc = h264gpu_frame_dev(ctx, d_rbsp, d_off, n, sc_len, d_out, dcap, d_out_off, d_total, st);
-	if (rc < 0)
-		goto out;
-	FR_TRY(cudaMemcpyAsync(total, d_total, 8, cudaMemcpyDeviceToHost, st));
-	FR_TRY(cudaStreamSynchronize(st));
+		CU_TRY(cudaMemcpyAsync(d_rbsp, h_rbsp, len, cudaMemcpyHostToDevice, st));
+	CU_TRY(cudaMemcpyAsync(d_off, h_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	r = h264gpu_frame_dev(ctx, d_rbsp, d_off, n, sc_len, d_out, out_cap, d_out_off, d_total, st);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaMemcpyAsync(total, d_total, 8, cudaMemcpyDeviceToHost, st));
+	CU_TRY(cudaStreamSynchronize(st));
 	if (h_out_off)
-		FR_TRY(cudaMemcpyAsync(h_out_off, d_out_off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-	{
-		const uint64_t ncopy = *total < out_cap ? *total : out_cap;
-		if (ncopy)
-			FR_TRY(cudaMemcpyAsync(h_out, d_out, ncopy, cudaMemcpyDeviceToHost, st));
-	}
-	FR_TRY(cudaStreamSynchronize(st));
-	if (*total > out_cap)
-		rc = -ENOBUFS;
-out:
-#undef FR_TRY
-	cudaFree(d_rbsp);
-	cudaFree(d_out);
-	cudaFree(d_off);
-	cudaFree(d_out_off);
-	return rc;
+		CU_TRY(cudaMemcpyAsync(h_out_off, d_out_off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+	const uint64_t ncopy = *total < out_cap ? *total : out_cap;
+	if (ncopy)
+		CU_TRY(cudaMemcpyAsync(h_out, d_out, ncopy, cudaMemcpyDeviceToHost, st));
+	CU_TRY(cudaStreamSynchronize(st));
+	return *total > out_cap ? -ENOBUFS : 0;
 }

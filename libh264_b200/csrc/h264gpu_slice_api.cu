@@ -70,12 +70,15 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 						    env != NULL && atoi(env) == 0 ? 0u : 1u);
 	ctx->launches++;
 	const size_t smem = (size_t)CAVLC2_SM_WORDS * threads * 4;
-	if (d_syntax == NULL)
-		cavlc2::cavlc_steps_kernel<false><<<blocks, threads, smem, st>>>(a);
-	else
-		cavlc2::cavlc_steps_kernel<true><<<blocks, threads, smem, st>>>(a);
+	if (d_syntax == NULL) {
+		cavlc2::cavlc_steps_kernel<false, false><<<blocks, threads, smem, st>>>(a);
+		cavlc2::cavlc_steps_kernel<false, true><<<blocks, threads, smem, st>>>(a);
+	} else {
+		cavlc2::cavlc_steps_kernel<true, false><<<blocks, threads, smem, st>>>(a);
+		cavlc2::cavlc_steps_kernel<true, true><<<blocks, threads, smem, st>>>(a);
+	}
 	CU_TRY(cudaGetLastError());
-	ctx->launches++;
+	ctx->launches += 2;
 	return 0;
 }
 

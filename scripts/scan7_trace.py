@@ -15,6 +15,7 @@ size = args.size_mb << 20
 stream, rbsp_ref, offs = make_workload(L, size, SEED, nthreads=min(os.cpu_count() or 1, 64))
 n_in, cap = len(stream), len(offs) + 1024
 d_in, d_rbsp = g.alloc(n_in + 16), g.alloc(n_in + 16)
+L._check(g.lib.h264gpu_scan_reserve(g.h, C.c_uint64(n_in), C.c_uint64(cap)), "reserve")  # workspace next to the stream buffers
 d_tab, d_res = g.alloc(cap * 32), g.alloc(C.sizeof(L.ScanResult))
 d_in.upload(stream)
 def step():
