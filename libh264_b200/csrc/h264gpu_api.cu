@@ -415,12 +415,7 @@ static int ws7_reserve(h264gpu_ctx *ctx, size_t bytes)
 		CU_TRY(cudaFree(ctx->ws7));
 	ctx->ws7 = NULL;
 	ctx->ws7_bytes = 0;
-	size_t want = (bytes + (bytes >> 3) + (1u << 20)) & ~(size_t)((1u << 20) - 1);
-	{
-		const char *e = getenv("H264GPU_WS7_MIN_MB");
-		if (e != NULL && atoi(e) > 0 && want < ((size_t)atoi(e) << 20))
-			want = (size_t)atoi(e) << 20;
-	}
+	const size_t want = (bytes + (bytes >> 3) + (1u << 20)) & ~(size_t)((1u << 20) - 1);
 	CU_TRY(cudaMalloc(&ctx->ws7, want));
 	if (getenv("H264GPU_DEBUG_WS") != NULL)
 		fprintf(stderr, "h264gpu: ws7 %p + %zu\n", ctx->ws7, want);

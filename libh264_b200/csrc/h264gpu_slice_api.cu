@@ -62,6 +62,10 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 	a.lanes_log2 = lanes_log2;
 	a.syntax = d_syntax;
 	a.group_maps = d_group_maps;
+	a.burst = CAVLC2_BURST;
+	env = getenv("H264GPU_CAVLC_BURST");
+	if (env != NULL && atoi(env) >= 1 && atoi(env) <= 64)
+		a.burst = (uint32_t)atoi(env);
 	a.next_slice = (uint32_t *)((uint8_t *)ctx->ws + counter_off);
 	a.order = (uint32_t *)((uint8_t *)ctx->ws + order_off);
 	/* longest slices first; the first grid_lanes tickets are the lanes' own numbers */
