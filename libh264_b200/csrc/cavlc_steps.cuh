@@ -126,7 +126,6 @@ enum {
 #else
 #define CAVLC2_STRIDE 128u /* threads per block: shared words of a lane are interleaved by thread */
 #endif
-#define CAVLC2_BURST 4 /* residual steps per header step of the warp loop (measured: 4 > 8 > 16) */
 #define CAVLC2_SM_WORDS 56u /* per lane: 4 x 12 words of counts (this and the previous macroblock or pair), 8 words of levels */
 #define CAVLC2_RING_SLOT 32u /* bytes per macroblock (or pair) in the ring of bottom-row counts */
 
@@ -1381,7 +1380,6 @@ struct CavlcArgs {
 	uint32_t *next_slice; /* [0] ticket counter of the frame / field kernel, [1] of the MBAFF kernel,
 				 [2] number of MBAFF slices; set by order_kernel */
 	uint32_t *order;      /* slice indices, longest NAL first */
-	uint32_t burst;       /* residual steps per header step of the warp loop */
 };
 
 /*
@@ -1498,13 +1496,17 @@ __global__ void __launch_bounds__(CAVLC2_STRIDE) cavlc_steps_kernel(const CavlcA
 		}
 		if (__all_sync(FULL_MASK, out))
 			break;
-		/* the residual blocks are where the steps are (~10 per header step): a burst of residual
-		 * steps for the lanes inside one (a short loop body: one table probe or one level; lanes
-		 * elsewhere wait, at most `burst` steps), then one header step for every lane outside */
-#pragma unroll 1
-		for (uint32_t k = 0; k < a.burst; k++) {
-			const bool res = !out && CAVLC2_IS_RES(l.state);
-			if (!__any_sync(FULL_MASK, res))
+		/* the residual blocks are where the steps are: while most of the warp's running lanes are
+		 * inside one, only those lanes step (a short loop body: one table probe or one level); then
+		 * every lane outside takes one header step.  (Measured against a fixed burst of 2 / 4 / 8
+		 * residual steps per header step, with and without a vote: this rule is the fastest at 300
+		 * and at 16000 slices, profiles/r02_k4_loop_variants.txt) */
+		for (;;) {
+			const bool run = !out; /* a lane waiting for its next slice votes for leaving too */
+			const bool res = run && CAVLC2_IS_RES(l.state);
+			const uint32_t n_res = (uint32_t)__popc(__ballot_sync(FULL_MASK, res));
+			const uint32_t n_run = (uint32_t)__popc(__ballot_sync(FULL_MASK, run));
+			if (n_res == 0 || 2 * n_res < n_run)
 				break;
 			if (res)
 				res_step<FULL>(l);

@@ -62,10 +62,6 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 	a.lanes_log2 = lanes_log2;
 	a.syntax = d_syntax;
 	a.group_maps = d_group_maps;
-	a.burst = CAVLC2_BURST;
-	env = getenv("H264GPU_CAVLC_BURST");
-	if (env != NULL && atoi(env) >= 1 && atoi(env) <= 64)
-		a.burst = (uint32_t)atoi(env);
 	a.next_slice = (uint32_t *)((uint8_t *)ctx->ws + counter_off);
 	a.order = (uint32_t *)((uint8_t *)ctx->ws + order_off);
 	/* longest slices first; the first grid_lanes tickets are the lanes' own numbers */
@@ -372,7 +368,12 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 			lanes_log2++;
 	}
 	a.lanes_log2 = lanes_log2;
-	const uint32_t threads = 32; /* one warp per block */
+	uint32_t threads = 32; /* one warp per block */
+	{
+		const char *e = getenv("H264GPU_CABAC_WARPS");
+		if (e != NULL && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4))
+			threads = 32u * (uint32_t)atoi(e);
+	}
 	const uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
 	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
 	const size_t smem = cabac::smem_bytes((threads / 32) << lanes_log2);
