@@ -640,7 +640,7 @@ __device__ __forceinline__ void block_done(Lane &l, uint32_t tc)
  * instructions around a common load; levels are arithmetic (9.2.2.1).
  */
 template <bool FULL>
-__device__ __forceinline__ void res_step(Lane &l)
+__device__ __forceinline__ void res_step1(Lane &l)
 {
 	if (l.nbits < 32)
 		refill(l);
@@ -1340,6 +1340,22 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 	}
 }
 
+/* up to CAVLC2_RES_REPEAT elements while the lane stays inside residual blocks: the warp loop's
+ * vote is paid once for them (the levels and runs of a block follow each other) */
+#ifndef CAVLC2_RES_REPEAT
+#define CAVLC2_RES_REPEAT 1
+#endif
+template <bool FULL>
+__device__ __forceinline__ void res_step(Lane &l, uint32_t repeat = CAVLC2_RES_REPEAT)
+{
+#pragma unroll 1
+	for (uint32_t k = 0; k < repeat; k++) {
+		res_step1<FULL>(l);
+		if (!CAVLC2_IS_RES(l.state))
+			break;
+	}
+}
+
 template <bool FULL>
 __device__ __forceinline__ void step(Lane &l)
 {
@@ -1380,6 +1396,7 @@ struct CavlcArgs {
 	uint32_t *next_slice; /* [0] ticket counter of the frame / field kernel, [1] of the MBAFF kernel,
 				 [2] number of MBAFF slices; set by order_kernel */
 	uint32_t *order;      /* slice indices, longest NAL first */
+	uint32_t repeat;      /* residual elements a lane takes per vote of the warp loop */
 };
 
 /*
@@ -1509,7 +1526,7 @@ __global__ void __launch_bounds__(CAVLC2_STRIDE) cavlc_steps_kernel(const CavlcA
 			if (n_res == 0 || 2 * n_res < n_run)
 				break;
 			if (res)
-				res_step<FULL>(l);
+				res_step<FULL>(l, a.repeat);
 		}
 		if (!out && l.state != S_DONE && !CAVLC2_IS_RES(l.state))
 			hdr_step<FULL>(l);

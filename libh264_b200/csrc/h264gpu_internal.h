@@ -46,6 +46,8 @@ struct h264gpu_ctx {
 	} rd_stream, rd_tab, rd_res, rd_params, rd_records, rd_results, rd_maps; /* device */
 	struct h264gpu_pool rh_tab, rh_res, rh_records, rh_results;         /* pinned host */
 	uint64_t rd_stream_len; /* bytes of the buffer resident in rd_stream */
+	uint32_t ring_w_hint;   /* widest picture (in macroblocks) of the parameter blocks the host forms have seen
+				   for the launch they are about to make (0: unknown, rings sized for 512) */
 	uint64_t rd_maps_len;   /* bytes of slice group maps in rd_maps for the next pooled parse (0: none) */
 	size_t cabac_smem_set;  /* dynamic shared memory the CABAC kernel is configured for on this device */
 };

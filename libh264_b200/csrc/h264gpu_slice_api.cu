@@ -42,7 +42,9 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 	const uint64_t warps = (lanes + (1u << lanes_log2) - 1) >> lanes_log2;
 	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
 	const uint64_t grid_lanes = ((uint64_t)blocks * threads / 32) << lanes_log2;
-	const uint32_t ring_w = 512;
+	/* rings sized for pictures up to 8192 luma samples wide unless the caller's parameter blocks
+	 * were seen on the host (the host forms): then for the widest picture among them */
+	const uint32_t ring_w = ctx->ring_w_hint ? ctx->ring_w_hint : 512;
 	const uint64_t ring_stride = (uint64_t)(ring_w + 1) * CAVLC2_RING_SLOT;
 	const size_t counter_off = (size_t)(grid_lanes * ring_stride);
 	const size_t order_off = counter_off + 16;
@@ -62,6 +64,10 @@ static int cavlc_steps_launch(h264gpu_ctx *ctx, const uint8_t *d_stream, uint64_
 	a.lanes_log2 = lanes_log2;
 	a.syntax = d_syntax;
 	a.group_maps = d_group_maps;
+	a.repeat = CAVLC2_RES_REPEAT;
+	env = getenv("H264GPU_CAVLC_REPEAT");
+	if (env != NULL && atoi(env) >= 1 && atoi(env) <= 64)
+		a.repeat = (uint32_t)atoi(env);
 	a.next_slice = (uint32_t *)((uint8_t *)ctx->ws + counter_off);
 	a.order = (uint32_t *)((uint8_t *)ctx->ws + order_off);
 	/* longest slices first; the first grid_lanes tickets are the lanes' own numbers */
@@ -207,6 +213,11 @@ static int parse_pooled(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_str
 		return r;
 	CU_TRY(cudaMemcpyAsync(ctx->rd_params.p, h_params, (size_t)n_slices * sizeof(*h_params),
 			       cudaMemcpyHostToDevice, st));
+	uint32_t wmax = 1;
+	for (uint32_t i = 0; i < n_slices; i++)
+		if (h_params[i].pic_width_in_mbs > wmax)
+			wmax = h_params[i].pic_width_in_mbs;
+	ctx->ring_w_hint = wmax;
 	r = dev(ctx, (const uint8_t *)ctx->rd_stream.p, ctx->rd_stream_len,
 		(const struct h264gpu_slice_params *)ctx->rd_params.p, n_slices,
 		(struct h264gpu_mb_record *)ctx->rd_records.p, (struct h264gpu_slice_result *)ctx->rd_results.p, st);
@@ -222,6 +233,7 @@ static int parse_pooled(parse_dev_fn dev, h264gpu_ctx *ctx, const uint8_t *h_str
 		if (r < 0)
 			return r;
 	}
+	ctx->ring_w_hint = 0;
 	if (n_records)
 		CU_TRY(cudaMemcpyAsync(ctx->rh_records.p, ctx->rd_records.p, n_records * sizeof(struct h264gpu_mb_record),
 				       cudaMemcpyDeviceToHost, st));
@@ -340,7 +352,7 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	cudaStream_t st = (cudaStream_t)stream;
 	/* neighbour ring per slice: (PicWidthInMbs + 1) records of 64 B, sized for pictures up
 	 * to 8192 luma samples wide (512 MBs); wider slices get -E2BIG. */
-	const uint32_t ring_w = 512;
+	const uint32_t ring_w = ctx->ring_w_hint ? ctx->ring_w_hint : 512;
 	const uint64_t ring_stride = (uint64_t)(ring_w + 1);
 	r = h264gpu_ws_reserve(ctx, (size_t)n_slices * ring_stride * sizeof(cabac::Nb));
 	if (r < 0)
