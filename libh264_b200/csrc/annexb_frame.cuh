@@ -49,6 +49,11 @@ struct FrameArgs {
 	uint64_t *first;  /* num_tiles+1: first payload starting at/after the tile */
 	uint32_t *tail;   /* num_tiles: trailing zero run | all-zero << 31 */
 	uint32_t num_tiles;
+	/* gen 7 (annexb_frame7.cuh): desc = one word per span, plus the upper levels of its chain */
+	uint64_t *group_w; /* num_tiles / 32 + 1 */
+	uint64_t *super_w; /* num_tiles / 1024 + 1 */
+	uint64_t *super_p; /* num_tiles / 1024 + 1 */
+	uint64_t *trace;   /* diagnostics (H264GPU_FRAME_TRACE): 8 words per span, or NULL */
 };
 
 /* first k in [0,n) with off[k] >= x */

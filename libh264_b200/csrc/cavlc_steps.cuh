@@ -1343,7 +1343,7 @@ __device__ __forceinline__ void hdr_step(Lane &l)
 /* up to CAVLC2_RES_REPEAT elements while the lane stays inside residual blocks: the warp loop's
  * vote is paid once for them (the levels and runs of a block follow each other) */
 #ifndef CAVLC2_RES_REPEAT
-#define CAVLC2_RES_REPEAT 1
+#define CAVLC2_RES_REPEAT 4
 #endif
 template <bool FULL>
 __device__ __forceinline__ void res_step(Lane &l, uint32_t repeat = CAVLC2_RES_REPEAT)

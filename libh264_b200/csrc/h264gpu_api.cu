@@ -26,6 +26,7 @@ int h264gpu_device_count(void)
 }
 
 static int ws7_reserve(h264gpu_ctx *ctx, size_t bytes);
+static void ws7_free(h264gpu_ctx *ctx);
 
 int h264gpu_create(int device, h264gpu_ctx **out)
 {
@@ -96,7 +97,7 @@ int h264gpu_destroy(h264gpu_ctx *ctx)
 	cudaDeviceSynchronize();
 	free_pipeline(ctx);
 	cudaFree(ctx->ws);
-	cudaFree(ctx->ws7);
+	ws7_free(ctx);
 	cudaFree(ctx->rd_stream.p);
 	cudaFree(ctx->rd_tab.p);
 	cudaFree(ctx->rd_res.p);
@@ -406,21 +407,131 @@ extern "C" int h264gpu_split_strip_dev(h264gpu_ctx *ctx, const uint8_t *d_in, ui
 /* the scan's own workspace: control words are zero at allocation and re-armed by the last
  * finalize block of every launch; chain words carry the launch epoch, so nothing is cleared
  * between launches */
+/*
+ * Placement of the workspace.  The in-place kernel polls and publishes chain words here, and the
+ * same launch runs 2.00 or 2.85 ms per 4 GiB depending on where cudaMalloc happened to put the
+ * buffer (profiles/r02_scan_workspace_placement.txt: fast only when it lands directly below the
+ * stream buffers, slow next to a page-locked host mapping or among the context's first small
+ * allocations).  H264GPU_WS7_VMM=1 takes cudaMalloc out of the picture: the workspace gets a
+ * virtual range of its own (1 GiB aligned, 1 GiB reserved, so no other mapping shares its page
+ * directory entries) backed by one physical allocation of the recommended (2 MiB) granularity,
+ * through the driver's virtual memory management entry points (fetched from the runtime, no
+ * link-time dependency on libcuda).
+ */
+#include <cuda.h>
+
+struct vmm_api {
+	CUresult (*granularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags);
+	CUresult (*reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long);
+	CUresult (*create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long);
+	CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+	CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t);
+	CUresult (*unmap)(CUdeviceptr, size_t);
+	CUresult (*release)(CUmemGenericAllocationHandle);
+	CUresult (*addr_free)(CUdeviceptr, size_t);
+	int ok;
+};
+
+static const vmm_api *vmm(void)
+{
+	static vmm_api api;
+	static int tried = 0;
+	if (!tried) {
+		tried = 1;
+		cudaDriverEntryPointQueryResult q;
+		int ok = 1;
+#define H264_VMM_SYM(field, name)                                                                   \
+	ok = ok && cudaGetDriverEntryPoint(name, (void **)&api.field, cudaEnableDefault, &q) == cudaSuccess && \
+	     q == cudaDriverEntryPointSuccess && api.field != NULL
+		H264_VMM_SYM(granularity, "cuMemGetAllocationGranularity");
+		H264_VMM_SYM(reserve, "cuMemAddressReserve");
+		H264_VMM_SYM(create, "cuMemCreate");
+		H264_VMM_SYM(map, "cuMemMap");
+		H264_VMM_SYM(set_access, "cuMemSetAccess");
+		H264_VMM_SYM(unmap, "cuMemUnmap");
+		H264_VMM_SYM(release, "cuMemRelease");
+		H264_VMM_SYM(addr_free, "cuMemAddressFree");
+#undef H264_VMM_SYM
+		api.ok = ok;
+	}
+	return api.ok ? &api : NULL;
+}
+
+static void ws7_free(h264gpu_ctx *ctx)
+{
+	if (ctx->ws7 == NULL)
+		return;
+	if (ctx->ws7_vmm) {
+		const vmm_api *v = vmm();
+		v->unmap((CUdeviceptr)ctx->ws7, ctx->ws7_bytes);
+		v->release((CUmemGenericAllocationHandle)ctx->ws7_handle);
+		v->addr_free((CUdeviceptr)ctx->ws7, ctx->ws7_va_bytes);
+	} else {
+		cudaFree(ctx->ws7);
+	}
+	ctx->ws7 = NULL;
+	ctx->ws7_bytes = 0;
+	ctx->ws7_vmm = 0;
+}
+
+/* 0: mapped, < 0: not available (the caller falls back to cudaMalloc) */
+static int ws7_map_own_range(h264gpu_ctx *ctx, size_t want)
+{
+	const vmm_api *v = vmm();
+	if (v == NULL)
+		return -ENOSYS;
+	CUmemAllocationProp prop;
+	memset(&prop, 0, sizeof(prop));
+	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	prop.location.id = ctx->device;
+	size_t gran = 0;
+	if (v->granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0)
+		return -ENOSYS;
+	const size_t size = (want + gran - 1) / gran * gran;
+	const size_t gib = (size_t)1 << 30;
+	const size_t va_bytes = (size + gib - 1) / gib * gib;
+	CUdeviceptr va = 0;
+	if (v->reserve(&va, va_bytes, gib, 0, 0) != CUDA_SUCCESS)
+		return -ENOMEM;
+	CUmemGenericAllocationHandle h;
+	if (v->create(&h, size, &prop, 0) != CUDA_SUCCESS) {
+		v->addr_free(va, va_bytes);
+		return -ENOMEM;
+	}
+	CUmemAccessDesc acc;
+	memset(&acc, 0, sizeof(acc));
+	acc.location = prop.location;
+	acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	if (v->map(va, size, 0, h, 0) != CUDA_SUCCESS || v->set_access(va, size, &acc, 1) != CUDA_SUCCESS) {
+		v->unmap(va, size);
+		v->release(h);
+		v->addr_free(va, va_bytes);
+		return -ENOMEM;
+	}
+	ctx->ws7 = (void *)va;
+	ctx->ws7_bytes = size;
+	ctx->ws7_va_bytes = va_bytes;
+	ctx->ws7_handle = (unsigned long long)h;
+	ctx->ws7_vmm = 1;
+	return 0;
+}
+
 static int ws7_reserve(h264gpu_ctx *ctx, size_t bytes)
 {
 	if (bytes <= ctx->ws7_bytes)
 		return 0;
 	CU_TRY(cudaDeviceSynchronize());
-	if (ctx->ws7)
-		CU_TRY(cudaFree(ctx->ws7));
-	ctx->ws7 = NULL;
-	ctx->ws7_bytes = 0;
+	ws7_free(ctx);
 	const size_t want = (bytes + (bytes >> 3) + (1u << 20)) & ~(size_t)((1u << 20) - 1);
-	CU_TRY(cudaMalloc(&ctx->ws7, want));
+	const char *e = getenv("H264GPU_WS7_VMM");
+	if (e == NULL || atoi(e) == 0 || ws7_map_own_range(ctx, want) < 0) {
+		CU_TRY(cudaMalloc(&ctx->ws7, want));
+		ctx->ws7_bytes = want;
+	}
 	if (getenv("H264GPU_DEBUG_WS") != NULL)
-		fprintf(stderr, "h264gpu: ws7 %p + %zu\n", ctx->ws7, want);
-	CU_TRY(cudaMemset(ctx->ws7, 0, want));
-	ctx->ws7_bytes = want;
+		fprintf(stderr, "h264gpu: ws7 %p + %zu%s\n", ctx->ws7, ctx->ws7_bytes, ctx->ws7_vmm ? " (own range)" : "");
+	CU_TRY(cudaMemset(ctx->ws7, 0, ctx->ws7_bytes));
 	return 0;
 }
 
@@ -1180,6 +1291,53 @@ extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, u
 
 #include "annexb_frame.cuh"
 #include "annexb_frame6.cuh"
+#include "annexb_frame7.cuh"
+
+/* writer kernel generation: 7 (warp-autonomous spans, annexb_frame7.cuh; the default) or 6
+ * (block-wide 32 KiB tiles, annexb_frame6.cuh): H264GPU_FRAME_GEN */
+static int frame_gen(void)
+{
+	const char *e = getenv("H264GPU_FRAME_GEN");
+	return (e != NULL && atoi(e) == 6) ? 6 : 7;
+}
+
+template <int ROWS, int NW, int MINB>
+static cudaError_t launch_frame7_cfg(const frame::FrameArgs &a, cudaStream_t st, int sms)
+{
+	cudaFuncSetAttribute(frame7::frame7_kernel<ROWS, NW, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+			     cudaSharedmemCarveoutMaxShared);
+	/* persistent warps: as many CTAs as fit, fewer when there are fewer spans than warps */
+	const uint64_t cap = (uint64_t)sms * MINB;
+	const uint64_t want = ((uint64_t)a.num_tiles + NW - 1) / NW;
+	frame7::frame7_kernel<ROWS, NW, MINB><<<(unsigned)(want < cap ? want : cap), 32 * NW, 0, st>>>(a);
+	return cudaGetLastError();
+}
+
+template <int ROWS>
+static cudaError_t launch_frame7(const frame::FrameArgs &a, cudaStream_t st)
+{
+	const uint32_t pthreads = 128;
+	const uint32_t pblocks = (a.num_tiles + 1 + pthreads - 1) / pthreads;
+	frame7::frame7_prepass<ROWS><<<pblocks, pthreads, 0, st>>>(a);
+	int sms = 0, dev = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (sms <= 0)
+		sms = 148;
+	/* warps per CTA (every warp works alone; the CTA size only decides how the 227 KB of shared
+	 * memory of an SM divide): H264GPU_FRAME7_NW = 1 (default), 2 or 3 */
+	const char *e = getenv("H264GPU_FRAME7_NW");
+	const int nw = (e != NULL && atoi(e) >= 1 && atoi(e) <= 3) ? atoi(e) : 1;
+	constexpr int per_warp = (int)sizeof(frame7::WSmem<ROWS>);
+	constexpr int fit1 = (227 * 1024) / (per_warp + 1024) > 32 ? 32 : (227 * 1024) / (per_warp + 1024);
+	constexpr int fit2 = (227 * 1024) / (2 * per_warp + 1024) > 24 ? 24 : (227 * 1024) / (2 * per_warp + 1024);
+	constexpr int fit3 = (227 * 1024) / (3 * per_warp + 1024) > 16 ? 16 : (227 * 1024) / (3 * per_warp + 1024);
+	if (nw == 2)
+		return launch_frame7_cfg<ROWS, 2, fit2>(a, st, sms);
+	if (nw == 3)
+		return launch_frame7_cfg<ROWS, 3, fit3>(a, st, sms);
+	return launch_frame7_cfg<ROWS, 1, fit1>(a, st, sms);
+}
 
 template <int ROWS>
 static cudaError_t launch_frame6(const frame::FrameArgs &a, cudaStream_t st)
@@ -1240,15 +1398,35 @@ extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const 
 		ntiles = 1;
 	if (ntiles > 0x7fffffffull)
 		return -E2BIG;
-	/* workspace: [256 control][desc: ntiles u64][first: ntiles+1 u64][tail: ntiles u32] */
+	/* workspace: [256 control][desc: ntiles u64][first: ntiles+1 u64][tail: ntiles u32]
+	 * [group_w][super_w][super_p] (gen 7: ntiles = spans of 512 x items bytes) */
+	const int gen = frame_gen();
+	int rows = items; /* 512-byte rows per span of the gen-7 kernel: H264GPU_FRAME7_ROWS = 1, 2, 4, 6 or 8 */
+	{
+		const char *e = getenv("H264GPU_FRAME7_ROWS");
+		const int v = e != NULL ? atoi(e) : 0;
+		if (v == 1 || v == 2 || v == 4 || v == 6 || v == 8)
+			rows = v;
+	}
+	if (gen == 7) {
+		const uint64_t span = (uint64_t)512 * rows;
+		ntiles = (len + span - 1) / span;
+		if (ntiles == 0)
+			ntiles = 1;
+		if (ntiles > 0x7fffffffull)
+			return -E2BIG;
+	}
 	const size_t desc_bytes = 256 + (size_t)ntiles * 8;
 	const size_t first_off = (desc_bytes + 15) & ~(size_t)15;
 	const size_t tail_off = first_off + ((size_t)ntiles + 1) * 8;
-	const size_t need = tail_off + (size_t)ntiles * 4;
+	const size_t group_off = (tail_off + (size_t)ntiles * 4 + 15) & ~(size_t)15;
+	const size_t ngroup = (size_t)(ntiles >> 5) + 1, nsuper = (size_t)(ntiles >> 10) + 1;
+	const size_t need = group_off + (ngroup + 2 * nsuper) * 8;
 	r = h264gpu_ws_reserve(ctx, need);
 	if (r < 0)
 		return r;
-	CU_TRY(cudaMemsetAsync(ctx->ws, 0xff, desc_bytes, st));
+	if (gen != 7) /* gen 7: the pre-pass clears its chain words */
+		CU_TRY(cudaMemsetAsync(ctx->ws, 0xff, desc_bytes, st));
 
 	frame::FrameArgs a;
 	memset(&a, 0, sizeof(a));
@@ -1266,12 +1444,43 @@ extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const 
 	a.first = (uint64_t *)((uint8_t *)ctx->ws + first_off);
 	a.tail = (uint32_t *)((uint8_t *)ctx->ws + tail_off);
 	a.num_tiles = (uint32_t)ntiles;
+	a.group_w = (uint64_t *)((uint8_t *)ctx->ws + group_off);
+	a.super_w = a.group_w + ngroup;
+	a.super_p = a.super_w + nsuper;
+	/* diagnostics: phase timestamps of every span of the gen-7 kernel, written to the named file */
+	const char *trace_path = gen == 7 ? getenv("H264GPU_FRAME_TRACE") : NULL;
+	uint64_t *d_trace = NULL;
+	if (trace_path != NULL && trace_path[0] != 0) {
+		CU_TRY(cudaMalloc(&d_trace, (size_t)ntiles * 64));
+		CU_TRY(cudaMemsetAsync(d_trace, 0, (size_t)ntiles * 64, st));
+		a.trace = d_trace;
+	}
 	cudaError_t ce;
-	ce = items == 1 ? launch_frame6<1>(a, st)
-	   : items == 2 ? launch_frame6<2>(a, st)
-	   : items == 4 ? launch_frame6<4>(a, st)
-			: launch_frame6<8>(a, st);
+	if (gen == 7)
+		ce = rows == 1 ? launch_frame7<1>(a, st)
+		   : rows == 2 ? launch_frame7<2>(a, st)
+		   : rows == 4 ? launch_frame7<4>(a, st)
+		   : rows == 6 ? launch_frame7<6>(a, st)
+			       : launch_frame7<8>(a, st);
+	else
+		ce = items == 1 ? launch_frame6<1>(a, st)
+		   : items == 2 ? launch_frame6<2>(a, st)
+		   : items == 4 ? launch_frame6<4>(a, st)
+				: launch_frame6<8>(a, st);
 	CU_TRY(ce);
+	if (d_trace != NULL) {
+		uint64_t *h = (uint64_t *)malloc((size_t)ntiles * 64);
+		if (h != NULL && cudaMemcpyAsync(h, d_trace, (size_t)ntiles * 64, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+		    cudaStreamSynchronize(st) == cudaSuccess) {
+			FILE *f = fopen(trace_path, "wb");
+			if (f != NULL) {
+				fwrite(h, 64, ntiles, f);
+				fclose(f);
+			}
+		}
+		free(h);
+		cudaFree(d_trace);
+	}
 	ctx->launches += 2;
 	return 0;
 }

@@ -23,6 +23,9 @@ struct h264gpu_ctx {
 	void *ws7;
 	size_t ws7_bytes;
 	uint32_t epoch7;
+	int ws7_vmm;          /* 1: ws7 is a mapped range of its own (ws7_va_bytes reserved, ws7_handle mapped) */
+	size_t ws7_va_bytes;
+	unsigned long long ws7_handle;
 	uint64_t ws7_spans; /* spans of the last launch: another length moves the arrays behind the chain words */
 	uint32_t attr_set; /* per-context (= per-device) cudaFuncSetAttribute done: bit 0 scan7 */
 	int sms;

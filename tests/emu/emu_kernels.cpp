@@ -8,6 +8,7 @@
 #include "annexb_scan7.cuh"
 #include "annexb_frame.cuh"
 #include "annexb_frame6.cuh"
+#include "annexb_frame7.cuh"
 
 #include <vector>
 
@@ -264,6 +265,62 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 			 uint64_t *total, int items)
 {
 	using namespace frame;
+	/* 70 + rows: frame7_kernel with 1/2/4/6/8 rows per span, three warps per CTA */
+	if (items > 70) {
+		const int rows = items - 70;
+		const uint64_t span = 512ull * rows;
+		uint32_t ns = (uint32_t)((len + span - 1) / span);
+		if (ns == 0)
+			ns = 1;
+		std::vector<uint64_t> desc(ns, ~0ull), first(ns + 1, ~0ull), gw((ns >> 5) + 1, ~0ull),
+			sw((ns >> 10) + 1, ~0ull), sp((ns >> 10) + 1, ~0ull);
+		uint32_t ticket = 0xffffffffu;
+		uint8_t *buf = (uint8_t *)aligned_alloc(16, ((len + 15) & ~15ull) + 16);
+		memcpy(buf, rbsp, len);
+		FrameArgs a;
+		memset(&a, 0, sizeof(a));
+		a.rbsp = buf;
+		a.len = len;
+		a.off = off;
+		a.n = n;
+		a.sc_len = (uint32_t)sc_len;
+		a.out = out;
+		a.out_cap = out_cap;
+		a.out_off = out_off;
+		a.total = total;
+		a.desc = desc.data();
+		a.ticket = &ticket;
+		a.first = first.data();
+		a.num_tiles = ns;
+		a.group_w = gw.data();
+		a.super_w = sw.data();
+		a.super_p = sp.data();
+		dim3 pgrid((ns + 1 + 127) / 128), pblock(128), block(96), grid(2);
+		switch (rows) {
+		case 1:
+			EMU_LAUNCH((frame7::frame7_prepass<1>), pgrid, pblock, a);
+			EMU_LAUNCH((frame7::frame7_kernel<1, 3, 1>), grid, block, a);
+			break;
+		case 2:
+			EMU_LAUNCH((frame7::frame7_prepass<2>), pgrid, pblock, a);
+			EMU_LAUNCH((frame7::frame7_kernel<2, 3, 1>), grid, block, a);
+			break;
+		case 4:
+			EMU_LAUNCH((frame7::frame7_prepass<4>), pgrid, pblock, a);
+			EMU_LAUNCH((frame7::frame7_kernel<4, 3, 1>), grid, block, a);
+			break;
+		case 6:
+			EMU_LAUNCH((frame7::frame7_prepass<6>), pgrid, pblock, a);
+			EMU_LAUNCH((frame7::frame7_kernel<6, 3, 1>), grid, block, a);
+			break;
+		default:
+			EMU_LAUNCH((frame7::frame7_prepass<8>), pgrid, pblock, a);
+			EMU_LAUNCH((frame7::frame7_kernel<8, 3, 1>), grid, block, a);
+			break;
+		}
+		free(buf);
+		return 0;
+	}
 	/* items (or 60 + items): frame6_kernel with 1/2/4/8 rows per warp */
 	if (items > 60)
 		items -= 60;

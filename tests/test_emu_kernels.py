@@ -290,6 +290,89 @@ def test_emu_frame6_output_capacity_is_respected():
         assert np.array_equal(out[:cap], exp[:cap]) and (out[cap:] == 0xAA).all(), cap
 
 
+# ---- K3 gen 7 (frame7_kernel): items 71/72/74/76/78 = 1/2/4/6/8 rows per warp-owned span ----
+
+G7 = [71, 72, 74, 76, 78]
+
+
+def test_emu_frame7_known_answer():
+    p = KA.hx(KA.INSERT_IN)
+    for items in G7:
+        out, oo, tot = emu_frame(p, np.array([0, len(p)], np.uint64), 0, items)
+        assert bytes(out[:tot]) == bytes(KA.hx(KA.INSERT_OUT))
+
+
+def test_emu_frame7_random_and_adversarial():
+    rng = np.random.default_rng(75)
+    for it in range(10):
+        data, offs = S.gen_payloads(rng, int(rng.integers(1, 60)), 1, 5000)
+        check_frame(data, offs, 4 if it % 2 else 3, int(rng.choice(G7)), ("rand7", it))
+    for it in range(20):
+        tot = int(rng.integers(0, 40000))
+        data = rng.choice(np.array([0, 0, 0, 0, 1, 2, 3, 4, 0xFF], np.uint8), tot)
+        n = int(rng.integers(0, 30))
+        cuts = np.sort(rng.integers(0, tot + 1, n)) if n else np.zeros(0, np.int64)
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        check_frame(data, offs, int(rng.choice([0, 3, 4])), int(rng.choice(G7)), ("adv7", it))
+    for it in range(8):  # zero runs spanning whole rows and spans (the run entering a span is longer than its 16-byte halo)
+        tot = int(rng.integers(9000, 70000))
+        data = np.zeros(tot, np.uint8)
+        for p in rng.integers(0, tot, 3):
+            data[p] = rng.choice([1, 3, 7])
+        check_frame(data, np.array([0, tot // 3, tot // 3, tot], np.uint64), 4, int(rng.choice(G7)), ("zeros7", it))
+    for items in (71, 78):
+        check_frame(np.zeros(0, np.uint8), np.array([0, 0, 0], np.uint64), 4, items, "empty payloads only")
+        check_frame(np.zeros(0, np.uint8), np.array([0], np.uint64), 4, items, "no payloads")
+        check_frame(np.array([0, 0, 1], np.uint8), np.array([0, 3], np.uint64), 3, items, "three bytes")
+
+
+def test_emu_frame7_groups_and_supergroups():
+    """More than 1024 spans of 512 bytes: every level of the chain (span words, group sums, supergroup
+    sums and prefixes) carries inserts; payload starts at span seams."""
+    rng = np.random.default_rng(76)
+    tot = 512 * 2100 + 77
+    data = rng.choice(np.array([0, 0, 0, 1, 3, 0x55, 0xFF], np.uint8), tot)
+    cuts = np.sort(np.concatenate([rng.integers(0, tot + 1, 40), [512 * 1024, 512 * 1024 + 1, 512 * 33]]))
+    offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+    check_frame(data, offs, 4, 71, "chain7")
+    data = rng.integers(0, 256, tot).astype(np.uint8)
+    data[rng.random(tot) < 0.1875] = 0
+    check_frame(data, np.array([0, tot], np.uint64), 3, 71, "chain7 one payload")
+
+
+def test_emu_frame7_stream_shaped_and_dense_starts():
+    rng = np.random.default_rng(77)
+    for it in range(3):  # the bench's byte statistics, a handful of payloads
+        tot = int(rng.integers(100000, 250000))
+        data = rng.integers(0, 256, tot).astype(np.uint8)
+        data[rng.random(tot) < 0.1875] = 0
+        cuts = np.sort(rng.integers(0, tot + 1, int(rng.integers(1, 8))))
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        check_frame(data, offs, 4, 78, ("stream7", it))
+        check_frame(data, offs, 3, 76, ("stream7", it))
+    for it in range(4):  # payloads of a few bytes: every row goes byte by byte, more starts than staged
+        tot = int(rng.integers(3000, 20000))
+        data = rng.choice(np.array([0, 0, 0, 1, 3, 0xFF], np.uint8), tot)
+        cuts = np.sort(rng.integers(0, tot + 1, tot // 3))
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        check_frame(data, offs, 4, int(rng.choice(G7)), ("dense7", it))
+
+
+def test_emu_frame7_output_capacity_is_respected():
+    lib = S.emu()
+    rng = np.random.default_rng(78)
+    data = rng.choice(np.array([0, 0, 0, 1, 3, 0xFF], np.uint8), 20000)
+    offs = np.array([0, 7000, 20000], np.uint64)
+    exp, eoo = S.oracle_frame(data, offs, 4)
+    for cap in (0, 5, 4099, len(exp) - 1):
+        out = np.full(len(exp) + 64, 0xAA, np.uint8)
+        oo = np.full(3, S.NONE64, np.uint64)
+        tot = C.c_uint64(0)
+        lib.emu_frame(S.ptr(data), len(data), S.ptr(offs), 2, 4, S.ptr(out), cap, S.ptr(oo), C.byref(tot), 72)
+        assert tot.value == len(exp)
+        assert np.array_equal(out[:cap], exp[:cap]) and (out[cap:] == 0xAA).all(), cap
+
+
 def test_emu_frame_then_scan_round_trip():
     rng = np.random.default_rng(8)
     data, offs = S.gen_payloads(rng, 50, 2, 3000)

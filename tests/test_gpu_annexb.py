@@ -264,6 +264,38 @@ def test_frame_small_tiles():
             os.environ["H264GPU_SCAN_ITEMS"] = old
 
 
+@pytest.mark.parametrize("env", [{"H264GPU_FRAME_GEN": "6"}, {"H264GPU_FRAME7_ROWS": "6"},
+                                 {"H264GPU_FRAME7_NW": "2"}, {"H264GPU_FRAME7_NW": "3", "H264GPU_FRAME7_ROWS": "1"}])
+def test_frame_kernel_variants(env):
+    """The writer's other builds: gen 6 (block-wide tiles), gen 7 with 3 KiB spans / 2 or 3 warps per
+    CTA / 512-byte spans (> 1024 spans: every level of the chain), on stream-shaped and zero-heavy
+    payloads against the oracle."""
+    rng = np.random.default_rng(59)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        g = L.Gpu(0)
+        try:
+            for it in range(3):
+                tot = int(rng.integers(600000, 3000000))
+                data = rng.integers(0, 256, tot).astype(np.uint8)
+                data[rng.random(tot) < (0.1875 if it % 2 == 0 else 0.6)] = 0
+                n = int(rng.integers(0, 60))
+                cuts = np.sort(rng.integers(0, tot + 1, n)) if n else np.zeros(0, np.int64)
+                offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+                exp, eoo = S.oracle_frame(data, offs, 4)
+                out, oo = g.frame_host(data, offs, sc_len=4)
+                assert np.array_equal(out, exp) and np.array_equal(oo, eoo), (env, it)
+        finally:
+            g.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def test_writer_round_trip_full_size(gpu):
     """Config 5 shape at 64 MiB: frame on the GPU, then the reference-side reader
     semantics (GPU scan+strip, itself oracle-checked above) give back the payloads."""
