@@ -83,18 +83,33 @@ template <int ROWS> struct Cfg {
 	static constexpr int SPAN = SPAN_CH * 16; /* bytes per span */
 };
 
-/* one staged span: source bytes with the 16 bytes before them, insert masks, payload starts */
-template <int ROWS> struct __align__(128) Buf {
-	uint8_t raw[16 + Cfg<ROWS>::SPAN + 32]; /* [16 bytes before the span][span][pad] */
-	uint16_t M[Cfg<ROWS>::SPAN_CH + 8];     /* insert mask per chunk (bit j = 03 before byte j) */
-	uint32_t krow[ROWS + 2];                /* payload starts of the span before the row start */
-	uint32_t soff[kSoff];                   /* the span's first payload starts, relative to the span */
+/* the staged bytes of a span: the 16 bytes before it, the span, the 16 bytes after it */
+template <int ROWS> struct __align__(128) Data {
+	uint8_t raw[16 + Cfg<ROWS>::SPAN + 32]; /* [16 bytes before the span][span][16 bytes after][pad] */
 	uint64_t bar;
 };
 
-/* the slice of shared memory a warp owns */
-template <int ROWS> struct __align__(128) WSmem {
-	Buf<ROWS> b[2];
+/* what classification leaves for the emission of a span */
+template <int ROWS> struct __align__(16) Meta {
+	uint16_t M[Cfg<ROWS>::SPAN_CH + 8]; /* insert mask per chunk (bit j = 03 before byte j) */
+	uint32_t krow[ROWS + 2];            /* payload starts of the span before the row start */
+	uint32_t soff[kSoff];               /* the span's first payload starts, relative to the span */
+};
+
+template <int ROWS> struct Buf { /* a span as the routines see it */
+	Data<ROWS> &d;
+	Meta<ROWS> &m;
+};
+
+/*
+ * The slice of shared memory a warp owns.  NBUF = 2: span B's bytes stay staged from its
+ * classification to its emission an iteration later (20 warps per SM at 4 KiB spans).  NBUF = 1:
+ * only the masks stay; the bytes are staged a second time (from L2, the first read was ~10 us
+ * ago) for the emission, and an SM holds 32 warps.
+ */
+template <int ROWS, int NBUF> struct __align__(128) WSmem {
+	Data<ROWS> d[NBUF];
+	Meta<ROWS> m[2];
 	uint16_t E[Cfg<ROWS>::SPAN_CH]; /* inserts of the span before the chunk; candidate list before that */
 	uint8_t dl[Cfg<ROWS>::SPAN_CH]; /* chunks that take the byte-exact path */
 };
@@ -128,7 +143,7 @@ template <int ROWS> __global__ void frame7_prepass(const FrameArgs a)
 
 /* payload starts of the span (off[k_lo .. k_hi)) at or before span position x */
 template <int ROWS>
-__device__ __forceinline__ uint32_t starts_le(const Buf<ROWS> &s, const FrameArgs &a, uint64_t span_off, uint64_t k_lo,
+__device__ __forceinline__ uint32_t starts_le(const Buf<ROWS> s, const FrameArgs &a, uint64_t span_off, uint64_t k_lo,
 					      uint64_t k_hi, uint32_t x)
 {
 	if (k_hi - k_lo > (uint64_t)kSoff)
@@ -136,7 +151,7 @@ __device__ __forceinline__ uint32_t starts_le(const Buf<ROWS> &s, const FrameArg
 	uint32_t lo = 0, hi = (uint32_t)(k_hi - k_lo);
 	while (lo < hi) {
 		const uint32_t mid = (lo + hi) >> 1;
-		if (s.soff[mid] <= x)
+		if (s.m.soff[mid] <= x)
 			lo = mid + 1;
 		else
 			hi = mid;
@@ -146,20 +161,20 @@ __device__ __forceinline__ uint32_t starts_le(const Buf<ROWS> &s, const FrameArg
 
 /* span position of the span's payload start number i */
 template <int ROWS>
-__device__ __forceinline__ uint32_t start_at(const Buf<ROWS> &s, const FrameArgs &a, uint64_t span_off, uint64_t k_lo,
+__device__ __forceinline__ uint32_t start_at(const Buf<ROWS> s, const FrameArgs &a, uint64_t span_off, uint64_t k_lo,
 					     uint64_t k_hi, uint32_t i)
 {
-	return k_hi - k_lo > (uint64_t)kSoff ? (uint32_t)(a.off[k_lo + i] - span_off) : s.soff[i];
+	return k_hi - k_lo > (uint64_t)kSoff ? (uint32_t)(a.off[k_lo + i] - span_off) : s.m.soff[i];
 }
 
 /* bytes [from, to) of chunk c's own output sequence (its 03s included), byte stores; dst = where
  * output offset 0 of the chunk goes */
 template <int ROWS>
-__device__ __noinline__ void chunk_bytes(const Buf<ROWS> &s, uint32_t c, uint32_t from, uint32_t to, uint8_t *dst,
+__device__ __noinline__ void chunk_bytes(const Buf<ROWS> s, uint32_t c, uint32_t from, uint32_t to, uint8_t *dst,
 					    const uint8_t *capend)
 {
-	const uint8_t *rawb = s.raw + 16 + c * 16;
-	const uint32_t m = s.M[c];
+	const uint8_t *rawb = s.d.raw + 16 + c * 16;
+	const uint32_t m = s.m.M[c];
 	uint32_t o = 0;
 	for (uint32_t j = 0; j < 16 && o < to; j++) {
 		if ((m >> j) & 1) {
@@ -178,9 +193,9 @@ __device__ __noinline__ void chunk_bytes(const Buf<ROWS> &s, uint32_t c, uint32_
 /* the aligned unit that starts ub bytes into chunk c's output (ub < 16 + inserts of c): 16 output
  * bytes from the source window that starts at the byte (or at the 03 before the byte) found there */
 template <int ROWS>
-__device__ __forceinline__ void gen_unit(const Buf<ROWS> &s, uint32_t c, uint32_t ub, uint8_t *dst, const uint8_t *capend)
+__device__ __forceinline__ void gen_unit(const Buf<ROWS> s, uint32_t c, uint32_t ub, uint8_t *dst, const uint8_t *capend)
 {
-	const uint32_t m = s.M[c];
+	const uint32_t m = s.m.M[c];
 	/* smallest source byte j of the chunk whose output offset j + inserts(<= j) is >= ub */
 	uint32_t j = ub < 15u ? ub : 15u;
 	while (j > 0) {
@@ -191,12 +206,12 @@ __device__ __forceinline__ void gen_unit(const Buf<ROWS> &s, uint32_t c, uint32_
 			break;
 	}
 	const uint32_t idx = j + (uint32_t)__popc(m & ((2u << j) - 1u));
-	uint32_t dm = (m | (uint32_t)s.M[c + 1] << 16) >> j;
+	uint32_t dm = (m | (uint32_t)s.m.M[c + 1] << 16) >> j;
 	if (idx == ub)
 		dm &= ~1u; /* the 03 before byte j, if any, belongs to the unit before */
 	dm &= 0xffffu;
 	const uint32_t S = c * 16 + j;
-	const uint32_t *raw32 = (const uint32_t *)(s.raw + 16);
+	const uint32_t *raw32 = (const uint32_t *)(s.d.raw + 16);
 	const uint32_t wi = S >> 2, sh = (S & 3) * 8;
 	const uint32_t y0 = raw32[wi], y1 = raw32[wi + 1], y2 = raw32[wi + 2], y3 = raw32[wi + 3], y4 = raw32[wi + 4];
 	uint64_t q0 = (uint64_t)__funnelshift_r(y0, y1, sh) | (uint64_t)__funnelshift_r(y1, y2, sh) << 32;
@@ -225,7 +240,7 @@ __device__ __forceinline__ void gen_unit(const Buf<ROWS> &s, uint32_t c, uint32_
 /* chunk c of a byte-wise row: payload starts (out_off, start code), 03s and bytes one by one;
  * d0 = inserts before the span + sc_len * payloads before the span */
 template <int ROWS>
-__device__ __noinline__ void bytewise_chunk(const Buf<ROWS> &s, const uint16_t *E, const FrameArgs &a, uint32_t c,
+__device__ __noinline__ void bytewise_chunk(const Buf<ROWS> s, const uint16_t *E, const FrameArgs &a, uint32_t c,
 					       uint64_t span_off, uint32_t nvalid, uint64_t k_lo, uint64_t k_hi, uint64_t d0)
 {
 	const uint32_t p0 = c * 16;
@@ -237,8 +252,8 @@ __device__ __noinline__ void bytewise_chunk(const Buf<ROWS> &s, const uint16_t *
 	uint32_t next = (nb && p0) ? starts_le<ROWS>(s, a, span_off, k_lo, k_hi, p0 - 1) : 0u;
 	uint64_t pos = span_off + p0 + d0 + (uint64_t)E[c] + a.sc_len * next;
 	const uint8_t *capend = a.out + a.out_cap;
-	const uint8_t *rawb = s.raw + 16 + p0;
-	const uint32_t m = s.M[c];
+	const uint8_t *rawb = s.d.raw + 16 + p0;
+	const uint32_t m = s.m.M[c];
 	uint32_t noff = next < nb ? start_at<ROWS>(s, a, span_off, k_lo, k_hi, next) : 0xffffffffu;
 	for (uint32_t j = 0; j < nv; j++) {
 		while (noff == p0 + j) {
@@ -257,9 +272,9 @@ __device__ __noinline__ void bytewise_chunk(const Buf<ROWS> &s, const uint16_t *
 
 /* the span the input ends in (once per launch): plain loads, zero fill past the end */
 template <int ROWS>
-__device__ __noinline__ void load_partial_span(Buf<ROWS> &s, const FrameArgs &a, uint64_t span_off, uint32_t lane)
+__device__ __noinline__ void load_partial_span(const Buf<ROWS> s, const FrameArgs &a, uint64_t span_off, uint32_t lane)
 {
-	uint32_t *raw32 = (uint32_t *)(s.raw + 16);
+	uint32_t *raw32 = (uint32_t *)(s.d.raw + 16);
 	for (int c = (int)lane - 1; c < Cfg<ROWS>::SPAN_CH; c += 32) {
 		const int64_t o = (int64_t)span_off + (int64_t)c * 16;
 		uint32_t w[4] = {0, 0, 0, 0};
@@ -297,24 +312,43 @@ __device__ __forceinline__ uint32_t take_ticket(const FrameArgs &a, uint32_t lan
 	return __shfl_sync(FULL_MASK, t, 0);
 }
 
-/* P0: the span's bulk copy (with the 16 bytes before it) and cleared insert masks */
+/* P0: the span's bulk copy (with the 16 bytes before and, when the input has them, after it) */
 template <int ROWS>
-__device__ __forceinline__ void stage_issue(Buf<ROWS> &s, const FrameArgs &a, uint32_t t, uint32_t lane)
+__device__ __forceinline__ void copy_issue(const Buf<ROWS> s, const FrameArgs &a, uint32_t t, uint32_t lane)
 {
 	using C = Cfg<ROWS>;
 	const uint64_t span_off = (uint64_t)t * C::SPAN;
 	if (lane == 0 && span_off + (uint64_t)C::SPAN <= a.len) {
-		/* the 16 bytes after the span come along when the input has them (soft seams, see classify) */
 		const uint32_t right = span_off + (uint64_t)C::SPAN + 16 <= a.len ? 16u : 0u;
 		if (t > 0) {
-			bulk_load_issue(s.raw, a.rbsp + span_off - 16, C::SPAN + 16 + right, &s.bar);
+			bulk_load_issue(s.d.raw, a.rbsp + span_off - 16, C::SPAN + 16 + right, &s.d.bar);
 		} else {
-			((uint32_t *)(s.raw + 16))[-1] = 0xffffffffu; /* nothing before the input */
-			bulk_load_issue(s.raw + 16, a.rbsp, C::SPAN + right, &s.bar);
+			((uint32_t *)(s.d.raw + 16))[-1] = 0xffffffffu; /* nothing before the input */
+			bulk_load_issue(s.d.raw + 16, a.rbsp, C::SPAN + right, &s.d.bar);
 		}
 	}
-	uint4 *m4 = (uint4 *)s.M;
-	for (uint32_t i = lane; i < (uint32_t)(C::SPAN_CH + 8) / 8; i += 32)
+}
+
+/* ... and its arrival (the span the input ends in: plain loads) */
+template <int ROWS>
+__device__ __forceinline__ void copy_wait(const Buf<ROWS> s, const FrameArgs &a, uint32_t t, uint32_t lane, uint32_t &par,
+					  uint32_t bufi)
+{
+	using C = Cfg<ROWS>;
+	const uint64_t span_off = (uint64_t)t * C::SPAN;
+	if (span_off + (uint64_t)C::SPAN <= a.len) {
+		bulk_load_wait_parity(&s.d.bar, (par >> bufi) & 1u);
+		par ^= 1u << bufi;
+	} else {
+		load_partial_span<ROWS>(s, a, span_off, lane);
+	}
+	__syncwarp();
+}
+
+template <int ROWS> __device__ __forceinline__ void clear_masks(const Buf<ROWS> s, uint32_t lane)
+{
+	uint4 *m4 = (uint4 *)s.m.M;
+	for (uint32_t i = lane; i < (uint32_t)(Cfg<ROWS>::SPAN_CH + 8) / 8; i += 32)
 		m4[i] = make_uint4(0, 0, 0, 0);
 }
 
@@ -323,13 +357,13 @@ __device__ __forceinline__ void stage_issue(Buf<ROWS> &s, const FrameArgs &a, ui
  * set) and returns with the span's insert count in r.count.
  */
 template <int ROWS>
-__device__ __forceinline__ void classify(Buf<ROWS> &s, uint16_t *cand, const FrameArgs &a, SpanRegs &r, uint32_t lane,
+__device__ __forceinline__ void classify(const Buf<ROWS> s, uint16_t *cand, const FrameArgs &a, SpanRegs &r, uint32_t lane,
 					 uint32_t &par, uint32_t bufi)
 {
 	using C = Cfg<ROWS>;
 	const uint32_t ltmask = (1u << lane) - 1u;
-	uint32_t *raw32 = (uint32_t *)(s.raw + 16);
-	const uint8_t *rawb = s.raw + 16;
+	uint32_t *raw32 = (uint32_t *)(s.d.raw + 16);
+	const uint8_t *rawb = s.d.raw + 16;
 	const uint32_t t = r.t;
 	const uint64_t span_off = (uint64_t)t * C::SPAN;
 	const uint32_t nvalid = span_off >= a.len ? 0u
@@ -341,21 +375,15 @@ __device__ __forceinline__ void classify(Buf<ROWS> &s, uint16_t *cand, const Fra
 	r.k_lo = k_lo;
 	r.k_hi = k_hi;
 	if (lane < (uint32_t)kSoff && k_lo + lane < k_hi)
-		s.soff[lane] = (uint32_t)(a.off[k_lo + lane] - span_off);
-	if (full) {
-		bulk_load_wait_parity(&s.bar, (par >> bufi) & 1u);
-		par ^= 1u << bufi;
-	} else {
-		load_partial_span<ROWS>(s, a, span_off, lane);
-	}
-	__syncwarp();
+		s.m.soff[lane] = (uint32_t)(a.off[k_lo + lane] - span_off);
+	copy_wait<ROWS>(s, a, t, lane, par, bufi);
 	/* payload starts of the span before row `lane` (entry ROWS: all of them); byte-wise rows: a
 	 * payload start inside, or the input ends in (or before) the row */
 	uint32_t kr = 0;
 	if (has_b && lane >= 1 && lane <= (uint32_t)ROWS)
 		kr = starts_le<ROWS>(s, a, span_off, k_lo, k_hi, lane * 512u - 1u);
 	if (lane <= (uint32_t)ROWS)
-		s.krow[lane] = kr;
+		s.m.krow[lane] = kr;
 	const uint32_t krn = __shfl_down_sync(FULL_MASK, kr, 1);
 	const uint32_t BW = __ballot_sync(FULL_MASK, lane < (uint32_t)ROWS && (krn > kr || (lane + 1) * 512u > nvalid));
 	/*
@@ -424,7 +452,7 @@ __device__ __forceinline__ void classify(Buf<ROWS> &s, uint16_t *cand, const Fra
 		uint32_t B16 = 0;
 		int32_t lim = -1;
 		if (has_b) {
-			uint32_t cnt0 = s.krow[R];
+			uint32_t cnt0 = s.m.krow[R];
 			if ((BW >> R) & 1) {
 				cnt0 = starts_le<ROWS>(s, a, span_off, k_lo, k_hi, p0);
 				const uint32_t cnt1 = starts_le<ROWS>(s, a, span_off, k_lo, k_hi, p0 + 15);
@@ -470,7 +498,7 @@ __device__ __forceinline__ void classify(Buf<ROWS> &s, uint16_t *cand, const Fra
 		}
 		ins16 &= vm;
 		if (ins16)
-			s.M[c] = (uint16_t)ins16;
+			s.m.M[c] = (uint16_t)ins16;
 		if (c < (uint32_t)C::SPAN_CH) /* the next span counts its own */
 			cnt += (uint32_t)__popc(ins16);
 	}
@@ -588,23 +616,23 @@ __device__ __forceinline__ uint64_t lb_eval(const FrameArgs &a, uint32_t t, uint
  * the span, shl = its low bits.  Returns the number of chunks listed for the byte-exact pass.
  */
 template <int ROWS, bool LEAN>
-__device__ __forceinline__ uint32_t emit_span(const Buf<ROWS> &s, const uint16_t *E, uint8_t *dl, const FrameArgs &a,
+__device__ __forceinline__ uint32_t emit_span(const Buf<ROWS> s, const uint16_t *E, uint8_t *dl, const FrameArgs &a,
 					      uint32_t lane, uint32_t bwl, uint8_t *base, uint32_t shl, bool has_b, bool safe,
 					      const uint8_t *capend)
 {
 	const uint32_t ltmask = (1u << lane) - 1u;
-	const uint32_t *raw32 = (const uint32_t *)(s.raw + 16);
+	const uint32_t *raw32 = (const uint32_t *)(s.d.raw + 16);
 	uint32_t ndirty = 0;
 #pragma unroll(LEAN ? ROWS : 1)
 	for (int i = 0; i < ROWS; i++) {
 		if (!LEAN && ((bwl >> (i + 1)) & 1))
 			continue;
-		const uint32_t koff = (!LEAN && has_b) ? a.sc_len * s.krow[i] : 0u;
+		const uint32_t koff = (!LEAN && has_b) ? a.sc_len * s.m.krow[i] : 0u;
 		const uint32_t c = i * 32 + lane;
 		const uint32_t p0 = c * 16;
 		const uint32_t e = E[c];
-		const uint32_t m = s.M[c];
-		const uint32_t mn = s.M[c + 1];
+		const uint32_t m = s.m.M[c];
+		const uint32_t mn = s.m.M[c + 1];
 		uint8_t *o = base + (p0 + e + koff); /* the chunk's first output byte */
 		const uint32_t b = (0u - (shl + e + koff)) & 15u;
 		uint32_t bad = m | (mn & ((1u << b) - 1u));
@@ -637,7 +665,7 @@ __device__ __forceinline__ uint32_t emit_span(const Buf<ROWS> &s, const uint16_t
  * pin = inserts before the span.  The ticket of the span after next is asked for on the way
  * (next: the atomic's round trip hides behind the rows). */
 template <int ROWS>
-__device__ __forceinline__ void emit(WSmem<ROWS> &ws, const Buf<ROWS> &s, const FrameArgs &a, const SpanRegs &r,
+__device__ __forceinline__ void emit(uint16_t *E, uint8_t *dl, const Buf<ROWS> s, const FrameArgs &a, const SpanRegs &r,
 				     uint64_t pin, uint32_t lane, uint32_t &tnext, bool early)
 {
 	using C = Cfg<ROWS>;
@@ -651,13 +679,12 @@ __device__ __forceinline__ void emit(WSmem<ROWS> &ws, const Buf<ROWS> &s, const 
 	const uint32_t BW = r.bw & 0xffffu;
 	const bool hard_before = !(r.bw & kSoftBefore), hard_after = !(r.bw & kSoftAfter);
 	const uint8_t *capend = a.out + a.out_cap;
-	uint16_t *E = ws.E;
 
 	/* inserts of the span before every chunk (a lane sums ROWS consecutive chunks) */
 	{
 		uint32_t ex[ROWS];
 		uint32_t run = 0;
-		const uint16_t *mp = s.M + lane * ROWS;
+		const uint16_t *mp = s.m.M + lane * ROWS;
 #pragma unroll
 		for (int k = 0; k < ROWS; k++) {
 			ex[k] = run;
@@ -687,9 +714,9 @@ __device__ __forceinline__ void emit(WSmem<ROWS> &ws, const Buf<ROWS> &s, const 
 	uint8_t *base = a.out + (span_off + d0);
 	uint32_t ndirty;
 	if (BW == 0)
-		ndirty = emit_span<ROWS, true>(s, E, ws.dl, a, lane, bwl, base, (uint32_t)d0, has_b, safe, capend);
+		ndirty = emit_span<ROWS, true>(s, E, dl, a, lane, bwl, base, (uint32_t)d0, has_b, safe, capend);
 	else
-		ndirty = emit_span<ROWS, false>(s, E, ws.dl, a, lane, bwl, base, (uint32_t)d0, has_b, safe, capend);
+		ndirty = emit_span<ROWS, false>(s, E, dl, a, lane, bwl, base, (uint32_t)d0, has_b, safe, capend);
 	__syncwarp();
 	/* the ticket asked for before the rows is back: its span on the way into L2 under the byte-exact pass */
 	if (early) {
@@ -702,11 +729,11 @@ __device__ __forceinline__ void emit(WSmem<ROWS> &ws, const Buf<ROWS> &s, const 
 		bytewise_chunk<ROWS>(s, E, a, ((uint32_t)__ffs((int)x) - 1) * 32 + lane, span_off, nvalid, k_lo, k_hi, d0);
 	const uint8_t *cap2 = safe ? (const uint8_t *)~(uintptr_t)0 : capend;
 	for (uint32_t g = lane; g < ndirty; g += 32) {
-		const uint32_t c = ws.dl[g];
+		const uint32_t c = dl[g];
 		const uint32_t R = c >> 5;
-		const uint64_t rd = d0 + (has_b ? a.sc_len * s.krow[R] : 0u);
+		const uint64_t rd = d0 + (has_b ? a.sc_len * s.m.krow[R] : 0u);
 		const uint32_t e = E[c];
-		const uint32_t kins = (uint32_t)__popc(s.M[c]);
+		const uint32_t kins = (uint32_t)__popc(s.m.M[c]);
 		uint8_t *o = a.out + (span_off + rd + (uint64_t)c * 16 + e);
 		const uint32_t b = (0u - ((uint32_t)rd + e)) & 15u;
 		const bool seam_after = (c & 31u) == 31u && (R == (uint32_t)ROWS - 1 ? hard_after : ((BW >> (R + 1)) & 1) != 0);
@@ -726,24 +753,25 @@ __device__ __forceinline__ void emit(WSmem<ROWS> &ws, const Buf<ROWS> &s, const 
 
 /*
  * NW warps per CTA, every warp on its own.  Per loop iteration (A = the span classified an
- * iteration ago, B = the span whose ticket was taken an iteration ago):
- *   bulk copy of B issued | look-back words of A fetched | B classified and published |
- *   look-back of A evaluated | ticket C asked for | A emitted (L2 prefetch of C on the way).
- * The ticket is taken AFTER the look-back, the only place a warp can wait: a waiting warp never
- * holds an unpublished span.  (A first build took it at the top of the iteration: every wait was
- * then handed on, plus a polling delay, to the warps that needed the held span, and the waits
- * grew linearly along the stream: 16 us per look-back in the first eighth of 1 GiB, 256 us in
- * the last, profiles/r02_frame7_phase_trace.txt.)
+ * iteration ago, B = the span whose ticket was just taken):
+ *   bulk copy of B | look-back words of A fetched | B classified and published |
+ *   (NBUF = 1: bulk copy of A, again) | look-back of A evaluated | A emitted | next ticket.
+ * The ticket is taken AFTER the look-back, the only place a warp can wait, and after the emit
+ * unless that is short: a warp never holds an unpublished span for long.  (A first build took it
+ * at the top of the iteration: every wait was then handed on, plus a polling delay, to the warps
+ * that needed the held span, and the waits grew linearly along the stream: 16 us per look-back
+ * in the first eighth of 1 GiB, 256 us in the last, profiles/r02_frame7_trace_ticket_at_top.txt.)
  */
-template <int ROWS, int NW, int MINB>
+template <int ROWS, int NW, int MINB, int NBUF>
 __global__ void __launch_bounds__(32 * NW, MINB) frame7_kernel(const FrameArgs a)
 {
-	__shared__ WSmem<ROWS> sm[NW];
+	__shared__ WSmem<ROWS, NBUF> sm[NW];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	WSmem<ROWS> &ws = sm[warp];
+	WSmem<ROWS, NBUF> &ws = sm[warp];
 	if (lane == 0) {
-		bulk_bar_init(&ws.b[0].bar);
-		bulk_bar_init(&ws.b[1].bar);
+#pragma unroll
+		for (int i = 0; i < NBUF; i++)
+			bulk_bar_init(&ws.d[i].bar);
 	}
 	__syncwarp();
 	uint32_t par = 0; /* bit i: phase parity of buffer i's barrier */
@@ -751,23 +779,25 @@ __global__ void __launch_bounds__(32 * NW, MINB) frame7_kernel(const FrameArgs a
 	A.t = 0xffffffffu;
 	uint32_t tB = take_ticket(a, lane);
 	trace_mark(a, tB, lane, 0);
-	uint32_t cur = 0; /* buffer of A; B goes to the other one */
+	uint32_t cur = 0; /* masks (and, NBUF = 2, bytes) of A; B goes to the other slot */
 	for (;;) {
 		const bool hasA = A.t != 0xffffffffu;
 		const bool hasB = tB < a.num_tiles;
 		if (!hasA && !hasB)
 			break;
-		Buf<ROWS> &bufA = ws.b[cur], &bufB = ws.b[cur ^ 1u];
+		const uint32_t da = NBUF == 2 ? cur : 0u, db = NBUF == 2 ? cur ^ 1u : 0u;
+		const Buf<ROWS> bufA = {ws.d[da], ws.m[cur]}, bufB = {ws.d[db], ws.m[cur ^ 1u]};
 		if (hasB) {
 			trace_mark(a, tB, lane, 1);
-			stage_issue<ROWS>(bufB, a, tB, lane);
+			copy_issue<ROWS>(bufB, a, tB, lane);
+			clear_masks<ROWS>(bufB, lane);
 		}
 		Probe pr;
-		if (hasA)
+		if (hasA && NBUF == 2)
 			pr = lb_fetch(a, A.t, lane);
 		if (hasB) {
 			B.t = tB;
-			classify<ROWS>(bufB, ws.E, a, B, lane, par, cur ^ 1u);
+			classify<ROWS>(bufB, ws.E, a, B, lane, par, db);
 			trace_mark(a, tB, lane, 2);
 			if (lane == 0)
 				publish(a, tB, B.count);
@@ -776,9 +806,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) frame7_kernel(const FrameArgs a
 		uint32_t tC = 0xffffffffu;
 		if (hasA) {
 			uint32_t spins = 0;
+			if (NBUF == 1) { /* the bytes of A again, under its look-back */
+				__syncwarp();
+				copy_issue<ROWS>(bufA, a, A.t, lane);
+				pr = lb_fetch(a, A.t, lane);
+			}
 			trace_mark(a, A.t, lane, 4);
 			const uint64_t pin = lb_eval(a, A.t, lane, pr, spins);
 			trace_mark(a, A.t, lane, 5);
+			if (NBUF == 1)
+				copy_wait<ROWS>(bufA, a, A.t, lane, par, da);
 			/* the next ticket before the emit (its span prefetched into L2 on the way) only when the
 			 * emit is short and uniform: a span with byte-wise rows can take 30 us, and a ticket held
 			 * unpublished that long makes every later span wait (kTicketEarly: 0 never, 1 when A has
@@ -786,13 +823,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) frame7_kernel(const FrameArgs a
 			const bool early = hasB && (kTicketEarly == 2 || (kTicketEarly == 1 && (A.bw & 0xffffu) == 0));
 			if (early && lane == 0)
 				tC = atomicAdd(a.ticket, 1u);
-			emit<ROWS>(ws, bufA, a, A, pin, lane, tC, early);
+			emit<ROWS>(ws.E, ws.dl, bufA, a, A, pin, lane, tC, early);
+			trace_mark(a, A.t, lane, 6);
+			trace_mark(a, A.t, lane, 7, spins);
 			if (!early && hasB) {
 				tC = take_ticket(a, lane);
 				trace_mark(a, tC, lane, 0);
 			}
-			trace_mark(a, A.t, lane, 6);
-			trace_mark(a, A.t, lane, 7, spins);
 		} else {
 			tC = take_ticket(a, lane);
 			trace_mark(a, tC, lane, 0);

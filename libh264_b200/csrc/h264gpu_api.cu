@@ -1293,23 +1293,28 @@ extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, u
 #include "annexb_frame6.cuh"
 #include "annexb_frame7.cuh"
 
-/* writer kernel generation: 7 (warp-autonomous spans, annexb_frame7.cuh; the default) or 6
- * (block-wide 32 KiB tiles, annexb_frame6.cuh): H264GPU_FRAME_GEN */
+/* writer kernel generation: 6 (block-wide 32 KiB tiles, annexb_frame6.cuh; the default) or 7
+ * (warp-autonomous spans, annexb_frame7.cuh; the same speed on B200, see its header):
+ * H264GPU_FRAME_GEN */
 static int frame_gen(void)
 {
 	const char *e = getenv("H264GPU_FRAME_GEN");
-	return (e != NULL && atoi(e) == 6) ? 6 : 7;
+	return (e != NULL && atoi(e) == 7) ? 7 : 6;
 }
 
-template <int ROWS, int NW, int MINB>
+template <int ROWS, int NW, int NBUF>
 static cudaError_t launch_frame7_cfg(const frame::FrameArgs &a, cudaStream_t st, int sms)
 {
-	cudaFuncSetAttribute(frame7::frame7_kernel<ROWS, NW, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+	/* resident CTAs per SM: what 227 KB of shared memory hold (1 KB per CTA is the system's) */
+	constexpr int per_cta = NW * (int)sizeof(frame7::WSmem<ROWS, NBUF>) + 1024;
+	constexpr int fit = (227 * 1024) / per_cta;
+	constexpr int MINB = fit * NW > 48 ? 48 / NW : (fit > 32 ? 32 : fit);
+	cudaFuncSetAttribute(frame7::frame7_kernel<ROWS, NW, MINB, NBUF>, cudaFuncAttributePreferredSharedMemoryCarveout,
 			     cudaSharedmemCarveoutMaxShared);
 	/* persistent warps: as many CTAs as fit, fewer when there are fewer spans than warps */
 	const uint64_t cap = (uint64_t)sms * MINB;
 	const uint64_t want = ((uint64_t)a.num_tiles + NW - 1) / NW;
-	frame7::frame7_kernel<ROWS, NW, MINB><<<(unsigned)(want < cap ? want : cap), 32 * NW, 0, st>>>(a);
+	frame7::frame7_kernel<ROWS, NW, MINB, NBUF><<<(unsigned)(want < cap ? want : cap), 32 * NW, 0, st>>>(a);
 	return cudaGetLastError();
 }
 
@@ -1324,19 +1329,13 @@ static cudaError_t launch_frame7(const frame::FrameArgs &a, cudaStream_t st)
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	if (sms <= 0)
 		sms = 148;
-	/* warps per CTA (every warp works alone; the CTA size only decides how the 227 KB of shared
-	 * memory of an SM divide): H264GPU_FRAME7_NW = 1 (default), 2 or 3 */
-	const char *e = getenv("H264GPU_FRAME7_NW");
-	const int nw = (e != NULL && atoi(e) >= 1 && atoi(e) <= 3) ? atoi(e) : 1;
-	constexpr int per_warp = (int)sizeof(frame7::WSmem<ROWS>);
-	constexpr int fit1 = (227 * 1024) / (per_warp + 1024) > 32 ? 32 : (227 * 1024) / (per_warp + 1024);
-	constexpr int fit2 = (227 * 1024) / (2 * per_warp + 1024) > 24 ? 24 : (227 * 1024) / (2 * per_warp + 1024);
-	constexpr int fit3 = (227 * 1024) / (3 * per_warp + 1024) > 16 ? 16 : (227 * 1024) / (3 * per_warp + 1024);
-	if (nw == 2)
-		return launch_frame7_cfg<ROWS, 2, fit2>(a, st, sms);
-	if (nw == 3)
-		return launch_frame7_cfg<ROWS, 3, fit3>(a, st, sms);
-	return launch_frame7_cfg<ROWS, 1, fit1>(a, st, sms);
+	/* H264GPU_FRAME7_NBUF = 2 (default): a span's bytes stay staged from classification to
+	 * emission, one warp per CTA, 20 warps per SM; 1: staged twice, four warps per CTA, 32 warps per
+	 * SM (measured slower: 1064 vs 1207 GB/s, the instruction cache misses of 32 unrelated warps) */
+	const char *e = getenv("H264GPU_FRAME7_NBUF");
+	if (e != NULL && atoi(e) == 1)
+		return launch_frame7_cfg<ROWS, 4, 1>(a, st, sms);
+	return launch_frame7_cfg<ROWS, 1, 2>(a, st, sms);
 }
 
 template <int ROWS>

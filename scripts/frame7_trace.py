@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size-mb", type=int, default=1024)
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "frame7_trace.bin"))
 args = ap.parse_args()
+os.environ.setdefault("H264GPU_FRAME_GEN", "7")
 g = L.Gpu(0)
 offs = L.synth_offsets(SEED + 100, args.size_mb << 20)
 rbsp = L.synth_payloads(SEED + 100, offs)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """The writer kernel (EPB insert + framing) on one GPU, device resident, CUDA events; prints
 GB/s of payload, the roofline fraction and a hash of the output (to compare builds).
-Knobs: H264GPU_FRAME_GEN (6 | 7), H264GPU_FRAME7_NW (1-3), H264GPU_FRAME7_ROWS (1,2,4,6,8).
+Knobs: H264GPU_FRAME_GEN (6 | 7), H264GPU_FRAME7_NBUF (2 | 1), H264GPU_FRAME7_ROWS (1,2,4,6,8).
    python scripts/frame_ab.py [--size-mb 1024] [--steps 10] [--hash 1]"""
 import argparse, hashlib, json, os, sys
 import numpy as np

@@ -265,9 +265,11 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 			 uint64_t *total, int items)
 {
 	using namespace frame;
-	/* 70 + rows: frame7_kernel with 1/2/4/6/8 rows per span, three warps per CTA */
+	/* 70 + rows: frame7_kernel with 1/2/4/6/8 rows per span, three warps per CTA, the bytes of a
+	 * span staged twice; 80 + rows: staged once (two buffers per warp) */
 	if (items > 70) {
-		const int rows = items - 70;
+		const int nbuf = items > 80 ? 2 : 1;
+		const int rows = items > 80 ? items - 80 : items - 70;
 		const uint64_t span = 512ull * rows;
 		uint32_t ns = (uint32_t)((len + span - 1) / span);
 		if (ns == 0)
@@ -299,23 +301,38 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 		switch (rows) {
 		case 1:
 			EMU_LAUNCH((frame7::frame7_prepass<1>), pgrid, pblock, a);
-			EMU_LAUNCH((frame7::frame7_kernel<1, 3, 1>), grid, block, a);
+			if (nbuf == 2)
+				EMU_LAUNCH((frame7::frame7_kernel<1, 3, 1, 2>), grid, block, a);
+			else
+				EMU_LAUNCH((frame7::frame7_kernel<1, 3, 1, 1>), grid, block, a);
 			break;
 		case 2:
 			EMU_LAUNCH((frame7::frame7_prepass<2>), pgrid, pblock, a);
-			EMU_LAUNCH((frame7::frame7_kernel<2, 3, 1>), grid, block, a);
+			if (nbuf == 2)
+				EMU_LAUNCH((frame7::frame7_kernel<2, 3, 1, 2>), grid, block, a);
+			else
+				EMU_LAUNCH((frame7::frame7_kernel<2, 3, 1, 1>), grid, block, a);
 			break;
 		case 4:
 			EMU_LAUNCH((frame7::frame7_prepass<4>), pgrid, pblock, a);
-			EMU_LAUNCH((frame7::frame7_kernel<4, 3, 1>), grid, block, a);
+			if (nbuf == 2)
+				EMU_LAUNCH((frame7::frame7_kernel<4, 3, 1, 2>), grid, block, a);
+			else
+				EMU_LAUNCH((frame7::frame7_kernel<4, 3, 1, 1>), grid, block, a);
 			break;
 		case 6:
 			EMU_LAUNCH((frame7::frame7_prepass<6>), pgrid, pblock, a);
-			EMU_LAUNCH((frame7::frame7_kernel<6, 3, 1>), grid, block, a);
+			if (nbuf == 2)
+				EMU_LAUNCH((frame7::frame7_kernel<6, 3, 1, 2>), grid, block, a);
+			else
+				EMU_LAUNCH((frame7::frame7_kernel<6, 3, 1, 1>), grid, block, a);
 			break;
 		default:
 			EMU_LAUNCH((frame7::frame7_prepass<8>), pgrid, pblock, a);
-			EMU_LAUNCH((frame7::frame7_kernel<8, 3, 1>), grid, block, a);
+			if (nbuf == 2)
+				EMU_LAUNCH((frame7::frame7_kernel<8, 3, 1, 2>), grid, block, a);
+			else
+				EMU_LAUNCH((frame7::frame7_kernel<8, 3, 1, 1>), grid, block, a);
 			break;
 		}
 		free(buf);

@@ -290,9 +290,10 @@ def test_emu_frame6_output_capacity_is_respected():
         assert np.array_equal(out[:cap], exp[:cap]) and (out[cap:] == 0xAA).all(), cap
 
 
-# ---- K3 gen 7 (frame7_kernel): items 71/72/74/76/78 = 1/2/4/6/8 rows per warp-owned span ----
+# ---- K3 gen 7 (frame7_kernel): items 71/72/74/76/78 = 1/2/4/6/8 rows per warp-owned span, bytes
+# staged twice (one buffer per warp); 81/.../88: staged once (two buffers per warp) ----
 
-G7 = [71, 72, 74, 76, 78]
+G7 = [71, 72, 74, 76, 78, 81, 82, 84, 86, 88]
 
 
 def test_emu_frame7_known_answer():
@@ -320,7 +321,7 @@ def test_emu_frame7_random_and_adversarial():
         for p in rng.integers(0, tot, 3):
             data[p] = rng.choice([1, 3, 7])
         check_frame(data, np.array([0, tot // 3, tot // 3, tot], np.uint64), 4, int(rng.choice(G7)), ("zeros7", it))
-    for items in (71, 78):
+    for items in (71, 78, 81, 88):
         check_frame(np.zeros(0, np.uint8), np.array([0, 0, 0], np.uint64), 4, items, "empty payloads only")
         check_frame(np.zeros(0, np.uint8), np.array([0], np.uint64), 4, items, "no payloads")
         check_frame(np.array([0, 0, 1], np.uint8), np.array([0, 3], np.uint64), 3, items, "three bytes")
@@ -335,9 +336,11 @@ def test_emu_frame7_groups_and_supergroups():
     cuts = np.sort(np.concatenate([rng.integers(0, tot + 1, 40), [512 * 1024, 512 * 1024 + 1, 512 * 33]]))
     offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
     check_frame(data, offs, 4, 71, "chain7")
+    check_frame(data, offs, 4, 81, "chain7")
     data = rng.integers(0, 256, tot).astype(np.uint8)
     data[rng.random(tot) < 0.1875] = 0
     check_frame(data, np.array([0, tot], np.uint64), 3, 71, "chain7 one payload")
+    check_frame(data, np.array([0, tot], np.uint64), 3, 81, "chain7 one payload")
 
 
 def test_emu_frame7_stream_shaped_and_dense_starts():
@@ -350,6 +353,7 @@ def test_emu_frame7_stream_shaped_and_dense_starts():
         offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
         check_frame(data, offs, 4, 78, ("stream7", it))
         check_frame(data, offs, 3, 76, ("stream7", it))
+        check_frame(data, offs, 4, 88, ("stream7", it))
     for it in range(4):  # payloads of a few bytes: every row goes byte by byte, more starts than staged
         tot = int(rng.integers(3000, 20000))
         data = rng.choice(np.array([0, 0, 0, 1, 3, 0xFF], np.uint8), tot)

@@ -264,12 +264,14 @@ def test_frame_small_tiles():
             os.environ["H264GPU_SCAN_ITEMS"] = old
 
 
-@pytest.mark.parametrize("env", [{"H264GPU_FRAME_GEN": "6"}, {"H264GPU_FRAME7_ROWS": "6"},
-                                 {"H264GPU_FRAME7_NW": "2"}, {"H264GPU_FRAME7_NW": "3", "H264GPU_FRAME7_ROWS": "1"}])
+@pytest.mark.parametrize("env", [{"H264GPU_FRAME_GEN": "7"}, {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_ROWS": "6"},
+                                 {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_NBUF": "1"},
+                                 {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_ROWS": "1"},
+                                 {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_NBUF": "1", "H264GPU_FRAME7_ROWS": "2"}])
 def test_frame_kernel_variants(env):
-    """The writer's other builds: gen 6 (block-wide tiles), gen 7 with 3 KiB spans / 2 or 3 warps per
-    CTA / 512-byte spans (> 1024 spans: every level of the chain), on stream-shaped and zero-heavy
-    payloads against the oracle."""
+    """The writer's other generation (gen 7, warp-autonomous spans): 4 KiB and 3 KiB spans, bytes
+    staged once or twice, 512-byte spans (> 1024 spans: every level of the chain), on stream-shaped
+    and zero-heavy payloads against the oracle."""
     rng = np.random.default_rng(59)
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
