@@ -27,6 +27,7 @@ int h264gpu_device_count(void)
 
 static int ws7_reserve(h264gpu_ctx *ctx, size_t bytes);
 static void ws7_free(h264gpu_ctx *ctx);
+static void frame_pipe_free(h264gpu_ctx *ctx);
 
 int h264gpu_create(int device, h264gpu_ctx **out)
 {
@@ -96,6 +97,7 @@ int h264gpu_destroy(h264gpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	free_pipeline(ctx);
+	frame_pipe_free(ctx);
 	cudaFree(ctx->ws);
 	ws7_free(ctx);
 	cudaFree(ctx->rd_stream.p);
@@ -1370,9 +1372,10 @@ static cudaError_t launch_frame6(const frame::FrameArgs &a, cudaStream_t st)
 	return cudaGetLastError();
 }
 
-extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const uint64_t *d_off,
-				 uint64_t n, int sc_len, uint8_t *d_out, uint64_t out_cap,
-				 uint64_t *d_out_off, uint64_t *d_total, void *stream)
+/* len_known: the host already knows off[n] (the host forms); otherwise it is read back */
+static int frame_dev_impl(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const uint64_t *d_off, uint64_t n, int sc_len,
+			  uint8_t *d_out, uint64_t out_cap, uint64_t *d_out_off, uint64_t *d_total, void *stream,
+			  bool len_known, uint64_t known_len)
 {
 	int r = h264gpu_use(ctx);
 	if (r < 0)
@@ -1385,9 +1388,11 @@ extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const 
 		return -EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
 	/* total payload length = off[n]: needed on the host to size the grid */
-	uint64_t len = 0;
-	CU_TRY(cudaMemcpyAsync(&len, d_off + n, sizeof(len), cudaMemcpyDeviceToHost, st));
-	CU_TRY(cudaStreamSynchronize(st));
+	uint64_t len = known_len;
+	if (!len_known) {
+		CU_TRY(cudaMemcpyAsync(&len, d_off + n, sizeof(len), cudaMemcpyDeviceToHost, st));
+		CU_TRY(cudaStreamSynchronize(st));
+	}
 	if (len && d_rbsp == NULL)
 		return -EINVAL;
 	const int items = ctx->scan_items;
@@ -1484,6 +1489,148 @@ extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const 
 	return 0;
 }
 
+extern "C" int h264gpu_frame_dev(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const uint64_t *d_off,
+				 uint64_t n, int sc_len, uint8_t *d_out, uint64_t out_cap,
+				 uint64_t *d_out_off, uint64_t *d_total, void *stream)
+{
+	return frame_dev_impl(ctx, d_rbsp, d_off, n, sc_len, d_out, out_cap, d_out_off, d_total, stream, false, 0);
+}
+
+/*
+ * Host buffers, long inputs: chunks of whole payloads (>= chunk_bytes of payload each) through two
+ * device slots and three streams, so that the upload of chunk c + 1, the kernel of chunk c and
+ * the download of chunk c - 1 overlap.  A chunk is framed on its own (offsets rebased to the
+ * chunk); its output goes where the chunks before it ended, known once their kernels are done.
+ */
+static void frame_pipe_free(h264gpu_ctx *ctx)
+{
+	if (ctx->fp.s_up == NULL)
+		return;
+	for (int b = 0; b < 2; b++) {
+		cudaEventDestroy(ctx->fp.ev_up[b]);
+		cudaEventDestroy(ctx->fp.ev_k[b]);
+		cudaEventDestroy(ctx->fp.ev_dn[b]);
+		cudaFree(ctx->fp.d_in[b].p);
+		cudaFree(ctx->fp.d_out[b].p);
+		cudaFree(ctx->fp.d_tab[b].p);
+		cudaFreeHost(ctx->fp.h_tab[b].p);
+	}
+	cudaStreamDestroy(ctx->fp.s_up);
+	cudaStreamDestroy(ctx->fp.s_k);
+	cudaStreamDestroy(ctx->fp.s_dn);
+	memset(&ctx->fp, 0, sizeof(ctx->fp));
+}
+
+static int frame_pipe_init(h264gpu_ctx *ctx)
+{
+	if (ctx->fp.s_up != NULL)
+		return 0;
+	CU_TRY(cudaStreamCreateWithFlags(&ctx->fp.s_up, cudaStreamNonBlocking));
+	CU_TRY(cudaStreamCreateWithFlags(&ctx->fp.s_k, cudaStreamNonBlocking));
+	CU_TRY(cudaStreamCreateWithFlags(&ctx->fp.s_dn, cudaStreamNonBlocking));
+	for (int b = 0; b < 2; b++) {
+		CU_TRY(cudaEventCreateWithFlags(&ctx->fp.ev_up[b], cudaEventDisableTiming));
+		CU_TRY(cudaEventCreateWithFlags(&ctx->fp.ev_k[b], cudaEventDisableTiming));
+		CU_TRY(cudaEventCreateWithFlags(&ctx->fp.ev_dn[b], cudaEventDisableTiming));
+	}
+	return 0;
+}
+
+/* a slot's buffer, grown only when nothing of the pipeline is in flight */
+static int frame_pipe_grow(h264gpu_ctx *ctx, struct h264gpu_ctx::h264gpu_pool *pl, size_t bytes, bool pinned)
+{
+	if (bytes <= pl->cap)
+		return 0;
+	CU_TRY(cudaStreamSynchronize(ctx->fp.s_up));
+	CU_TRY(cudaStreamSynchronize(ctx->fp.s_k));
+	CU_TRY(cudaStreamSynchronize(ctx->fp.s_dn));
+	return pinned ? h264gpu_pool_host(ctx, pl, bytes) : h264gpu_pool_dev(ctx, pl, bytes);
+}
+
+static int frame_host_pipelined(h264gpu_ctx *ctx, const uint8_t *h_rbsp, const uint64_t *h_off, uint64_t n, int sc_len,
+				uint8_t *h_out, uint64_t out_cap, uint64_t *h_out_off, uint64_t *total)
+{
+	int r = frame_pipe_init(ctx);
+	if (r < 0)
+		return r;
+	const uint64_t target = ctx->chunk_bytes;
+	uint64_t k0[2] = {0, 0}, k1[2] = {0, 0}; /* payloads of the chunk in each slot */
+	bool used[2] = {false, false};
+	uint64_t base = 0;  /* output bytes of the chunks finished so far */
+	uint64_t next_k = 0; /* first payload of the next chunk to issue */
+	uint64_t issued = 0, finished = 0;
+	while (finished < issued || next_k < n) {
+		/* issue the next chunk (one ahead of the chunk being finished) */
+		if (next_k < n && issued - finished < 2) {
+			const int b = (int)(issued & 1);
+			const uint64_t a0 = next_k;
+			uint64_t lo = a0 + 1, hi = n; /* smallest a1 > a0 with off[a1] - off[a0] >= target, else n */
+			while (lo < hi) {
+				const uint64_t mid = (lo + hi) >> 1;
+				if (h_off[mid] - h_off[a0] >= target)
+					hi = mid;
+				else
+					lo = mid + 1;
+			}
+			const uint64_t a1 = lo, nc = a1 - a0, len_c = h_off[a1] - h_off[a0];
+			const uint64_t bound = len_c + len_c / 2 + (uint64_t)sc_len * nc + 64;
+			if ((r = frame_pipe_grow(ctx, &ctx->fp.d_in[b], len_c + 64, false)) < 0 ||
+			    (r = frame_pipe_grow(ctx, &ctx->fp.d_out[b], bound + 64, false)) < 0 ||
+			    (r = frame_pipe_grow(ctx, &ctx->fp.d_tab[b], (2 * nc + 4) * 8, false)) < 0 ||
+			    (r = frame_pipe_grow(ctx, &ctx->fp.h_tab[b], (2 * nc + 4) * 8, true)) < 0)
+				return r;
+			uint64_t *roff = (uint64_t *)ctx->fp.h_tab[b].p, *back = roff + nc + 1;
+			for (uint64_t i = 0; i <= nc; i++)
+				roff[i] = h_off[a0 + i] - h_off[a0];
+			uint64_t *d_off = (uint64_t *)ctx->fp.d_tab[b].p, *d_out_off = d_off + nc + 1, *d_total = d_out_off + nc + 1;
+			if (used[b]) /* the kernel that read this slot's input is done */
+				CU_TRY(cudaStreamWaitEvent(ctx->fp.s_up, ctx->fp.ev_k[b], 0));
+			if (len_c)
+				CU_TRY(cudaMemcpyAsync(ctx->fp.d_in[b].p, h_rbsp + h_off[a0], len_c, cudaMemcpyHostToDevice, ctx->fp.s_up));
+			CU_TRY(cudaMemcpyAsync(d_off, roff, (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->fp.s_up));
+			CU_TRY(cudaEventRecord(ctx->fp.ev_up[b], ctx->fp.s_up));
+			CU_TRY(cudaStreamWaitEvent(ctx->fp.s_k, ctx->fp.ev_up[b], 0));
+			if (used[b]) /* the slot's previous output has been downloaded */
+				CU_TRY(cudaStreamWaitEvent(ctx->fp.s_k, ctx->fp.ev_dn[b], 0));
+			r = frame_dev_impl(ctx, (const uint8_t *)ctx->fp.d_in[b].p, d_off, nc, sc_len, (uint8_t *)ctx->fp.d_out[b].p,
+					   bound, d_out_off, d_total, ctx->fp.s_k, true, len_c);
+			if (r < 0)
+				return r;
+			/* out_off[0 .. nc) and the chunk's total come back with the kernel */
+			CU_TRY(cudaMemcpyAsync(back, d_out_off, (nc + 2) * 8, cudaMemcpyDeviceToHost, ctx->fp.s_k));
+			CU_TRY(cudaEventRecord(ctx->fp.ev_k[b], ctx->fp.s_k));
+			k0[b] = a0;
+			k1[b] = a1;
+			used[b] = true;
+			next_k = a1;
+			issued++;
+			if (next_k < n && issued - finished < 2)
+				continue; /* fill the pipeline before waiting */
+		}
+		/* finish the oldest chunk in flight: its size places it (and everything after it) */
+		const int b = (int)(finished & 1);
+		const uint64_t nc = k1[b] - k0[b];
+		CU_TRY(cudaEventSynchronize(ctx->fp.ev_k[b]));
+		const uint64_t *back = (const uint64_t *)ctx->fp.h_tab[b].p + nc + 1;
+		const uint64_t total_c = back[nc + 1];
+		if (h_out_off)
+			for (uint64_t i = 0; i < nc; i++)
+				h_out_off[k0[b] + i] = back[i] + base;
+		const uint64_t room = out_cap > base ? out_cap - base : 0;
+		const uint64_t ncopy = total_c < room ? total_c : room;
+		if (ncopy)
+			CU_TRY(cudaMemcpyAsync(h_out + base, ctx->fp.d_out[b].p, ncopy, cudaMemcpyDeviceToHost, ctx->fp.s_dn));
+		CU_TRY(cudaEventRecord(ctx->fp.ev_dn[b], ctx->fp.s_dn));
+		base += total_c;
+		finished++;
+	}
+	CU_TRY(cudaStreamSynchronize(ctx->fp.s_dn));
+	if (h_out_off)
+		h_out_off[n] = base;
+	*total = base;
+	return base > out_cap ? -ENOBUFS : 0;
+}
+
 extern "C" int h264gpu_frame_host(h264gpu_ctx *ctx, const uint8_t *h_rbsp, const uint64_t *h_off,
 				  uint64_t n, int sc_len, uint8_t *h_out, uint64_t out_cap,
 				  uint64_t *h_out_off, uint64_t *total)
@@ -1496,6 +1643,14 @@ extern "C" int h264gpu_frame_host(h264gpu_ctx *ctx, const uint8_t *h_rbsp, const
 	const uint64_t len = h_off[n];
 	if (len && h_rbsp == NULL)
 		return -EINVAL;
+	if (sc_len != 0 && sc_len != 3 && sc_len != 4)
+		return -EINVAL;
+	/* long inputs: chunked, copies and kernels overlapped (H264GPU_FRAME_PIPE=0: one shot) */
+	{
+		const char *e = getenv("H264GPU_FRAME_PIPE");
+		if (n >= 2 && len >= 2 * (uint64_t)ctx->chunk_bytes && !(e != NULL && atoi(e) == 0))
+			return frame_host_pipelined(ctx, h_rbsp, h_off, n, sc_len, h_out, out_cap, h_out_off, total);
+	}
 	/* pooled device buffers of the reader session on its private stream: a call costs no
 	 * cudaMalloc / cudaFree (round 1 allocated four buffers per call on the default stream) */
 	cudaStream_t st;
@@ -1510,7 +1665,7 @@ extern "C" int h264gpu_frame_host(h264gpu_ctx *ctx, const uint8_t *h_rbsp, const
 	if (len)
 		CU_TRY(cudaMemcpyAsync(d_rbsp, h_rbsp, len, cudaMemcpyHostToDevice, st));
 	CU_TRY(cudaMemcpyAsync(d_off, h_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-	r = h264gpu_frame_dev(ctx, d_rbsp, d_off, n, sc_len, d_out, out_cap, d_out_off, d_total, st);
+	r = frame_dev_impl(ctx, d_rbsp, d_off, n, sc_len, d_out, out_cap, d_out_off, d_total, st, true, len);
 	if (r < 0)
 		return r;
 	CU_TRY(cudaMemcpyAsync(total, d_total, 8, cudaMemcpyDeviceToHost, st));

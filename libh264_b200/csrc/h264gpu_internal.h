@@ -53,6 +53,13 @@ struct h264gpu_ctx {
 				   for the launch they are about to make (0: unknown, rings sized for 512) */
 	uint64_t rd_maps_len;   /* bytes of slice group maps in rd_maps for the next pooled parse (0: none) */
 	size_t cabac_smem_set;  /* dynamic shared memory the CABAC kernel is configured for on this device */
+	/* h264gpu_frame_host pipeline: upload / kernel / download streams over two chunk slots */
+	struct {
+		cudaStream_t s_up, s_k, s_dn;
+		cudaEvent_t ev_up[2], ev_k[2], ev_dn[2];
+		struct h264gpu_pool d_in[2], d_out[2], d_tab[2]; /* device */
+		struct h264gpu_pool h_tab[2];                   /* pinned: offsets in, [out_off | total] back */
+	} fp;
 };
 
 int h264gpu_pool_dev(h264gpu_ctx *ctx, struct h264gpu_ctx::h264gpu_pool *pl, size_t bytes);

@@ -298,6 +298,56 @@ def test_frame_kernel_variants(env):
                 os.environ[k] = v
 
 
+def test_frame_host_pipeline():
+    """h264gpu_frame_host on long inputs: chunks of whole payloads through two device slots (upload /
+    kernel / download overlapped).  1 MiB chunks here: many chunks, payloads longer than a chunk,
+    empty payloads at chunk seams and at the end, a capacity that ends inside a chunk."""
+    rng = np.random.default_rng(61)
+    old = os.environ.get("H264GPU_CHUNK_MB")
+    os.environ["H264GPU_CHUNK_MB"] = "1"
+    try:
+        g = L.Gpu(0)
+        try:
+            for it in range(4):
+                sizes = []
+                while sum(sizes) < (9 << 20):
+                    kind = rng.integers(0, 10)
+                    sizes.append(0 if kind == 0 else int(rng.integers(1, 200)) if kind < 3 else
+                                 int(rng.integers(2 << 20, 3 << 20)) if kind == 9 and it % 2 else int(rng.integers(1000, 400000)))
+                sizes += [0, 0] if it == 1 else []
+                offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+                tot = int(offs[-1])
+                data = rng.integers(0, 256, tot).astype(np.uint8)
+                data[rng.random(tot) < (0.1875 if it < 3 else 0.7)] = 0
+                sc = 3 if it == 2 else 4
+                exp, eoo = S.oracle_frame(data, offs, sc)
+                out, oo = g.frame_host(data, offs, sc_len=sc)
+                assert np.array_equal(out, exp) and np.array_equal(oo, eoo), it
+                if it == 0:  # the one-shot path gives the same bytes
+                    os.environ["H264GPU_FRAME_PIPE"] = "0"
+                    try:
+                        out1, oo1 = g.frame_host(data, offs, sc_len=sc)
+                    finally:
+                        os.environ.pop("H264GPU_FRAME_PIPE")
+                    assert np.array_equal(out1, exp) and np.array_equal(oo1, eoo)
+                    # capacity that ends inside a chunk: -ENOBUFS, the total still reported, nothing past the capacity
+                    cap = len(exp) * 2 // 3
+                    buf = np.full(cap + 64, 0xAA, np.uint8)
+                    oo2 = np.zeros(len(offs), np.uint64)
+                    tot2 = C.c_uint64(0)
+                    rc = g.lib.h264gpu_frame_host(g.h, S.ptr(data), S.ptr(offs), len(offs) - 1, sc, S.ptr(buf), cap,
+                                                  S.ptr(oo2), C.byref(tot2))
+                    assert rc == -105 and tot2.value == len(exp)
+                    assert np.array_equal(buf[:cap], exp[:cap]) and (buf[cap:] == 0xAA).all()
+        finally:
+            g.close()
+    finally:
+        if old is None:
+            os.environ.pop("H264GPU_CHUNK_MB", None)
+        else:
+            os.environ["H264GPU_CHUNK_MB"] = old
+
+
 def test_writer_round_trip_full_size(gpu):
     """Config 5 shape at 64 MiB: frame on the GPU, then the reference-side reader
     semantics (GPU scan+strip, itself oracle-checked above) give back the payloads."""
