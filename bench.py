@@ -322,7 +322,9 @@ def frame_leg(g, L, size, steps, warmup, rank, with_cpu):
     peak, _ = measured_peak()
     alg = len(rbsp) + total + 8 * (n + 1)
     out = {"workload": "EPB insert + framing of %.0f MiB RBSP in %d payloads (BASELINE config 5)" % (size / 2**20, n),
-           "kernel": "frame::frame_prepass<8> + frame6::frame6_kernel<8> (persistent CTAs, 32 KiB tiles)",
+           "kernel": ("frame7::frame7_prepass<8> + frame7::frame7_kernel<8> (warp-autonomous 4 KiB spans, counts published "
+                      "ahead of the look-back)" if os.environ.get("H264GPU_FRAME_GEN") == "7" else
+                      "frame::frame_prepass<8> + frame6::frame6_kernel<8> (persistent CTAs, 32 KiB tiles)"),
            "gb_per_s": len(rbsp) / (ms / 1e3) / 1e9, "ms_per_step": ms, "out_bytes": total,
            "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(alg)},

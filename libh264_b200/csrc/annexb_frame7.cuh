@@ -1,25 +1,30 @@
 /*
- * annexb_frame7.cuh — K3 third generation: writer-side emulation-prevention-byte insertion and
- * start-code framing with WARP-AUTONOMOUS SPANS, the aggregate of a span published one loop
- * iteration AHEAD of its look-back, and a three-level chain (span / group of 32 spans /
- * supergroup of 32 groups).
+ * annexb_frame7.cuh — K3 third generation (opt-in: H264GPU_FRAME_GEN=7): writer-side
+ * emulation-prevention-byte insertion and start-code framing with WARP-AUTONOMOUS SPANS, the
+ * insert count of a span published an iteration AHEAD of its look-back, a three-level chain
+ * (span / group of 32 spans / supergroup of 32 groups) and soft seams.
  *
- * Why: frame6_kernel (annexb_frame6.cuh, block-wide 32 KiB tiles) is issue-bound at 18.7 k
- * warp-instructions per tile but only 59 % of its issue slots are busy
- * (profiles/r02_frame_kernel_raw.csv): 21 % of warp time sits at the barrier behind the look-back
- * (the tile waits for the AGGREGATES of the ~100 tiles in flight before it, i.e. for the slowest
- * of them) and 15 % at the end-of-tile barrier (the slowest of eight warps).  The writer's output
- * is packed, so its chain is a true stream-long prefix: it cannot be cut at start codes the way
- * the in-place scan kernel (annexb_scan7.cuh) cuts its chain, and that kernel's round-robin
- * regions do not carry over.  What does carry over is that nothing needs to be block-wide, and
- * the wait can be removed instead of cut:
+ * Why it was written: frame6_kernel (annexb_frame6.cuh, block-wide 32 KiB tiles) issues 18.7 k
+ * warp-instructions per tile with 59 % of its issue slots busy (profiles/r02_frame_kernel_raw.csv):
+ * 21 % of warp time sits at the barrier behind the look-back (the tile waits for the AGGREGATES
+ * of the ~100 tiles in flight before it, i.e. for the slowest of them) and 15 % at the
+ * end-of-tile barrier (the slowest of eight warps).  The writer's output is packed, so its chain
+ * is a true stream-long prefix: it cannot be cut at start codes the way the in-place scan kernel
+ * (annexb_scan7.cuh) cuts its chain.  Here the wait is removed instead of cut:
  *
- *  * A warp owns TWO span buffers.  In one loop iteration it classifies span B (ticket taken an
- *    iteration ago, bulk copy already in flight), publishes B's insert count, and only then looks
- *    back for span A (classified an iteration ago) and emits A.  Every predecessor of A took its
- *    ticket before A did, i.e. more than an iteration ago, and published right after its own
- *    classification: the look-back of A finds all of them there.  No barrier, no polling in the
- *    steady state (the loops are there for the first spans and for stragglers).
+ *  * A warp owns TWO span buffers.  In one loop iteration it classifies span B, publishes B's
+ *    insert count, and only then looks back for span A (classified an iteration ago) and emits A.
+ *    Every predecessor of A took its ticket before A did and published right after its own
+ *    classification, an iteration ago: the look-back of A finds all of them there.  No barrier,
+ *    no polling in the steady state (measured: 0.00 / 0.01 misses per span on the first two
+ *    levels, profiles/r02_frame7_trace_two_buffers.txt).
+ *  * A TICKET IS NEVER HELD ACROSS A WAIT.  The next span's ticket is taken after the look-back
+ *    (the only place a warp can wait) and after the emit, unless the emit is short (no byte-wise
+ *    row in span A; then before it, with an L2 prefetch).  The first build took the ticket at the
+ *    top of the iteration: a waiting warp then held an unpublished span, its wait (plus a polling
+ *    delay) was handed on to every warp that needed that span, and the waits grew linearly along
+ *    the stream (16 us per look-back in the first eighth of 1 GiB, 256 us in the last: 10.3 ms
+ *    per GiB, profiles/r02_frame7_trace_ticket_at_top.txt, profiles/r02_frame7_steps.txt).
  *  * Publishing that far ahead means the nearest span with a known PREFIX is thousands of spans
  *    back (every span in flight has an aggregate and no prefix), too deep for a linear look-back.
  *    The chain therefore has three levels, all single 64-bit self-validating words:
@@ -28,20 +33,33 @@
  *                  warp that completes a group adds its sum into
  *      super_w[q]  groups completed << 40 | sum (4 MiB of source per supergroup)
  *      super_p[q]  1 + inserts before supergroup q: a decoupled look-back over supergroups,
- *                  resolved by whoever needs it first (identical values, benign duplicates)
+ *                  resolved by the first spans of the supergroup, read as one word by the others
  *    A look-back is three coalesced probes issued together: the spans of the own group before
  *    the span, the groups of the own supergroup before the group, super_p of the supergroup.
- *  * The 16 bytes before a span are loaded with it (one bulk copy of SPAN + 16 bytes), so the
- *    zero run entering the span is read off the staged bytes: the pre-pass only finds the first
- *    payload of every span and clears the chain words (no per-tile tail array, no memset).
+ *  * The 16 bytes before and after a span are loaded with it (one bulk copy of SPAN + 32 bytes).
+ *    The zero run entering the span is read off the staged bytes, so the pre-pass only finds the
+ *    first payload of every span and clears the chain words (no per-tile tail array, no memset).
+ *    SOFT SEAMS: a 16-byte unit that straddles two spans is written whole by the span it starts
+ *    in (which works out the insert mask of the chunk after its end itself) unless a payload
+ *    starts or the input ends next to the seam; a hard seam costs ~290 warp-instructions of
+ *    byte stores per side.
  *
  * Deadlock freedom: a warp publishes span B before it waits for anything but B's own bulk copy;
  * its look-backs wait only for spans with smaller tickets.  The smallest unpublished span is
- * owned by a resident warp (tickets are taken by running warps) whose pending look-backs depend
- * on still smaller, hence published, spans: it always gets to publish.
+ * owned by a resident warp (tickets are taken by running warps) that is between its ticket and
+ * its publication, where nothing waits for another warp.
+ *
+ * What it reaches (B200, 1 GiB of RBSP, config 5): 0.885 ms = 1213 GB/s of payload, the same as
+ * gen 6 (0.876 ms), which stays the default.  The chain wait is gone, the kernel is not faster:
+ * both generations issue 2100-2300 warp-instructions per 4 KiB at 56-60 % of the issue slots.
+ * Gen 6 loses its slots to barriers; gen 7, at two 4 KiB buffers per warp, has 5 warps per
+ * scheduler and loses them to dependent-issue latency; with ONE buffer per warp (NBUF = 1: the
+ * bytes are staged a second time for the emit, 11 % more DRAM reads) an SM holds 32 warps, the
+ * issue slots are 61 % busy, and instruction fetch becomes the top stall (32 unrelated warps in
+ * ~3500 instructions of code): 1.01 ms.  The writer is bound by its instruction count.
  *
  * Output per chunk, the byte-exact units, byte-wise rows and capacity rules are those of gen 6
- * (see annexb_frame6.cuh); a span is its own tile, so both span ends are seams.
+ * (see annexb_frame6.cuh).
  *
  * Reference behaviour reproduced bit-exactly (Parrot-Developers/libh264):
  *   h264_bs_flush        src/h264_bitstream.c:54-81

@@ -21,6 +21,7 @@
  * There is no CPU path for the bulk stages: without a GPU h264_reader_parse and the
  * slice-data part of h264_reader_parse_nalu fail with -ENODEV.
  */
+#include <time.h>
 #include "h264_priv.h"
 
 int h264_reader_new(const struct h264_ctx_cbs *cbs, void *userdata, struct h264_reader **ret_obj)
@@ -337,9 +338,19 @@ static int collect_slices(struct h264_reader *reader, const uint8_t *buf, const 
 	return res;
 }
 
+/* H264_READER_TIMING=1: phase times of h264_reader_parse on stderr (diagnostics) */
+static double now_ms(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+
 int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t *buf, size_t len,
 		      size_t *off)
 {
+	const int timing = getenv("H264_READER_TIMING") != NULL;
+	double t0 = timing ? now_ms() : 0, t1 = 0, t2 = 0, t3 = 0;
 	if (reader == NULL || buf == NULL || off == NULL)
 		return -EINVAL;
 	reader->stop = 0;
@@ -356,6 +367,8 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 	res = h264gpu_reader_scan(reader->gpu, buf, len, &st, &en, &n_nal, &final_off);
 	if (res < 0)
 		return res;
+	if (timing)
+		t1 = now_ms();
 
 	/* 2. macroblock layer of every CAVLC slice, one launch on the resident copy */
 	struct slice_list sl;
@@ -365,6 +378,8 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 		const struct h264gpu_mb_record *records = NULL;
 		const struct h264gpu_slice_result *results = NULL;
 		res = collect_slices(reader, buf, st, en, n_nal, &sl);
+		if (timing)
+			t2 = now_ms();
 		if (res >= 0 && sl.n > 0 && sl.maps_len > 0)
 			res = h264gpu_reader_set_group_maps(reader->gpu, sl.maps, sl.maps_len);
 		if (res >= 0 && sl.n > 0)
@@ -383,6 +398,8 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 		}
 	}
 
+	if (timing)
+		t3 = now_ms();
 	/* 3. callbacks, in stream order (per-NAL errors are ignored like the reference
 	 * ignores them, src/h264_reader.c:137) */
 	reader->flags = flags;
@@ -397,6 +414,10 @@ int h264_reader_parse(struct h264_reader *reader, uint32_t flags, const uint8_t 
 	}
 	if (!reader->stop)
 		*off = (size_t)final_off;
+	if (timing)
+		fprintf(stderr, "h264_reader_parse: %zu bytes, %llu NALs, %u slices: upload + scan %.2f ms, header pass %.2f, "
+			"slice kernels + records back %.2f, callbacks %.2f\n", len, (unsigned long long)n_nal, sl.n, t1 - t0,
+			t2 > 0 ? t2 - t1 : 0.0, t2 > 0 ? t3 - t2 : 0.0, now_ms() - t3);
 	res = 0;
 	reader->records = NULL;
 	reader->results = NULL;
