@@ -18,5 +18,12 @@ H264_API int h264_write_skipped_p_slice(struct h264_bitstream *bs, struct h264_c
 /* patch the slice header of the NAL in bs in place (same bit length only) */
 H264_API int h264_rewrite_slice_header(struct h264_bitstream *bs, struct h264_ctx *ctx,
 				       const struct h264_slice_header *sh);
+/* Extension of this library (not in the reference): the same header rewrite (same checks, same
+ * return codes, same bytes) left in a patch record for h264gpu_patch_slice_headers
+ * (include/h264gpu_slice.h), which applies any number of them to a stream resident on the GPU in
+ * one launch; the caller fills patch->nal_off */
+struct h264gpu_hdr_patch;
+H264_API int h264_rewrite_slice_header_patch(struct h264_ctx *ctx, const struct h264_slice_header *sh,
+					     struct h264gpu_hdr_patch *patch);
 
 #endif /* H264B200_WRITER_H */

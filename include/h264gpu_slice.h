@@ -289,6 +289,32 @@ H264GPU_API int h264gpu_conceal_slices_host(h264gpu_ctx *ctx, const struct h264g
 					    uint8_t *h_out, uint64_t out_cap, uint64_t *h_out_off,
 					    uint64_t *total);
 
+/*
+ * N4, second half: h264_rewrite_slice_header (src/h264_writer.c:311-370) in bulk on a stream that
+ * is resident on the device.  The reference writes the new NAL header + slice header into a
+ * 64-byte scratch bitstream (emulation prevention on), requires the same bit length as the old
+ * header, copies the whole bytes over the NAL and blends the leading bits of the byte the header
+ * shares with the slice data.  Here the scratch bytes come from the host syntax walk
+ * (h264_rewrite_slice_header_patch, include/h264/h264_writer.h, same checks and return codes),
+ * one patch per slice, and one launch applies them all:
+ *     stream[nal_off + j] = bytes[j]                         for j < nbytes
+ *     stream[nal_off + nbytes] = (bytes[nbytes] & ~keep) | (stream[..] & keep),
+ *         keep = (1 << (8 - tail_bits)) - 1                  if tail_bits != 0
+ * Patches whose bytes would reach past stream_len are skipped (status -EINVAL from the call).
+ */
+struct h264gpu_hdr_patch {
+	uint64_t nal_off;   /* offset of the NAL's header byte in the stream */
+	uint32_t nbytes;    /* whole bytes of the new header, NAL header byte included (<= 63) */
+	uint32_t tail_bits; /* 0..7 header bits in the byte after them */
+	uint8_t bytes[64];  /* the scratch bitstream: nbytes whole bytes, then the byte holding tail_bits */
+};
+H264GPU_API int h264gpu_patch_slice_headers_dev(h264gpu_ctx *ctx, uint8_t *d_stream, uint64_t stream_len,
+						const struct h264gpu_hdr_patch *d_patches, uint32_t n, void *stream);
+/* the same with the patches in host memory (pooled device copy, the context's own stream when
+ * stream is NULL; returns after the launch has been queued and the patches have been uploaded) */
+H264GPU_API int h264gpu_patch_slice_headers(h264gpu_ctx *ctx, uint8_t *d_stream, uint64_t stream_len,
+					    const struct h264gpu_hdr_patch *h_patches, uint32_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,7 +75,8 @@ SLICE_SYMBOLS = ["h264gpu_cavlc_parse_dev", "h264gpu_cavlc_parse_host",
                  "h264gpu_reader_parse_cavlc", "h264gpu_reader_parse_cabac",
                  "h264gpu_reader_parse_slices", "h264gpu_cavlc_parse_full_dev",
                  "h264gpu_cavlc_parse_fmo_dev", "h264gpu_fmo_mb_map", "h264gpu_reader_set_group_maps",
-                 "h264gpu_conceal_slices_dev", "h264gpu_conceal_slices_host"]
+                 "h264gpu_conceal_slices_dev", "h264gpu_conceal_slices_host",
+                 "h264gpu_patch_slice_headers_dev", "h264gpu_patch_slice_headers"]
 
 # every symbol include/h264gpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = [

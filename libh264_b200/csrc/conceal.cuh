@@ -283,6 +283,33 @@ __global__ void __launch_bounds__(1024) conceal_scan(uint64_t *off, uint32_t n)
 #endif
 }
 
+/*
+ * h264_rewrite_slice_header in bulk (src/h264_writer.c:351-361: memcpy of the whole header bytes,
+ * blend of the byte shared with the slice data): 64 threads per patch, one byte each.  A patch
+ * that does not fit the stream (or is malformed) is left out.
+ */
+__global__ void patch_headers_kernel(uint8_t *stream, uint64_t stream_len, const struct h264gpu_hdr_patch *patches,
+				     uint32_t n)
+{
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t p = g >> 6, j = g & 63u;
+	if (p >= n)
+		return;
+	const struct h264gpu_hdr_patch &q = patches[p];
+	const uint32_t nb = q.nbytes, tb = q.tail_bits;
+	if (nb > 63u || tb > 7u)
+		return;
+	const uint64_t end = q.nal_off + nb + (tb ? 1u : 0u);
+	if (end > stream_len || end < q.nal_off)
+		return;
+	if (j < nb) {
+		stream[q.nal_off + j] = q.bytes[j];
+	} else if (j == nb && tb) {
+		const uint32_t keep = (1u << (8 - tb)) - 1u;
+		stream[q.nal_off + j] = (uint8_t)((q.bytes[j] & ~keep) | (stream[q.nal_off + j] & keep));
+	}
+}
+
 } /* namespace conceal */
 
 #endif /* CONCEAL_CUH */

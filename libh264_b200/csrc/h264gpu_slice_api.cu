@@ -402,6 +402,55 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 
 /* ---- N4: concealment slices ------------------------------------------------------------- */
 
+/* ---- N4: slice headers rewritten in bulk ------------------------------------------------------ */
+
+extern "C" int h264gpu_patch_slice_headers_dev(h264gpu_ctx *ctx, uint8_t *d_stream, uint64_t stream_len,
+					       const struct h264gpu_hdr_patch *d_patches, uint32_t n, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (n == 0)
+		return 0;
+	if (d_stream == NULL || d_patches == NULL)
+		return -EINVAL;
+	const uint64_t threads = (uint64_t)n * 64;
+	conceal::patch_headers_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_stream, stream_len,
+													     d_patches, n);
+	CU_TRY(cudaGetLastError());
+	ctx->launches++;
+	return 0;
+}
+
+extern "C" int h264gpu_patch_slice_headers(h264gpu_ctx *ctx, uint8_t *d_stream, uint64_t stream_len,
+					   const struct h264gpu_hdr_patch *h_patches, uint32_t n, void *stream)
+{
+	int r = h264gpu_use(ctx);
+	if (r < 0)
+		return r;
+	if (n == 0)
+		return 0;
+	if (d_stream == NULL || h_patches == NULL)
+		return -EINVAL;
+	for (uint32_t i = 0; i < n; i++) {
+		const struct h264gpu_hdr_patch *q = &h_patches[i];
+		const uint64_t end = q->nal_off + q->nbytes + (q->tail_bits ? 1u : 0u);
+		if (q->nbytes > 63u || q->tail_bits > 7u || end > stream_len || end < q->nal_off)
+			return -EINVAL;
+	}
+	cudaStream_t st = (cudaStream_t)stream;
+	if (st == NULL && (r = h264gpu_reader_stream(ctx, &st)) < 0)
+		return r;
+	if ((r = h264gpu_pool_dev(ctx, &ctx->rd_params, (size_t)n * sizeof(*h_patches))) < 0)
+		return r;
+	CU_TRY(cudaMemcpyAsync(ctx->rd_params.p, h_patches, (size_t)n * sizeof(*h_patches), cudaMemcpyHostToDevice, st));
+	r = h264gpu_patch_slice_headers_dev(ctx, d_stream, stream_len, (const struct h264gpu_hdr_patch *)ctx->rd_params.p, n, st);
+	if (r < 0)
+		return r;
+	CU_TRY(cudaStreamSynchronize(st)); /* h_patches is the caller's again, the stream is patched */
+	return 0;
+}
+
 extern "C" int h264gpu_conceal_slices_dev(h264gpu_ctx *ctx, const struct h264gpu_conceal_params *d_params,
 					  uint32_t n, const uint8_t *d_hdr, uint8_t *d_payload,
 					  uint64_t payload_cap, uint64_t *d_off, void *stream)

@@ -92,6 +92,27 @@ int h264_write_skipped_p_slice(struct h264_bitstream *bs, struct h264_ctx *ctx, 
 
 /* ---- slice header patch, only when the bit length is unchanged ----------------------------- */
 
+/* the new NAL header + slice header in a 64-byte scratch bitstream, as the reference builds it
+ * (src/h264_writer.c:327-349); on failure the context's slice header is what it was */
+static int rewrite_scratch(struct h264_ctx *ctx, const struct h264_slice_header *sh, struct h264_bitstream *tmp,
+			   uint8_t scratch[64])
+{
+	h264_bs_init(tmp, scratch, 64, 1);
+	const struct h264_slice_header saved = ctx->sh;
+	const size_t saved_bits = ctx->sh_bits;
+	int r = h264_ctx_set_slice_header(ctx, sh);
+	if (r < 0)
+		return r;
+	r = h264_write_nalu(tmp, ctx);
+	if (r >= 0 && ctx->sh_bits != saved_bits)
+		r = -EPROTO;
+	if (r < 0) {
+		ctx->sh = saved;
+		ctx->sh_bits = saved_bits;
+	}
+	return r;
+}
+
 int h264_rewrite_slice_header(struct h264_bitstream *bs, struct h264_ctx *ctx,
 			      const struct h264_slice_header *sh)
 {
@@ -99,25 +120,38 @@ int h264_rewrite_slice_header(struct h264_bitstream *bs, struct h264_ctx *ctx,
 		return -EINVAL;
 	uint8_t scratch[64];
 	struct h264_bitstream tmp;
-	h264_bs_init(&tmp, scratch, sizeof(scratch), 1);
-	const struct h264_slice_header saved = ctx->sh;
-	const size_t saved_bits = ctx->sh_bits;
-	int r = h264_ctx_set_slice_header(ctx, sh);
+	const int r = rewrite_scratch(ctx, sh, &tmp, scratch);
 	if (r < 0)
 		return r;
-	r = h264_write_nalu(&tmp, ctx);
-	if (r >= 0 && ctx->sh_bits != saved_bits)
-		r = -EPROTO;
-	if (r < 0) {
-		ctx->sh = saved;
-		ctx->sh_bits = saved_bits;
-		return r;
-	}
 	/* whole bytes, then the leading bits of the byte shared with the slice data */
 	memcpy(bs->data, tmp.data, tmp.off);
 	if (tmp.cachebits != 0) {
 		const uint8_t keep = (uint8_t)((1u << (8 - tmp.cachebits)) - 1);
 		bs->data[tmp.off] = (uint8_t)((tmp.cache & ~keep) | (bs->data[tmp.off] & keep));
 	}
+	return 0;
+}
+
+/* Extension: the same checks and the same bytes, left in a patch record for
+ * h264gpu_patch_slice_headers (a stream resident on the device) instead of being copied over
+ * the NAL; the caller sets patch->nal_off */
+int h264_rewrite_slice_header_patch(struct h264_ctx *ctx, const struct h264_slice_header *sh,
+				    struct h264gpu_hdr_patch *patch)
+{
+	if (ctx == NULL || sh == NULL || patch == NULL)
+		return -EINVAL;
+	uint8_t scratch[64];
+	struct h264_bitstream tmp;
+	memset(scratch, 0, sizeof(scratch));
+	const int r = rewrite_scratch(ctx, sh, &tmp, scratch);
+	if (r < 0)
+		return r;
+	if (tmp.off + (tmp.cachebits != 0) > 64)
+		return -ENOBUFS;
+	memcpy(patch->bytes, scratch, sizeof(patch->bytes));
+	patch->nbytes = (uint32_t)tmp.off;
+	patch->tail_bits = (uint32_t)tmp.cachebits;
+	if (tmp.cachebits != 0 && tmp.off < 64)
+		patch->bytes[tmp.off] = (uint8_t)tmp.cache;
 	return 0;
 }

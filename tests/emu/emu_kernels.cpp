@@ -412,6 +412,17 @@ extern "C" int emu_cavlc_steps(const uint8_t *stream, uint64_t stream_len,
 /* N4: concealment slice synthesis, both passes of the kernel; the scan in between on the host */
 #include "conceal.cuh"
 
+/* N4: bulk slice header patches */
+extern "C" int emu_patch_headers(uint8_t *stream, uint64_t stream_len, const struct h264gpu_hdr_patch *patches, uint32_t n)
+{
+	if (n == 0)
+		return 0;
+	dim3 grid((unsigned)(((uint64_t)n * 64 + 255) / 256)), block(256);
+	EMU_LAUNCH((conceal::patch_headers_kernel), grid, block, stream, stream_len, patches, n);
+	return 0;
+}
+
+
 extern "C" int emu_conceal(const struct h264gpu_conceal_params *params, uint32_t n, const uint8_t *hdr,
 			   uint8_t *out, uint64_t cap, uint64_t *off)
 {

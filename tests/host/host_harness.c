@@ -489,6 +489,73 @@ long hh_rewrite(const char *libpath, const uint8_t *buf, size_t len, int mode, u
 	return (long)st.n;
 }
 
+/* the same edits through this library's h264_rewrite_slice_header_patch: one patch record per
+ * slice whose rewrite succeeds (nal_off relative to buf), rcs[k] = return code for slice k */
+#include "h264gpu_slice.h"
+struct rwp_state {
+	int (*patch_fn)(struct h264_ctx *, const struct h264_slice_header *, struct h264gpu_hdr_patch *);
+	const uint8_t *base;
+	struct h264gpu_hdr_patch *patches;
+	int mode;
+	int32_t *rcs;
+	uint32_t n, np, cap;
+};
+
+static void rwp_slice(struct h264_ctx *c, const uint8_t *buf, size_t len, const struct h264_slice_header *sh,
+		      void *u)
+{
+	struct rwp_state *st = u;
+	struct h264_slice_header nsh = *sh;
+	(void)len;
+	if (st->mode == 0)
+		nsh.frame_num ^= 1;
+	else
+		nsh.slice_qp_delta += 17;
+	struct h264gpu_hdr_patch pt;
+	memset(&pt, 0, sizeof(pt));
+	const int r = st->patch_fn(c, &nsh, &pt);
+	if (st->n < st->cap) {
+		st->rcs[st->n] = r;
+		if (r == 0) {
+			pt.nal_off = (uint64_t)(buf - st->base);
+			st->patches[st->np++] = pt;
+		}
+	}
+	st->n++;
+}
+
+long hh_rewrite_patches(const char *libpath, const uint8_t *buf, size_t len, int mode,
+			struct h264gpu_hdr_patch *patches, int32_t *rcs, uint32_t cap, uint32_t *n_patches)
+{
+	struct api a;
+	int r = api_open(&a, libpath);
+	if (r < 0)
+		return r;
+	struct rwp_state st = {NULL, buf, patches, mode, rcs, 0, 0, cap};
+	*(void **)&st.patch_fn = dlsym(a.h, "h264_rewrite_slice_header_patch");
+	if (st.patch_fn == NULL)
+		return -ENOSYS;
+	struct h264_ctx_cbs cbs;
+	memset(&cbs, 0, sizeof(cbs));
+	cbs.slice = rwp_slice;
+	struct h264_reader *rd = NULL;
+	r = a.reader_new(&cbs, &st, &rd);
+	if (r < 0)
+		return r;
+	size_t off = 0, start = 0, end = 0;
+	while (off < len) {
+		int fr = a.find_nalu(buf + off, len - off, &start, &end);
+		if (fr < 0 && fr != -EAGAIN)
+			break;
+		a.reader_parse_nalu(rd, 0, buf + off + start, end - start);
+		off += end;
+	}
+	a.reader_destroy(rd);
+	dlclose(a.h);
+	*n_patches = st.np;
+	return (long)st.n;
+}
+
 /* ---- generator ----------------------------------------------------------------------------- */
 
 static uint64_t rng_state;

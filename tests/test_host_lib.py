@@ -34,6 +34,9 @@ def harness():
                              C.c_size_t, C.POINTER(C.c_size_t)]
     lib.hh_rewrite.restype = C.c_long
     lib.hh_rewrite.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.hh_rewrite_patches.restype = C.c_long
+    lib.hh_rewrite_patches.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.POINTER(C.c_uint32)]
     lib.hh_time_parse.restype = C.c_double
     lib.hh_time_parse.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
     return lib
@@ -199,6 +202,62 @@ def test_small_utilities_match_reference():
     assert np.array_equal(a, b) and not np.array_equal(a, base)
     assert ours.h264_avcc_to_byte_stream(a.ctypes.data, len(a)) == ref.h264_avcc_to_byte_stream(b.ctypes.data, len(b))
     assert np.array_equal(a, b) and np.array_equal(a, base)
+
+
+PATCH_DT = np.dtype([("nal_off", "<u8"), ("nbytes", "<u4"), ("tail_bits", "<u4"), ("bytes", "u1", 64)])
+
+
+def rewrite_patches(lib, stream, mode):
+    """Patch records of this library's h264_rewrite_slice_header_patch for every slice of the stream
+    (same edits as hh_rewrite), and the per-slice return codes."""
+    stream = np.ascontiguousarray(stream)
+    patches = np.zeros(4096, PATCH_DT)
+    rc = np.full(4096, 99, np.int32)
+    npatch = C.c_uint32(0)
+    n = lib.hh_rewrite_patches(OURS.encode(), stream.ctypes.data, len(stream), mode, patches.ctypes.data,
+                               rc.ctypes.data, len(rc), C.byref(npatch))
+    assert n >= 0
+    return patches[:npatch.value].copy(), rc[:n].copy()
+
+
+def rewrite_streams(lib):
+    import libh264_b200 as L
+    streams = [gen(lib, REF, 400 + k, rounds=6) for k in range(3)]
+    streams.append(L.synth_video(frames=4, width_mbs=20, height_mbs=12, slices_per_frame=3, profile_idc=100,
+                                 transform_8x8=1, b_frames=1, num_ref_frames=2, idr_period=3, pct_skip=30,
+                                 coef_density=50, seed=21)[0])
+    return [np.ascontiguousarray(s) for s in streams]
+
+
+def test_rewrite_slice_header_patches_in_bulk():
+    """N4: h264_rewrite_slice_header_patch + the bulk patch kernel (here on the CPU emulator) give the
+    bytes of the REFERENCE's h264_rewrite_slice_header applied NAL by NAL, with its return codes."""
+    import support as S
+    lib = harness()
+    emu = S.emu()
+    applied = 0
+    for s in rewrite_streams(lib):
+        for mode in (0, 1):
+            ref_out = np.zeros(len(s), np.uint8)
+            ref_rc = np.full(4096, 99, np.int32)
+            n = lib.hh_rewrite(REF.encode(), s.ctypes.data, len(s), mode, ref_out.ctypes.data, ref_rc.ctypes.data, len(ref_rc))
+            patches, rc = rewrite_patches(lib, s, mode)
+            assert np.array_equal(rc, ref_rc[:n])
+            assert len(patches) == int((rc == 0).sum())
+            out = s.copy()
+            assert emu.emu_patch_headers(C.c_void_p(out.ctypes.data), C.c_uint64(len(out)),
+                                         C.c_void_p(patches.ctypes.data), C.c_uint32(len(patches))) == 0
+            assert np.array_equal(out, ref_out), mode
+            applied += len(patches)
+    assert applied > 10
+    # a patch that does not fit the stream is left out
+    s = rewrite_streams(lib)[0]
+    patches, _ = rewrite_patches(lib, s, 0)
+    bad = patches[:1].copy()
+    bad["nal_off"] = len(s) - 1
+    out = s.copy()
+    emu.emu_patch_headers(C.c_void_p(out.ctypes.data), C.c_uint64(len(out)), C.c_void_p(bad.ctypes.data), C.c_uint32(1))
+    assert np.array_equal(out, s)
 
 
 def test_rewrite_slice_header_behaviour():

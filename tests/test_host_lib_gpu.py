@@ -148,3 +148,42 @@ def test_mbaff_and_field_pictures_through_the_api(fmo):
             ours = T.trace(lib, T.OURS, stream, 1, mode)
             T.assert_same_trace(ours, T.trace(lib, T.REF, stream, 1, mode), "fmo %x mode %d" % (fmo, mode))
             assert sum(1 for t, _ in T.split_log(ours) if t == T_SD_MB) == nmb
+
+
+def test_rewrite_slice_headers_in_bulk_on_the_device(gpu):
+    """N4: the stream stays on the device; every slice header is rewritten by one launch of the patch
+    kernel from the host syntax walk's patch records; the bytes are the REFERENCE's
+    h264_rewrite_slice_header applied NAL by NAL (frame_num edits succeed, qp edits that change the
+    header length are refused with the reference's return code and leave the NAL alone)."""
+    import ctypes as C
+    import test_host_lib as T
+    lib = T.harness()
+    applied = 0
+    for s in T.rewrite_streams(lib):
+        for mode in (0, 1):
+            ref_out = np.zeros(len(s), np.uint8)
+            ref_rc = np.full(4096, 99, np.int32)
+            n = lib.hh_rewrite(T.REF.encode(), s.ctypes.data, len(s), mode, ref_out.ctypes.data, ref_rc.ctypes.data,
+                               len(ref_rc))
+            patches, rc = T.rewrite_patches(lib, s, mode)
+            assert np.array_equal(rc, ref_rc[:n])
+            d = gpu.alloc(len(s) + 64)
+            d.upload(s)
+            r = gpu.lib.h264gpu_patch_slice_headers(gpu.h, C.c_void_p(d.ptr), C.c_uint64(len(s)),
+                                                    C.c_void_p(patches.ctypes.data), C.c_uint32(len(patches)), None)
+            assert r == 0
+            out = d.download(len(s))
+            d.free()
+            assert np.array_equal(out, ref_out), mode
+            applied += len(patches)
+    assert applied > 10
+    # a patch past the end of the stream is refused on the host
+    s = T.rewrite_streams(lib)[0]
+    patches, _ = T.rewrite_patches(lib, s, 0)
+    bad = patches[:1].copy()
+    bad["nal_off"] = len(s) - 1
+    d = gpu.alloc(len(s) + 64)
+    d.upload(s)
+    assert gpu.lib.h264gpu_patch_slice_headers(gpu.h, C.c_void_p(d.ptr), C.c_uint64(len(s)), C.c_void_p(bad.ctypes.data),
+                                               C.c_uint32(1), None) == -22
+    d.free()
