@@ -86,7 +86,9 @@ static void free_pipeline(h264gpu_ctx *ctx)
 		cudaStreamDestroy(ctx->s_in);
 		cudaStreamDestroy(ctx->s_out);
 		cudaStreamDestroy(ctx->s_tab);
-		ctx->s_in = ctx->s_out = ctx->s_tab = NULL;
+		if (ctx->s_up)
+			cudaStreamDestroy(ctx->s_up);
+		ctx->s_in = ctx->s_out = ctx->s_tab = ctx->s_up = NULL;
 	}
 }
 
@@ -1163,6 +1165,7 @@ static int pipeline_init(h264gpu_ctx *ctx)
 	CU_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
 	CU_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
 	CU_TRY(cudaStreamCreateWithFlags(&ctx->s_tab, cudaStreamNonBlocking));
+	CU_TRY(cudaStreamCreateWithFlags(&ctx->s_up, cudaStreamNonBlocking));
 	if (ctx->tab_cap == 0)
 		ctx->tab_cap = ctx->chunk_bytes / 64 > 4096 ? ctx->chunk_bytes / 64 : 4096;
 	for (int b = 0; b < 2; b++) {
@@ -1178,10 +1181,30 @@ static int pipeline_init(h264gpu_ctx *ctx)
 	return 0;
 }
 
+static int split_strip_host_impl(h264gpu_ctx *ctx, const uint8_t *h_in, uint64_t len, uint8_t *h_rbsp,
+				 uint64_t *h_nal_start, uint64_t *h_nal_end, uint64_t *h_nal_rbsp, uint64_t *n_nal,
+				 uint64_t *rbsp_bytes, uint64_t *final_off);
+
 extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, uint64_t len,
 					uint8_t *h_rbsp, uint64_t *h_nal_start,
 					uint64_t *h_nal_end, uint64_t *h_nal_rbsp, uint64_t *n_nal,
 					uint64_t *rbsp_bytes, uint64_t *final_off)
+{
+	const int r = split_strip_host_impl(ctx, h_in, len, h_rbsp, h_nal_start, h_nal_end, h_nal_rbsp, n_nal, rbsp_bytes,
+					    final_off);
+	if (r < 0 && r != -ENOBUFS && ctx != NULL && ctx->s_in != NULL) {
+		/* an early return: copies from / into the caller's buffers may still be in flight */
+		cudaStreamSynchronize(ctx->s_up);
+		cudaStreamSynchronize(ctx->s_in);
+		cudaStreamSynchronize(ctx->s_tab);
+		cudaStreamSynchronize(ctx->s_out);
+	}
+	return r;
+}
+
+static int split_strip_host_impl(h264gpu_ctx *ctx, const uint8_t *h_in, uint64_t len, uint8_t *h_rbsp,
+				 uint64_t *h_nal_start, uint64_t *h_nal_end, uint64_t *h_nal_rbsp, uint64_t *n_nal,
+				 uint64_t *rbsp_bytes, uint64_t *final_off)
 {
 	int r = h264gpu_use(ctx);
 	if (r < 0)
@@ -1226,10 +1249,18 @@ extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, u
 				e.right[1] = lo + n + 1 < len ? h_in[lo + n + 1] : 0xff;
 			}
 			e.assume_in = c > 0;
-			if (used[b]) /* chunk c-2's downloads must have left buffer b */
-				CU_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[b], 0));
+			/* the upload has a stream of its own and waits only for the kernel that read this slot's
+			 * input two chunks ago; the kernel waits for the upload and for the download that empties
+			 * the slot's output.  (Round 1 had upload and kernel on one stream behind the download:
+			 * every upload started a kernel + table copy + merge late, 85 % of the copy ceiling.) */
+			if (used[b])
+				CU_TRY(cudaStreamWaitEvent(ctx->s_up, ctx->ev_k[b], 0));
 			CU_TRY(cudaMemcpyAsync(ctx->d_chunk_in[b], h_in + lo, n, cudaMemcpyHostToDevice,
-					       ctx->s_in));
+					       ctx->s_up));
+			CU_TRY(cudaEventRecord(ctx->ev_in[b], ctx->s_up));
+			CU_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_in[b], 0));
+			if (used[b]) /* chunk c-2's download must have left the slot's output */
+				CU_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[b], 0));
 			r = h264gpu_split_strip_dev(ctx, ctx->d_chunk_in[b], n, lo, &e,
 						    h_rbsp ? ctx->d_chunk_out[b] : NULL, ctx->d_tab[b],
 						    ctx->d_tab[b] + ctx->tab_cap,
@@ -1294,6 +1325,7 @@ extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, u
 #include "annexb_frame.cuh"
 #include "annexb_frame6.cuh"
 #include "annexb_frame7.cuh"
+#include "annexb_frame8.cuh"
 
 /* writer kernel generation: 6 (block-wide 32 KiB tiles, annexb_frame6.cuh; the default) or 7
  * (warp-autonomous spans, annexb_frame7.cuh; the same speed on B200, see its header):
@@ -1301,7 +1333,7 @@ extern "C" int h264gpu_split_strip_host(h264gpu_ctx *ctx, const uint8_t *h_in, u
 static int frame_gen(void)
 {
 	const char *e = getenv("H264GPU_FRAME_GEN");
-	return (e != NULL && atoi(e) == 7) ? 7 : 6;
+	return (e != NULL && (atoi(e) == 7 || atoi(e) == 8)) ? atoi(e) : 6;
 }
 
 template <int ROWS, int NW, int NBUF>
@@ -1338,6 +1370,28 @@ static cudaError_t launch_frame7(const frame::FrameArgs &a, cudaStream_t st)
 	if (e != NULL && atoi(e) == 1)
 		return launch_frame7_cfg<ROWS, 4, 1>(a, st, sms);
 	return launch_frame7_cfg<ROWS, 1, 2>(a, st, sms);
+}
+
+/* gen 8: the tiles of gen 6, counts published an iteration ahead over the chain of gen 7 */
+template <int ROWS>
+static cudaError_t launch_frame8(const frame::FrameArgs &a, cudaStream_t st)
+{
+	const uint32_t pthreads = 128;
+	const uint32_t pblocks = (a.num_tiles + 1 + pthreads - 1) / pthreads;
+	frame8::frame8_prepass<ROWS><<<pblocks, pthreads, 0, st>>>(a);
+	int sms = 0, dev = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (sms <= 0)
+		sms = 148;
+	constexpr int per_cta = (int)sizeof(frame8::Smem8<ROWS>) + 1024;
+	constexpr int fit = (227 * 1024) / per_cta;
+	constexpr int MINB = fit > 8 ? 8 : fit;
+	cudaFuncSetAttribute(frame8::frame8_kernel<ROWS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+			     cudaSharedmemCarveoutMaxShared);
+	const uint32_t cap = (uint32_t)sms * MINB;
+	frame8::frame8_kernel<ROWS, MINB><<<a.num_tiles < cap ? a.num_tiles : cap, frame6::kT, 0, st>>>(a);
+	return cudaGetLastError();
 }
 
 template <int ROWS>
@@ -1429,7 +1483,7 @@ static int frame_dev_impl(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const uint64_
 	r = h264gpu_ws_reserve(ctx, need);
 	if (r < 0)
 		return r;
-	if (gen != 7) /* gen 7: the pre-pass clears its chain words */
+	if (gen == 6) /* gen 7 / 8: the pre-pass clears the chain words */
 		CU_TRY(cudaMemsetAsync(ctx->ws, 0xff, desc_bytes, st));
 
 	frame::FrameArgs a;
@@ -1466,6 +1520,11 @@ static int frame_dev_impl(h264gpu_ctx *ctx, const uint8_t *d_rbsp, const uint64_
 		   : rows == 4 ? launch_frame7<4>(a, st)
 		   : rows == 6 ? launch_frame7<6>(a, st)
 			       : launch_frame7<8>(a, st);
+	else if (gen == 8)
+		ce = items == 1 ? launch_frame8<1>(a, st)
+		   : items == 2 ? launch_frame8<2>(a, st)
+		   : items == 4 ? launch_frame8<4>(a, st)
+				: launch_frame8<8>(a, st);
 	else
 		ce = items == 1 ? launch_frame6<1>(a, st)
 		   : items == 2 ? launch_frame6<2>(a, st)
@@ -1648,8 +1707,16 @@ extern "C" int h264gpu_frame_host(h264gpu_ctx *ctx, const uint8_t *h_rbsp, const
 	/* long inputs: chunked, copies and kernels overlapped (H264GPU_FRAME_PIPE=0: one shot) */
 	{
 		const char *e = getenv("H264GPU_FRAME_PIPE");
-		if (n >= 2 && len >= 2 * (uint64_t)ctx->chunk_bytes && !(e != NULL && atoi(e) == 0))
-			return frame_host_pipelined(ctx, h_rbsp, h_off, n, sc_len, h_out, out_cap, h_out_off, total);
+		if (n >= 2 && len >= 2 * (uint64_t)ctx->chunk_bytes && !(e != NULL && atoi(e) == 0)) {
+			r = frame_host_pipelined(ctx, h_rbsp, h_off, n, sc_len, h_out, out_cap, h_out_off, total);
+			if (r < 0 && r != -ENOBUFS) {
+				/* copies from / to the caller's buffers may still be in flight */
+				cudaStreamSynchronize(ctx->fp.s_up);
+				cudaStreamSynchronize(ctx->fp.s_k);
+				cudaStreamSynchronize(ctx->fp.s_dn);
+			}
+			return r;
+		}
 	}
 	/* pooled device buffers of the reader session on its private stream: a call costs no
 	 * cudaMalloc / cudaFree (round 1 allocated four buffers per call on the default stream) */

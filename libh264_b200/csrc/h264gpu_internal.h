@@ -30,7 +30,7 @@ struct h264gpu_ctx {
 	uint32_t attr_set; /* per-context (= per-device) cudaFuncSetAttribute done: bit 0 scan7 */
 	int sms;
 	/* host-buffer pipeline */
-	cudaStream_t s_in, s_out, s_tab;
+	cudaStream_t s_in, s_out, s_tab, s_up; /* kernels, RBSP downloads, table downloads, uploads */
 	uint8_t *d_chunk_in[2];
 	uint8_t *d_chunk_out[2];
 	uint64_t *d_tab[2]; /* start | end | rbsp, tab_cap entries each */

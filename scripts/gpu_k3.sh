@@ -8,6 +8,7 @@ L=gpurun_out/${T}_frame_ab.log
 : > $L
 W="--warmup 10 --steps 20"
 timeout 300 python scripts/frame_ab.py $W 2>&1 | tail -1 | tee -a $L
+H264GPU_FRAME_GEN=8 timeout 300 python scripts/frame_ab.py $W 2>&1 | tail -1 | tee -a $L
 H264GPU_FRAME_GEN=7 timeout 300 python scripts/frame_ab.py $W 2>&1 | tail -1 | tee -a $L
 H264GPU_FRAME_GEN=7 H264GPU_FRAME7_NBUF=1 timeout 300 python scripts/frame_ab.py $W 2>&1 | tail -1 | tee -a $L
 H264GPU_FRAME_GEN=7 H264GPU_FRAME7_ROWS=6 timeout 300 python scripts/frame_ab.py $W 2>&1 | tail -1 | tee -a $L

@@ -9,6 +9,7 @@
 #include "annexb_frame.cuh"
 #include "annexb_frame6.cuh"
 #include "annexb_frame7.cuh"
+#include "annexb_frame8.cuh"
 
 #include <vector>
 
@@ -265,6 +266,60 @@ extern "C" int emu_frame(const uint8_t *rbsp, uint64_t len, const uint64_t *off,
 			 uint64_t *total, int items)
 {
 	using namespace frame;
+	/* 90 + rows: frame8_kernel (tiles of gen 6, chain of gen 7) with 1/2/4/8 rows per warp */
+	if (items > 90) {
+		const int rows = items - 90;
+		const uint64_t tile8 = (uint64_t)kBlock * rows * 16;
+		uint32_t nt = (uint32_t)((len + tile8 - 1) / tile8);
+		if (nt == 0)
+			nt = 1;
+		std::vector<uint64_t> desc(nt, ~0ull), first(nt + 1, ~0ull), gw((nt >> 5) + 1, ~0ull), sw((nt >> 10) + 1, ~0ull),
+			sp((nt >> 10) + 1, ~0ull);
+		std::vector<uint32_t> tail(nt, ~0u);
+		uint32_t ticket = 0xffffffffu;
+		uint8_t *buf = (uint8_t *)aligned_alloc(16, ((len + 15) & ~15ull) + 16);
+		memcpy(buf, rbsp, len);
+		FrameArgs a;
+		memset(&a, 0, sizeof(a));
+		a.rbsp = buf;
+		a.len = len;
+		a.off = off;
+		a.n = n;
+		a.sc_len = (uint32_t)sc_len;
+		a.out = out;
+		a.out_cap = out_cap;
+		a.out_off = out_off;
+		a.total = total;
+		a.desc = desc.data();
+		a.ticket = &ticket;
+		a.first = first.data();
+		a.tail = tail.data();
+		a.num_tiles = nt;
+		a.group_w = gw.data();
+		a.super_w = sw.data();
+		a.super_p = sp.data();
+		dim3 pgrid((nt + 1 + 127) / 128), pblock(128), block(kBlock), grid(nt < 2 ? nt : 2);
+		switch (rows) {
+		case 1:
+			EMU_LAUNCH((frame8::frame8_prepass<1>), pgrid, pblock, a);
+			EMU_LAUNCH((frame8::frame8_kernel<1, 1>), grid, block, a);
+			break;
+		case 2:
+			EMU_LAUNCH((frame8::frame8_prepass<2>), pgrid, pblock, a);
+			EMU_LAUNCH((frame8::frame8_kernel<2, 1>), grid, block, a);
+			break;
+		case 4:
+			EMU_LAUNCH((frame8::frame8_prepass<4>), pgrid, pblock, a);
+			EMU_LAUNCH((frame8::frame8_kernel<4, 1>), grid, block, a);
+			break;
+		default:
+			EMU_LAUNCH((frame8::frame8_prepass<8>), pgrid, pblock, a);
+			EMU_LAUNCH((frame8::frame8_kernel<8, 1>), grid, block, a);
+			break;
+		}
+		free(buf);
+		return 0;
+	}
 	/* 70 + rows: frame7_kernel with 1/2/4/6/8 rows per span, three warps per CTA, the bytes of a
 	 * span staged twice; 80 + rows: staged once (two buffers per warp) */
 	if (items > 70) {

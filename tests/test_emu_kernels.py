@@ -377,6 +377,83 @@ def test_emu_frame7_output_capacity_is_respected():
         assert np.array_equal(out[:cap], exp[:cap]) and (out[cap:] == 0xAA).all(), cap
 
 
+# ---- K3 gen 8 (frame8_kernel): the tiles of gen 6 with the chain of gen 7; items 91/92/94/98 ----
+
+G8 = [91, 92, 94, 98]
+
+
+def test_emu_frame8_known_answer_and_edges():
+    p = KA.hx(KA.INSERT_IN)
+    for items in G8:
+        out, oo, tot = emu_frame(p, np.array([0, len(p)], np.uint64), 0, items)
+        assert bytes(out[:tot]) == bytes(KA.hx(KA.INSERT_OUT))
+    for items in (91, 98):
+        check_frame(np.zeros(0, np.uint8), np.array([0, 0, 0], np.uint64), 4, items, "empty payloads only")
+        check_frame(np.zeros(0, np.uint8), np.array([0], np.uint64), 4, items, "no payloads")
+        check_frame(np.array([0, 0, 1], np.uint8), np.array([0, 3], np.uint64), 3, items, "three bytes")
+
+
+def test_emu_frame8_random_and_adversarial():
+    rng = np.random.default_rng(85)
+    for it in range(8):
+        data, offs = S.gen_payloads(rng, int(rng.integers(1, 60)), 1, 5000)
+        check_frame(data, offs, 4 if it % 2 else 3, int(rng.choice(G8)), ("rand8", it))
+    for it in range(16):
+        tot = int(rng.integers(0, 60000))
+        data = rng.choice(np.array([0, 0, 0, 0, 1, 2, 3, 4, 0xFF], np.uint8), tot)
+        n = int(rng.integers(0, 30))
+        cuts = np.sort(rng.integers(0, tot + 1, n)) if n else np.zeros(0, np.int64)
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        check_frame(data, offs, int(rng.choice([0, 3, 4])), int(rng.choice(G8)), ("adv8", it))
+    for it in range(6):  # zero runs spanning whole rows, spans and tiles
+        tot = int(rng.integers(9000, 90000))
+        data = np.zeros(tot, np.uint8)
+        for p in rng.integers(0, tot, 3):
+            data[p] = rng.choice([1, 3, 7])
+        check_frame(data, np.array([0, tot // 3, tot // 3, tot], np.uint64), 4, int(rng.choice(G8)), ("zeros8", it))
+
+
+def test_emu_frame8_chain_levels_and_stream_shape():
+    """More than 1024 tiles of 4 KiB (every level of the chain), the bench's byte statistics over
+    32 KiB tiles, payloads of a few bytes."""
+    rng = np.random.default_rng(86)
+    tot = 4096 * 1100 + 77
+    data = rng.integers(0, 256, tot).astype(np.uint8)
+    data[rng.random(tot) < 0.1875] = 0
+    cuts = np.sort(np.concatenate([rng.integers(0, tot + 1, 40), [4096 * 1024, 4096 * 1024 + 1, 4096 * 33]]))
+    offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+    check_frame(data, offs, 4, 91, "chain8")
+    for it in range(2):
+        tot = int(rng.integers(100000, 250000))
+        data = rng.integers(0, 256, tot).astype(np.uint8)
+        data[rng.random(tot) < 0.1875] = 0
+        cuts = np.sort(rng.integers(0, tot + 1, int(rng.integers(1, 8))))
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        check_frame(data, offs, 4, 98, ("stream8", it))
+        check_frame(data, offs, 3, 92, ("stream8", it))
+    for it in range(2):
+        tot = int(rng.integers(3000, 20000))
+        data = rng.choice(np.array([0, 0, 0, 1, 3, 0xFF], np.uint8), tot)
+        cuts = np.sort(rng.integers(0, tot + 1, tot // 3))
+        offs = np.concatenate([[0], cuts, [tot]]).astype(np.uint64)
+        check_frame(data, offs, 4, int(rng.choice([91, 94])), ("dense8", it))
+
+
+def test_emu_frame8_output_capacity_is_respected():
+    lib = S.emu()
+    rng = np.random.default_rng(88)
+    data = rng.choice(np.array([0, 0, 0, 1, 3, 0xFF], np.uint8), 20000)
+    offs = np.array([0, 7000, 20000], np.uint64)
+    exp, eoo = S.oracle_frame(data, offs, 4)
+    for cap in (0, 5, 4099, len(exp) - 1):
+        out = np.full(len(exp) + 64, 0xAA, np.uint8)
+        oo = np.full(3, S.NONE64, np.uint64)
+        tot = C.c_uint64(0)
+        lib.emu_frame(S.ptr(data), len(data), S.ptr(offs), 2, 4, S.ptr(out), cap, S.ptr(oo), C.byref(tot), 92)
+        assert tot.value == len(exp)
+        assert np.array_equal(out[:cap], exp[:cap]) and (out[cap:] == 0xAA).all(), cap
+
+
 def test_emu_frame_then_scan_round_trip():
     rng = np.random.default_rng(8)
     data, offs = S.gen_payloads(rng, 50, 2, 3000)

@@ -264,14 +264,17 @@ def test_frame_small_tiles():
             os.environ["H264GPU_SCAN_ITEMS"] = old
 
 
-@pytest.mark.parametrize("env", [{"H264GPU_FRAME_GEN": "7"}, {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_ROWS": "6"},
+@pytest.mark.parametrize("env", [{"H264GPU_FRAME_GEN": "8"}, {"H264GPU_FRAME_GEN": "8", "H264GPU_SCAN_ITEMS": "1"},
+                                 {"H264GPU_FRAME_GEN": "6"},
+                                 {"H264GPU_FRAME_GEN": "7"}, {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_ROWS": "6"},
                                  {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_NBUF": "1"},
                                  {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_ROWS": "1"},
                                  {"H264GPU_FRAME_GEN": "7", "H264GPU_FRAME7_NBUF": "1", "H264GPU_FRAME7_ROWS": "2"}])
 def test_frame_kernel_variants(env):
-    """The writer's other generation (gen 7, warp-autonomous spans): 4 KiB and 3 KiB spans, bytes
-    staged once or twice, 512-byte spans (> 1024 spans: every level of the chain), on stream-shaped
-    and zero-heavy payloads against the oracle."""
+    """The writer's generations: gen 8 (tiles of gen 6, counts published ahead over the chain of gen 7;
+    32 KiB and 4 KiB tiles), gen 6, gen 7 (warp-autonomous spans: 4 KiB and 3 KiB spans, bytes staged
+    once or twice, 512-byte spans: > 1024 spans, every level of the chain), on stream-shaped and
+    zero-heavy payloads against the oracle."""
     rng = np.random.default_rng(59)
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
