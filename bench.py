@@ -480,11 +480,6 @@ def main():
     numa_note = pin_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not pinned"
     dist = None
     torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
         if dist is not None:
@@ -528,6 +523,26 @@ def main():
     pin_in = g.pinned(size + DELTA + 8192)
     stream, rbsp_ref, offs = make_workload(L, size, SEED + rank, out=pin_in.array, nthreads=nthreads)
     n_own = len(stream)
+    n_in = n_own + (DELTA if rank < world - 1 else 0) - (DELTA if rank > 0 else 0)
+    n_nal_piece = len(offs) - 1
+    cap = n_nal_piece + 4096
+    # The stream buffers and, right after them, the scan workspace are the FIRST device allocations of
+    # the process, before torch / NCCL allocate anything: where the workspace lands decides 2.0 vs
+    # 2.8 ms per 4 GiB (include/h264gpu.h, profiles/r02_scan_workspace_placement.txt), and with the
+    # communicator's buffers allocated first every rank of a multi-GPU run landed in the slow case
+    # (2966 GB/s on 2 GPUs against 2137 on one).
+    d_in = g.alloc(n_in + 64)
+    d_rbsp = g.alloc(n_in + 64)
+    d_tab = g.alloc(cap * 8 * 4)
+    d_res = g.alloc(C.sizeof(L.ScanResult))
+    L._check(g.lib.h264gpu_scan_reserve(g.h, C.c_uint64(n_in), C.c_uint64(cap)), "h264gpu_scan_reserve")
+
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
     pieces_len = [int(x.view(np.int64)[0]) for x in gather_bytes(np.array([n_own], np.int64).view(np.uint8))]
     heads = gather_bytes(stream[:DELTA + 2] if world > 1 else np.zeros(0, np.uint8))
     tails = gather_bytes(stream[n_own - 2:] if world > 1 else np.zeros(0, np.uint8))
@@ -539,27 +554,15 @@ def main():
         if rank < world - 1:  # append the head of the next piece
             pin_in.array[n_own:n_own + DELTA] = heads[rank + 1][:DELTA]
         shard = pin_in.array[(DELTA if rank > 0 else 0):n_own + (DELTA if rank < world - 1 else 0)]
-        if len(shard) % 16 or (DELTA and DELTA % 16):
-            pass
     else:
         shard = stream
-    n_in = len(shard)
-    assert n_in == hi - lo
+    assert n_in == len(shard) == hi - lo
     # generator's NAL table of this piece in job coordinates (for the merged-table check on rank 0)
     tz = 0
     while tz < n_own and stream[n_own - 1 - tz] == 0:
         tz += 1
     gen_s = time.time() - t0
 
-    n_nal_piece = len(offs) - 1
-    cap = n_nal_piece + 4096
-    d_in = g.alloc(n_in + 64)
-    d_rbsp = g.alloc(n_in + 64)
-    d_tab = g.alloc(cap * 8 * 4)
-    d_res = g.alloc(C.sizeof(L.ScanResult))
-    # the scan workspace right after the stream buffers, before any other allocation (include/h264gpu.h:
-    # where it lands decides 2.0 vs 2.8 ms per 4 GiB)
-    L._check(g.lib.h264gpu_scan_reserve(g.h, C.c_uint64(n_in), C.c_uint64(cap)), "h264gpu_scan_reserve")
     # the shard must start 16-byte aligned in device memory: copy from the (possibly unaligned) host view
     stage = g.pinned(n_in + 64)
     stage.array[:n_in] = shard
