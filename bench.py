@@ -235,7 +235,7 @@ def mb_parse_leg(g, L, cfg, label, steps, warmup, with_cpu=False, cabac=False, r
         d.free()
     out = {"workload": "%s%s (%d slices, %d MBs, %.1f MB stream)"
                        % (label, " x %d copies laid end to end" % reps if reps > 1 else "", nsl, nmb, len(stream) / 1e6),
-           "kernel": "cabac::cabac_parse_kernel" if cabac else "cavlc2::cavlc_steps_kernel (per-lane state machine, one syntax element per lane per step) + order_kernel (longest slices first)",
+           "kernel": "cabac::cabac_parse_kernel (persistent grid, slices pulled longest first from a ticket counter, one fused table entry per bin) + order_kernel" if cabac else "cavlc2::cavlc_steps_kernel (per-lane state machine, one syntax element per lane per step) + order_kernel (longest slices first)",
            "macroblocks_per_s": nmb / (ms / 1e3), "ms_per_step": ms, "parity_counts_ok": ok}
     if e2e_reps > 0:
         parse_host(stream, params, nmb)  # warm-up: pools

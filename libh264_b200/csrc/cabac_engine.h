@@ -37,7 +37,22 @@ struct Tables {
 	const uint8_t *range_lps; /* [64][4] */
 	const uint8_t *trans_lps; /* [64] */
 	const uint8_t *trans_mps; /* [64] */
+	/* device: one 8-byte entry per context state byte s = pStateIdx << 1 | valMPS:
+	 * bytes 0..3 rangeTabLPS[pStateIdx][0..3], byte 4 the state byte after an MPS, byte 5 after
+	 * an LPS (valMPS flipped at pStateIdx 0).  One shared-memory load per bin instead of a
+	 * chain of three (fused_entry() builds it from the three tables above). */
+	const uint64_t *fused; /* [128] */
 };
+
+CABAC_HD static inline uint64_t fused_entry(uint32_t s, const uint8_t (*range_lps)[4], const uint8_t *trans_lps,
+					     const uint8_t *trans_mps)
+{
+	const uint32_t ps = s >> 1, mps = s & 1u;
+	const uint32_t after_mps = (uint32_t)trans_mps[ps] << 1 | mps;
+	const uint32_t after_lps = (uint32_t)trans_lps[ps] << 1 | (ps == 0 ? mps ^ 1u : mps);
+	return (uint64_t)range_lps[ps][0] | (uint64_t)range_lps[ps][1] << 8 | (uint64_t)range_lps[ps][2] << 16 |
+	       (uint64_t)range_lps[ps][3] << 24 | (uint64_t)after_mps << 32 | (uint64_t)after_lps << 40;
+}
 
 CABAC_HD static inline uint8_t init_state(int m, int n, int slice_qp)
 {
@@ -139,6 +154,34 @@ struct Dec {
 
 	CABAC_OUTLINE uint32_t bin(uint32_t ctx, uint32_t)
 	{
+#ifdef __CUDA_ARCH__
+		/* the serial chain of a slice: state byte -> ONE table entry -> compare -> state byte;
+		 * context bytes and table addressed as shared memory (through the generic pointers the
+		 * loads are LD.E and the store makes the compiler reload range from memory) */
+		const uint32_t sa = (uint32_t)__cvta_generic_to_shared(st) + ctx * stride;
+		uint32_t s, lo, next;
+		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s) : "r"(sa) : "memory"); /* after init_contexts' plain stores */
+		asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+			     : "=r"(lo), "=r"(next)
+			     : "r"((uint32_t)__cvta_generic_to_shared(t.fused) + s * 8));
+		uint32_t r = range, o = offset;
+		const uint32_t rlps = (lo >> (((r >> 6) & 3) * 8)) & 0xffu;
+		r -= rlps;
+		const bool lps = o >= r;
+		if (lps) {
+			o -= r;
+			r = rlps;
+		}
+		asm volatile("st.shared.u8 [%0], %1;" : : "r"(sa), "r"(lps ? next >> 8 : next) : "memory");
+		if (r < 256) {
+			const int sh = clz32(r) - 23;
+			r <<= sh;
+			o = (o << sh) | get(sh);
+		}
+		range = r;
+		offset = o;
+		return (s & 1u) ^ (lps ? 1u : 0u);
+#else
 		uint8_t *sp = st + ctx * stride;
 		const uint32_t s = *sp;
 		uint32_t ps = s >> 1, mps = s & 1u;
@@ -163,6 +206,7 @@ struct Dec {
 			offset = (offset << sh) | get(sh);
 		}
 		return b;
+#endif
 	}
 
 	CABAC_OUTLINE uint32_t byp(uint32_t)

@@ -49,9 +49,11 @@ struct CabacArgs {
 	uint64_t ring_stride; /* in Nb units */
 	uint32_t ring_w;      /* widest picture (in MBs) a ring row can hold */
 	uint32_t lanes_log2;  /* log2 of the slices carried by one warp (0..5) */
+	uint32_t *next_slice; /* ticket counter (starts at the number of working lanes), or NULL */
+	const uint32_t *order; /* slice indices, longest NAL first, or NULL: list order */
 };
 
-constexpr uint32_t kTabBytes = 256 + 64 + 64;
+constexpr uint32_t kTabBytes = 128 * 8; /* Tables::fused */
 /* per-slice working set kept in SHARED memory (walker state + the macroblock being decoded):
  * as thread-local data it would live in lane-interleaved local memory, where a warp that runs
  * one or a few slices still occupies 32 lanes' worth of cache lines and thrashes L1 */
@@ -88,9 +90,7 @@ __device__ __forceinline__ void parse_slice(const uint8_t *stream, uint64_t stre
 	w.begin_slice(&sp, ring);
 	w.c.st = ctx_states;
 	w.c.stride = ctx_stride;
-	w.c.t.range_lps = tabs;
-	w.c.t.trans_lps = tabs + 256;
-	w.c.t.trans_mps = tabs + 320;
+	w.c.t.fused = reinterpret_cast<const uint64_t *>(tabs);
 	init_contexts(ctx_states, ctx_stride, cabac_init_mn[sp.slice_type == ST_I ? 0 : 1 + (sp.cabac_init_idc % 3)],
 		      sp.slice_qp);
 	w.c.start(stream + sp.nal_off, sp.nal_len, sp.data_bit_off);
@@ -121,40 +121,48 @@ __device__ __forceinline__ void parse_slice(const uint8_t *stream, uint64_t stre
 }
 
 /*
- * Like K4, slices diverge completely, so few slices are spread one per warp and only packed
- * into the lanes of a warp once there are more slices than resident warps.  Dynamic shared
- * memory: [384 B tables][460 x (slices per block) context bytes][slices x working set].
+ * A slice is one serial chain of bins: a warp carries ONE slice (one working lane) while the
+ * slices fit the resident warps, because two slices in one warp diverge at every branch and
+ * take turns (measured: 2 lanes per warp = half the speed per warp).  What matters is that every
+ * SM sub-partition always has its ~8 chains to switch between and that the longest chains start
+ * first: the grid is persistent (at most 32 one-warp blocks per SM, the register file's limit at
+ * 64 registers x 32 lanes), working lanes pull slices from a ticket counter, and the tickets run
+ * over the slices in descending order of NAL length (cavlc2::order_kernel).  The round-1 launch
+ * (slice i -> warp i in list order, 4 slices per warp at 16000 slices) ran ~3.4 waves each as
+ * long as its longest I slice: 14.7 % of the issue slots.
+ * The neighbour ring belongs to the working lane, not to the slice.
+ * Dynamic shared memory: [1 KB fused table][460 x (slices per block) context bytes][slices x working set].
  */
-__global__ void __launch_bounds__(128) cabac_parse_kernel(const CabacArgs a)
+__global__ void __launch_bounds__(128, 8) cabac_parse_kernel(const CabacArgs a)
 {
 	extern __shared__ uint8_t smem[];
-	for (uint32_t i = threadIdx.x; i < kTabBytes; i += blockDim.x)
-		smem[i] = i < 256 ? cabac_range_lps[i >> 2][i & 3]
-				  : i < 320 ? cabac_trans_lps[i - 256] : cabac_trans_mps[i - 320];
+	for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x)
+		reinterpret_cast<uint64_t *>(smem)[i] = fused_entry(i, cabac_range_lps, cabac_trans_lps, cabac_trans_mps);
 	__syncthreads();
 	const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t step = 32u >> a.lanes_log2; /* active lanes are multiples of this */
 	if (lane & (step - 1))
 		return;
-	const uint32_t i = (gwarp << a.lanes_log2) + lane / step;
-	if (i >= a.n_slices)
-		return;
+	const uint32_t unit = (gwarp << a.lanes_log2) + lane / step; /* working-lane number = first ticket */
 	const uint32_t per_block = (blockDim.x >> 5) << a.lanes_log2;
 	const uint32_t slot = ((threadIdx.x >> 5) << a.lanes_log2) + lane / step;
-	const h264gpu_slice_params sp = a.params[i];
-	h264gpu_slice_result res;
-	if (sp.pic_width_in_mbs > a.ring_w) {
-		res.status = -7; /* -E2BIG */
-		res.mb_count = 0;
-		res.end_bit = 0;
-		a.results[i] = res;
-		return;
-	}
 	uint8_t *slots = smem + ((kTabBytes + kNumCtx * per_block + 15) & ~15u);
-	parse_slice(a.stream, a.stream_len, sp, a.ring + (uint64_t)i * a.ring_stride, a.records + sp.mb_out_off, res,
-		    smem + kTabBytes + slot, per_block, smem, slots + (size_t)slot * kSlotBytes);
-	a.results[i] = res;
+	for (uint32_t t = unit; t < a.n_slices; t = a.next_slice ? atomicAdd(a.next_slice, 1u) : a.n_slices) {
+		const uint32_t i = a.order ? a.order[t] : t;
+		const h264gpu_slice_params sp = a.params[i];
+		h264gpu_slice_result res;
+		if (sp.pic_width_in_mbs > a.ring_w) {
+			res.status = -7; /* -E2BIG */
+			res.mb_count = 0;
+			res.end_bit = 0;
+			a.results[i] = res;
+			continue;
+		}
+		parse_slice(a.stream, a.stream_len, sp, a.ring + (uint64_t)unit * a.ring_stride, a.records + sp.mb_out_off,
+			    res, smem + kTabBytes + slot, per_block, smem, slots + (size_t)slot * kSlotBytes);
+		a.results[i] = res;
+	}
 }
 
 } /* namespace cabac */

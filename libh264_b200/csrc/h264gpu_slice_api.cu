@@ -350,11 +350,62 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	if (d_stream == NULL || d_params == NULL || d_records == NULL || d_results == NULL)
 		return -EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
-	/* neighbour ring per slice: (PicWidthInMbs + 1) records of 64 B, sized for pictures up
-	 * to 8192 luma samples wide (512 MBs); wider slices get -E2BIG. */
+	/* neighbour ring per WORKING LANE: (PicWidthInMbs + 1) records of 64 B, sized for pictures up
+	 * to 8192 luma samples wide (512 MBs) unless the host forms saw the parameter blocks; wider
+	 * slices get -E2BIG. */
 	const uint32_t ring_w = ctx->ring_w_hint ? ctx->ring_w_hint : 512;
 	const uint64_t ring_stride = (uint64_t)(ring_w + 1);
-	r = h264gpu_ws_reserve(ctx, (size_t)n_slices * ring_stride * sizeof(cabac::Nb));
+	/* One warp per block (a block's shared memory stays at tables + 1.1 KB per slice), a persistent
+	 * grid of at most 32 blocks per SM (what the register file holds), slices handed out longest
+	 * first through a ticket counter; one slice per warp while the slices fit the grid.
+	 *   H264GPU_CABAC_LANES_LOG2  log2 of the working lanes per warp (default: by slice count)
+	 *   H264GPU_CABAC_WARPS       warps per block (1, 2, 4; default 1)
+	 *   H264GPU_CABAC_PER_SM      resident warps per SM the grid is sized for (default 32)
+	 *   H264GPU_CABAC_SORT=0      tickets in list order (A/B) */
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	uint32_t lanes_log2 = 0;
+	const char *env = getenv("H264GPU_CABAC_LANES_LOG2");
+	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
+		lanes_log2 = (uint32_t)atoi(env);
+	} else {
+		/* more slices than resident warps: pack them into lanes (measured at 16000 slices with
+		 * the persistent grid: 1 lane 258 ms, 2 lanes 235 ms, 4 lanes 206 ms; at 4000 slices 1 lane
+		 * 74 ms, 2 lanes 93 ms: a warp's slices take turns, so packing only pays once every
+		 * warp slot is taken) */
+		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > (uint64_t)sms * 32)
+			lanes_log2++;
+	}
+	uint32_t threads = 32;
+	env = getenv("H264GPU_CABAC_WARPS");
+	if (env != NULL && (atoi(env) == 1 || atoi(env) == 2 || atoi(env) == 4))
+		threads = 32u * (uint32_t)atoi(env);
+	uint32_t per_sm = 32;
+	env = getenv("H264GPU_CABAC_PER_SM");
+	if (env != NULL && atoi(env) >= 1 && atoi(env) <= 64)
+		per_sm = (uint32_t)atoi(env);
+	const size_t smem = cabac::smem_bytes((threads / 32) << lanes_log2);
+	if (smem > ctx->cabac_smem_set) { /* function attributes are per device: cached per context */
+		CU_TRY(cudaFuncSetAttribute(cabac::cabac_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					    (int)smem));
+		ctx->cabac_smem_set = smem;
+	}
+	/* the grid must be resident as a whole: a block that starts late starts with one of the longest
+	 * slices (the first tickets are the working lanes' own numbers) */
+	int resident = 0;
+	CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, cabac::cabac_parse_kernel, (int)threads, smem));
+	if (resident < 1)
+		return -ENOMEM;
+	if (per_sm > (uint32_t)resident * (threads / 32))
+		per_sm = (uint32_t)resident * (threads / 32);
+	uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
+	if (warps > (uint64_t)sms * per_sm)
+		warps = (uint64_t)sms * per_sm;
+	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
+	const uint64_t grid_lanes = ((uint64_t)blocks * threads / 32) << lanes_log2;
+	const size_t counter_off = (size_t)(grid_lanes * ring_stride * sizeof(cabac::Nb));
+	const size_t order_off = counter_off + 16;
+	r = h264gpu_ws_reserve(ctx, order_off + (size_t)n_slices * 4);
 	if (r < 0)
 		return r;
 	cabac::CabacArgs a;
@@ -367,33 +418,14 @@ extern "C" int h264gpu_cabac_parse_dev(h264gpu_ctx *ctx, const uint8_t *d_stream
 	a.ring = (cabac::Nb *)ctx->ws;
 	a.ring_stride = ring_stride;
 	a.ring_w = ring_w;
-	/* slices per warp: same rule as the CAVLC parse; one warp per block so that a block's
-	 * shared memory (tables + 1.1 KB per slice) stays small and many blocks fit an SM */
-	int sms = 148;
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-	uint32_t lanes_log2 = 0;
-	const char *env = getenv("H264GPU_CABAC_LANES_LOG2");
-	if (env != NULL && atoi(env) >= 0 && atoi(env) <= 5) {
-		lanes_log2 = (uint32_t)atoi(env);
-	} else {
-		while (lanes_log2 < 5 && ((uint64_t)n_slices >> lanes_log2) > (uint64_t)sms * 32)
-			lanes_log2++;
-	}
 	a.lanes_log2 = lanes_log2;
-	uint32_t threads = 32; /* one warp per block */
-	{
-		const char *e = getenv("H264GPU_CABAC_WARPS");
-		if (e != NULL && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4))
-			threads = 32u * (uint32_t)atoi(e);
-	}
-	const uint64_t warps = ((uint64_t)n_slices + (1u << lanes_log2) - 1) >> lanes_log2;
-	const uint32_t blocks = (uint32_t)((warps * 32 + threads - 1) / threads);
-	const size_t smem = cabac::smem_bytes((threads / 32) << lanes_log2);
-	if (smem > ctx->cabac_smem_set) { /* function attributes are per device: cached per context */
-		CU_TRY(cudaFuncSetAttribute(cabac::cabac_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-					    (int)smem));
-		ctx->cabac_smem_set = smem;
-	}
+	a.next_slice = (uint32_t *)((uint8_t *)ctx->ws + counter_off);
+	a.order = (uint32_t *)((uint8_t *)ctx->ws + order_off);
+	env = getenv("H264GPU_CABAC_SORT");
+	cavlc2::order_kernel<<<1, CAVLC2_ORDER_T, 0, st>>>(d_params, n_slices, (uint32_t *)((uint8_t *)ctx->ws + order_off),
+							    a.next_slice, (uint32_t)grid_lanes,
+							    env != NULL && atoi(env) == 0 ? 0u : 1u);
+	ctx->launches++;
 	cabac::cabac_parse_kernel<<<blocks, threads, smem, st>>>(a);
 	CU_TRY(cudaGetLastError());
 	ctx->launches++;
