@@ -61,7 +61,13 @@ namespace annexb7 {
 
 constexpr int kT = 256;
 constexpr int kW = kT / 32;
-constexpr size_t kCtrlBytes = 256; /* control words at the head of the workspace */
+constexpr size_t kCtrlBytes = 4096; /* control words at the head of the workspace */
+/* span tickets of the first pass come from up to kTickMax counters, 256 bytes apart (words
+ * kTickBase + c * kTickStride of the control area): ONE counter hands out a ticket per ~1.9 ns at
+ * best (same-address atomics are served one after the other by the L2 slice that owns the word:
+ * 4 KiB / 1.9 ns = the 2140 GB/s the kernel ran at) and per 2.6-2.9 ns when the word lands on a
+ * less lucky slice (the 'workspace placement' of profiles/r02_scan_workspace_placement.txt) */
+constexpr uint32_t kTickBase = 64, kTickStride = 64, kTickMax = 15;
 constexpr uint64_t kValMask = (1ull << 40) - 1;
 constexpr uint64_t kPfxBit = 1ull << 41;
 
@@ -88,12 +94,28 @@ struct Scan7Args {
 	uint32_t regions;   /* K: tickets go round robin over K regions of region_len spans */
 	uint32_t region_len;
 	uint32_t pass2;     /* 1: the launch works off the deferred list */
+	uint32_t tick_n;    /* ticket counters of the first pass (0 or 1: the single word ctrl[0]) */
 	uint32_t *deferred; /* spans whose look-back would cross a region start before the region before it is done */
 	uint8_t right[2];
 	uint8_t has_right;
 	uint8_t pad;
 	uint64_t *trace; /* diagnostics (H264GPU_SCAN_TRACE): 8 timestamps per span, or NULL */
 };
+
+/* The next span ticket of this warp.  Counter c hands out c, c + n, c + 2n, ...: the counters
+ * advance at the same pace (each serves 1/n of the resident warps), so tickets are still taken
+ * in (nearly) increasing order, which is all the K-ticket lead of a span over its successor in
+ * the region needs.  Progress: the smallest unfinished ticket is either being worked on (all its
+ * predecessors in the stream have smaller tickets: its look-back ends) or is the next one of a
+ * counter whose warps have all finished their spans and are asking for it. */
+__device__ __forceinline__ uint32_t take_ticket(const Scan7Args &a, uint32_t c, uint32_t n)
+{
+	if (a.pass2)
+		return atomicAdd(a.ctrl + 6, 1u);
+	if (n <= 1)
+		return atomicAdd(a.ctrl, 1u);
+	return atomicAdd(a.ctrl + kTickBase + c * kTickStride, 1u) * n + c;
+}
 
 /* phase timestamps of a span (diagnostics build of the kernel only) */
 template <bool TRACE> __device__ __forceinline__ void trace_mark(const Scan7Args &a, uint32_t t, uint32_t lane, int k)
@@ -513,7 +535,7 @@ __device__ __forceinline__ uint32_t emit_span(WSmem<ROWS> &s, uint32_t lane, uin
 /* one span, all of it, by one warp */
 template <int ROWS, bool TRACE>
 __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint32_t t, uint32_t rstart,
-					uint32_t lane, uint32_t &parity, uint32_t &next)
+					uint32_t lane, uint32_t &parity, uint32_t &next, uint32_t tc, uint32_t tn)
 {
 	using C = Cfg<ROWS>;
 	const uint32_t ltmask = (1u << lane) - 1u;
@@ -731,7 +753,7 @@ __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint
 			/* the shift depends on the region before, which is not done: second pass */
 			if (lane == 0) {
 				a.deferred[atomicAdd(a.ctrl + 5, 1u)] = t;
-				next = atomicAdd(a.ctrl + (a.pass2 ? 6 : 0), 1u);
+				next = take_ticket(a, tc, tn);
 			}
 			__syncwarp();
 			return;
@@ -823,7 +845,7 @@ __device__ __forceinline__ void do_span(WSmem<ROWS> &s, const Scan7Args &a, uint
 		/* the next span's ticket is asked for here: its round trip (the one contended word of
 		 * the kernel, ~1.7 us under load) hides behind the byte-exact pass */
 		if (lane == 0)
-			next = atomicAdd(a.ctrl + (a.pass2 ? 6 : 0), 1u);
+			next = take_ticket(a, tc, tn);
 		for (uint32_t g = lane; g < ndirty; g += 32) {
 			const uint32_t c = s.dl[g];
 			const uint32_t R = c >> 5;
@@ -851,9 +873,12 @@ __global__ void __launch_bounds__(kT, MINB) scan7_kernel(const Scan7Args a)
 	__syncwarp();
 	uint32_t parity = 0;
 	uint32_t next = 0;
-	uint32_t *const tick = a.ctrl + (a.pass2 ? 6 : 0);
+	/* every counter needs a warp of its own: no more counters than warps in the grid */
+	const uint32_t gw = gridDim.x * (uint32_t)kW;
+	const uint32_t tn = a.pass2 || a.tick_n <= 1 ? 1u : (a.tick_n < gw ? a.tick_n : gw);
+	const uint32_t tc = (blockIdx.x * (uint32_t)kW + warp) % tn;
 	if (lane == 0)
-		next = atomicAdd(tick, 1u);
+		next = take_ticket(a, tc, tn);
 	/* first pass: ticket -> (region, index): consecutive spans of the stream are taken `regions`
 	 * tickets apart, so a span's predecessors published their chain words microseconds ago;
 	 * second pass: the spans the first one deferred */
@@ -871,11 +896,11 @@ __global__ void __launch_bounds__(kT, MINB) scan7_kernel(const Scan7Args a)
 			t = rstart + i;
 			if (t >= a.num_spans) { /* the last regions are ragged */
 				if (lane == 0)
-					next = atomicAdd(tick, 1u);
+					next = take_ticket(a, tc, tn);
 				continue;
 			}
 		}
-		do_span<ROWS, TRACE>(s, a, t, rstart, lane, parity, next);
+		do_span<ROWS, TRACE>(s, a, t, rstart, lane, parity, next, tc, tn);
 	}
 }
 
@@ -1216,6 +1241,8 @@ __global__ void __launch_bounds__(256) fin7_table(const Fin7Args f)
 	f.ctrl[4] = 0;
 	f.ctrl[5] = 0;
 	f.ctrl[6] = 0;
+	for (uint32_t c = 0; c < kTickMax; c++)
+		f.ctrl[kTickBase + c * kTickStride] = 0;
 }
 
 /*
@@ -1253,6 +1280,8 @@ __global__ void __launch_bounds__(256) avcc_write_kernel(const uint64_t *ordered
 __global__ void avcc_rearm_kernel(uint32_t *ctrl)
 {
 	ctrl[0] = ctrl[1] = ctrl[2] = ctrl[3] = ctrl[4] = ctrl[5] = ctrl[6] = 0;
+	for (uint32_t c = 0; c < kTickMax; c++)
+		ctrl[kTickBase + c * kTickStride] = 0;
 }
 
 } /* namespace annexb7 */

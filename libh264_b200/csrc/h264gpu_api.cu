@@ -528,7 +528,13 @@ static int ws7_reserve(h264gpu_ctx *ctx, size_t bytes)
 	CU_TRY(cudaDeviceSynchronize());
 	ws7_free(ctx);
 	const size_t want = (bytes + (bytes >> 3) + (1u << 20)) & ~(size_t)((1u << 20) - 1);
-	const char *e = getenv("H264GPU_WS7_VMM");
+	const char *e = getenv("H264GPU_WS7_PAD_MB");
+	if (e != NULL && atoi(e) > 0) {
+		/* diagnostics: a spacer allocation (kept until the process ends) moves the workspace */
+		void *pad = NULL;
+		cudaMalloc(&pad, (size_t)atoi(e) << 20);
+	}
+	e = getenv("H264GPU_WS7_VMM");
 	if (e == NULL || atoi(e) == 0 || ws7_map_own_range(ctx, want) < 0) {
 		CU_TRY(cudaMalloc(&ctx->ws7, want));
 		ctx->ws7_bytes = want;
@@ -567,8 +573,8 @@ static int scan7_launch_t(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, u
 	if (ev_cap >= 0xffffffffull)
 		ev_cap = 0xfffffffeull;
 	const uint64_t nblk = (nspans + annexb7::kFinT - 1) / annexb7::kFinT;
-	/* [256 control][chain][fin][span_pre][blk: 2 per fin block][totals][events][ordered events] */
-	const size_t chain_off = 256;
+	/* [control][chain][fin][span_pre][blk: 2 per fin block][totals][events][ordered events] */
+	const size_t chain_off = annexb7::kCtrlBytes;
 	const size_t fin_off = chain_off + (size_t)nspans * 8;
 	const size_t pre_off = fin_off + (size_t)nspans * 8;
 	const size_t blk_off = pre_off + (size_t)nspans * 8;
@@ -647,6 +653,13 @@ static int scan7_launch_t(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, u
 			const char *e = getenv("H264GPU_SCAN7_PF");
 			if (e != NULL)
 				a.pf_dist = (uint32_t)atoi(e);
+		}
+		/* ticket counters: one word cannot hand out more than a ticket per ~1.9 ns (annexb_scan7.cuh) */
+		a.tick_n = 8;
+		{
+			const char *e = getenv("H264GPU_SCAN7_TICKS");
+			if (e != NULL && atoi(e) >= 1 && atoi(e) <= (int)annexb7::kTickMax)
+				a.tick_n = (uint32_t)atoi(e);
 		}
 		{
 			const char *e = getenv("H264GPU_SCAN7_NAP");
@@ -743,7 +756,7 @@ static size_t scan7_workspace_bytes(uint64_t len, uint64_t nal_cap)
 	if (ev_cap > len / 3 + 2)
 		ev_cap = len / 3 + 2;
 	const uint64_t nblk = (nspans + annexb7::kFinT - 1) / annexb7::kFinT;
-	return 256 + (size_t)nspans * 28 + (size_t)nblk * 16 + 64 + (size_t)ev_cap * 40;
+	return annexb7::kCtrlBytes + (size_t)nspans * 28 + (size_t)nblk * 16 + 64 + (size_t)ev_cap * 40;
 }
 
 extern "C" int h264gpu_scan_reserve(h264gpu_ctx *ctx, uint64_t len, uint64_t nal_cap)

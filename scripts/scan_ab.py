@@ -18,11 +18,14 @@ ap.add_argument("--alloc-extra", type=int, default=16)
 ap.add_argument("--stage", type=int, default=0, help="1: copy through a second pinned buffer like bench.py")
 ap.add_argument("--sampler", type=int, default=0, help="1: nvidia-smi clock sampler running like bench.py")
 ap.add_argument("--order", default="strip,only")
+ap.add_argument("--dev", type=int, default=0, help="CUDA device index")
+ap.add_argument("--regrow", type=int, default=0, help="after timing, grow the scan workspace N times (free + allocate) and time again")
+ap.add_argument("--threads", type=int, default=0, help="generator threads (0 = all)")
 args = ap.parse_args()
-g = L.Gpu(0)
+g = L.Gpu(args.dev)
 size = args.size_mb << 20
 pin = g.pinned(size + 4096)
-stream, rbsp_ref, offs = make_workload(L, size, SEED, out=pin.array, nthreads=min(os.cpu_count() or 1, 64))
+stream, rbsp_ref, offs = make_workload(L, size, SEED, out=pin.array, nthreads=args.threads or min(os.cpu_count() or 1, 64))
 n_in, n_nal = len(stream), len(offs) - 1
 tz = 0
 while stream[n_in - 1 - tz] == 0:
@@ -84,4 +87,21 @@ for strip in [x == "strip" for x in args.order.split(",")]:
         out[key] = {"ms": ms, "GBps": n_in / ms / 1e6, "ok": bool(ok), "n_nal": int(res.n_nal),
                     "rbsp_bytes": int(res.rbsp_bytes)}
         print(key, out[key], flush=True)
+for k in range(args.regrow):
+    # a larger reservation frees the workspace and allocates a new one somewhere else
+    L._check(g.lib.h264gpu_scan_reserve(g.h, C.c_uint64(n_in + (k + 1) * (n_in >> 2)), C.c_uint64(cap)), "reserve")
+    def step():
+        g.split_strip_inplace_dev(d_in.ptr, n_in, d_rbsp.ptr, d_tab.ptr, d_tab.ptr + cap * 8,
+                                  d_tab.ptr + cap * 16, d_tab.ptr + cap * 24, cap, d_res.ptr)
+    for _ in range(args.warmup):
+        step()
+    g.sync()
+    tm = g.timer()
+    g.timer_start(tm)
+    for _ in range(args.steps):
+        step()
+    g.timer_stop(tm)
+    out["regrow%d" % (k + 1)] = {"ms": g.timer_ms(tm) / args.steps}
+    print("dev", args.dev, "regrow", k + 1, out["regrow%d" % (k + 1)], flush=True)
+out["dev"] = args.dev
 print(json.dumps(out))

@@ -119,7 +119,7 @@ static int emu_scan7(const uint8_t *buf, uint64_t len, uint64_t base, const stru
 	std::vector<uint64_t> fin(nspans, ~0ull), pre(nspans, ~0ull), blk(2 * (size_t)nblk, ~0ull);
 	std::vector<uint64_t> evbuf(2 * (ev_cap ? ev_cap : 1), 0), ordered(3 * (ev_cap ? ev_cap : 1), 0);
 	uint64_t totals[8] = {0};
-	static uint32_t ctrl[64] = {0}; /* zero once; the finalize kernels re-arm it */
+	static uint32_t ctrl[annexb7::kCtrlBytes / 4] = {0}; /* zero once; the finalize kernels re-arm it */
 	Scan7Args a;
 	memset(&a, 0, sizeof(a));
 	a.in = buf;
@@ -142,6 +142,11 @@ static int emu_scan7(const uint8_t *buf, uint64_t len, uint64_t base, const stru
 	if (a.regions > nspans)
 		a.regions = nspans;
 	a.region_len = (nspans + a.regions - 1) / a.regions;
+	/* ticket counters: 0 (the single word), 2, 3, 8, 5 in turn.  Never more than the warps of a
+	 * CTA: the emulator runs one CTA at a time, so the first one must serve every counter. */
+	static uint32_t ktick = 0;
+	static const uint32_t tick_ns[5] = {0, 2, 3, 8, 5};
+	a.tick_n = tick_ns[ktick++ % 5];
 	std::vector<uint32_t> deferred(nspans + 1, 0);
 	a.deferred = deferred.data();
 	a.right[0] = a.right[1] = 0xff;
@@ -182,9 +187,9 @@ static int emu_scan7(const uint8_t *buf, uint64_t len, uint64_t base, const stru
 	else if (rows == 2) emu_scan7_run<2>(a, f, rbsp != NULL, ev_cap);
 	else if (rows == 6) emu_scan7_run<6>(a, f, rbsp != NULL, ev_cap);
 	else emu_scan7_run<8>(a, f, rbsp != NULL, ev_cap);
-	for (int i = 0; i < 7; i++)
+	for (size_t i = 0; i < sizeof(ctrl) / 4; i++)
 		if (ctrl[i] != 0)
-			return -2; /* control words not re-armed */
+			return -2; /* control words (ticket counters included) not re-armed */
 	return 0;
 }
 
@@ -200,7 +205,7 @@ extern "C" int emu_avcc(uint8_t *data, uint64_t len, uint64_t ev_cap, uint64_t *
 	std::vector<uint64_t> fin(nspans, ~0ull), pre(nspans, ~0ull), blk(2 * (size_t)nblk, ~0ull);
 	std::vector<uint64_t> evbuf(2 * (ev_cap ? ev_cap : 1), 0), ordered(3 * (ev_cap ? ev_cap : 1), 0);
 	uint64_t totals[8] = {0};
-	static uint32_t ctrl[64] = {0};
+	static uint32_t ctrl[annexb7::kCtrlBytes / 4] = {0};
 	uint8_t *buf = (uint8_t *)aligned_alloc(16, (len + 15) & ~15ull);
 	memcpy(buf, data, len);
 	Scan7Args a;
