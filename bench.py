@@ -527,10 +527,10 @@ def main():
     n_nal_piece = len(offs) - 1
     cap = n_nal_piece + 4096
     # The stream buffers and, right after them, the scan workspace are the FIRST device allocations of
-    # the process, before torch / NCCL allocate anything: where the workspace lands decides 2.0 vs
-    # 2.8 ms per 4 GiB (include/h264gpu.h, profiles/r02_scan_workspace_placement.txt), and with the
-    # communicator's buffers allocated first every rank of a multi-GPU run landed in the slow case
-    # (2966 GB/s on 2 GPUs against 2137 on one).
+    # the process, before torch / NCCL allocate anything.  (With ONE span-ticket word in the kernel,
+    # where the workspace landed decided 2.0 vs 2.8 ms per 4 GiB: include/h264gpu.h,
+    # profiles/r02_scan_workspace_placement.txt.  The tickets now come from 8 counters and the
+    # placement no longer matters, profiles/r02_scan7_ticket_counters.txt; the order is kept.)
     d_in = g.alloc(n_in + 64)
     d_rbsp = g.alloc(n_in + 64)
     d_tab = g.alloc(cap * 8 * 4)

@@ -145,11 +145,12 @@ H264GPU_API int h264gpu_split_strip_inplace_dev(h264gpu_ctx *ctx, const uint8_t 
 
 /*
  * Reserve the workspace of h264gpu_split_strip_inplace_dev for streams of up to len bytes and
- * nal_cap NAL units now, instead of at the first call.  WHEN it is allocated matters on B200:
- * the kernel's look-back polls chain words in this buffer, and the same launch over the same 4 GiB
- * took 2.0 ms when the workspace had been allocated right after the stream buffers and 2.8 - 2.9 ms
- * when it had been allocated before them, or after a large page-locked host buffer
- * (profiles/r02_scan_workspace_placement.txt).  Call it right after allocating d_in / d_rbsp.
+ * nal_cap NAL units now, instead of at the first call (which otherwise pays a device-wide
+ * synchronisation and the allocation).  Until the span tickets of the kernel were spread over
+ * several counters, WHEN the buffer was allocated also decided 2.0 against 2.8 - 2.9 ms per 4 GiB:
+ * the one ticket word was served at the rate of the L2 slice it happened to land on
+ * (profiles/r02_scan_workspace_placement.txt, profiles/r02_scan7_ticket_counters.txt).  With the
+ * counters the launch takes 2.05 ms wherever the buffer is; the call is kept for the first reason.
  */
 H264GPU_API int h264gpu_scan_reserve(h264gpu_ctx *ctx, uint64_t len, uint64_t nal_cap);
 

@@ -22,7 +22,13 @@
  * of the same kernel over the deferred list (~17 spans per region), by which time every chain
  * word exists.  1719 -> 2136 GB/s at 4 GiB.
  *
- * Measured and NOT kept: a CTA-level ticket pool (spans
+ * TICKETS COME FROM SEVERAL COUNTERS (take_ticket, kTickBase): with one ticket word the kernel
+ * ran at the rate same-address atomics are served by the L2 slice that owns the word, one per
+ * 1.9 ns at best = 4 KiB / 1.9 ns = 2140 GB/s, one per 2.6 - 2.9 ns on another slice.
+ *
+ * Measured and NOT kept -- all of it WITH ONE TICKET WORD, i.e. under that bound (3 KiB spans
+ * cost 4/3 of the tickets: the 1687 below is 2136 x 3/4 + a little; worth measuring again):
+ * a CTA-level ticket pool (spans
  * reserved early are published late: 1636 GB/s), 3 KiB spans at 48 warps per SM (1687), two
  * 16-byte loads + word select instead of five conflicting 4-byte loads (no change: the kernel is
  * not bound by a pipe), and running the emit phase one loop iteration after the classify phase

@@ -776,7 +776,13 @@ static int scan7_launch(h264gpu_ctx *ctx, const uint8_t *d_in, uint64_t len, uin
 			uint64_t *d_nal_end, uint64_t *d_nal_rbsp, uint64_t *d_nal_rbsp_len, uint64_t nal_cap,
 			struct h264gpu_scan_result *d_result, cudaStream_t st)
 {
-	/* 8 rows = 4 KiB spans, 5 CTAs per SM (3 KiB spans at 6 CTAs per SM measured 11 % slower) */
+	/* 8 rows = 4 KiB spans, 5 CTAs per SM.  3 KiB spans at 6 CTAs per SM (H264GPU_SCAN7_ROWS=6) were
+	 * measured 11 % slower when all tickets came from one word (4/3 of the tickets at a fixed ticket
+	 * rate); kept selectable for a measurement with the ticket counters */
+	const char *e = getenv("H264GPU_SCAN7_ROWS");
+	if (e != NULL && atoi(e) == 6)
+		return scan7_launch_t<6, 6>(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp,
+					    d_nal_rbsp_len, nal_cap, d_result, st);
 	return scan7_launch_t<8, 5>(ctx, d_in, len, base, edge, d_rbsp, d_nal_start, d_nal_end, d_nal_rbsp,
 				    d_nal_rbsp_len, nal_cap, d_result, st);
 }
