@@ -39,8 +39,8 @@ sys.path.insert(0, ROOT)
 METRIC = "annexb_split_strip_throughput"
 UNIT = "GB/s"
 SEED = 0x264
-SCAN_KERNEL = ("annexb7::scan7_kernel<8> (warp-autonomous 4 KiB spans, tickets round robin over regions, RBSP in "
-               "place per NAL) + second pass over deferred region heads + fin7_spans/fin7_order/fin7_table")
+SCAN_KERNEL = ("annexb7::scan7_kernel<8> (warp-autonomous 4 KiB spans, tickets from 8 counters, round robin over regions, "
+               "RBSP in place per NAL) + second pass over deferred region heads + fin7_spans/fin7_order/fin7_table")
 
 
 def measured_peak():
