@@ -288,6 +288,26 @@ def test_gpu_config2_full_size_properties(gpu):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"H264GPU_SCAN7_TICKS": "1"}, {"H264GPU_SCAN7_TICKS": "2"},
+                                 {"H264GPU_SCAN7_TICKS": "15"}, {"H264GPU_SCAN7_ROWS": "6"},
+                                 {"H264GPU_SCAN7_TICKS": "15", "H264GPU_SCAN7_REGIONS": "7"}])
+def test_gpu_ticket_counters_and_span_size(gpu, env, monkeypatch):
+    """The span tickets of scan7_kernel come from 8 counters by default; any number of counters
+    (1 = the single word of the first builds) and the 3 KiB-span instantiation give the same NAL
+    table and RBSP bytes (the launcher reads the knobs at every launch).  Streams from one span to
+    hundreds of regions, so that small grids (fewer warps than counters) are covered too."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(23)
+    for it, hi in enumerate([40, 3000, 40000, 300000]):
+        buf = S.gen_annexb(rng, int(rng.integers(1, 300)), lo=1, hi=hi, p_zero=3 / 16)
+        check_per_nal(gpu.split_strip_inplace(buf), S.oracle_split_strip(buf), ("ticket counters", env, it))
+    offs = L.synth_offsets(7, 24 << 20)
+    stream, _ = L.synth_annexb(7, L.synth_payloads(7, offs), offs)
+    check_per_nal(gpu.split_strip_inplace(stream, cap=len(offs) + 64), S.oracle_split_strip(stream), ("config2 24 MiB", env))
+
+
+@pytest.mark.gpu
 def test_gpu_sharded_merge(gpu):
     rng = np.random.default_rng(17)
     run = lambda buf, e, lo: gpu.split_strip_inplace(buf, edge=e, base=lo)
