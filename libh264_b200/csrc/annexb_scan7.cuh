@@ -113,7 +113,10 @@ struct Scan7Args {
  * in (nearly) increasing order, which is all the K-ticket lead of a span over its successor in
  * the region needs.  Progress: the smallest unfinished ticket is either being worked on (all its
  * predecessors in the stream have smaller tickets: its look-back ends) or is the next one of a
- * counter whose warps have all finished their spans and are asking for it. */
+ * counter whose warps have all finished their spans and are asking for it.  With the default of
+ * 8 counters = the warps of a CTA, warp w of EVERY CTA asks counter w: any one resident CTA serves
+ * all counters, so this holds even when part of the grid is not resident (another kernel on the
+ * GPU); more counters than that (the knob goes to 15) rely on the whole grid being resident. */
 __device__ __forceinline__ uint32_t take_ticket(const Scan7Args &a, uint32_t c, uint32_t n)
 {
 	if (a.pass2)
