@@ -3,7 +3,7 @@
  * start-code framing with the tile organisation of the gen-6 scan kernel (annexb_scan6.cuh).
  *
  * Why: frame_kernel (annexb_frame.cuh) spends ~20 k warp-instructions per 16 KiB tile
- * (profiles/r01_frame_kernel_raw.csv): exact zero-run bookkeeping for every chunk, a byte shifter
+ * (profiles/r01_frame_gen1_kernel_raw.csv): exact zero-run bookkeeping for every chunk, a byte shifter
  * per inserted 03, a swizzled shared staging buffer and a copy-out pass; 0.14 of the HBM peak.
  *
  * Here the source tile (32 KiB) is staged once with a bulk copy and the OUTPUT is produced in

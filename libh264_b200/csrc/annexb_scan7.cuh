@@ -14,7 +14,7 @@
  * TICKETS GO ROUND ROBIN OVER K REGIONS of the stream.  With tickets in stream order a span's
  * look-back needs the words of ~16 predecessors that took their tickets within nanoseconds of
  * it, i.e. it waits for the slowest of them: 4.8 us of a 12.8 us span life
- * (profiles/r02_scan7_phase_trace.txt).  With ticket -> (region tk % K, index tk / K) the
+ * (profiles/r02_scan_phase_trace.txt).  With ticket -> (region tk % K, index tk / K) the
  * predecessor of a span was taken K tickets earlier (K = 1480: ~3 us, the time from a ticket to
  * its chain word), so the look-back finds it published, usually already as a PFX.  The spans at
  * the head of a region (up to its first start code) would have to wait for the END of the
