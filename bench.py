@@ -816,7 +816,8 @@ def main():
                          "frac": achieved / peak,
                          "traffic": measured_traffic(n_in) if world == 1 else None,
                          "traffic_source": "profiles/r02_traffic.json (ncu dram__bytes of this workload's launch; a committed "
-                                           "measurement, not re-measured in this run)",
+                                           "measurement, not re-measured in this run; final build at 1 GiB: "
+                                           "profiles/r02g_traffic_1gib.json, 0.97 x algorithmic)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes),
                          "note": "duration = CUDA-event step time on the launch stream: both scan7_kernel launches "
